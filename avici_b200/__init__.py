@@ -1,0 +1,15 @@
+"""avici_b200 — B200-native implementation of AVICI's inference hot path.
+
+Public surface mirrors `avici/__init__.py:1-4` for the path in scope:
+`load_pretrained`, `AVICIModel`, `simulate_data` (+ `InferenceModel`, `BaseModel`).
+Importing the package does not need a GPU; any compute call needs the in-tree CUDA extension
+(`avici_b200/csrc/libavici_b200.so`, built by `__graft_entry__.build()`) and an sm_100 device.
+"""
+from .model import AVICIModel, BaseModel, InferenceModel
+from .params import init_params, param_count
+from .pretrain import load_checkpoint, load_pretrained, random_init_model, save_checkpoint
+from .synthetic import simulate_data
+
+__all__ = ["load_pretrained", "AVICIModel", "simulate_data", "InferenceModel", "BaseModel", "init_params",
+           "param_count", "load_checkpoint", "save_checkpoint", "random_init_model"]
+__version__ = "0.1.0"

@@ -1,0 +1,745 @@
+// C-ABI of the B200-native AVICI inference forward (see include/avici_b200.h).
+//
+// Host-side driver: weight packing (LayerNorm / softmax-scale folding for the bf16 path), the
+// per-block kernel schedule and workspace carving.  The device work lives in kernels_f32.cuh
+// (prologue / epilogue kernels + the true-fp32 parity path) and kernels_tc.cuh (bf16 tcgen05 path).
+#include "../../include/avici_b200.h"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels_f32.cuh"
+#include "kernels_tc.cuh"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+thread_local std::string g_create_error;
+
+struct Block {
+  // exact fp32 parameters (both modes keep them; 17 MB in total)
+  const float *ln_g[4], *ln_b[4];  // q, k, v, ffn LayerNorms
+  const float *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo, *w1, *b1, *w2, *b2;
+  // bf16 tensor-core copies: K-major [N,K], LayerNorm affine and softmax scale folded in
+  const bf16 *wqkv_t, *wo_t, *w1_t, *w2_t;
+  const float *bqkv_f, *b1_f;
+  CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2;
+};
+
+}  // namespace
+
+struct avb_model_s {
+  avb_config cfg{};
+  std::string err;
+  int device = 0;
+  int num_sms = 148;
+  bool loaded = false;
+  void* arena = nullptr;  // all weights
+  std::vector<Block> blocks;
+  const float *emb_w = nullptr, *emb_b = nullptr;
+  const float *lnf_g = nullptr, *lnf_b = nullptr;  // final LN
+  const float *lnu_g = nullptr, *lnu_b = nullptr, *wu = nullptr, *bu = nullptr;
+  const float *lnv_g = nullptr, *lnv_b = nullptr, *wv = nullptr, *bv = nullptr;
+  const float *temp = nullptr, *bias = nullptr;
+  void* host_ws = nullptr;  // internal workspace of avb_forward_host
+  size_t host_ws_bytes = 0;
+  long long launches = 0;
+};
+
+namespace {
+
+int fail(avb_handle h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define AVB_CUDA(h, expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail((h), AVB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define AVB_LAUNCH_CHECK(h)                                                                        \
+  do {                                                                                             \
+    (h)->launches++;                                                                               \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail((h), AVB_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ Haiku parameter names
+std::string sfx(int i) { return i == 0 ? std::string() : "_" + std::to_string(i); }
+
+// ------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [rows, cols] bf16 row-major, box [box_rows x 64 cols], 128B swizzle
+bool make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// qkv [B,n,d,C] bf16 as a 4-D map; box = 32 channels x 128 positions along the attended axis, 64B swizzle
+bool make_tmap_qkv(CUtensorMap* tm, const void* ptr, int B, int n, int d, int C, int axis) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)d, (cuuint64_t)n, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)d * C * 2, (cuuint64_t)n * d * C * 2};
+  cuuint32_t box[4] = {32, axis == 0 ? 128u : 1u, axis == 0 ? 1u : 128u, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// ------------------------------------------------------------------ kernel launchers
+template <int BN, int EPI>
+int launch_gemm_tc(avb_handle h, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const float* bias, void* out,
+                   int ldo, int M, int N, int K, cudaStream_t st, int num_sms, long long* launches) {
+  using Cfg = avb::GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(avb::gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(gemm_tc): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = ((M + 127) / 128) * (N / BN);
+  const int grid = std::min(tiles, num_sms);
+  avb::gemm_tc_kernel<BN, EPI><<<grid, avb::kGemmThreads, Cfg::kSmemBytes, st>>>(tm_a, tm_b, bias, out, ldo, M, N, K);
+  if (launches) ++*launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "gemm_tc launch: %s", cudaGetErrorString(e));
+  return AVB_OK;
+}
+
+int launch_attention_tc(avb_handle h, const void* qkv, void* out, int B, int n, int d, int H, int axis,
+                        cudaStream_t st, int num_sms, long long* launches) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(avb::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         avb::kAttnSmemBytes);
+    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(attention_tc): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  CUtensorMap tm;
+  if (!make_tmap_qkv(&tm, qkv, B, n, d, 3 * H * 32, axis)) return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled(qkv) failed");
+  const int T = axis == 0 ? d : n;
+  const long long S = axis == 0 ? (long long)B * n : (long long)B * d;
+  const long long items = S * H * ((T + 127) / 128);
+  const int grid = (int)std::min<long long>(items, num_sms);
+  avb::attention_tc_kernel<<<grid, avb::kAttnThreads, avb::kAttnSmemBytes, st>>>(
+      tm, reinterpret_cast<bf16*>(out), B, n, d, H, axis);
+  if (launches) ++*launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention_tc launch: %s", cudaGetErrorString(e));
+  return AVB_OK;
+}
+
+template <int EPI, bool LN>
+void launch_sgemm(const float* A, int lda, const float* W, int ldw, const float* bias, const float* g,
+                  const float* b, const float* R, int ldr, float* C, int ldc, size_t M, int N, int K,
+                  cudaStream_t st) {
+  dim3 grid((unsigned)((M + 63) / 64), N / 64);
+  avb::sgemm_kernel<EPI, LN><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, g, b, R, ldr, C, ldc, M, N, K);
+}
+
+// ------------------------------------------------------------------ workspace carving
+struct BlockWs {
+  // bf16 mode: xhat bf16[N,128] | big (qkv bf16[N,768] aliased with h bf16[N,512]) | attn bf16[N,256]
+  // f32 mode:  big (qkv f32[N,768] aliased with h f32[N,512]) | attn f32[N,256]
+  size_t xhat_off, big_off, attn_off, total;
+};
+BlockWs block_ws_layout(const avb_config& c, size_t ntok) {
+  BlockWs w{};
+  const size_t HD = (size_t)c.num_heads * c.key_size, F = (size_t)c.widening_factor * c.dim;
+  size_t off = 0;
+  if (c.compute_dtype == AVB_DTYPE_BF16) {
+    w.xhat_off = off; off = align_up(off + ntok * c.dim * 2, 1024);
+    w.big_off = off;  off = align_up(off + ntok * std::max(3 * HD, F) * 2, 1024);
+    w.attn_off = off; off = align_up(off + ntok * HD * 2, 1024);
+  } else {
+    w.big_off = off;  off = align_up(off + ntok * std::max(3 * HD, F) * 4, 1024);
+    w.attn_off = off; off = align_up(off + ntok * HD * 4, 1024);
+  }
+  w.total = off;
+  return w;
+}
+
+struct FwdWs {
+  size_t xs_off, iv_off, stat_off, pooled_off, pooled_c_off, uv_off, z_off, blk_off, total;
+  int Bc;  // datasets (after chunk expansion) processed per pass
+};
+constexpr size_t kWsBudget = (size_t)40 << 30;  // cap on the per-pass activation working set
+
+FwdWs fwd_ws_layout(const avb_config& c, int B, int n, int d, int chunks) {
+  FwdWs w{};
+  const int Be = B * chunks, ne = n / chunks;
+  const size_t cells = (size_t)B * n * d;
+  size_t off = 0;
+  w.xs_off = off; off = align_up(off + cells * 4, 1024);
+  w.iv_off = off; off = align_up(off + (chunks > 1 ? cells * 4 : 0), 1024);
+  w.stat_off = off; off = align_up(off + (size_t)B * (n + d + 8) * 8, 1024);
+  w.pooled_off = off; off = align_up(off + (size_t)B * d * c.dim * 4, 1024);
+  w.pooled_c_off = off; off = align_up(off + (chunks > 1 ? (size_t)Be * d * c.dim * 4 : 0), 1024);
+  w.uv_off = off; off = align_up(off + (size_t)2 * B * d * c.out_dim * 4, 1024);
+  const size_t tok1 = (size_t)ne * d;
+  const size_t per_ds = tok1 * c.dim * 4 + block_ws_layout(c, tok1).total + 4096;
+  int Bc = (int)std::max<size_t>(1, std::min<size_t>((size_t)Be, kWsBudget / per_ds));
+  w.Bc = Bc;
+  w.z_off = off; off = align_up(off + (size_t)Bc * tok1 * c.dim * 4, 1024);
+  w.blk_off = off; off += block_ws_layout(c, (size_t)Bc * tok1).total;
+  w.total = off;
+  return w;
+}
+
+// rows i -> (chunk i % chunks, position i / chunks)   (model.py:105-106)
+__global__ void chunk_gather_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int n, int d,
+                                    int chunks) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * n * d;
+  if (idx >= total) return;
+  const int j = (int)(idx % d);
+  const size_t bi = idx / d;
+  const int i = (int)(bi % n);
+  const size_t b = bi / n;
+  const int cs = n / chunks;
+  const int c = i % chunks, r = i / chunks;
+  dst[(((b * chunks + c) * cs) + r) * d + j] = src[idx];
+}
+__global__ void chunk_max_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t per_ds, int chunks,
+                                 size_t total) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const size_t b = idx / per_ds, e = idx % per_ds;
+  float m = -INFINITY;
+  for (int c = 0; c < chunks; ++c) m = fmaxf(m, src[(b * chunks + c) * per_ds + e]);
+  dst[idx] = m;
+}
+
+bool shape_ok(avb_handle h, int B, int n, int d) { return h && B >= 1 && n >= 1 && d >= 1; }
+
+}  // namespace
+
+// ====================================================================================== C ABI
+extern "C" {
+
+const char* avb_version(void) { return "avici_b200 0.1.0 sm_100a"; }
+
+const char* avb_last_error(avb_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int avb_create(avb_handle* out, const avb_config* cfg) {
+  if (!out || !cfg) return fail(nullptr, AVB_ERR_INVALID, "avb_create: null argument");
+  *out = nullptr;
+  if (cfg->dim != 128) return fail(nullptr, AVB_ERR_INVALID, "unsupported dim=%d (kernels are built for dim=128)", cfg->dim);
+  if (cfg->key_size != 32) return fail(nullptr, AVB_ERR_INVALID, "unsupported key_size=%d (kernels are built for 32)", cfg->key_size);
+  if (cfg->num_heads < 1 || cfg->num_heads > 16 || (cfg->num_heads * cfg->key_size) % 64 != 0)
+    return fail(nullptr, AVB_ERR_INVALID, "unsupported num_heads=%d", cfg->num_heads);
+  if (cfg->widening_factor < 1 || (cfg->widening_factor * cfg->dim) % 256 != 0)
+    return fail(nullptr, AVB_ERR_INVALID, "unsupported widening_factor=%d (FFN width must be a multiple of 256)", cfg->widening_factor);
+  if (cfg->layers < 1) return fail(nullptr, AVB_ERR_INVALID, "layers must be >= 1");
+  if (cfg->out_dim < 1 || cfg->out_dim > 128) return fail(nullptr, AVB_ERR_INVALID, "unsupported out_dim=%d (1..128)", cfg->out_dim);
+  if (cfg->compute_dtype != AVB_DTYPE_F32 && cfg->compute_dtype != AVB_DTYPE_BF16)
+    return fail(nullptr, AVB_ERR_INVALID, "unknown compute_dtype=%d", cfg->compute_dtype);
+  if (cfg->compute_dtype == AVB_DTYPE_BF16 && (cfg->num_heads * cfg->key_size * 3) % 256 != 0)
+    return fail(nullptr, AVB_ERR_INVALID, "bf16 path needs 3*num_heads*key_size to be a multiple of 256");
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10) return fail(nullptr, AVB_ERR_CUDA, "device sm_%d%d is not Blackwell sm_100 (kernels are sm_100a only)", prop.major, prop.minor);
+  avb_handle h = new avb_model_s();
+  h->cfg = *cfg;
+  h->device = dev;
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  return AVB_OK;
+}
+
+void avb_destroy(avb_handle h) {
+  if (!h) return;
+  if (h->arena) cudaFree(h->arena);
+  if (h->host_ws) cudaFree(h->host_ws);
+  delete h;
+}
+
+int64_t avb_param_count(avb_handle h) {
+  if (!h) return -1;
+  const avb_config& c = h->cfg;
+  const int64_t k = c.dim, HD = (int64_t)c.num_heads * c.key_size, F = (int64_t)c.widening_factor * c.dim;
+  const int64_t per_block = 4 * 2 * k + 3 * (k * HD + HD) + (HD * k + k) + (k * F + F) + (F * k + k);
+  return 2 * k + k + 2 * (int64_t)c.layers * per_block + 2 * k + 2 * (2 * k + k * c.out_dim + c.out_dim) + 2;
+}
+
+int64_t avb_launch_count(avb_handle h) { return h ? h->launches : -1; }
+
+int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count) {
+  if (!h || !tensors) return fail(h, AVB_ERR_INVALID, "avb_load_weights: null argument");
+  const avb_config& c = h->cfg;
+  const int k = c.dim, HD = c.num_heads * c.key_size, F = c.widening_factor * c.dim, nb = 2 * c.layers;
+  std::map<std::string, std::pair<const float*, int64_t>> tab;
+  for (int i = 0; i < count; ++i) tab[tensors[i].name] = {tensors[i].data, tensors[i].numel};
+  std::string missing;
+  auto get = [&](const std::string& name, int64_t numel) -> const float* {
+    auto it = tab.find(name);
+    if (it == tab.end() || it->second.second != numel || !it->second.first) {
+      if (missing.empty()) missing = name + (it == tab.end() ? " (absent)" : " (wrong size)");
+      return nullptr;
+    }
+    return it->second.first;
+  };
+
+  // host staging: one fp32 arena and one bf16 arena, then a single upload each
+  std::vector<float> f32;
+  std::vector<bf16> b16;
+  f32.reserve((size_t)avb_param_count(h) + (size_t)nb * (3 * HD + F) + 1024);
+  auto push_f32 = [&](const float* src, size_t nel) -> size_t {
+    size_t off = align_up(f32.size(), 64);
+    f32.resize(off + nel);
+    if (src) memcpy(f32.data() + off, src, nel * sizeof(float));
+    return off;
+  };
+  auto push_b16 = [&](size_t nel) -> size_t {
+    size_t off = align_up(b16.size(), 512);
+    b16.resize(off + nel);
+    return off;
+  };
+  struct BlockOff {
+    size_t ln_g[4], ln_b[4], wq, bq, wk, bk, wv, bv, wo, bo, w1, b1, w2, b2, bqkv_f, b1_f;
+    size_t wqkv_t, wo_t, w1_t, w2_t;
+  };
+  std::vector<BlockOff> offs(nb);
+  const std::string R = "BaseModel/";
+  const size_t emb_w = push_f32(get(R + "linear/w", 2 * k), 2 * k);
+  const size_t emb_b = push_f32(get(R + "linear/b", k), k);
+  const double qscale = 1.4426950408889634 / std::sqrt((double)c.key_size);  // log2(e)/sqrt(key_size)
+  for (int i = 0; i < nb; ++i) {
+    BlockOff& o = offs[i];
+    const float *g[4], *b[4];
+    for (int t = 0; t < 4; ++t) {
+      const std::string ln = R + "layer_norm" + sfx(4 * i + t);
+      g[t] = get(ln + "/scale", k); b[t] = get(ln + "/offset", k);
+      o.ln_g[t] = push_f32(g[t], k); o.ln_b[t] = push_f32(b[t], k);
+    }
+    const std::string mha = R + "multi_head_attention" + sfx(i);
+    const float* wq = get(mha + "/query/w", (int64_t)k * HD); const float* bq = get(mha + "/query/b", HD);
+    const float* wk = get(mha + "/key/w", (int64_t)k * HD);   const float* bk = get(mha + "/key/b", HD);
+    const float* wv = get(mha + "/value/w", (int64_t)k * HD); const float* bv = get(mha + "/value/b", HD);
+    const float* wo = get(mha + "/linear/w", (int64_t)HD * k); const float* bo = get(mha + "/linear/b", k);
+    const float* w1 = get(R + "linear" + sfx(2 * i + 1) + "/w", (int64_t)k * F);
+    const float* b1 = get(R + "linear" + sfx(2 * i + 1) + "/b", F);
+    const float* w2 = get(R + "linear" + sfx(2 * i + 2) + "/w", (int64_t)F * k);
+    const float* b2 = get(R + "linear" + sfx(2 * i + 2) + "/b", k);
+    o.wq = push_f32(wq, (size_t)k * HD); o.bq = push_f32(bq, HD);
+    o.wk = push_f32(wk, (size_t)k * HD); o.bk = push_f32(bk, HD);
+    o.wv = push_f32(wv, (size_t)k * HD); o.bv = push_f32(bv, HD);
+    o.wo = push_f32(wo, (size_t)HD * k); o.bo = push_f32(bo, k);
+    o.w1 = push_f32(w1, (size_t)k * F);  o.b1 = push_f32(b1, F);
+    o.w2 = push_f32(w2, (size_t)F * k);  o.b2 = push_f32(b2, k);
+    o.bqkv_f = push_f32(nullptr, 3 * HD);
+    o.b1_f = push_f32(nullptr, F);
+    if (!missing.empty()) continue;
+    if (c.compute_dtype == AVB_DTYPE_BF16) {
+      // LN(x) @ W + b = xhat @ (diag(gamma) W) + (beta @ W + b); q additionally carries log2e/sqrt(key)
+      o.wqkv_t = push_b16((size_t)3 * HD * k);
+      const float* ws[3] = {wq, wk, wv}; const float* bs[3] = {bq, bk, bv};
+      for (int t = 0; t < 3; ++t) {
+        const double sc = t == 0 ? qscale : 1.0;
+        for (int col = 0; col < HD; ++col) {
+          double acc = bs[t][col];
+          for (int r = 0; r < k; ++r) {
+            acc += (double)b[t][r] * ws[t][(size_t)r * HD + col];
+            b16[o.wqkv_t + ((size_t)t * HD + col) * k + r] =
+                __float2bfloat16((float)((double)g[t][r] * ws[t][(size_t)r * HD + col] * sc));
+          }
+          f32[o.bqkv_f + (size_t)t * HD + col] = (float)(acc * sc);
+        }
+      }
+      o.wo_t = push_b16((size_t)k * HD);
+      for (int col = 0; col < k; ++col)
+        for (int r = 0; r < HD; ++r) b16[o.wo_t + (size_t)col * HD + r] = __float2bfloat16(wo[(size_t)r * k + col]);
+      o.w1_t = push_b16((size_t)F * k);
+      for (int col = 0; col < F; ++col) {
+        double acc = b1[col];
+        for (int r = 0; r < k; ++r) {
+          acc += (double)b[3][r] * w1[(size_t)r * F + col];
+          b16[o.w1_t + (size_t)col * k + r] = __float2bfloat16((float)((double)g[3][r] * w1[(size_t)r * F + col]));
+        }
+        f32[o.b1_f + col] = (float)acc;
+      }
+      o.w2_t = push_b16((size_t)k * F);
+      for (int col = 0; col < k; ++col)
+        for (int r = 0; r < F; ++r) b16[o.w2_t + (size_t)col * F + r] = __float2bfloat16(w2[(size_t)r * k + col]);
+    }
+  }
+  const size_t lnf_g = push_f32(get(R + "layer_norm" + sfx(4 * nb) + "/scale", k), k);
+  const size_t lnf_b = push_f32(get(R + "layer_norm" + sfx(4 * nb) + "/offset", k), k);
+  const size_t lnu_g = push_f32(get(R + "layer_norm" + sfx(4 * nb + 1) + "/scale", k), k);
+  const size_t lnu_b = push_f32(get(R + "layer_norm" + sfx(4 * nb + 1) + "/offset", k), k);
+  const size_t wu = push_f32(get(R + "linear" + sfx(2 * nb + 1) + "/w", (int64_t)k * c.out_dim), (size_t)k * c.out_dim);
+  const size_t bu = push_f32(get(R + "linear" + sfx(2 * nb + 1) + "/b", c.out_dim), c.out_dim);
+  const size_t lnv_g = push_f32(get(R + "layer_norm" + sfx(4 * nb + 2) + "/scale", k), k);
+  const size_t lnv_b = push_f32(get(R + "layer_norm" + sfx(4 * nb + 2) + "/offset", k), k);
+  const size_t wv = push_f32(get(R + "linear" + sfx(2 * nb + 2) + "/w", (int64_t)k * c.out_dim), (size_t)k * c.out_dim);
+  const size_t bv = push_f32(get(R + "linear" + sfx(2 * nb + 2) + "/b", c.out_dim), c.out_dim);
+  const size_t temp = push_f32(get("BaseModel/learned_temp", 1), 1);
+  const size_t bias = push_f32(get("BaseModel/final_matrix_bias", 1), 1);
+  if (!missing.empty()) return fail(h, AVB_ERR_MISSING, "weight tensor missing or mis-sized: %s", missing.c_str());
+
+  const size_t f32_bytes = align_up(f32.size() * 4, 1024), b16_bytes = align_up(b16.size() * 2, 1024);
+  if (h->arena) { cudaFree(h->arena); h->arena = nullptr; }
+  AVB_CUDA(h, cudaMalloc(&h->arena, f32_bytes + b16_bytes + 1024));
+  float* df = reinterpret_cast<float*>(h->arena);
+  bf16* db = reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(h->arena) + f32_bytes);
+  AVB_CUDA(h, cudaMemcpy(df, f32.data(), f32.size() * 4, cudaMemcpyHostToDevice));
+  if (!b16.empty()) AVB_CUDA(h, cudaMemcpy(db, b16.data(), b16.size() * 2, cudaMemcpyHostToDevice));
+
+  h->emb_w = df + emb_w; h->emb_b = df + emb_b;
+  h->lnf_g = df + lnf_g; h->lnf_b = df + lnf_b;
+  h->lnu_g = df + lnu_g; h->lnu_b = df + lnu_b; h->wu = df + wu; h->bu = df + bu;
+  h->lnv_g = df + lnv_g; h->lnv_b = df + lnv_b; h->wv = df + wv; h->bv = df + bv;
+  h->temp = df + temp; h->bias = df + bias;
+  h->blocks.assign(nb, Block{});
+  for (int i = 0; i < nb; ++i) {
+    Block& B = h->blocks[i]; const BlockOff& o = offs[i];
+    for (int t = 0; t < 4; ++t) { B.ln_g[t] = df + o.ln_g[t]; B.ln_b[t] = df + o.ln_b[t]; }
+    B.wq = df + o.wq; B.bq = df + o.bq; B.wk = df + o.wk; B.bk = df + o.bk; B.wv = df + o.wv; B.bv = df + o.bv;
+    B.wo = df + o.wo; B.bo = df + o.bo; B.w1 = df + o.w1; B.b1 = df + o.b1; B.w2 = df + o.w2; B.b2 = df + o.b2;
+    B.bqkv_f = df + o.bqkv_f; B.b1_f = df + o.b1_f;
+    if (c.compute_dtype == AVB_DTYPE_BF16) {
+      B.wqkv_t = db + o.wqkv_t; B.wo_t = db + o.wo_t; B.w1_t = db + o.w1_t; B.w2_t = db + o.w2_t;
+      bool ok = make_tmap_2d(&B.tm_wqkv, B.wqkv_t, 3 * HD, k, 256) && make_tmap_2d(&B.tm_wo, B.wo_t, k, HD, 128) &&
+                make_tmap_2d(&B.tm_w1, B.w1_t, F, k, 256) && make_tmap_2d(&B.tm_w2, B.w2_t, k, F, 128);
+      if (!ok) return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for block %d weights", i);
+    }
+  }
+  h->loaded = true;
+  return AVB_OK;
+}
+
+// ----------------------------------------------------------------------------------- stages
+int avb_standardize(avb_handle h, const float* x, int32_t B, int32_t n, int32_t d, int32_t mode, float* xs,
+                    void* scratch, size_t scratch_bytes, void* stream) {
+  if (!shape_ok(h, B, n, d) || !x || !xs) return fail(h, AVB_ERR_INVALID, "avb_standardize: bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t total = (size_t)B * n * d;
+  if (mode == AVB_STANDARDIZE_NONE) {
+    if (xs != x) AVB_CUDA(h, cudaMemcpyAsync(xs, x, total * 4, cudaMemcpyDeviceToDevice, st));
+    return AVB_OK;
+  }
+  if (scratch_bytes < (size_t)B * (n + d + 8) * 8 || !scratch) return fail(h, AVB_ERR_WORKSPACE, "avb_standardize: scratch too small");
+  float* sc = reinterpret_cast<float*>(scratch);
+  if (mode == AVB_STANDARDIZE_DEFAULT) {
+    float* mean = sc; float* stdv = sc + (size_t)B * d;
+    avb::zscore_stats_kernel<<<dim3((d + 31) / 32, B), dim3(32, 8), 0, st>>>(x, n, d, mean, stdv);
+    AVB_LAUNCH_CHECK(h);
+    avb::zscore_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, mean, stdv, n, d, total, xs);
+    AVB_LAUNCH_CHECK(h);
+  } else if (mode == AVB_STANDARDIZE_COUNT) {
+    const size_t rows = (size_t)B * n;
+    avb::cpm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, rows, d, xs);
+    AVB_LAUNCH_CHECK(h);
+    avb::cpm_stats_kernel<<<B, 1024, 0, st>>>(xs, (size_t)n * d, sc);
+    AVB_LAUNCH_CHECK(h);
+    avb::cpm_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xs, sc, (size_t)n * d, total);
+    AVB_LAUNCH_CHECK(h);
+  } else {
+    return fail(h, AVB_ERR_INVALID, "unknown standardize mode %d", mode);
+  }
+  return AVB_OK;
+}
+
+int avb_embed(avb_handle h, const float* xs, const float* interv, int64_t ntok, float* z, void* stream) {
+  if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_embed: weights not loaded");
+  if (!xs || !z || ntok < 1) return fail(h, AVB_ERR_INVALID, "avb_embed: bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (int)std::min<int64_t>((ntok + 7) / 8, (int64_t)h->num_sms * 16);
+  avb::embed_kernel<<<grid, 256, 0, st>>>(xs, interv, h->emb_w, h->emb_b, (size_t)ntok, z);
+  AVB_LAUNCH_CHECK(h);
+  return AVB_OK;
+}
+
+size_t avb_block_workspace_bytes(avb_handle h, int32_t B, int32_t n, int32_t d) {
+  if (!shape_ok(h, B, n, d)) return 0;
+  return block_ws_layout(h->cfg, (size_t)B * n * d).total;
+}
+
+int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t d, int32_t axis, void* ws,
+              size_t ws_bytes, void* stream) {
+  if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_block: weights not loaded");
+  if (!shape_ok(h, B, n, d) || !z || (axis != 0 && axis != 1) || bi < 0 || bi >= (int)h->blocks.size())
+    return fail(h, AVB_ERR_INVALID, "avb_block: bad argument");
+  const avb_config& c = h->cfg;
+  const size_t ntok = (size_t)B * n * d;
+  if (ntok > (size_t)0x7fffff00) return fail(h, AVB_ERR_INVALID, "avb_block: too many tokens per call (%zu)", ntok);
+  const BlockWs L = block_ws_layout(c, ntok);
+  if (!ws || ws_bytes < L.total) return fail(h, AVB_ERR_WORKSPACE, "avb_block: workspace %zu < %zu", ws_bytes, L.total);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  const Block& W = h->blocks[bi];
+  const int k = c.dim, H = c.num_heads, HD = H * c.key_size, F = c.widening_factor * c.dim;
+  const int M = (int)ntok;
+
+  if (c.compute_dtype == AVB_DTYPE_BF16) {
+    bf16* xhat = reinterpret_cast<bf16*>(w8 + L.xhat_off);
+    bf16* qkv = reinterpret_cast<bf16*>(w8 + L.big_off);
+    bf16* hid = qkv;  // aliased: qkv is dead once attention has run
+    bf16* attn = reinterpret_cast<bf16*>(w8 + L.attn_off);
+    CUtensorMap tm_x, tm_attn, tm_h;
+    if (!make_tmap_2d(&tm_x, xhat, ntok, k, 128) || !make_tmap_2d(&tm_attn, attn, ntok, HD, 128) ||
+        !make_tmap_2d(&tm_h, hid, ntok, F, 128))
+      return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for activations");
+    const int ln_grid = (int)std::min<size_t>((ntok + 7) / 8, (size_t)h->num_sms * 16);
+    int rc;
+    // attention half: LN -> QKV -> attention -> out-proj + residual
+    avb::ln_bf16_kernel<<<ln_grid, 256, 0, st>>>(z, ntok, xhat);
+    AVB_LAUNCH_CHECK(h);
+    if ((rc = launch_gemm_tc<256, 0>(h, tm_x, W.tm_wqkv, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, k, st, h->num_sms, &h->launches))) return rc;
+    if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches))) return rc;
+    if ((rc = launch_gemm_tc<128, 2>(h, tm_attn, W.tm_wo, W.bo, z, k, M, k, HD, st, h->num_sms, &h->launches))) return rc;
+    // FFN half: LN -> Linear + ReLU -> Linear + residual
+    avb::ln_bf16_kernel<<<ln_grid, 256, 0, st>>>(z, ntok, xhat);
+    AVB_LAUNCH_CHECK(h);
+    if ((rc = launch_gemm_tc<256, 1>(h, tm_x, W.tm_w1, W.b1_f, hid, F, M, F, k, st, h->num_sms, &h->launches))) return rc;
+    if ((rc = launch_gemm_tc<128, 2>(h, tm_h, W.tm_w2, W.b2, z, k, M, k, F, st, h->num_sms, &h->launches))) return rc;
+  } else {
+    float* qkv = reinterpret_cast<float*>(w8 + L.big_off);
+    float* hid = qkv;
+    float* attn = reinterpret_cast<float*>(w8 + L.attn_off);
+    launch_sgemm<0, true>(z, k, W.wq, HD, W.bq, W.ln_g[0], W.ln_b[0], nullptr, 0, qkv, 3 * HD, ntok, HD, k, st);
+    AVB_LAUNCH_CHECK(h);
+    launch_sgemm<0, true>(z, k, W.wk, HD, W.bk, W.ln_g[1], W.ln_b[1], nullptr, 0, qkv + HD, 3 * HD, ntok, HD, k, st);
+    AVB_LAUNCH_CHECK(h);
+    launch_sgemm<0, true>(z, k, W.wv, HD, W.bv, W.ln_g[2], W.ln_b[2], nullptr, 0, qkv + 2 * HD, 3 * HD, ntok, HD, k, st);
+    AVB_LAUNCH_CHECK(h);
+    const int T = axis == 0 ? d : n;
+    const long long S = axis == 0 ? (long long)B * n : (long long)B * d;
+    const long long inner = axis == 0 ? 1 : d;
+    const long long outer_stride = axis == 0 ? d : (long long)n * d;
+    const long long inner_stride = axis == 0 ? 0 : 1;
+    const long long tok_stride = axis == 0 ? 1 : d;
+    for (long long s0 = 0; s0 < S; s0 += 65535) {  // grid.z is limited to 65535
+      const int sz = (int)std::min<long long>(65535, S - s0);
+      avb::attention_f32_kernel<<<dim3((T + 127) / 128, H, sz), 128, 0, st>>>(
+          qkv, attn, T, H, s0, inner, outer_stride, inner_stride, tok_stride, 1.0f / sqrtf((float)c.key_size));
+      AVB_LAUNCH_CHECK(h);
+    }
+    launch_sgemm<2, false>(attn, HD, W.wo, k, W.bo, nullptr, nullptr, z, k, z, k, ntok, k, HD, st);
+    AVB_LAUNCH_CHECK(h);
+    launch_sgemm<1, true>(z, k, W.w1, F, W.b1, W.ln_g[3], W.ln_b[3], nullptr, 0, hid, F, ntok, F, k, st);
+    AVB_LAUNCH_CHECK(h);
+    launch_sgemm<2, false>(hid, F, W.w2, k, W.b2, nullptr, nullptr, z, k, z, k, ntok, k, F, st);
+    AVB_LAUNCH_CHECK(h);
+  }
+  return AVB_OK;
+}
+
+int avb_pool(avb_handle h, const float* z, int32_t B, int32_t n, int32_t d, float* pooled, int32_t accumulate,
+             void* stream) {
+  if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_pool: weights not loaded");
+  if (!shape_ok(h, B, n, d) || !z || !pooled) return fail(h, AVB_ERR_INVALID, "avb_pool: bad argument");
+  if (B > 65535) return fail(h, AVB_ERR_INVALID, "avb_pool: B > 65535");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  avb::ln_max_kernel<<<dim3(d, B), 256, 0, st>>>(z, h->lnf_g, h->lnf_b, n, d, pooled, accumulate);
+  AVB_LAUNCH_CHECK(h);
+  return AVB_OK;
+}
+
+int avb_head(avb_handle h, const float* pooled, int32_t B, int32_t d, float* probs, void* scratch,
+             size_t scratch_bytes, void* stream) {
+  if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_head: weights not loaded");
+  if (!h || B < 1 || d < 1 || !pooled || !probs) return fail(h, AVB_ERR_INVALID, "avb_head: bad argument");
+  const avb_config& c = h->cfg;
+  const size_t need = (size_t)2 * B * d * c.out_dim * 4;
+  if (!scratch || scratch_bytes < need) return fail(h, AVB_ERR_WORKSPACE, "avb_head: scratch %zu < %zu", scratch_bytes, need);
+  if (B > 65535) return fail(h, AVB_ERR_INVALID, "avb_head: B > 65535");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* u = reinterpret_cast<float*>(scratch);
+  float* v = u + (size_t)B * d * c.out_dim;
+  avb::head_uv_kernel<<<(unsigned)((size_t)B * d), 128, 0, st>>>(pooled, h->lnu_g, h->lnu_b, h->wu, h->bu, h->lnv_g,
+                                                               h->lnv_b, h->wv, h->bv, c.out_dim, u, v);
+  AVB_LAUNCH_CHECK(h);
+  avb::head_logits_kernel<<<dim3((d + 15) / 16, (d + 15) / 16, B), dim3(16, 16), 0, st>>>(
+      u, v, d, c.out_dim, h->temp, h->bias, c.mask_diag, probs);
+  AVB_LAUNCH_CHECK(h);
+  return AVB_OK;
+}
+
+// ----------------------------------------------------------------------------------- forward
+static int resolve_chunks(avb_handle h, int n, int chunk_size, int* chunks) {
+  *chunks = 1;
+  if (chunk_size > 0 && chunk_size < n) {  // model.py:100
+    if (n % chunk_size) return fail(h, AVB_ERR_INVALID, "observations `n` must be divisible by `experimental_chunk_size`");
+    *chunks = n / chunk_size;
+  }
+  return AVB_OK;
+}
+
+size_t avb_workspace_bytes(avb_handle h, int32_t B, int32_t n, int32_t d, int32_t chunk_size) {
+  if (!shape_ok(h, B, n, d)) return 0;
+  int chunks = 1;
+  if (resolve_chunks(h, n, chunk_size, &chunks)) return 0;
+  return fwd_ws_layout(h->cfg, B, n, d, chunks).total;
+}
+
+int avb_forward(avb_handle h, const float* x, const float* interv, int32_t B, int32_t n, int32_t d,
+                int32_t standardize, int32_t chunk_size, float* probs, void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_forward: weights not loaded");
+  if (!shape_ok(h, B, n, d) || !x || !probs) return fail(h, AVB_ERR_INVALID, "avb_forward: bad argument");
+  int chunks = 1, rc;
+  if ((rc = resolve_chunks(h, n, chunk_size, &chunks))) return rc;
+  const avb_config& c = h->cfg;
+  const FwdWs L = fwd_ws_layout(c, B, n, d, chunks);
+  if (!ws || ws_bytes < L.total) return fail(h, AVB_ERR_WORKSPACE, "avb_forward: workspace %zu < %zu", ws_bytes, L.total);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  float* xs = reinterpret_cast<float*>(w8 + L.xs_off);
+  float* pooled = reinterpret_cast<float*>(w8 + L.pooled_off);
+  float* z = reinterpret_cast<float*>(w8 + L.z_off);
+  const size_t cells = (size_t)B * n * d;
+
+  if ((rc = avb_standardize(h, x, B, n, d, standardize, xs, w8 + L.stat_off, (size_t)B * (n + d + 8) * 8, stream))) return rc;
+  const float* iv = interv;
+  float* pool_dst = pooled;
+  int Be = B, ne = n;
+  if (chunks > 1) {
+    // chunk c of dataset b becomes dataset b*chunks + c with n/chunks rows (model.py:105-106)
+    float* tmp = reinterpret_cast<float*>(w8 + L.z_off);  // z region is free until embed
+    AVB_CUDA(h, cudaMemcpyAsync(tmp, xs, cells * 4, cudaMemcpyDeviceToDevice, st));
+    chunk_gather_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(tmp, xs, B, n, d, chunks);
+    AVB_LAUNCH_CHECK(h);
+    if (interv) {
+      float* ivp = reinterpret_cast<float*>(w8 + L.iv_off);
+      chunk_gather_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(interv, ivp, B, n, d, chunks);
+      AVB_LAUNCH_CHECK(h);
+      iv = ivp;
+    }
+    Be = B * chunks; ne = n / chunks;
+    pool_dst = reinterpret_cast<float*>(w8 + L.pooled_c_off);
+  }
+  const int nb = (int)h->blocks.size();
+  const size_t tok1 = (size_t)ne * d;
+  for (int b0 = 0; b0 < Be; b0 += L.Bc) {
+    const int bc = std::min(L.Bc, Be - b0);
+    const size_t ntok = (size_t)bc * tok1;
+    if ((rc = avb_embed(h, xs + (size_t)b0 * tok1, iv ? iv + (size_t)b0 * tok1 : nullptr, (int64_t)ntok, z, stream))) return rc;
+    const size_t bws = block_ws_layout(c, ntok).total;
+    for (int i = 0; i < nb; ++i)
+      if ((rc = avb_block(h, i, z, bc, ne, d, (i & 1) ? AVB_AXIS_N : AVB_AXIS_D, w8 + L.blk_off, bws, stream))) return rc;
+    if ((rc = avb_pool(h, z, bc, ne, d, pool_dst + (size_t)b0 * d * c.dim, 0, stream))) return rc;
+  }
+  if (chunks > 1) {
+    const size_t per_ds = (size_t)d * c.dim, total = (size_t)B * per_ds;
+    chunk_max_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pool_dst, pooled, per_ds, chunks, total);
+    AVB_LAUNCH_CHECK(h);
+  }
+  return avb_head(h, pooled, B, d, probs, w8 + L.uv_off, (size_t)2 * B * d * c.out_dim * 4, stream);
+}
+
+int avb_forward_host(avb_handle h, const float* x_host, const float* interv_host, int32_t B, int32_t n, int32_t d,
+                     int32_t standardize, int32_t chunk_size, float* probs_host) {
+  if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_forward_host: weights not loaded");
+  if (!shape_ok(h, B, n, d) || !x_host || !probs_host) return fail(h, AVB_ERR_INVALID, "avb_forward_host: bad argument");
+  int chunks = 1, rc;
+  if ((rc = resolve_chunks(h, n, chunk_size, &chunks))) return rc;
+  const size_t cells = (size_t)B * n * d, pbytes = (size_t)B * d * d * 4;
+  const size_t io = align_up(cells * 4, 1024) * 2 + align_up(pbytes, 1024);
+  const size_t need = io + fwd_ws_layout(h->cfg, B, n, d, chunks).total;
+  if (h->host_ws_bytes < need) {
+    if (h->host_ws) cudaFree(h->host_ws);
+    h->host_ws = nullptr; h->host_ws_bytes = 0;
+    AVB_CUDA(h, cudaMalloc(&h->host_ws, need));
+    h->host_ws_bytes = need;
+  }
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(h->host_ws);
+  float* dx = reinterpret_cast<float*>(w8);
+  float* di = reinterpret_cast<float*>(w8 + align_up(cells * 4, 1024));
+  float* dp = reinterpret_cast<float*>(w8 + 2 * align_up(cells * 4, 1024));
+  cudaStream_t st = 0;
+  AVB_CUDA(h, cudaMemcpyAsync(dx, x_host, cells * 4, cudaMemcpyHostToDevice, st));
+  if (interv_host) AVB_CUDA(h, cudaMemcpyAsync(di, interv_host, cells * 4, cudaMemcpyHostToDevice, st));
+  if ((rc = avb_forward(h, dx, interv_host ? di : nullptr, B, n, d, standardize, chunk_size, dp, w8 + io,
+                        h->host_ws_bytes - io, nullptr)))
+    return rc;
+  AVB_CUDA(h, cudaMemcpyAsync(probs_host, dp, pbytes, cudaMemcpyDeviceToHost, st));
+  AVB_CUDA(h, cudaStreamSynchronize(st));
+  return AVB_OK;
+}
+
+// ----------------------------------------------------------------------------------- test hooks
+int avb_test_gemm_bf16(const void* a, const void* wt, const float* bias, void* out, int32_t M, int32_t N, int32_t K,
+                       int32_t epilogue, void* stream) {
+  if (!a || !wt || !bias || !out || M < 1 || K % 64 || (N != 128 && N % 256)) return fail(nullptr, AVB_ERR_INVALID, "avb_test_gemm_bf16: bad shape");
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device");
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap ta, tb;
+  if (!make_tmap_2d(&ta, a, M, K, 128) || !make_tmap_2d(&tb, wt, N, K, N == 128 ? 128 : 256))
+    return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  if (N == 128) {
+    if (epilogue == 0) return launch_gemm_tc<128, 0>(nullptr, ta, tb, bias, out, N, M, N, K, st, sms, nullptr);
+    if (epilogue == 1) return launch_gemm_tc<128, 1>(nullptr, ta, tb, bias, out, N, M, N, K, st, sms, nullptr);
+    if (epilogue == 2) return launch_gemm_tc<128, 2>(nullptr, ta, tb, bias, out, N, M, N, K, st, sms, nullptr);
+  } else {
+    if (epilogue == 0) return launch_gemm_tc<256, 0>(nullptr, ta, tb, bias, out, N, M, N, K, st, sms, nullptr);
+    if (epilogue == 1) return launch_gemm_tc<256, 1>(nullptr, ta, tb, bias, out, N, M, N, K, st, sms, nullptr);
+    if (epilogue == 2) return launch_gemm_tc<256, 2>(nullptr, ta, tb, bias, out, N, M, N, K, st, sms, nullptr);
+  }
+  return fail(nullptr, AVB_ERR_INVALID, "avb_test_gemm_bf16: bad epilogue");
+}
+
+int avb_test_attention_bf16(const void* qkv, void* out, int32_t B, int32_t n, int32_t d, int32_t H, int32_t axis,
+                            void* stream) {
+  if (!qkv || !out || B < 1 || n < 1 || d < 1 || H < 1 || (axis != 0 && axis != 1))
+    return fail(nullptr, AVB_ERR_INVALID, "avb_test_attention_bf16: bad argument");
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device");
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return launch_attention_tc(nullptr, qkv, out, B, n, d, H, axis, reinterpret_cast<cudaStream_t>(stream), sms, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+/* avici_b200.h — C-ABI of the B200-native AVICI inference forward.
+ *
+ * Drop-in boundary.  The reference (larslorch/avici) is pure Python/JAX and has no
+ * FFI; its operator seam for this path is
+ *
+ *   InferenceModel.net.apply(params, rng, x[...,n,d,2], is_training=False, experimental_chunk_size)
+ *        -> logits[...,d,d]                                   avici/model.py:217 (class at :93-144)
+ *   AVICIModel.__call_main__(x[n,d], interv[n,d])  -> p[d,d]  avici/pretrain.py:53-67
+ *
+ * Every entry point below replaces one piece of that seam and cites it.  Plain pointers and sizes
+ * only; no torch types.  All `*_dev` pointers are CUDA device pointers on the current device, all
+ * work is enqueued on `stream` (a cudaStream_t passed as void*) and is asynchronous unless stated.
+ * The library never falls back to a CPU path: without a CUDA device every compute call returns
+ * AVB_ERR_CUDA.
+ */
+#ifndef AVICI_B200_H
+#define AVICI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVB_OK 0
+#define AVB_ERR_INVALID 1     /* bad argument / unsupported shape (reference: AssertionError)      */
+#define AVB_ERR_CUDA 2        /* CUDA runtime / driver failure                                      */
+#define AVB_ERR_MISSING 3     /* a required weight tensor was not supplied                          */
+#define AVB_ERR_WORKSPACE 4   /* caller workspace too small                                         */
+
+#define AVB_DTYPE_F32 0       /* fp32 SIMT kernels, true-fp32 accumulate (parity mode, <=1e-4)      */
+#define AVB_DTYPE_BF16 1      /* bf16 tcgen05/TMEM tensor-core kernels, fp32 accumulate (<=1e-2)    */
+
+#define AVB_STANDARDIZE_NONE 0
+#define AVB_STANDARDIZE_DEFAULT 1 /* jax_standardize_default_simple, avici/utils/data_jax.py:72-79 */
+#define AVB_STANDARDIZE_COUNT 2   /* jax_standardize_count_simple,   avici/utils/data_jax.py:48-59 */
+
+#define AVB_AXIS_D 0 /* attend over the variable axis d (even blocks, model.py:82-84)    */
+#define AVB_AXIS_N 1 /* attend over the observation axis n (odd blocks)                  */
+
+typedef struct avb_model_s* avb_handle;
+
+/* Network shape: the kwargs of BaseModel.__init__ (avici/model.py:26-50) plus
+ * InferenceModel's mask_diag (model.py:156).  `layers` is the reference's `layers`
+ * (layer PAIRS; the network has 2*layers blocks, model.py:42). */
+typedef struct {
+  int32_t layers;
+  int32_t dim;
+  int32_t key_size;
+  int32_t num_heads;
+  int32_t widening_factor;
+  int32_t out_dim;
+  int32_t mask_diag;
+  int32_t compute_dtype; /* AVB_DTYPE_* */
+} avb_config;
+
+/* One leaf of the Haiku parameter dict (SURVEY.md §8c naming), e.g.
+ * name = "BaseModel/multi_head_attention_3/query/w", host fp32, row-major in Haiku's own
+ * shape (Linear w:[in,out]).  Replaces `state.params` (avici/pretrain.py:267). */
+typedef struct {
+  const char* name;
+  const float* data; /* HOST pointer */
+  int64_t numel;
+} avb_tensor_desc;
+
+/* Library / build info: "avici_b200 <ver> sm_100a". */
+const char* avb_version(void);
+
+/* Replaces InferenceModel.__init__ + hk.transform(model_class(**kwargs)) (model.py:150-172).
+ * Unsupported shapes (dim!=128, key_size!=32, ...) -> AVB_ERR_INVALID, never a fallback. */
+int avb_create(avb_handle* out, const avb_config* cfg);
+void avb_destroy(avb_handle h);
+const char* avb_last_error(avb_handle h); /* h may be NULL: last error of avb_create */
+
+/* Replaces passing `params` to net.apply (model.py:217): copies, folds LayerNorm affine
+ * parameters and the softmax scale into the projections (bf16 mode), packs K-major bf16
+ * copies for the tensor-core kernels and uploads.  Synchronous. */
+int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count);
+
+/* Number of fp32 parameters the configured network expects (4 269 442 for the defaults). */
+int64_t avb_param_count(avb_handle h);
+
+/* Bytes of scratch `avb_forward` needs for a batch of B datasets of shape [n,d] (0 on a bad
+ * argument, e.g. a chunk_size that does not divide n). */
+size_t avb_workspace_bytes(avb_handle h, int32_t B, int32_t n, int32_t d, int32_t chunk_size);
+
+/* Replaces AVICIModel.__call_main__ (pretrain.py:53-67) on a batch (leading dims as in
+ * train.py:61): stack interv channel (NULL = zeros, pretrain.py:56-57) -> standardize ->
+ * BaseModel forward -> exp(log_sigmoid(logits)), diag = 0 (model.py:203-240).
+ * x_dev/interv_dev: [B,n,d] fp32; probs_dev: [B,d,d] fp32.
+ * chunk_size: experimental_chunk_size (model.py:99-116); <=0 or >=n = off; must divide n. */
+int avb_forward(avb_handle h, const float* x_dev, const float* interv_dev, int32_t B, int32_t n,
+                int32_t d, int32_t standardize, int32_t chunk_size, float* probs_dev,
+                void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers (what the Python wrapper's numpy path uses): copies x/interv to
+ * the device, runs avb_forward on an internal workspace and copies probs back.  Synchronous. */
+int avb_forward_host(avb_handle h, const float* x_host, const float* interv_host, int32_t B,
+                     int32_t n, int32_t d, int32_t standardize, int32_t chunk_size,
+                     float* probs_host);
+
+/* ---- stage-level entry points (used by the axially-sharded multi-GPU driver, which puts an
+ * all-to-all between blocks; also by the parity tests).  All operate on a residual stream
+ * z_dev[B,n,d,dim] fp32, token index t = (b*n + i)*d + j. ---- */
+
+/* The standardizers alone: xs_dev[B,n,d] <- standardize(x_dev)[...,0].  scratch_dev needs
+ * >= B*(n+d+8)*8 bytes. */
+int avb_standardize(avb_handle h, const float* x_dev, int32_t B, int32_t n, int32_t d, int32_t mode,
+                    float* xs_dev, void* scratch_dev, size_t scratch_bytes, void* stream);
+
+/* hk.Linear(dim) embedding of the [.,2] (value, interv) pairs (model.py:95).
+ * xs_dev/interv_dev: [ntok]; z_dev: [ntok,dim]. */
+int avb_embed(avb_handle h, const float* xs_dev, const float* interv_dev, int64_t ntok,
+              float* z_dev, void* stream);
+
+/* One `_block` (model.py:53-75) applied in place; `axis` selects the attended axis (the
+ * reference alternates it with swapaxes, model.py:84; here z is never physically transposed). */
+size_t avb_block_workspace_bytes(avb_handle h, int32_t B, int32_t n, int32_t d);
+int avb_block(avb_handle h, int32_t block_idx, float* z_dev, int32_t B, int32_t n, int32_t d,
+              int32_t axis, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Final LayerNorm + max over n (model.py:86-89): pooled_dev[B,d,dim].  When `accumulate` != 0
+ * the result is max-combined into pooled_dev (chunk path model.py:116, n-sharded ranks). */
+int avb_pool(avb_handle h, const float* z_dev, int32_t B, int32_t n, int32_t d, float* pooled_dev,
+             int32_t accumulate, void* stream);
+
+/* u/v heads, cosine logits, temperature, bias, sigmoid, zero diagonal
+ * (model.py:121-141, 218-220, 239): probs_dev[B,d,d].  scratch_dev >= 2*B*d*out_dim*4 bytes. */
+int avb_head(avb_handle h, const float* pooled_dev, int32_t B, int32_t d, float* probs_dev,
+             void* scratch_dev, size_t scratch_bytes, void* stream);
+
+/* Kernel launches issued by this handle since creation (bench.py's `gpu_launches`). */
+int64_t avb_launch_count(avb_handle h);
+
+/* ---- unit-test hooks for the tensor-core kernels (bf16 handles only) ---- */
+/* C[M,N] = A[M,K] @ Wt[N,K]^T + bias, bf16 in, fp32 accumulate in TMEM.
+ * epilogue 0: out bf16 [M,N]; 1: relu, out bf16; 2: out fp32 [M,N] += (residual add in place). */
+int avb_test_gemm_bf16(const void* a_bf16_dev, const void* wt_bf16_dev, const float* bias_dev,
+                       void* out_dev, int32_t M, int32_t N, int32_t K, int32_t epilogue,
+                       void* stream);
+/* Axial attention on packed qkv[B,n,d,3*H*32] bf16 (q pre-scaled by log2e/sqrt(32)):
+ * out[B,n,d,H*32] bf16. */
+int avb_test_attention_bf16(const void* qkv_bf16_dev, void* out_bf16_dev, int32_t B, int32_t n,
+                            int32_t d, int32_t H, int32_t axis, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVICI_B200_H */

@@ -1,0 +1,151 @@
+"""CPU tests of the host-side logic: Haiku naming / init, checkpoint IO, simulate_data, input validation
+of the reference-facing wrapper, and the multi-rank layout transforms (gloo, world_size 2)."""
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import avici_b200
+from avici_b200 import sharded
+from avici_b200.params import flatten_params, init_params, param_shapes
+from avici_b200.pretrain import ModelState, load_checkpoint, save_checkpoint
+
+
+class _FakeOptState:
+    """stands in for an optax state class inside a reference pickle"""
+    def __init__(self):
+        self.mu = np.zeros(3)
+
+
+_FakeOptState.__qualname__ = _FakeOptState.__name__ = "ScaleByLambState"
+
+
+def test_haiku_names_and_flatten():
+    shapes = param_shapes()
+    names = list(shapes)
+    assert names[0] == "BaseModel/linear" and names[-1] == "BaseModel"
+    assert "BaseModel/layer_norm_66" in shapes and "BaseModel/linear_34" in shapes
+    assert "BaseModel/multi_head_attention_15/linear" in shapes and "BaseModel/layer_norm_67" not in shapes
+    assert shapes["BaseModel/multi_head_attention/query"]["w"] == (128, 256)
+    flat = flatten_params(init_params(dict(layers=1), seed=0))
+    assert all(a.dtype == np.float32 and a.flags.c_contiguous for _, a in flat)
+    assert ("BaseModel/learned_temp" in dict(flat)) and dict(flat)["BaseModel/linear/w"].shape == (2, 128)
+
+
+def test_init_distributions():
+    p = init_params(seed=0)
+    w = p["BaseModel/linear_1"]["w"]  # kaiming-uniform, fan_in 128
+    assert abs(np.abs(w).max() - np.sqrt(6 / 128)) < 1e-3 and abs(w.std() - np.sqrt(2 / 128)) < 2e-3
+    q = p["BaseModel/multi_head_attention/query"]["w"]  # truncated normal, var 2/fan_in
+    assert abs(q.std() - np.sqrt(2 / 128)) < 3e-3 and np.abs(q).max() <= 2 * np.sqrt(2 / 128) / 0.8796 + 1e-6
+    assert np.all(p["BaseModel/layer_norm"]["scale"] == 1) and np.all(p["BaseModel/linear"]["b"] == 0)
+    pp = init_params(seed=0, perturb=True)
+    assert pp["BaseModel/layer_norm"]["scale"].std() > 0.05 and pp["BaseModel/linear_2"]["b"].std() > 0.005
+
+
+def test_checkpoint_roundtrip_and_legacy_alias(tmp_path):
+    kw = dict(layers=1, dim=128, key_size=32, num_heads=8, widening_factor=4, dropout=0.1, some_deprecated_key=3)
+    params = init_params(kw, seed=3)
+    folder = save_checkpoint(tmp_path / "ckpt", params, kw, {"mask_diag": True, "acyclicity": 0.1, "old_kwarg": 1})
+    state, kwargs = load_checkpoint(folder)
+    assert kwargs["inference_model_kwargs"]["acyclicity"] is None
+    assert np.array_equal(state.params["BaseModel/linear"]["w"], params["BaseModel/linear"]["w"])
+    # a pickle written by the reference names avici.backbone.ModelState (or the legacy amortibs alias) and
+    # carries optax classes we do not have: emulate both
+    import sys, types
+    mod = types.ModuleType("amortibs"); sub = types.ModuleType("amortibs.backbone")
+    fake_optax = types.ModuleType("optax_fake")
+    ScaleByLambState = _FakeOptState
+    from collections import namedtuple
+    MS = namedtuple("ModelState", ModelState._fields)
+    MS.__module__ = "amortibs.backbone"; sub.ModelState = MS
+    ScaleByLambState.__module__ = "optax_fake"; fake_optax.ScaleByLambState = ScaleByLambState
+    sys.modules.update({"amortibs": mod, "amortibs.backbone": sub, "optax_fake": fake_optax})
+    try:
+        blob = pickle.dumps(MS(7, None, ScaleByLambState(), params, None, None, None))
+    finally:
+        for k in ("amortibs", "amortibs.backbone", "optax_fake"):
+            sys.modules.pop(k)
+    (tmp_path / "legacy").mkdir()
+    (tmp_path / "legacy" / "checkpoint_0000007.pkl").write_bytes(blob)
+    (tmp_path / "legacy" / "kwargs.json").write_text(json.dumps(
+        {"neural_net_kwargs": {"model_kwargs": kw}, "inference_model_kwargs": {}}))
+    state2, _ = load_checkpoint(tmp_path / "legacy")
+    assert state2.step == 7 and np.array_equal(state2.params["BaseModel/linear"]["w"], params["BaseModel/linear"]["w"])
+    model = avici_b200.load_pretrained(checkpoint_dir=str(tmp_path / "legacy"), expects_counts=False, verbose=False)
+    assert model._model.model_kwargs["layers"] == 1 and "some_deprecated_key" not in model._model.model_kwargs
+
+
+def test_load_pretrained_argument_errors(tmp_path):
+    with pytest.raises(AssertionError):
+        avici_b200.load_pretrained()
+    with pytest.raises(ValueError):
+        avici_b200.load_pretrained(download="nope")
+    with pytest.raises(AssertionError):
+        avici_b200.load_pretrained(checkpoint_dir=str(tmp_path))  # expects_counts missing
+    with pytest.raises(FileNotFoundError):
+        avici_b200.load_pretrained(download="scm-v0", cache_path=str(tmp_path), verbose=False)
+
+
+@pytest.mark.parametrize("domain", ["lin-gauss", "rff-gauss", "gene-ecoli"])
+def test_simulate_data_contract(domain):
+    g, x, interv = avici_b200.simulate_data(d=15, n=40, n_interv=10, seed=0, domain=domain)
+    assert g.shape == (15, 15) and g.dtype.kind == "i" and x.shape == (50, 15) and interv.shape == (50, 15)
+    assert set(np.unique(interv)) <= {0.0, 1.0} and interv.sum() == 10
+    assert np.trace(np.linalg.matrix_power(np.eye(15) + g, 15)) == 15  # DAG (metrics.py:34-43 style check)
+    g2, x2, none = avici_b200.simulate_data(d=15, n=40, seed=0, domain=domain)
+    assert none is None and x2.shape == (40, 15)
+    if domain == "gene-ecoli":
+        assert np.all(x >= 0) and np.allclose(np.mod(x, 1), 0) and (x == 0).mean() > 0.02
+    _, x3, _ = avici_b200.simulate_data(d=15, n=40, seed=0, domain=domain)
+    assert np.array_equal(x2, x3)
+
+
+def test_wrapper_validation_matches_reference_asserts():
+    model = avici_b200.random_init_model(dict(layers=1))
+    x = np.zeros((10, 4), dtype=np.float32)
+    with pytest.raises(AssertionError, match="2D array"):
+        model(x=np.zeros((2, 10, 4), dtype=np.float32))
+    with pytest.raises(AssertionError, match="same shape"):
+        model(x=x, interv=np.zeros((10, 5)))
+    with pytest.raises(AssertionError, match="binary"):
+        model(x=x, interv=np.full((10, 4), 0.5))
+
+
+def test_batch_slice_partitions():
+    for B, G in ((64, 8), (10, 4), (3, 8), (512, 8)):
+        idx = np.concatenate([np.arange(B)[sharded.batch_slice(B, r, G)] for r in range(G)])
+        assert np.array_equal(idx, np.arange(B))
+        sizes = [len(range(B)[sharded.batch_slice(B, r, G)]) for r in range(G)]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _reshard_worker(rank, world, port, n, d, k, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        z = torch.arange(n * d * k, dtype=torch.float32).reshape(n, d, k)
+        nl, dl = n // world, d // world
+        z_n = z[rank * nl:(rank + 1) * nl].clone()
+        z_d = sharded.reshard_n_to_d(z_n)
+        ok1 = torch.equal(z_d, z[:, rank * dl:(rank + 1) * dl])
+        back = sharded.reshard_d_to_n(z_d)
+        ok2 = torch.equal(back, z_n)
+        # per-token work is layout agnostic: a token-wise function commutes with the re-shard
+        f = lambda t: t * 2 + 1
+        ok3 = torch.equal(sharded.reshard_d_to_n(f(z_d)), f(z_n))
+        ret[rank] = bool(ok1 and ok2 and ok3 and sharded.world_size() == world and sharded.rank() == rank)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_axial_reshard_world2_gloo():
+    world, port = 2, 29500 + os.getpid() % 2000
+    ret = mp.Manager().dict()
+    mp.spawn(_reshard_worker, args=(world, port, 8, 6, 4, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
