@@ -56,6 +56,14 @@ struct avb_model_s {
   void* host_ws = nullptr;  // internal workspace of avb_forward_host
   size_t host_ws_bytes = 0;
   long long launches = 0;
+  // optional per-kernel-category CUDA-event timing (avb_profile_*)
+  bool prof = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct ProfRec { int cat; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  double prof_ms[AVB_PROF_CATEGORIES] = {0};
+  long long prof_n[AVB_PROF_CATEGORIES] = {0};
 };
 
 namespace {
@@ -69,6 +77,21 @@ int fail(avb_handle h, int code, const char* fmt, ...) {
   if (h) h->err = buf; else g_create_error = buf;
   return code;
 }
+
+// Records a CUDA-event pair around the launches issued while it is alive (only when profiling is on).
+struct ProfScope {
+  avb_handle h; cudaStream_t st; int cat; cudaEvent_t a = nullptr, b = nullptr;
+  static cudaEvent_t take(avb_handle h) {
+    if (h->ev_used == h->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+    return h->ev_pool[h->ev_used++];
+  }
+  ProfScope(avb_handle h_, int cat_, cudaStream_t st_) : h(h_), st(st_), cat(cat_) {
+    if (h && h->prof) { a = take(h); b = take(h); cudaEventRecord(a, st); }
+  }
+  ~ProfScope() {
+    if (a) { cudaEventRecord(b, st); h->prof_recs.push_back({cat, a, b}); }
+  }
+};
 
 #define AVB_CUDA(h, expr)                                                                          \
   do {                                                                                             \
@@ -303,6 +326,7 @@ void avb_destroy(avb_handle h) {
   if (!h) return;
   if (h->arena) cudaFree(h->arena);
   if (h->host_ws) cudaFree(h->host_ws);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
 
@@ -315,6 +339,29 @@ int64_t avb_param_count(avb_handle h) {
 }
 
 int64_t avb_launch_count(avb_handle h) { return h ? h->launches : -1; }
+
+int avb_profile_enable(avb_handle h, int32_t on) {
+  if (!h) return AVB_ERR_INVALID;
+  h->prof = on != 0;
+  return AVB_OK;
+}
+
+int avb_profile_read(avb_handle h, double* ms_out, int64_t* count_out, int32_t reset) {
+  if (!h) return AVB_ERR_INVALID;
+  AVB_CUDA(h, cudaDeviceSynchronize());
+  for (const auto& r : h->prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { h->prof_ms[r.cat] += ms; h->prof_n[r.cat]++; }
+  }
+  h->prof_recs.clear();
+  h->ev_used = 0;
+  for (int i = 0; i < AVB_PROF_CATEGORIES; ++i) {
+    if (ms_out) ms_out[i] = h->prof_ms[i];
+    if (count_out) count_out[i] = h->prof_n[i];
+    if (reset) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+  }
+  return AVB_OK;
+}
 
 int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count) {
   if (!h || !tensors) return fail(h, AVB_ERR_INVALID, "avb_load_weights: null argument");
@@ -466,6 +513,7 @@ int avb_standardize(avb_handle h, const float* x, int32_t B, int32_t n, int32_t 
   if (!shape_ok(h, B, n, d) || !x || !xs) return fail(h, AVB_ERR_INVALID, "avb_standardize: bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t total = (size_t)B * n * d;
+  ProfScope ps(h, AVB_PROF_PROLOGUE, st);
   if (mode == AVB_STANDARDIZE_NONE) {
     if (xs != x) AVB_CUDA(h, cudaMemcpyAsync(xs, x, total * 4, cudaMemcpyDeviceToDevice, st));
     return AVB_OK;
@@ -497,6 +545,7 @@ int avb_embed(avb_handle h, const float* xs, const float* interv, int64_t ntok, 
   if (!xs || !z || ntok < 1) return fail(h, AVB_ERR_INVALID, "avb_embed: bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = (int)std::min<int64_t>((ntok + 7) / 8, (int64_t)h->num_sms * 16);
+  ProfScope ps(h, AVB_PROF_PROLOGUE, st);
   avb::embed_kernel<<<grid, 256, 0, st>>>(xs, interv, h->emb_w, h->emb_b, (size_t)ntok, z);
   AVB_LAUNCH_CHECK(h);
   return AVB_OK;
@@ -535,44 +584,59 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
     const int ln_grid = (int)std::min<size_t>((ntok + 7) / 8, (size_t)h->num_sms * 16);
     int rc;
     // attention half: LN -> QKV -> attention -> out-proj + residual
-    avb::ln_bf16_kernel<<<ln_grid, 256, 0, st>>>(z, ntok, xhat);
-    AVB_LAUNCH_CHECK(h);
-    if ((rc = launch_gemm_tc<256, 0>(h, tm_x, W.tm_wqkv, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, k, st, h->num_sms, &h->launches))) return rc;
-    if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches))) return rc;
-    if ((rc = launch_gemm_tc<128, 2>(h, tm_attn, W.tm_wo, W.bo, z, k, M, k, HD, st, h->num_sms, &h->launches))) return rc;
+    { ProfScope ps(h, AVB_PROF_LN, st);
+      avb::ln_bf16_kernel<<<ln_grid, 256, 0, st>>>(z, ntok, xhat);
+      AVB_LAUNCH_CHECK(h); }
+    { ProfScope ps(h, AVB_PROF_QKV, st);
+      if ((rc = launch_gemm_tc<256, 0>(h, tm_x, W.tm_wqkv, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, k, st, h->num_sms, &h->launches))) return rc; }
+    { ProfScope ps(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
+      if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches))) return rc; }
+    { ProfScope ps(h, AVB_PROF_OUT, st);
+      if ((rc = launch_gemm_tc<128, 2>(h, tm_attn, W.tm_wo, W.bo, z, k, M, k, HD, st, h->num_sms, &h->launches))) return rc; }
     // FFN half: LN -> Linear + ReLU -> Linear + residual
-    avb::ln_bf16_kernel<<<ln_grid, 256, 0, st>>>(z, ntok, xhat);
-    AVB_LAUNCH_CHECK(h);
-    if ((rc = launch_gemm_tc<256, 1>(h, tm_x, W.tm_w1, W.b1_f, hid, F, M, F, k, st, h->num_sms, &h->launches))) return rc;
-    if ((rc = launch_gemm_tc<128, 2>(h, tm_h, W.tm_w2, W.b2, z, k, M, k, F, st, h->num_sms, &h->launches))) return rc;
+    { ProfScope ps(h, AVB_PROF_LN, st);
+      avb::ln_bf16_kernel<<<ln_grid, 256, 0, st>>>(z, ntok, xhat);
+      AVB_LAUNCH_CHECK(h); }
+    { ProfScope ps(h, AVB_PROF_FFN1, st);
+      if ((rc = launch_gemm_tc<256, 1>(h, tm_x, W.tm_w1, W.b1_f, hid, F, M, F, k, st, h->num_sms, &h->launches))) return rc; }
+    { ProfScope ps(h, AVB_PROF_FFN2, st);
+      if ((rc = launch_gemm_tc<128, 2>(h, tm_h, W.tm_w2, W.b2, z, k, M, k, F, st, h->num_sms, &h->launches))) return rc; }
   } else {
     float* qkv = reinterpret_cast<float*>(w8 + L.big_off);
     float* hid = qkv;
     float* attn = reinterpret_cast<float*>(w8 + L.attn_off);
-    launch_sgemm<0, true>(z, k, W.wq, HD, W.bq, W.ln_g[0], W.ln_b[0], nullptr, 0, qkv, 3 * HD, ntok, HD, k, st);
-    AVB_LAUNCH_CHECK(h);
-    launch_sgemm<0, true>(z, k, W.wk, HD, W.bk, W.ln_g[1], W.ln_b[1], nullptr, 0, qkv + HD, 3 * HD, ntok, HD, k, st);
-    AVB_LAUNCH_CHECK(h);
-    launch_sgemm<0, true>(z, k, W.wv, HD, W.bv, W.ln_g[2], W.ln_b[2], nullptr, 0, qkv + 2 * HD, 3 * HD, ntok, HD, k, st);
-    AVB_LAUNCH_CHECK(h);
+    { ProfScope ps(h, AVB_PROF_QKV, st);
+      launch_sgemm<0, true>(z, k, W.wq, HD, W.bq, W.ln_g[0], W.ln_b[0], nullptr, 0, qkv, 3 * HD, ntok, HD, k, st);
+      AVB_LAUNCH_CHECK(h);
+      launch_sgemm<0, true>(z, k, W.wk, HD, W.bk, W.ln_g[1], W.ln_b[1], nullptr, 0, qkv + HD, 3 * HD, ntok, HD, k, st);
+      AVB_LAUNCH_CHECK(h);
+      launch_sgemm<0, true>(z, k, W.wv, HD, W.bv, W.ln_g[2], W.ln_b[2], nullptr, 0, qkv + 2 * HD, 3 * HD, ntok, HD, k, st);
+      AVB_LAUNCH_CHECK(h); }
     const int T = axis == 0 ? d : n;
     const long long S = axis == 0 ? (long long)B * n : (long long)B * d;
     const long long inner = axis == 0 ? 1 : d;
     const long long outer_stride = axis == 0 ? d : (long long)n * d;
     const long long inner_stride = axis == 0 ? 0 : 1;
     const long long tok_stride = axis == 0 ? 1 : d;
+    ProfScope* pa = new ProfScope(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
     for (long long s0 = 0; s0 < S; s0 += 65535) {  // grid.z is limited to 65535
       const int sz = (int)std::min<long long>(65535, S - s0);
       avb::attention_f32_kernel<<<dim3((T + 127) / 128, H, sz), 128, 0, st>>>(
           qkv, attn, T, H, s0, inner, outer_stride, inner_stride, tok_stride, 1.0f / sqrtf((float)c.key_size));
-      AVB_LAUNCH_CHECK(h);
+      h->launches++;
     }
-    launch_sgemm<2, false>(attn, HD, W.wo, k, W.bo, nullptr, nullptr, z, k, z, k, ntok, k, HD, st);
-    AVB_LAUNCH_CHECK(h);
-    launch_sgemm<1, true>(z, k, W.w1, F, W.b1, W.ln_g[3], W.ln_b[3], nullptr, 0, hid, F, ntok, F, k, st);
-    AVB_LAUNCH_CHECK(h);
-    launch_sgemm<2, false>(hid, F, W.w2, k, W.b2, nullptr, nullptr, z, k, z, k, ntok, k, F, st);
-    AVB_LAUNCH_CHECK(h);
+    delete pa;
+    { cudaError_t e__ = cudaGetLastError();
+      if (e__ != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention_f32 launch failed: %s", cudaGetErrorString(e__)); }
+    { ProfScope ps(h, AVB_PROF_OUT, st);
+      launch_sgemm<2, false>(attn, HD, W.wo, k, W.bo, nullptr, nullptr, z, k, z, k, ntok, k, HD, st);
+      AVB_LAUNCH_CHECK(h); }
+    { ProfScope ps(h, AVB_PROF_FFN1, st);
+      launch_sgemm<1, true>(z, k, W.w1, F, W.b1, W.ln_g[3], W.ln_b[3], nullptr, 0, hid, F, ntok, F, k, st);
+      AVB_LAUNCH_CHECK(h); }
+    { ProfScope ps(h, AVB_PROF_FFN2, st);
+      launch_sgemm<2, false>(hid, F, W.w2, k, W.b2, nullptr, nullptr, z, k, z, k, ntok, k, F, st);
+      AVB_LAUNCH_CHECK(h); }
   }
   return AVB_OK;
 }
@@ -583,6 +647,7 @@ int avb_pool(avb_handle h, const float* z, int32_t B, int32_t n, int32_t d, floa
   if (!shape_ok(h, B, n, d) || !z || !pooled) return fail(h, AVB_ERR_INVALID, "avb_pool: bad argument");
   if (B > 65535) return fail(h, AVB_ERR_INVALID, "avb_pool: B > 65535");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ProfScope ps(h, AVB_PROF_POOL_HEAD, st);
   avb::ln_max_kernel<<<dim3(d, B), 256, 0, st>>>(z, h->lnf_g, h->lnf_b, n, d, pooled, accumulate);
   AVB_LAUNCH_CHECK(h);
   return AVB_OK;
@@ -599,6 +664,7 @@ int avb_head(avb_handle h, const float* pooled, int32_t B, int32_t d, float* pro
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* u = reinterpret_cast<float*>(scratch);
   float* v = u + (size_t)B * d * c.out_dim;
+  ProfScope ps(h, AVB_PROF_POOL_HEAD, st);
   avb::head_uv_kernel<<<(unsigned)((size_t)B * d), 128, 0, st>>>(pooled, h->lnu_g, h->lnu_b, h->wu, h->bu, h->lnv_g,
                                                                h->lnv_b, h->wv, h->bv, c.out_dim, u, v);
   AVB_LAUNCH_CHECK(h);

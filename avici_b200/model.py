@@ -86,6 +86,16 @@ class Engine:
     def launch_count(self):
         return int(self.lib.avb_launch_count(self.handle))
 
+    def profile(self, on=True):
+        self._check(self.lib.avb_profile_enable(self.handle, int(bool(on))))
+
+    def profile_read(self, reset=True):
+        """{category: (total_ms, scopes)} accumulated since the last reset (synchronises the device)."""
+        n = len(_lib.PROF_CATEGORIES)
+        ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+        self._check(self.lib.avb_profile_read(self.handle, ms, cnt, int(bool(reset))))
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(_lib.PROF_CATEGORIES)}
+
     def workspace(self, nbytes):
         torch = _torch()
         if self._ws is None or self._ws.numel() < nbytes:

@@ -133,6 +133,23 @@ int avb_head(avb_handle h, const float* pooled_dev, int32_t B, int32_t d, float*
 /* Kernel launches issued by this handle since creation (bench.py's `gpu_launches`). */
 int64_t avb_launch_count(avb_handle h);
 
+/* Optional per-kernel-category timing with CUDA events recorded on the launching stream (bench.py's
+ * `roofline`).  avb_profile_read synchronises the device, adds the elapsed times of all scopes
+ * recorded since the last read to running totals and copies totals (ms) and scope counts out. */
+#define AVB_PROF_PROLOGUE 0  /* standardize + embed            */
+#define AVB_PROF_LN 1        /* LayerNorm -> bf16 (bf16 mode)  */
+#define AVB_PROF_QKV 2       /* Q/K/V projections              */
+#define AVB_PROF_ATTN_D 3    /* attention over d               */
+#define AVB_PROF_ATTN_N 4    /* attention over n               */
+#define AVB_PROF_OUT 5       /* output projection + residual   */
+#define AVB_PROF_FFN1 6      /* FFN up-projection + ReLU       */
+#define AVB_PROF_FFN2 7      /* FFN down-projection + residual */
+#define AVB_PROF_POOL_HEAD 8 /* final LN + max-pool + head     */
+#define AVB_PROF_CATEGORIES 9
+int avb_profile_enable(avb_handle h, int32_t on);
+int avb_profile_read(avb_handle h, double* ms_out /*[AVB_PROF_CATEGORIES]*/,
+                     int64_t* count_out /*[AVB_PROF_CATEGORIES]*/, int32_t reset);
+
 /* ---- unit-test hooks for the tensor-core kernels (bf16 handles only) ---- */
 /* C[M,N] = A[M,K] @ Wt[N,K]^T + bias, bf16 in, fp32 accumulate in TMEM.
  * epilogue 0: out bf16 [M,N]; 1: relu, out bf16; 2: out fp32 [M,N] += (residual add in place). */
