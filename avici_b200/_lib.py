@@ -59,6 +59,7 @@ SIGNATURES = {
     "avb_launch_count": (C.c_int64, [C.c_void_p]),
     "avb_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "avb_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
+    "avb_debug_set_trace": (C.c_int, [C.c_void_p]),
     "avb_test_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_void_p]),
     "avb_test_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

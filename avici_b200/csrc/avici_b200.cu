@@ -143,19 +143,6 @@ bool make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// qkv [B,n,d,C] bf16 as a 4-D map; box = 32 channels x 128 positions along the attended axis, 64B swizzle
-bool make_tmap_qkv(CUtensorMap* tm, const void* ptr, int B, int n, int d, int C, int axis) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  if (!fn) return false;
-  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)d, (cuuint64_t)n, (cuuint64_t)B};
-  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)d * C * 2, (cuuint64_t)n * d * C * 2};
-  cuuint32_t box[4] = {32, axis == 0 ? 128u : 1u, axis == 0 ? 1u : 128u, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 // ------------------------------------------------------------------ kernel launchers
 template <int BN, int EPI>
 int launch_gemm_tc(avb_handle h, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const float* bias, void* out,
@@ -186,14 +173,12 @@ int launch_attention_tc(avb_handle h, const void* qkv, void* out, int B, int n, 
     if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(attention_tc): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  CUtensorMap tm;
-  if (!make_tmap_qkv(&tm, qkv, B, n, d, 3 * H * 32, axis)) return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled(qkv) failed");
   const int T = axis == 0 ? d : n;
   const long long S = axis == 0 ? (long long)B * n : (long long)B * d;
   const long long items = S * H * ((T + 127) / 128);
-  const int grid = (int)std::min<long long>(items, num_sms);
+  const int grid = (int)std::min<long long>((items + avb::kAttnStreams - 1) / avb::kAttnStreams, num_sms);
   avb::attention_tc_kernel<<<grid, avb::kAttnThreads, avb::kAttnSmemBytes, st>>>(
-      tm, reinterpret_cast<bf16*>(out), B, n, d, H, axis);
+      reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis);
   if (launches) ++*launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention_tc launch: %s", cudaGetErrorString(e));
@@ -796,6 +781,11 @@ int avb_test_gemm_bf16(const void* a, const void* wt, const float* bias, void* o
     if (epilogue == 2) return launch_gemm_tc<256, 2>(nullptr, ta, tb, bias, out, N, M, N, K, st, sms, nullptr);
   }
   return fail(nullptr, AVB_ERR_INVALID, "avb_test_gemm_bf16: bad epilogue");
+}
+
+int avb_debug_set_trace(void* trace_dev) {
+  long long* p = reinterpret_cast<long long*>(trace_dev);
+  return cudaMemcpyToSymbol(avb::g_attn_trace, &p, sizeof p) == cudaSuccess ? AVB_OK : AVB_ERR_CUDA;
 }
 
 int avb_test_attention_bf16(const void* qkv, void* out, int32_t B, int32_t n, int32_t d, int32_t H, int32_t axis,

@@ -67,7 +67,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   uint64_t* tempty = tfull + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform roles
   const int num_m = (M + 127) / 128, num_n = N / BN, num_k = K / 64;
   const int num_tiles = num_m * num_n;
 
@@ -90,45 +90,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
-        for (int kb = 0; kb < num_k; ++kb) {
-          ptx::mbar_wait(&empty[stage], phase ^ 1, 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+    // all 32 lanes run the loop (warp-uniform control flow keeps descriptors in uniform registers);
+    // one elected lane issues the TMA instructions
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int kb = 0; kb < num_k; ++kb) {
+        ptx::mbar_wait(&empty[stage], phase ^ 1, 1);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&full[stage], Cfg::kStageBytes);
           ptx::tma_load_2d(sa, &tm_a, &full[stage], kb * 64, m_blk * 128);
           ptx::tma_load_2d(sa + Cfg::kABytes, &tm_b, &full[stage], kb * 64, n_blk * BN);
-          if (++stage == ST) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == ST) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN, 0, 0);
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        ptx::mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1, 2);
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN, 0, 0);
+    const uint64_t dA0 = ptx::make_smem_desc(ptx::smem_u32(smem), 16, 1024, ptx::kSwz128);
+    const uint64_t dB0 = ptx::make_smem_desc(ptx::smem_u32(smem) + Cfg::kABytes, 16, 1024, ptx::kSwz128);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      ptx::mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1, 2);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        ptx::mbar_wait(&full[stage], phase, 3);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
-          ptx::mbar_wait(&full[stage], phase, 3);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
+        if (ptx::elect_one()) {
+          const uint64_t so = (uint64_t)stage * (Cfg::kStageBytes >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = ptx::make_smem_desc(sa + k * 32, 16, 1024, ptx::kSwz128);
-            const uint64_t db = ptx::make_smem_desc(sb + k * 32, 16, 1024, ptx::kSwz128);
-            ptx::umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
-          }
+          for (int k = 0; k < 4; ++k)  // +32 bytes per K=16 slice inside the 128-byte swizzled rows
+            ptx::umma_bf16(d_tmem, dA0 + so + (uint64_t)(k * 2), dB0 + so + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           ptx::umma_commit(&empty[stage]);
-          if (++stage == ST) { stage = 0; phase ^= 1; }
+          if (kb == num_k - 1) ptx::umma_commit(&tfull[as]);
         }
-        ptx::umma_commit(&tfull[as]);
+        __syncwarp();
+        if (++stage == ST) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -200,23 +202,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 //   [128 x 32] Q tile and streams [128 x 32] K / V tiles with a box of {32,128,1,1} (attend over d)
 //   or {32,1,128,1} (attend over n): the attended axis is only a different TMA stride, z is never
 //   transposed.  Rows beyond the sequence end are zero-filled by TMA and masked in the softmax.
-//   S = Q K^T : M=128, N<=128, K=32   (A,B K-major, 64B swizzle)        -> TMEM S[2] (fp32)
-//   P = exp2(S - m) (q is pre-scaled by log2e/sqrt(32)) -> bf16 smem (128B swizzle)
-//   O += P V : M=128, N=32, K<=128    (A K-major smem, B = V MN-major)  -> TMEM O[2] (fp32)
-//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM alloc
-//   warps 4-7: softmax, O rescale, epilogue (one query row per thread = one TMEM lane)
+//   S = Q K^T : M=128, N<=128, K=32   (A,B K-major, 64B swizzle)        -> TMEM S (fp32)
+//   P = exp2(S - m) (q is pre-scaled by log2e/sqrt(32)) -> bf16 pairs in TMEM (A operand from TMEM:
+//              no shared-memory round trip; measured: smem bandwidth was the limiter with P in smem)
+//   O += P V : M=128, N=32, K<=128    (A = P in TMEM, B = V MN-major smem)  -> TMEM O (fp32)
+//   L += P 1 : M=128, N=16             (B = a constant tile of ones)     -> TMEM L: the softmax
+//              denominator comes from the tensor core, summing exactly the bf16 P the PV MMA sees
+//
+//   Head dim 32 makes the softmax (16 ex2/clk/SM on the MUFU pipe), not the MMA, the floor, so the
+//   CTA runs TWO independent streams of work items (ping-pong): each stream owns a TMA-producer
+//   warp, a single-thread MMA issuer, 4 softmax warps (one query row per thread = one TMEM lane),
+//   its own smem ring and TMEM columns.  While one stream's softmax warps wait for their S tile,
+//   the other stream's warps keep the MUFU/FMA pipes busy and the tensor core alternates streams.
+//   The softmax reads S twice from TMEM (row max, then exp) to stay inside 168 registers, rescales
+//   O lazily (only when the running max grew by > 2^8, warp-uniform vote) and defers the epilogue
+//   of an item until the first softmax step of the next one has been handed to the tensor core.
+//   warp 0/1: TMA producers   warp 2/3: MMA issuers (warp 2 allocates TMEM)
+//   warps 4-7 / 8-11: softmax + O rescale + epilogue of stream 0 / 1
 // ------------------------------------------------------------------------------------------
-constexpr int kAttnThreads = 256;
-constexpr int kAttnKvStages = 4;
+constexpr int kAttnStreams = 2;
+constexpr int kAttnSoftmaxWarps = 8;  // per stream: 4 TMEM lane quarters x 2 column halves
+constexpr int kAttnSoftmaxThreads = kAttnSoftmaxWarps * 32;
+constexpr int kAttnThreads = 128 + kAttnStreams * kAttnSoftmaxThreads;  // 640
+constexpr int kAttnKvStages = 6;
 constexpr int kAttnTileBytes = 128 * 32 * 2;  // 8 KB: Q, K or V tile
-constexpr int kAttnPBytes = 128 * 128 * 2;    // 32 KB
-constexpr int kAttnSmemBytes = 2 * kAttnTileBytes + kAttnKvStages * 2 * kAttnTileBytes + 2 * kAttnPBytes + 1024 + 256;
+constexpr int kAttnStreamBytes = kAttnTileBytes + kAttnKvStages * 2 * kAttnTileBytes;  // Q | KV ring = 104 KB
+constexpr int kAttnXchgBytes = 2 /*parity*/ * kAttnStreams * 2 /*halves*/ * 128 * 4;  // row-max exchange, 4 KB
+constexpr int kAttnSmemBytes = kAttnStreams * kAttnStreamBytes + 1024 + 512 + 512 + kAttnXchgBytes;  // + align slack, barriers, ones tile
+constexpr int kAttnTmemStreamCols = 256;  // S 128 (fp32) | P 64 (bf16 pairs) | O 32 | L 16 | spare
+constexpr float kAttnRescaleThreshold = 8.0f;  // log2 units
 
-struct AttnStep {  // one (item, kv tile) step of a CTA's work list
-  long long item;  // global item index, -1 = end
-  int it;          // per-CTA item iteration
-  int j;           // kv tile within the item
-};
+// Debug timeline: when set (avb_debug_set_trace), block 0 records clock64() stamps of the first steps of each
+// role of stream 0 into trace[role * 4096 + step * 8 + event].
+__device__ long long* g_attn_trace = nullptr;
+#define AVB_TRACE(role, step, ev)                                                      \
+  do {                                                                                 \
+    if (trace && (step) < 500) trace[(role) * 4096 + (step) * 8 + (ev)] = clock64();  \
+  } while (0)
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -225,54 +247,74 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int B, int n,
-                    int d, int H, int axis) {
+attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int n, int d, int H,
+                    int axis) {
   constexpr int NS = kAttnKvStages;
+  constexpr int kBarsPerStream = 1 + 1 + NS + NS + 1 + 1 + 1 + 1 + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sQ = smem;                                   // [2][8K]
-  uint8_t* sKV = sQ + 2 * kAttnTileBytes;               // [NS][K 8K | V 8K]
-  uint8_t* sP = sKV + NS * 2 * kAttnTileBytes;          // [2][32K]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kAttnPBytes);
-  uint64_t* q_full = bars;             // [2]
-  uint64_t* q_empty = bars + 2;        // [2]
-  uint64_t* kv_full = bars + 4;        // [NS]
-  uint64_t* kv_empty = bars + 4 + NS;  // [NS]
-  uint64_t* s_full = bars + 4 + 2 * NS;  // [2]
-  uint64_t* p_full = s_full + 2;       // [2]
-  uint64_t* pv_done = p_full + 2;      // [2]
-  uint64_t* o_empty = pv_done + 2;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  uint64_t* bars_all = reinterpret_cast<uint64_t*>(smem + kAttnStreams * kAttnStreamBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_all + kAttnStreams * kBarsPerStream);
+  uint32_t* s_ones = reinterpret_cast<uint32_t*>(smem + kAttnStreams * kAttnStreamBytes + 512);  // 512 B of bf16 1.0
+  float* s_xchg = reinterpret_cast<float*>(smem + kAttnStreams * kAttnStreamBytes + 1024);      // [2][streams][2][128]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows the role branches are warp-uniform and keeps the
+  // MMA / TMA operands in uniform registers (no per-instruction R2UR chains on the single issuing thread)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  long long* trace = (blockIdx.x == 0 && (warp == 0 || warp == 2 || warp == 4) && lane == 0) ? g_attn_trace : nullptr;
   const int T = axis == 0 ? d : n;
   const long long S = axis == 0 ? (long long)B * n : (long long)B * d;
   const int nqt = (T + 127) / 128;  // query tiles == kv tiles per sequence
   const long long num_items = S * H * nqt;
   const int HD = H * 32;
 
-  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tm_qkv);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&q_full[i], 1); ptx::mbar_init(&q_empty[i], 1);
-      ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&p_full[i], 128);
-      ptx::mbar_init(&pv_done[i], 1); ptx::mbar_init(&o_empty[i], 128);
+    for (int sid = 0; sid < kAttnStreams; ++sid) {
+      uint64_t* b = bars_all + sid * kBarsPerStream;
+      ptx::mbar_init(&b[0], 32);  // q_full (32 producer lanes)
+      ptx::mbar_init(&b[1], 1);   // q_empty
+      for (int i = 0; i < NS; ++i) { ptx::mbar_init(&b[2 + i], 32); ptx::mbar_init(&b[2 + NS + i], 1); }  // kv_full, kv_empty
+      ptx::mbar_init(&b[2 + 2 * NS + 0], 1);                    // s_full
+      ptx::mbar_init(&b[2 + 2 * NS + 1], kAttnSoftmaxThreads);  // s_free
+      ptx::mbar_init(&b[2 + 2 * NS + 2], kAttnSoftmaxThreads);  // p_full
+      ptx::mbar_init(&b[2 + 2 * NS + 3], 1);                    // pv_done
+      ptx::mbar_init(&b[2 + 2 * NS + 4], kAttnSoftmaxThreads);  // o_empty
     }
-    for (int i = 0; i < NS; ++i) { ptx::mbar_init(&kv_full[i], 1); ptx::mbar_init(&kv_empty[i], 1); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
+  if (threadIdx.x >= 128 && threadIdx.x < 256) {
+    s_ones[threadIdx.x - 128] = 0x3F803F80u;
+    ptx::fence_proxy_async();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
-  const uint32_t tmem_O = tmem_base + 256;  // 2 x 32 columns
 
-  // item -> (sequence, head, query tile); TMA coordinates of a [128 x 32] tile of that sequence
+  // ---- per-stream view
+  const int sid = warp < 2 ? warp : (warp < 4 ? warp - 2 : (warp - 4) / kAttnSoftmaxWarps);
+  uint8_t* sQ = smem + sid * kAttnStreamBytes;          // [8K]
+  uint8_t* sKV = sQ + kAttnTileBytes;                   // [NS][K 8K | V 8K]
+  uint64_t* bars = bars_all + sid * kBarsPerStream;
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;
+  uint64_t* kv_empty = bars + 2 + NS;
+  uint64_t* s_full = bars + 2 + 2 * NS;
+  uint64_t* s_free = s_full + 1;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* pv_done = s_full + 3;
+  uint64_t* o_empty = s_full + 4;
+  const uint32_t tmem_S = tmem_base + sid * kAttnTmemStreamCols;
+  const uint32_t tmem_P = tmem_S + 128;  // 64 columns: P as packed bf16 pairs, A operand of the PV / L MMAs
+  const uint32_t tmem_O = tmem_S + 192;  // O 32 | L 16 columns
+  const long long item0 = (long long)blockIdx.x * kAttnStreams + sid;
+  const long long item_stride = (long long)gridDim.x * kAttnStreams;
+
   auto decode = [&](long long item, long long& s, int& h, int& qt) {
     qt = (int)(item % nqt);
     const long long sh = item / nqt;
@@ -280,170 +322,269 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     s = sh / H;
   };
 
-  if (warp == 0) {
-    if (lane == 0) {
-      long long g = 0;
-      int it = 0;
-      for (long long item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        long long s; int h, qt;
-        decode(item, s, h, qt);
-        int c1, c2, c3;  // coordinates along d, n, B; the attended one is filled per tile
-        if (axis == 0) { c3 = (int)(s / n); c2 = (int)(s % n); c1 = 0; }
-        else           { c3 = (int)(s / d); c1 = (int)(s % d); c2 = 0; }
-        const int qb = it & 1;
-        ptx::mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1, 10);
-        ptx::mbar_expect_tx(&q_full[qb], kAttnTileBytes);
-        if (axis == 0) ptx::tma_load_4d(sQ + qb * kAttnTileBytes, &tm_qkv, &q_full[qb], h * 32, qt * 128, c2, c3);
-        else           ptx::tma_load_4d(sQ + qb * kAttnTileBytes, &tm_qkv, &q_full[qb], h * 32, c1, qt * 128, c3);
-        for (int j = 0; j < nqt; ++j, ++g) {
-          const int st = (int)(g % NS);
-          ptx::mbar_wait(&kv_empty[st], (uint32_t)((g / NS) & 1) ^ 1, 11);
-          uint8_t* sk = sKV + st * 2 * kAttnTileBytes;
-          ptx::mbar_expect_tx(&kv_full[st], 2 * kAttnTileBytes);
-          if (axis == 0) {
-            ptx::tma_load_4d(sk, &tm_qkv, &kv_full[st], HD + h * 32, j * 128, c2, c3);
-            ptx::tma_load_4d(sk + kAttnTileBytes, &tm_qkv, &kv_full[st], 2 * HD + h * 32, j * 128, c2, c3);
-          } else {
-            ptx::tma_load_4d(sk, &tm_qkv, &kv_full[st], HD + h * 32, c1, j * 128, c3);
-            ptx::tma_load_4d(sk + kAttnTileBytes, &tm_qkv, &kv_full[st], 2 * HD + h * 32, c1, j * 128, c3);
-          }
-        }
+  if (warp < 2) {
+    // ======================= producer warp of stream `sid`: cp.async gathers of [128 x 32] bf16 tiles
+    // Measured on B200: the TMA unit needs ~3.6 cycles per box ROW whatever its width, i.e. ~450 cycles for a
+    // 128-row x 64-byte tile - more than this kernel can afford per K/V tile.  A warp-wide 16-byte cp.async
+    // moves 8 such rows per instruction, so the producers gather through the LSU path instead and write the
+    // 64B-swizzle pattern the UMMA descriptors expect (16-byte chunk index XOR ((row >> 1) & 3)).
+    const long long row_stride = axis == 0 ? (long long)(3 * HD) : (long long)d * (3 * HD);  // elements between positions
+    const int ch = lane & 3;
+    const uint32_t lane_dst = (uint32_t)((lane >> 2) * 64 + ((ch ^ ((lane >> 3) & 3)) << 4));
+    auto load_tile = [&](uint8_t* tile, const __nv_bfloat16* col0, int t0) {
+      // col0: element (position 0 of the sequence, first channel of the tile); rows t0 .. t0+127
+      const uint32_t dst = ptx::smem_u32(tile) + lane_dst;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int t = t0 + k * 8 + (lane >> 2);
+        const int tc = t < T ? t : T - 1;  // keep the address in range; src_bytes = 0 zero-fills
+        ptx::cp_async_16(dst + k * 512, col0 + (long long)tc * row_stride + ch * 8, t < T ? 16u : 0u);
+      }
+    };
+    long long g = 0;
+    int it = 0;
+    for (long long item = item0; item < num_items; item += item_stride, ++it) {
+      long long s; int h, qt;
+      decode(item, s, h, qt);
+      // first token of the sequence
+      const long long tok0 = axis == 0 ? s * d : (s / d) * (long long)n * d + (s % d);
+      const __nv_bfloat16* base = qkv + tok0 * (3 * HD) + h * 32;
+      ptx::mbar_wait(q_empty, (uint32_t)(it & 1) ^ 1, 10);
+      load_tile(sQ, base, qt * 128);
+      ptx::cp_async_mbar_arrive(q_full);
+      for (int j = 0; j < nqt; ++j, ++g) {
+        const int st = (int)(g % NS);
+        AVB_TRACE(0, g, 0);
+        ptx::mbar_wait(&kv_empty[st], (uint32_t)((g / NS) & 1) ^ 1, 11);
+        AVB_TRACE(0, g, 1);
+        uint8_t* sk = sKV + st * 2 * kAttnTileBytes;
+        load_tile(sk, base + HD, j * 128);
+        load_tile(sk + kAttnTileBytes, base + 2 * HD, j * 128);
+        ptx::cp_async_mbar_arrive(&kv_full[st]);
+        AVB_TRACE(0, g, 2);
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
+  } else if (warp < 4) {
+    // ======================= MMA issuer of stream `sid`
+    // One thread issues every tcgen05.mma of the stream, so per-MMA scalar work is on the critical path:
+    // all shared-memory descriptors are built once and advanced by adding (byte offset >> 4) to them.
+    if (item0 < num_items) {  // all 32 lanes run the control flow; one elected lane issues the tcgen05 instructions
       // number of key columns the MMAs of kv tile j touch (multiple of 16)
       auto kcols = [&](int j) { int v = T - j * 128; v = v > 128 ? 128 : v; return (v + 15) & ~15; };
+      const uint64_t dQ = ptx::make_smem_desc(ptx::smem_u32(sQ), 16, 512, ptx::kSwz64);
+      const uint64_t dK = ptx::make_smem_desc(ptx::smem_u32(sKV), 16, 512, ptx::kSwz64);
+      const uint64_t dV = ptx::make_smem_desc(ptx::smem_u32(sKV) + kAttnTileBytes, 16, 512, ptx::kSwz64);
+      // ones tile: K-major, no swizzle, 2 x 2 core matrices of 128 B (every element is 1.0, so any layout works)
+      const uint64_t d_ones = ptx::make_smem_desc(ptx::smem_u32(s_ones), 128, 256, ptx::kSwzNone);
+      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, 32, 0, 1);  // B = V is MN-major
+      constexpr uint32_t idesc_l = ptx::make_idesc_bf16(128, 16, 0, 0);
+      constexpr uint64_t kStageStep = (2 * kAttnTileBytes) >> 4;
       auto issue_S = [&](long long g, int it, int j) {
-        if (j == 0) { ptx::mbar_wait(&q_full[it & 1], (it >> 1) & 1, 20); }
+        if (j == 0) { ptx::mbar_wait(q_full, (uint32_t)(it & 1), 20); }
         const int st = (int)(g % NS);
         ptx::mbar_wait(&kv_full[st], (uint32_t)((g / NS) & 1), 21);
+        ptx::fence_proxy_async();  // cp.async (generic proxy) writes -> visible to the tensor core's async-proxy reads
         ptx::tc_fence_after();
-        const uint32_t idesc = ptx::make_idesc_bf16(128, kcols(j), 0, 0);
-        const uint32_t sq = ptx::smem_u32(sQ + (it & 1) * kAttnTileBytes);
-        const uint32_t sk = ptx::smem_u32(sKV + st * 2 * kAttnTileBytes);
-        const uint32_t dS = tmem_S + (uint32_t)(g & 1) * 128;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const uint64_t da = ptx::make_smem_desc(sq + k * 32, 16, 512, ptx::kSwz64);
-          const uint64_t db = ptx::make_smem_desc(sk + k * 32, 16, 512, ptx::kSwz64);
-          ptx::umma_bf16(dS, da, db, idesc, k != 0);
+        const int kc = kcols(j);
+        const uint32_t idesc = kc == 128 ? idesc_s : ptx::make_idesc_bf16(128, kc, 0, 0);
+        const uint64_t dk = dK + (uint64_t)st * kStageStep;
+        if (ptx::elect_one()) {
+          ptx::umma_bf16(tmem_S, dQ, dk, idesc, 0);
+          ptx::umma_bf16(tmem_S, dQ + 2, dk + 2, idesc, 1);  // +32 bytes: second K=16 slice of the 64-byte rows
+          ptx::umma_commit(s_full);
+          if (j == nqt - 1) ptx::umma_commit(q_empty);  // last S of the item: Q may be overwritten once it completes
         }
-        ptx::umma_commit(&s_full[g & 1]);
+        __syncwarp();
       };
-      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, 32, 0, 1);  // B = V is MN-major
       long long g = 0;
       int it = 0;
-      long long item = blockIdx.x;
-      if (item < num_items) issue_S(0, 0, 0);
+      long long item = item0;
+      issue_S(0, 0, 0);
       while (item < num_items) {
         for (int j = 0; j < nqt; ++j, ++g) {
-          // look ahead: S of the next step overlaps this step's softmax
-          if (j + 1 < nqt) issue_S(g + 1, it, j + 1);
-          else if (item + gridDim.x < num_items) issue_S(g + 1, it + 1, 0);
-          if (j == 0 && it >= 2) { ptx::mbar_wait(&o_empty[it & 1], (uint32_t)(((it >> 1) - 1) & 1), 22); }
-          ptx::mbar_wait(&p_full[g & 1], (uint32_t)((g >> 1) & 1), 23);
+          // S of the next step goes to the tensor core as soon as this step's softmax has read S
+          const bool more = (j + 1 < nqt) || (item + item_stride < num_items);
+          AVB_TRACE(1, g, 0);
+          if (more) {
+            ptx::mbar_wait(s_free, (uint32_t)(g & 1), 24);
+            AVB_TRACE(1, g, 1);
+            ptx::tc_fence_after();
+            if (j + 1 < nqt) issue_S(g + 1, it, j + 1);
+            else issue_S(g + 1, it + 1, 0);
+          }
+          if (j == 0 && it >= 1) { ptx::mbar_wait(o_empty, (uint32_t)((it - 1) & 1), 22); }  // epilogue of the previous item has read O
+          AVB_TRACE(1, g, 2);
+          ptx::mbar_wait(p_full, (uint32_t)(g & 1), 23);
+          AVB_TRACE(1, g, 3);
           ptx::tc_fence_after();
           const int st = (int)(g % NS);
-          const uint32_t sp = ptx::smem_u32(sP + (g & 1) * kAttnPBytes);
-          const uint32_t sv = ptx::smem_u32(sKV + st * 2 * kAttnTileBytes + kAttnTileBytes);
-          const uint32_t dO = tmem_O + (uint32_t)(it & 1) * 32;
+          const uint64_t dv = dV + (uint64_t)st * kStageStep;
           const int ksteps = kcols(j) >> 4;
-          for (int k = 0; k < ksteps; ++k) {
-            // P: [128 x 128] as two 128B-swizzled [128 x 64] K blocks; V: [keys x 32], 16 keys per step
-            const uint64_t da = ptx::make_smem_desc(sp + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024, ptx::kSwz128);
-            const uint64_t db = ptx::make_smem_desc(sv + k * (16 * 64), 16, 512, ptx::kSwz64);
-            ptx::umma_bf16(dO, da, db, idesc_pv, (j | k) != 0);
+          // P: 8 TMEM columns (16 bf16) per K=16 slice; V: [keys x 32], 16 keys (1 KB) per slice
+          if (ptx::elect_one()) {
+            if (ksteps == 8) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                ptx::umma_bf16_ts(tmem_O, tmem_P + k * 8, dv + (uint64_t)(k * 64), idesc_pv, (j | k) != 0);
+                ptx::umma_bf16_ts(tmem_O + 32, tmem_P + k * 8, d_ones, idesc_l, (j | k) != 0);
+              }
+            } else {
+              for (int k = 0; k < ksteps; ++k) {
+                ptx::umma_bf16_ts(tmem_O, tmem_P + k * 8, dv + (uint64_t)(k * 64), idesc_pv, (j | k) != 0);
+                ptx::umma_bf16_ts(tmem_O + 32, tmem_P + k * 8, d_ones, idesc_l, (j | k) != 0);
+              }
+            }
+            ptx::umma_commit(&kv_empty[st]);
+            ptx::umma_commit(pv_done);
           }
-          ptx::umma_commit(&kv_empty[st]);
-          ptx::umma_commit(&pv_done[g & 1]);
-          if (j == nqt - 1) ptx::umma_commit(&q_empty[it & 1]);
+          __syncwarp();
+          AVB_TRACE(1, g, 4);
         }
-        item += gridDim.x;
+        item += item_stride;
         ++it;
       }
     }
-  } else if (warp >= 4) {
-    const int q = warp & 3;
+  } else {
+    // ======================= softmax / rescale / epilogue warps of stream `sid`
+    // 8 warps: warp (q, half) owns TMEM lanes 32q..32q+31 (query rows) and key columns [64*half, 64*half+64).
+    const int w8 = (warp - 4) % kAttnSoftmaxWarps;
+    const int q = w8 & 3, half = w8 >> 2;
     const int r = q * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int bar_id = 1 + sid * 4 + q;  // named barrier shared by the two warps of a row quarter
+    const uint32_t tS = tmem_S + half * 64 + lane_off;   // this warp's 64 S columns
+    const uint32_t tP = tmem_P + half * 32 + lane_off;   // ... and the 32 packed P columns they become
+    const uint32_t tO = tmem_O + lane_off;
+
     long long g = 0;
     int it = 0;
-    for (long long item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+    for (long long item = item0; item < num_items; item += item_stride, ++it) {
       long long s; int h, qt;
       decode(item, s, h, qt);
-      float m = -INFINITY, l = 0.f;
+      float m = -INFINITY;
       for (int j = 0; j < nqt; ++j, ++g) {
-        const int sb = (int)(g & 1);
-        ptx::mbar_wait(&s_full[sb], (uint32_t)((g >> 1) & 1), 30);
+        AVB_TRACE(2, g, 0);
+        ptx::mbar_wait(s_full, (uint32_t)(g & 1), 30);
+        AVB_TRACE(2, g, 1);
         ptx::tc_fence_after();
-        uint32_t sv[4][32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) ptx::tmem_ld32(tmem_S + sb * 128 + c * 32 + lane_off, sv[c]);
-        ptx::tmem_wait_ld();
-        const int nvalid = T - j * 128;  // >= 1
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            float v = __uint_as_float(sv[c][e]);
-            v = (c * 32 + e < nvalid) ? v : -INFINITY;
-            sv[c][e] = __float_as_uint(v);
-            mx = fmaxf(mx, v);
-          }
-        const float m_new = fmaxf(m, mx);
-        const float alpha = fast_exp2(m - m_new);
-        if (j > 0) {
-          // rescale the running output once every PV MMA up to the previous step has landed
-          ptx::mbar_wait(&pv_done[(g - 1) & 1], (uint32_t)(((g - 1) >> 1) & 1), 31);
-          ptx::tc_fence_after();
-          uint32_t o[32];
-          ptx::tmem_ld32(tmem_O + (it & 1) * 32 + lane_off, o);
+        const int nv = T - j * 128 - half * 64;  // valid key columns in this warp's half (may be <= 0)
+        const bool full_half = nv >= 64;
+        // ---- pass 1: row maximum over this half, then exchange with the partner warp
+        float mx;
+        if (full_half) {
+          uint32_t sa[32], sb[32];
+          ptx::tmem_ld32(tS, sa);
+          ptx::tmem_ld32(tS + 32, sb);
           ptx::tmem_wait_ld();
+          float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-          ptx::tmem_st32(tmem_O + (it & 1) * 32 + lane_off, o);
+          for (int e = 0; e < 32; e += 2) {
+            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sa[e]), __uint_as_float(sa[e + 1])));
+            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sb[e]), __uint_as_float(sb[e + 1])));
+          }
+          mx = fmaxf(mx0, mx1);
+        } else {
+          mx = -INFINITY;
+#pragma unroll 1
+          for (int c = 0; c * 32 < nv; ++c) {
+            uint32_t sv[32];
+            ptx::tmem_ld32(tS + c * 32, sv);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (c * 32 + e < nv) ? __uint_as_float(sv[e]) : -INFINITY);
+          }
+        }
+        AVB_TRACE(2, g, 2);
+        float* xc = s_xchg + (((g & 1) * kAttnStreams + sid) * 2) * 128;
+        xc[half * 128 + r] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        mx = fmaxf(mx, xc[(half ^ 1) * 128 + r]);
+        // ---- lazy rescale: keep the stale reference max unless it grew by more than 2^8 (warp-uniform vote;
+        //      both warps of a row quarter see the same values and take the same decision)
+        const bool need = mx > m + kAttnRescaleThreshold;  // true on the first tile (m = -inf)
+        const bool any_need = __any_sync(0xffffffffu, need);
+        AVB_TRACE(2, g, 3);
+        if (g >= 1) {  // P is free and O complete once the PV / L MMAs of the previous step have finished
+          ptx::mbar_wait(pv_done, (uint32_t)((g - 1) & 1), 31);
+          ptx::tc_fence_after();
+        }
+        AVB_TRACE(2, g, 4);
+        if (any_need) {
+          const float m_new = need ? mx : m;
+          if (j > 0 && half == 0) {  // half 0 rescales O and the denominator column in TMEM
+            const float alpha = need ? fast_exp2(m - m_new) : 1.0f;
+            uint32_t o[32];
+            ptx::tmem_ld32(tO, o);
+            uint32_t lv = ptx::tmem_ld1(tO + 32);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            lv = __float_as_uint(__uint_as_float(lv) * alpha);
+            ptx::tmem_st32(tO, o);
+            ptx::tmem_st1(tO + 32, lv);
+            ptx::tmem_wait_st();
+          }
+          m = m_new;
+        }
+        // ---- pass 2: P = exp2(S - m) -> packed bf16 pairs -> TMEM (the row sum is done by the L MMA)
+        {
+          uint32_t pk[32];
+          if (full_half) {
+            uint32_t sa[32], sb[32];
+            ptx::tmem_ld32(tS, sa);
+            ptx::tmem_ld32(tS + 32, sb);
+            ptx::tmem_wait_ld();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(s_free);  // last read of S: hand the buffer back to the tensor core
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              pk[e] = ptx::pack_bf16(fast_exp2(__uint_as_float(sa[2 * e]) - m), fast_exp2(__uint_as_float(sa[2 * e + 1]) - m));
+              pk[16 + e] = ptx::pack_bf16(fast_exp2(__uint_as_float(sb[2 * e]) - m), fast_exp2(__uint_as_float(sb[2 * e + 1]) - m));
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) pk[e] = 0u;  // keys beyond the sequence end get probability 0
+            for (int c = 0; c < 2; ++c) {
+              if (c * 32 >= nv) break;
+              uint32_t sv[32];
+              ptx::tmem_ld32(tS + c * 32, sv);
+              ptx::tmem_wait_ld();
+              const int rem = nv - c * 32;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float p0 = (2 * e < rem) ? fast_exp2(__uint_as_float(sv[2 * e]) - m) : 0.f;
+                const float p1 = (2 * e + 1 < rem) ? fast_exp2(__uint_as_float(sv[2 * e + 1]) - m) : 0.f;
+                if (c == 0) pk[e] = ptx::pack_bf16(p0, p1); else pk[16 + e] = ptx::pack_bf16(p0, p1);
+              }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(s_free);
+          }
+          ptx::tmem_st32(tP, pk);
           ptx::tmem_wait_st();
         }
-        if (g >= 2) { ptx::mbar_wait(&pv_done[sb], (uint32_t)(((g >> 1) - 1) & 1), 32); }  // P[sb] free
-        float sum = 0.f;
-        uint8_t* prow = sP + sb * kAttnPBytes + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-        for (int c16 = 0; c16 < 16; ++c16) {
-          float p[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            p[e] = fast_exp2(__uint_as_float(sv[c16 >> 2][(c16 & 3) * 8 + e]) - m_new);
-          }
-          uint4 pk;
-          pk.x = ptx::pack_bf16(p[0], p[1]); pk.y = ptx::pack_bf16(p[2], p[3]);
-          pk.z = ptx::pack_bf16(p[4], p[5]); pk.w = ptx::pack_bf16(p[6], p[7]);
-          sum += ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
-          *reinterpret_cast<uint4*>(prow + (c16 >> 3) * (128 * 128) + (((c16 & 7) ^ (r & 7)) << 4)) = pk;
-        }
-        l = l * alpha + sum;
-        m = m_new;
-        ptx::fence_proxy_async();
+        AVB_TRACE(2, g, 5);
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&p_full[sb]);
+        ptx::mbar_arrive(p_full);
+        AVB_TRACE(2, g, 6);
       }
-      // epilogue: O / l -> bf16 -> out[token, h*32 ..]
-      const long long g_last = g - 1;
-      ptx::mbar_wait(&pv_done[g_last & 1], (uint32_t)((g_last >> 1) & 1), 33);
+      // ---- epilogue: O / L -> bf16 -> out[token, h*32 ..]; each half writes 16 of the 32 channels of its rows
+      ptx::mbar_wait(pv_done, (uint32_t)((g - 1) & 1), 33);
       ptx::tc_fence_after();
-      uint32_t o[32];
-      ptx::tmem_ld32(tmem_O + (it & 1) * 32 + lane_off, o);
+      uint32_t o[16];
+      ptx::tmem_ld16(tO + half * 16, o);
+      const float lsum = __uint_as_float(ptx::tmem_ld1(tO + 32));
       ptx::tmem_wait_ld();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&o_empty[it & 1]);
+      ptx::mbar_arrive(o_empty);
       const int t = qt * 128 + r;
       if (t < T) {
         const long long tok = axis == 0 ? s * d + t : (s / d) * (long long)n * d + (long long)t * d + (s % d);
-        const float inv = 1.0f / l;
-        uint4* op = reinterpret_cast<uint4*>(out + (size_t)tok * HD + h * 32);
+        const float inv = 1.0f / lsum;
+        uint4* op = reinterpret_cast<uint4*>(out + (size_t)tok * HD + h * 32 + half * 16);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 2; ++e) {
           uint4 pk;
           pk.x = ptx::pack_bf16(__uint_as_float(o[e * 8 + 0]) * inv, __uint_as_float(o[e * 8 + 1]) * inv);
           pk.y = ptx::pack_bf16(__uint_as_float(o[e * 8 + 2]) * inv, __uint_as_float(o[e * 8 + 3]) * inv);

@@ -161,6 +161,10 @@ int avb_test_gemm_bf16(const void* a_bf16_dev, const void* wt_bf16_dev, const fl
 int avb_test_attention_bf16(const void* qkv_bf16_dev, void* out_bf16_dev, int32_t B, int32_t n,
                             int32_t d, int32_t H, int32_t axis, void* stream);
 
+/* Debug: device buffer of 3*4096 int64 that block 0 of the attention kernel fills with clock64() stamps of
+ * its producer / MMA / softmax roles (NULL switches tracing off). */
+int avb_debug_set_trace(void* trace_dev);
+
 #ifdef __cplusplus
 }
 #endif
