@@ -164,6 +164,25 @@ int launch_gemm_tc(avb_handle h, const CUtensorMap& tm_a, const CUtensorMap& tm_
   return AVB_OK;
 }
 
+template <int EPI>
+int launch_ln_gemm_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, const float* bias, void* out, int ldo,
+                      int M, int N, cudaStream_t st, int num_sms, long long* launches) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(avb::ln_gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         avb::kLnGemmSmemBytes);
+    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(ln_gemm_tc): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = std::min((M + 127) / 128, num_sms);
+  avb::ln_gemm_tc_kernel<EPI><<<grid, avb::kLnGemmThreads, avb::kLnGemmSmemBytes, st>>>(
+      z, tm_b, bias, reinterpret_cast<bf16*>(out), ldo, M, N);
+  if (launches) ++*launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ln_gemm_tc launch: %s", cudaGetErrorString(e));
+  return AVB_OK;
+}
+
 int launch_attention_tc(avb_handle h, const void* qkv, void* out, int B, int n, int d, int H, int axis,
                         cudaStream_t st, int num_sms, long long* launches) {
   static bool attr_set = false;
@@ -195,7 +214,7 @@ void launch_sgemm(const float* A, int lda, const float* W, int ldw, const float*
 
 // ------------------------------------------------------------------ workspace carving
 struct BlockWs {
-  // bf16 mode: xhat bf16[N,128] | big (qkv bf16[N,768] aliased with h bf16[N,512]) | attn bf16[N,256]
+  // bf16 mode: big (qkv bf16[N,768] aliased with h bf16[N,512]) | attn bf16[N,256]
   // f32 mode:  big (qkv f32[N,768] aliased with h f32[N,512]) | attn f32[N,256]
   size_t xhat_off, big_off, attn_off, total;
 };
@@ -204,7 +223,7 @@ BlockWs block_ws_layout(const avb_config& c, size_t ntok) {
   const size_t HD = (size_t)c.num_heads * c.key_size, F = (size_t)c.widening_factor * c.dim;
   size_t off = 0;
   if (c.compute_dtype == AVB_DTYPE_BF16) {
-    w.xhat_off = off; off = align_up(off + ntok * c.dim * 2, 1024);
+    w.xhat_off = off;  // (the LayerNorm output lives only in shared memory)
     w.big_off = off;  off = align_up(off + ntok * std::max(3 * HD, F) * 2, 1024);
     w.attn_off = off; off = align_up(off + ntok * HD * 2, 1024);
   } else {
@@ -558,32 +577,23 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
   const int M = (int)ntok;
 
   if (c.compute_dtype == AVB_DTYPE_BF16) {
-    bf16* xhat = reinterpret_cast<bf16*>(w8 + L.xhat_off);
     bf16* qkv = reinterpret_cast<bf16*>(w8 + L.big_off);
     bf16* hid = qkv;  // aliased: qkv is dead once attention has run
     bf16* attn = reinterpret_cast<bf16*>(w8 + L.attn_off);
-    CUtensorMap tm_x, tm_attn, tm_h;
-    if (!make_tmap_2d(&tm_x, xhat, ntok, k, 128) || !make_tmap_2d(&tm_attn, attn, ntok, HD, 128) ||
-        !make_tmap_2d(&tm_h, hid, ntok, F, 128))
+    CUtensorMap tm_attn, tm_h;
+    if (!make_tmap_2d(&tm_attn, attn, ntok, HD, 128) || !make_tmap_2d(&tm_h, hid, ntok, F, 128))
       return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for activations");
-    const int ln_grid = (int)std::min<size_t>((ntok + 7) / 8, (size_t)h->num_sms * 16);
     int rc;
     // attention half: LN -> QKV -> attention -> out-proj + residual
-    { ProfScope ps(h, AVB_PROF_LN, st);
-      avb::ln_bf16_kernel<<<ln_grid, 256, 0, st>>>(z, ntok, xhat);
-      AVB_LAUNCH_CHECK(h); }
-    { ProfScope ps(h, AVB_PROF_QKV, st);
-      if ((rc = launch_gemm_tc<256, 0>(h, tm_x, W.tm_wqkv, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, k, st, h->num_sms, &h->launches))) return rc; }
+    { ProfScope ps(h, AVB_PROF_QKV, st);  // LayerNorm fused into the projection's prologue
+      if ((rc = launch_ln_gemm_tc<0>(h, z, W.tm_wqkv, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, st, h->num_sms, &h->launches))) return rc; }
     { ProfScope ps(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
       if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches))) return rc; }
     { ProfScope ps(h, AVB_PROF_OUT, st);
       if ((rc = launch_gemm_tc<128, 2>(h, tm_attn, W.tm_wo, W.bo, z, k, M, k, HD, st, h->num_sms, &h->launches))) return rc; }
     // FFN half: LN -> Linear + ReLU -> Linear + residual
-    { ProfScope ps(h, AVB_PROF_LN, st);
-      avb::ln_bf16_kernel<<<ln_grid, 256, 0, st>>>(z, ntok, xhat);
-      AVB_LAUNCH_CHECK(h); }
     { ProfScope ps(h, AVB_PROF_FFN1, st);
-      if ((rc = launch_gemm_tc<256, 1>(h, tm_x, W.tm_w1, W.b1_f, hid, F, M, F, k, st, h->num_sms, &h->launches))) return rc; }
+      if ((rc = launch_ln_gemm_tc<1>(h, z, W.tm_w1, W.b1_f, hid, F, M, F, st, h->num_sms, &h->launches))) return rc; }
     { ProfScope ps(h, AVB_PROF_FFN2, st);
       if ((rc = launch_gemm_tc<128, 2>(h, tm_h, W.tm_w2, W.b2, z, k, M, k, F, st, h->num_sms, &h->launches))) return rc; }
   } else {
@@ -781,6 +791,19 @@ int avb_test_gemm_bf16(const void* a, const void* wt, const float* bias, void* o
     if (epilogue == 2) return launch_gemm_tc<256, 2>(nullptr, ta, tb, bias, out, N, M, N, K, st, sms, nullptr);
   }
   return fail(nullptr, AVB_ERR_INVALID, "avb_test_gemm_bf16: bad epilogue");
+}
+
+int avb_test_ln_gemm_bf16(const float* z, const void* wt, const float* bias, void* out, int32_t M, int32_t N, int32_t relu,
+                          void* stream) {
+  if (!z || !wt || !bias || !out || M < 1 || N % 256) return fail(nullptr, AVB_ERR_INVALID, "avb_test_ln_gemm_bf16: bad shape");
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device");
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CUtensorMap tb;
+  if (!make_tmap_2d(&tb, wt, N, 128, 256)) return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return relu ? launch_ln_gemm_tc<1>(nullptr, z, tb, bias, out, N, M, N, st, sms, nullptr)
+              : launch_ln_gemm_tc<0>(nullptr, z, tb, bias, out, N, M, N, st, sms, nullptr);
 }
 
 int avb_debug_set_trace(void* trace_dev) {

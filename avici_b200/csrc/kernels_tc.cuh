@@ -197,6 +197,230 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused LayerNorm -> GEMM:  out[M, N] = act( LN(z)[M,128] @ Wt[N,128]^T + bias[N] ),  bf16 out.
+//   (QKV projection: N = 768, act = id;  FFN up-projection: N = 512, act = ReLU.  LayerNorm gamma/beta
+//    are folded into Wt / bias at load time, so the prologue only normalises.)
+//   The A operand never exists in HBM: 4 "LN" warps read the fp32 residual rows (one coalesced 512 B row
+//   per warp-load), normalise with warp shuffles and write bf16 straight into the 128B-swizzled K-major
+//   smem layout the UMMA descriptors expect; the [128 x 128] A tile is reused by all N/256 column chunks.
+//   Weights stream through a TMA ring; accumulators are double-buffered in TMEM (2 x 256 columns).
+//   The epilogue stages [32 x 64] pieces in smem and writes them out as 128-byte row segments, four rows per
+//   warp store (the 16-byte-per-lane pieces of a row-per-thread store waste HBM sectors).
+//   warps 0-3: LN producers   warp 4: weight TMA   warp 5: MMA issuer   warp 6: TMEM alloc
+//   warps 8-15: epilogue (warp = TMEM lane quarter x 128-column half of the 256-column accumulator)
+// ------------------------------------------------------------------------------------------
+constexpr int kLnGemmThreads = 512;
+constexpr int kLnGemmBStages = 3;
+constexpr int kLnGemmABytes = 128 * 128 * 2;               // 32 KB: two 128B-swizzled K blocks of 64
+constexpr int kLnGemmBBytes = 256 * 64 * 2;                // 32 KB per (256-column chunk, K block)
+constexpr int kLnGemmStagePitch = 64 * 2 + 16;             // bytes per staged row (64 bf16 + pad)
+constexpr int kLnGemmStageBytes = 8 * 32 * kLnGemmStagePitch;  // 8 epilogue warps x 32 rows = 36 KB
+constexpr int kLnGemmSmemBytes = 2 * kLnGemmABytes + kLnGemmBStages * kLnGemmBBytes + kLnGemmStageBytes + 1024 + 256;
+
+template <int EPI>  // 0: store, 1: ReLU + store
+__global__ void __launch_bounds__(kLnGemmThreads, 1)
+ln_gemm_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorMap tm_b,
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int M, int N) {
+  constexpr int ST = kLnGemmBStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                   // [2][32K]
+  uint8_t* sB = sA + 2 * kLnGemmABytes;                 // [ST][32K]
+  uint8_t* sStage = sB + ST * kLnGemmBBytes;            // [128][pitch]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + kLnGemmStageBytes);
+  uint64_t* a_full = bars;             // [2] 128 LN threads
+  uint64_t* a_empty = bars + 2;        // [2]
+  uint64_t* b_full = bars + 4;         // [ST]
+  uint64_t* b_empty = bars + 4 + ST;   // [ST]
+  uint64_t* t_full = bars + 4 + 2 * ST;  // [2]
+  uint64_t* t_empty = t_full + 2;      // [2] 128 epilogue threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int num_m = (M + 127) / 128, num_c = N / 256;
+
+  if (warp == 4 && lane == 0) ptx::prefetch_tmap(&tm_b);
+  if (warp == 5 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&a_full[i], 128); ptx::mbar_init(&a_empty[i], 1);
+      ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 256);
+    }
+    for (int i = 0; i < ST; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 6) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== LN producers: warp w normalises rows 32w .. 32w+31 of each tile
+    // lane l owns channels 4l..4l+3: K block (l >> 4), 16-byte chunk ((l & 15) >> 1), 8-byte half (l & 1)
+    const uint32_t lane_col = (uint32_t)((lane >> 4) * (128 * 128));
+    const int chunk = (lane & 15) >> 1;
+    const uint32_t half8 = (uint32_t)((lane & 1) * 8);
+    int it = 0;
+    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
+      const int buf = it & 1;
+      ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 40);
+      const uint32_t abase = ptx::smem_u32(sA + buf * kLnGemmABytes) + lane_col + half8;
+      // software pipeline: the loads of the next 8 rows are in flight while 8 rows are normalised
+      const float4* zrow = reinterpret_cast<const float4*>(z) + lane;
+      const int row_base = mt * 128 + warp * 32;
+      float4 cur[8], nxt[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        cur[u] = row_base + u < M ? __ldg(zrow + (size_t)(row_base + u) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        if (r0 + 8 < 32) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int row = row_base + r0 + 8 + u;
+            nxt[u] = row < M ? __ldg(zrow + (size_t)row * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 v = cur[u];
+          const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / 128.0f);
+          const float4 c = make_float4(v.x - mean, v.y - mean, v.z - mean, v.w - mean);
+          const float var = warp_sum(c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w) * (1.0f / 128.0f);
+          const float rs = rsqrtf(var + kLnEps);
+          const int r = warp * 32 + r0 + u;
+          const uint32_t addr = abase + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ptx::pack_bf16(c.x * rs, c.y * rs)),
+                       "r"(ptx::pack_bf16(c.z * rs, c.w * rs))
+                       : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+      }
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&a_full[buf]);
+    }
+  } else if (warp == 4) {
+    // ===================== weight TMA producer: for every m tile, N/256 chunks x 2 K blocks of [256 x 64]
+    int stage = 0; uint32_t phase = 0;
+    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
+      for (int c = 0; c < num_c; ++c) {
+        for (int kb = 0; kb < 2; ++kb) {
+          ptx::mbar_wait(&b_empty[stage], phase ^ 1, 41);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&b_full[stage], kLnGemmBBytes);
+            ptx::tma_load_2d(sB + stage * kLnGemmBBytes, &tm_b, &b_full[stage], kb * 64, c * 256);
+          }
+          __syncwarp();
+          if (++stage == ST) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 256, 0, 0);
+    const uint64_t dA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024, ptx::kSwz128);
+    const uint64_t dB0 = ptx::make_smem_desc(ptx::smem_u32(sB), 16, 1024, ptx::kSwz128);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0, acc_it = 0;
+    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
+      const int buf = it & 1;
+      ptx::mbar_wait(&a_full[buf], (it >> 1) & 1, 42);
+      for (int c = 0; c < num_c; ++c, ++acc_it) {
+        const int as = acc_it & 1;
+        ptx::mbar_wait(&t_empty[as], ((acc_it >> 1) & 1) ^ 1, 43);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int kb = 0; kb < 2; ++kb) {
+          ptx::mbar_wait(&b_full[stage], phase, 44);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint64_t da = dA0 + (uint64_t)(buf * (kLnGemmABytes >> 4) + kb * ((128 * 128) >> 4));
+            const uint64_t db = dB0 + (uint64_t)stage * (kLnGemmBBytes >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            ptx::umma_commit(&b_empty[stage]);
+            if (kb == 1) {
+              ptx::umma_commit(&t_full[as]);
+              if (c == num_c - 1) ptx::umma_commit(&a_empty[buf]);
+            }
+          }
+          __syncwarp();
+          if (++stage == ST) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue: TMEM -> +bias (ReLU) -> bf16 -> smem stage -> coalesced global stores
+    const int q = warp & 3, hf = (warp - 8) >> 2;
+    const uint32_t stage_warp = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 32 * kLnGemmStagePitch);
+    const uint32_t stage_row = stage_warp + (uint32_t)(lane * kLnGemmStagePitch);
+    const int sub = lane >> 3, l8 = lane & 7;  // copy-out: 4 rows per warp store, 8 lanes x 16 B per row
+    int acc_it = 0;
+    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
+      for (int c = 0; c < num_c; ++c, ++acc_it) {
+        const int as = acc_it & 1;
+        ptx::mbar_wait(&t_full[as], (acc_it >> 1) & 1, 45);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + as * 256 + hf * 128 + ((uint32_t)(q * 32) << 16);
+        const int col0 = c * 256 + hf * 128;
+#pragma unroll 1
+        for (int pc = 0; pc < 2; ++pc) {  // two pieces of 64 columns
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            float4 bb[8];  // bias of these 32 columns, requested before the TMEM load so the latencies overlap
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bias + col0 + pc * 64 + cc * 32) + e);
+            uint32_t v[32];
+            ptx::tmem_ld32(taddr + pc * 64 + cc * 32, v);
+            ptx::tmem_wait_ld();
+            if (pc == 1 && cc == 1) {  // accumulator fully read by this warp: hand it back to the MMA warp
+              ptx::tc_fence_before();
+              ptx::mbar_arrive(&t_empty[as]);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float f[8];
+              f[0] = __uint_as_float(v[e * 8 + 0]) + bb[e * 2].x;     f[1] = __uint_as_float(v[e * 8 + 1]) + bb[e * 2].y;
+              f[2] = __uint_as_float(v[e * 8 + 2]) + bb[e * 2].z;     f[3] = __uint_as_float(v[e * 8 + 3]) + bb[e * 2].w;
+              f[4] = __uint_as_float(v[e * 8 + 4]) + bb[e * 2 + 1].x; f[5] = __uint_as_float(v[e * 8 + 5]) + bb[e * 2 + 1].y;
+              f[6] = __uint_as_float(v[e * 8 + 6]) + bb[e * 2 + 1].z; f[7] = __uint_as_float(v[e * 8 + 7]) + bb[e * 2 + 1].w;
+              if (EPI == 1) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], 0.f);
+              }
+              uint4 pk;
+              pk.x = ptx::pack_bf16(f[0], f[1]); pk.y = ptx::pack_bf16(f[2], f[3]);
+              pk.z = ptx::pack_bf16(f[4], f[5]); pk.w = ptx::pack_bf16(f[6], f[7]);
+              ptx::st_shared_v4(stage_row + (uint32_t)(cc * 64 + e * 16), pk);
+            }
+          }
+          __syncwarp();  // the 32 staged rows are written and read by this warp only
+#pragma unroll
+          for (int rr = 0; rr < 32; rr += 4) {
+            const int row = rr + sub;
+            const int grow = mt * 128 + q * 32 + row;
+            uint4 pk;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w)
+                         : "r"(stage_warp + (uint32_t)(row * kLnGemmStagePitch + l8 * 16)));
+            if (grow < M) *reinterpret_cast<uint4*>(out + (size_t)grow * ldo + col0 + pc * 64 + l8 * 8) = pk;
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 6) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------
 // Flash-style axial attention on tensor cores.  head dim 32, 128-query x 128-key tiles.
 //   qkv viewed through ONE 4-D tensor map {3*H*32, d, n, B}; a work item (s, h, qt) loads its
 //   [128 x 32] Q tile and streams [128 x 32] K / V tiles with a box of {32,128,1,1} (attend over d)

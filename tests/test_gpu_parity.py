@@ -73,6 +73,25 @@ def test_gemm_tc_against_torch(built_lib, M, N, K, epi):
     assert err <= (2e-5 if epi == 2 else 2 ** -8) * max(scale, 1.0) + 1e-6, f"gemm_tc err {err} (scale {scale})"
 
 
+@pytest.mark.parametrize("M,N,relu", [(128, 768, 0), (1000, 768, 0), (333, 512, 1), (50000, 768, 0), (70001, 512, 1)])
+def test_ln_gemm_tc_against_torch(built_lib, M, N, relu):
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    z = torch.randn(M, 128, device="cuda", generator=g) * 3 + torch.randn(M, 1, device="cuda", generator=g)
+    wt = (torch.randn(N, 128, device="cuda", generator=g) / 128 ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    rc = built_lib.avb_test_ln_gemm_bf16(z.data_ptr(), wt.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, relu,
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(built_lib, None, rc)
+    torch.cuda.synchronize()
+    xhat = torch.nn.functional.layer_norm(z, (128,), eps=1e-5).to(torch.bfloat16).float()
+    ref = xhat @ wt.float().T + bias
+    if relu:
+        ref = ref.relu()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2 ** -7 * max(ref.abs().max().item(), 1.0), f"ln_gemm_tc err {err}"
+
+
 def attention_reference(qkv, B, n, d, H, axis):
     """fp32 softmax attention over axis `axis` of qkv[B,n,d,3*H*32]; q is pre-scaled by log2e/sqrt(32)."""
     x = qkv.float().reshape(B, n, d, 3, H, 32)
