@@ -448,9 +448,9 @@ constexpr int kAttnStreams = 2;
 constexpr int kAttnSoftmaxWarps = 8;  // per stream: 4 TMEM lane quarters x 2 column halves
 constexpr int kAttnSoftmaxThreads = kAttnSoftmaxWarps * 32;
 constexpr int kAttnThreads = 128 + kAttnStreams * kAttnSoftmaxThreads;  // 640
-constexpr int kAttnKvStages = 6;
+constexpr int kAttnKvStages = 5;
 constexpr int kAttnTileBytes = 128 * 32 * 2;  // 8 KB: Q, K or V tile
-constexpr int kAttnStreamBytes = kAttnTileBytes + kAttnKvStages * 2 * kAttnTileBytes;  // Q | KV ring = 104 KB
+constexpr int kAttnStreamBytes = 2 * kAttnTileBytes + kAttnKvStages * 2 * kAttnTileBytes;  // Q[2] | KV ring = 96 KB
 constexpr int kAttnXchgBytes = 2 /*parity*/ * kAttnStreams * 2 /*halves*/ * 128 * 4;  // row-max exchange, 4 KB
 constexpr int kAttnSmemBytes = kAttnStreams * kAttnStreamBytes + 1024 + 512 + 512 + kAttnXchgBytes;  // + align slack, barriers, ones tile
 constexpr int kAttnTmemStreamCols = 256;  // S 128 (fp32) | P 64 (bf16 pairs) | O 32 | L 16 | spare
@@ -474,11 +474,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int n, int d, int H,
                     int axis) {
   constexpr int NS = kAttnKvStages;
-  constexpr int kBarsPerStream = 1 + 1 + NS + NS + 1 + 1 + 1 + 1 + 1;
+  constexpr int kBarsPerStream = 2 + 2 + NS + NS + 1 + 1 + 1 + 1 + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars_all = reinterpret_cast<uint64_t*>(smem + kAttnStreams * kAttnStreamBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_all + kAttnStreams * kBarsPerStream);
+  uint64_t* turn_done = bars_all + kAttnStreams * kBarsPerStream;  // [2]: stream s finished the exp phase of a step
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn_done + 2);
   uint32_t* s_ones = reinterpret_cast<uint32_t*>(smem + kAttnStreams * kAttnStreamBytes + 512);  // 512 B of bf16 1.0
   float* s_xchg = reinterpret_cast<float*>(smem + kAttnStreams * kAttnStreamBytes + 1024);      // [2][streams][2][128]
 
@@ -495,15 +496,16 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   if (warp == 1 && lane == 0) {
     for (int sid = 0; sid < kAttnStreams; ++sid) {
       uint64_t* b = bars_all + sid * kBarsPerStream;
-      ptx::mbar_init(&b[0], 32);  // q_full (32 producer lanes)
-      ptx::mbar_init(&b[1], 1);   // q_empty
-      for (int i = 0; i < NS; ++i) { ptx::mbar_init(&b[2 + i], 32); ptx::mbar_init(&b[2 + NS + i], 1); }  // kv_full, kv_empty
-      ptx::mbar_init(&b[2 + 2 * NS + 0], 1);                    // s_full
-      ptx::mbar_init(&b[2 + 2 * NS + 1], kAttnSoftmaxThreads);  // s_free
-      ptx::mbar_init(&b[2 + 2 * NS + 2], kAttnSoftmaxThreads);  // p_full
-      ptx::mbar_init(&b[2 + 2 * NS + 3], 1);                    // pv_done
-      ptx::mbar_init(&b[2 + 2 * NS + 4], kAttnSoftmaxThreads);  // o_empty
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&b[i], 32); ptx::mbar_init(&b[2 + i], 1); }  // q_full (32 producer lanes), q_empty
+      for (int i = 0; i < NS; ++i) { ptx::mbar_init(&b[4 + i], 32); ptx::mbar_init(&b[4 + NS + i], 1); }  // kv_full, kv_empty
+      ptx::mbar_init(&b[4 + 2 * NS + 0], 1);                    // s_full
+      ptx::mbar_init(&b[4 + 2 * NS + 1], kAttnSoftmaxThreads);  // s_free
+      ptx::mbar_init(&b[4 + 2 * NS + 2], kAttnSoftmaxThreads);  // p_full
+      ptx::mbar_init(&b[4 + 2 * NS + 3], 1);                    // pv_done
+      ptx::mbar_init(&b[4 + 2 * NS + 4], kAttnSoftmaxThreads);  // o_empty
     }
+    ptx::mbar_init(&turn_done[0], kAttnSoftmaxThreads);
+    ptx::mbar_init(&turn_done[1], kAttnSoftmaxThreads);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -521,14 +523,14 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
 
   // ---- per-stream view
   const int sid = warp < 2 ? warp : (warp < 4 ? warp - 2 : (warp - 4) / kAttnSoftmaxWarps);
-  uint8_t* sQ = smem + sid * kAttnStreamBytes;          // [8K]
-  uint8_t* sKV = sQ + kAttnTileBytes;                   // [NS][K 8K | V 8K]
+  uint8_t* sQ = smem + sid * kAttnStreamBytes;          // [2][8K]
+  uint8_t* sKV = sQ + 2 * kAttnTileBytes;               // [NS][K 8K | V 8K]
   uint64_t* bars = bars_all + sid * kBarsPerStream;
-  uint64_t* q_full = bars;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* kv_full = bars + 2;
-  uint64_t* kv_empty = bars + 2 + NS;
-  uint64_t* s_full = bars + 2 + 2 * NS;
+  uint64_t* q_full = bars;        // [2]
+  uint64_t* q_empty = bars + 2;   // [2]
+  uint64_t* kv_full = bars + 4;
+  uint64_t* kv_empty = bars + 4 + NS;
+  uint64_t* s_full = bars + 4 + 2 * NS;
   uint64_t* s_free = s_full + 1;
   uint64_t* p_full = s_full + 2;
   uint64_t* pv_done = s_full + 3;
@@ -573,9 +575,10 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       // first token of the sequence
       const long long tok0 = axis == 0 ? s * d : (s / d) * (long long)n * d + (s % d);
       const __nv_bfloat16* base = qkv + tok0 * (3 * HD) + h * 32;
-      ptx::mbar_wait(q_empty, (uint32_t)(it & 1) ^ 1, 10);
-      load_tile(sQ, base, qt * 128);
-      ptx::cp_async_mbar_arrive(q_full);
+      const int qb = it & 1;
+      ptx::mbar_wait(&q_empty[qb], (uint32_t)((it >> 1) & 1) ^ 1, 10);
+      load_tile(sQ + qb * kAttnTileBytes, base, qt * 128);
+      ptx::cp_async_mbar_arrive(&q_full[qb]);
       for (int j = 0; j < nqt; ++j, ++g) {
         const int st = (int)(g % NS);
         AVB_TRACE(0, g, 0);
@@ -605,7 +608,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       constexpr uint32_t idesc_l = ptx::make_idesc_bf16(128, 16, 0, 0);
       constexpr uint64_t kStageStep = (2 * kAttnTileBytes) >> 4;
       auto issue_S = [&](long long g, int it, int j) {
-        if (j == 0) { ptx::mbar_wait(q_full, (uint32_t)(it & 1), 20); }
+        if (j == 0) { ptx::mbar_wait(&q_full[it & 1], (uint32_t)((it >> 1) & 1), 20); }
         const int st = (int)(g % NS);
         ptx::mbar_wait(&kv_full[st], (uint32_t)((g / NS) & 1), 21);
         ptx::fence_proxy_async();  // cp.async (generic proxy) writes -> visible to the tensor core's async-proxy reads
@@ -613,11 +616,12 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
         const int kc = kcols(j);
         const uint32_t idesc = kc == 128 ? idesc_s : ptx::make_idesc_bf16(128, kc, 0, 0);
         const uint64_t dk = dK + (uint64_t)st * kStageStep;
+        const uint64_t dq = dQ + (uint64_t)((it & 1) * (kAttnTileBytes >> 4));
         if (ptx::elect_one()) {
-          ptx::umma_bf16(tmem_S, dQ, dk, idesc, 0);
-          ptx::umma_bf16(tmem_S, dQ + 2, dk + 2, idesc, 1);  // +32 bytes: second K=16 slice of the 64-byte rows
+          ptx::umma_bf16(tmem_S, dq, dk, idesc, 0);
+          ptx::umma_bf16(tmem_S, dq + 2, dk + 2, idesc, 1);  // +32 bytes: second K=16 slice of the 64-byte rows
           ptx::umma_commit(s_full);
-          if (j == nqt - 1) ptx::umma_commit(q_empty);  // last S of the item: Q may be overwritten once it completes
+          if (j == nqt - 1) ptx::umma_commit(&q_empty[it & 1]);  // last S of the item: this Q buffer may be overwritten
         }
         __syncwarp();
       };
@@ -693,8 +697,9 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
         AVB_TRACE(2, g, 1);
         ptx::tc_fence_after();
         const int nv = T - j * 128 - half * 64;  // valid key columns in this warp's half (may be <= 0)
+        // ---- pass 1: row maximum over this half (S is re-read in pass 2: TMEM reads are cheap, registers are not:
+        //      640 threads leave 96 per thread), then exchange with the partner warp
         const bool full_half = nv >= 64;
-        // ---- pass 1: row maximum over this half, then exchange with the partner warp
         float mx;
         if (full_half) {
           uint32_t sa[32], sb[32];
@@ -710,13 +715,16 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
           mx = fmaxf(mx0, mx1);
         } else {
           mx = -INFINITY;
-#pragma unroll 1
-          for (int c = 0; c * 32 < nv; ++c) {
-            uint32_t sv[32];
-            ptx::tmem_ld32(tS + c * 32, sv);
-            ptx::tmem_wait_ld();
 #pragma unroll
-            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (c * 32 + e < nv) ? __uint_as_float(sv[e]) : -INFINITY);
+          for (int c = 0; c < 2; ++c) {
+            if (c * 32 < nv) {
+              uint32_t sv[32];
+              ptx::tmem_ld32(tS + c * 32, sv);
+              ptx::tmem_wait_ld();
+              const int rem = nv - c * 32;
+#pragma unroll
+              for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (e < rem) ? __uint_as_float(sv[e]) : -INFINITY);
+            }
           }
         }
         AVB_TRACE(2, g, 2);
@@ -768,30 +776,32 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
             }
           } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) pk[e] = 0u;  // keys beyond the sequence end get probability 0
-            for (int c = 0; c < 2; ++c) {
-              if (c * 32 >= nv) break;
-              uint32_t sv[32];
-              ptx::tmem_ld32(tS + c * 32, sv);
-              ptx::tmem_wait_ld();
-              const int rem = nv - c * 32;
+            for (int c = 0; c < 2; ++c) {  // static indices only: pk[] must stay in registers
+              if (c * 32 < nv) {
+                uint32_t sv[32];
+                ptx::tmem_ld32(tS + c * 32, sv);
+                ptx::tmem_wait_ld();
+                const int rem = nv - c * 32;  // keys beyond the sequence end get probability 0
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const float p0 = (2 * e < rem) ? fast_exp2(__uint_as_float(sv[2 * e]) - m) : 0.f;
-                const float p1 = (2 * e + 1 < rem) ? fast_exp2(__uint_as_float(sv[2 * e + 1]) - m) : 0.f;
-                if (c == 0) pk[e] = ptx::pack_bf16(p0, p1); else pk[16 + e] = ptx::pack_bf16(p0, p1);
+                for (int e = 0; e < 16; ++e) {
+                  const float p0 = (2 * e < rem) ? fast_exp2(__uint_as_float(sv[2 * e]) - m) : 0.f;
+                  const float p1 = (2 * e + 1 < rem) ? fast_exp2(__uint_as_float(sv[2 * e + 1]) - m) : 0.f;
+                  pk[c * 16 + e] = ptx::pack_bf16(p0, p1);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pk[c * 16 + e] = 0u;
               }
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(s_free);
           }
+          AVB_TRACE(2, g, 7);
           ptx::tmem_st32(tP, pk);
           ptx::tmem_wait_st();
         }
-        AVB_TRACE(2, g, 5);
         ptx::tc_fence_before();
         ptx::mbar_arrive(p_full);
-        AVB_TRACE(2, g, 6);
       }
       // ---- epilogue: O / L -> bf16 -> out[token, h*32 ..]; each half writes 16 of the 32 channels of its rows
       ptx::mbar_wait(pv_done, (uint32_t)((g - 1) & 1), 33);

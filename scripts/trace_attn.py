@@ -22,7 +22,7 @@ lib.avb_debug_set_trace(None)
 t = trace.cpu().numpy().reshape(3, 512, 8)
 t0 = t[t > 0].min()
 names = {0: ["wait_kv_empty", "got", "issued"], 1: ["top", "s_free", "S_issued/wait_p", "p_full", "PV_issued"],
-         2: ["top", "s_full", "pass1", "xchg+vote", "pv_done", "pass2", "arrived"]}
+         2: ["top", "s_full", "pass1", "xchg+vote", "pv_done", "turn", "S_loaded", "exps_done"]}
 for role, rn in ((0, "producer"), (1, "mma"), (2, "softmax")):
     print(f"== {rn}: events {names[role]} (cycles since kernel start; deltas within a step)")
     for step in list(range(40, 56)):
