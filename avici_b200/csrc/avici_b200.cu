@@ -35,7 +35,7 @@ struct Block {
   // bf16 tensor-core copies: K-major [N,K], LayerNorm affine and softmax scale folded in
   const bf16 *wqkv_t, *wo_t, *w1_t, *w2_t;
   const float *bqkv_f, *b1_f;
-  CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2;
+  CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2, tm_w1c;  // tm_w1c: W1t in [128 x 64] boxes for the fused FFN kernel
 };
 
 }  // namespace
@@ -180,6 +180,22 @@ int launch_ln_gemm_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, con
   if (launches) ++*launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ln_gemm_tc launch: %s", cudaGetErrorString(e));
+  return AVB_OK;
+}
+
+int launch_ffn_tc(avb_handle h, float* z, const CUtensorMap& tm_w1c, const CUtensorMap& tm_w2, const float* b1,
+                  const float* b2, int M, int F, cudaStream_t st, int num_sms, long long* launches) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(avb::ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kFfnSmemBytes);
+    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(ffn_tc): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = std::min((M + 127) / 128, num_sms);
+  avb::ffn_tc_kernel<<<grid, avb::kFfnThreads, avb::kFfnSmemBytes, st>>>(z, tm_w1c, tm_w2, b1, b2, M, F);
+  if (launches) ++*launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ffn_tc launch: %s", cudaGetErrorString(e));
   return AVB_OK;
 }
 
@@ -503,7 +519,8 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
     if (c.compute_dtype == AVB_DTYPE_BF16) {
       B.wqkv_t = db + o.wqkv_t; B.wo_t = db + o.wo_t; B.w1_t = db + o.w1_t; B.w2_t = db + o.w2_t;
       bool ok = make_tmap_2d(&B.tm_wqkv, B.wqkv_t, 3 * HD, k, 256) && make_tmap_2d(&B.tm_wo, B.wo_t, k, HD, 128) &&
-                make_tmap_2d(&B.tm_w1, B.w1_t, F, k, 256) && make_tmap_2d(&B.tm_w2, B.w2_t, k, F, 128);
+                make_tmap_2d(&B.tm_w1, B.w1_t, F, k, 256) && make_tmap_2d(&B.tm_w2, B.w2_t, k, F, 128) &&
+                make_tmap_2d(&B.tm_w1c, B.w1_t, F, k, 128);
       if (!ok) return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for block %d weights", i);
     }
   }
@@ -578,10 +595,9 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
 
   if (c.compute_dtype == AVB_DTYPE_BF16) {
     bf16* qkv = reinterpret_cast<bf16*>(w8 + L.big_off);
-    bf16* hid = qkv;  // aliased: qkv is dead once attention has run
     bf16* attn = reinterpret_cast<bf16*>(w8 + L.attn_off);
-    CUtensorMap tm_attn, tm_h;
-    if (!make_tmap_2d(&tm_attn, attn, ntok, HD, 128) || !make_tmap_2d(&tm_h, hid, ntok, F, 128))
+    CUtensorMap tm_attn;
+    if (!make_tmap_2d(&tm_attn, attn, ntok, HD, 128))
       return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for activations");
     int rc;
     // attention half: LN -> QKV -> attention -> out-proj + residual
@@ -592,10 +608,8 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
     { ProfScope ps(h, AVB_PROF_OUT, st);
       if ((rc = launch_gemm_tc<128, 2>(h, tm_attn, W.tm_wo, W.bo, z, k, M, k, HD, st, h->num_sms, &h->launches))) return rc; }
     // FFN half: LN -> Linear + ReLU -> Linear + residual
-    { ProfScope ps(h, AVB_PROF_FFN1, st);
-      if ((rc = launch_ln_gemm_tc<1>(h, z, W.tm_w1, W.b1_f, hid, F, M, F, st, h->num_sms, &h->launches))) return rc; }
-    { ProfScope ps(h, AVB_PROF_FFN2, st);
-      if ((rc = launch_gemm_tc<128, 2>(h, tm_h, W.tm_w2, W.b2, z, k, M, k, F, st, h->num_sms, &h->launches))) return rc; }
+    { ProfScope ps(h, AVB_PROF_FFN1, st);  // whole FFN sub-layer in one kernel (LN, up-projection, ReLU, down-projection, residual)
+      if ((rc = launch_ffn_tc(h, z, W.tm_w1c, W.tm_w2, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches))) return rc; }
   } else {
     float* qkv = reinterpret_cast<float*>(w8 + L.big_off);
     float* hid = qkv;
@@ -804,6 +818,18 @@ int avb_test_ln_gemm_bf16(const float* z, const void* wt, const float* bias, voi
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return relu ? launch_ln_gemm_tc<1>(nullptr, z, tb, bias, out, N, M, N, st, sms, nullptr)
               : launch_ln_gemm_tc<0>(nullptr, z, tb, bias, out, N, M, N, st, sms, nullptr);
+}
+
+int avb_test_ffn_bf16(float* z, const void* w1t, const void* w2t, const float* b1, const float* b2, int32_t M, int32_t F,
+                      void* stream) {
+  if (!z || !w1t || !w2t || !b1 || !b2 || M < 1 || F % 128) return fail(nullptr, AVB_ERR_INVALID, "avb_test_ffn_bf16: bad shape");
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device");
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CUtensorMap t1, t2;
+  if (!make_tmap_2d(&t1, w1t, F, 128, 128) || !make_tmap_2d(&t2, w2t, 128, F, 128))
+    return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return launch_ffn_tc(nullptr, z, t1, t2, b1, b2, M, F, reinterpret_cast<cudaStream_t>(stream), sms, nullptr);
 }
 
 int avb_debug_set_trace(void* trace_dev) {

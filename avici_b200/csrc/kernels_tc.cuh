@@ -421,6 +421,265 @@ ln_gemm_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorM
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused FFN sub-layer, in place on the fp32 residual stream (model.py:67-75):
+//     z += relu( LN(z) @ W1' + b1' ) @ W2 + b2          (LayerNorm affine folded into W1' / b1')
+//   Neither the LayerNorm output nor the 512-wide hidden activation ever touch HBM: per 128-token tile the
+//   hidden layer is produced in four 128-unit chunks,
+//     G1_c : D1[128x128 fp32, TMEM] = xhat[smem, bf16] . W1c^T[smem]            (8 MMAs 128x128x16)
+//     E1_c : D1 -> +b1, ReLU -> bf16 pairs -> H[TMEM]                            (8 epilogue warps)
+//     G2_c : D2[128x128 fp32, TMEM] += H[TMEM, A operand] . W2c[smem]            (8 MMAs, A from TMEM)
+//   and after the fourth chunk  E2 : z += D2 + b2.  D1 and H are double-buffered so the tensor core runs
+//   G1_{c+1} while the epilogue warps turn D1_c into H_c.  TMEM: 2x128 (D1) + 2x64 (H) + 128 (D2) = 512 columns.
+//   Weights stream from L2 through a 2-stage TMA ring (64 KB per chunk: W1c and W2c).
+//   warps 0-3: LN producers   warp 4: weight TMA   warp 5: MMA issuer   warp 6: TMEM alloc   warps 8-15: epilogues
+// ------------------------------------------------------------------------------------------
+constexpr int kFfnThreads = 512;
+constexpr int kFfnWBytes = 128 * 128 * 2;  // 32 KB: one [128 x 128] bf16 weight chunk = two 128B-swizzled K blocks
+constexpr int kFfnSmemBytes = 2 * kLnGemmABytes + 2 * 2 * kFfnWBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kFfnThreads, 1)
+ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
+              const float* __restrict__ b1, const float* __restrict__ b2, int M, int F) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                        // [2][32K] xhat
+  uint8_t* sW = sA + 2 * kLnGemmABytes;      // [2 stages][W1c 32K | W2c 32K]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 4 * kFfnWBytes);
+  uint64_t* a_full = bars;          // [2] 128 LN threads
+  uint64_t* a_empty = bars + 2;     // [2]
+  uint64_t* w1_full = bars + 4;     // [2]
+  uint64_t* w1_empty = bars + 6;    // [2]
+  uint64_t* w2_full = bars + 8;     // [2]
+  uint64_t* w2_empty = bars + 10;   // [2]
+  uint64_t* d1_full = bars + 12;    // [2]
+  uint64_t* d1_empty = bars + 14;   // [2] 256 epilogue threads
+  uint64_t* h_full = bars + 16;     // [2] 256 epilogue threads
+  uint64_t* h_empty = bars + 18;    // [2]
+  uint64_t* d2_full = bars + 20;    // [1]
+  uint64_t* d2_empty = bars + 21;   // [1] 256 epilogue threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int num_m = (M + 127) / 128, num_c = F / 128;
+
+  if (warp == 4 && lane == 0) { ptx::prefetch_tmap(&tm_w1); ptx::prefetch_tmap(&tm_w2); }
+  if (warp == 5 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&a_full[i], 128); ptx::mbar_init(&a_empty[i], 1);
+      ptx::mbar_init(&w1_full[i], 1); ptx::mbar_init(&w1_empty[i], 1);
+      ptx::mbar_init(&w2_full[i], 1); ptx::mbar_init(&w2_empty[i], 1);
+      ptx::mbar_init(&d1_full[i], 1); ptx::mbar_init(&d1_empty[i], 256);
+      ptx::mbar_init(&h_full[i], 256); ptx::mbar_init(&h_empty[i], 1);
+    }
+    ptx::mbar_init(d2_full, 1); ptx::mbar_init(d2_empty, 256);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 6) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_D1 = tmem_base;        // 2 x 128
+  const uint32_t tmem_H = tmem_base + 256;   // 2 x 64
+  const uint32_t tmem_D2 = tmem_base + 384;  // 128
+
+  if (warp < 4) {
+    // ===================== LN producers (same as ln_gemm_tc_kernel)
+    const uint32_t lane_col = (uint32_t)((lane >> 4) * (128 * 128));
+    const int chunk = (lane & 15) >> 1;
+    const uint32_t half8 = (uint32_t)((lane & 1) * 8);
+    int it = 0;
+    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
+      const int buf = it & 1;
+      ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 50);
+      const uint32_t abase = ptx::smem_u32(sA + buf * kLnGemmABytes) + lane_col + half8;
+      const float4* zrow = reinterpret_cast<const float4*>(z) + lane;
+      const int row_base = mt * 128 + warp * 32;
+      float4 cur[8], nxt[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        cur[u] = row_base + u < M ? __ldcg(zrow + (size_t)(row_base + u) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        if (r0 + 8 < 32) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int row = row_base + r0 + 8 + u;
+            nxt[u] = row < M ? __ldcg(zrow + (size_t)row * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 v = cur[u];
+          const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / 128.0f);
+          const float4 c = make_float4(v.x - mean, v.y - mean, v.z - mean, v.w - mean);
+          const float var = warp_sum(c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w) * (1.0f / 128.0f);
+          const float rs = rsqrtf(var + kLnEps);
+          const int r = warp * 32 + r0 + u;
+          const uint32_t addr = abase + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ptx::pack_bf16(c.x * rs, c.y * rs)),
+                       "r"(ptx::pack_bf16(c.z * rs, c.w * rs))
+                       : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+      }
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&a_full[buf]);
+    }
+  } else if (warp == 4) {
+    // ===================== weight TMA producer: per chunk W1c = W1t[128c.., 0..127], W2c = W2t[0..127, 128c..]
+    int g = 0;
+    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
+      for (int c = 0; c < num_c; ++c, ++g) {
+        const int st = g & 1;
+        const uint32_t ph = (uint32_t)((g >> 1) & 1) ^ 1;
+        uint8_t* w1 = sW + st * 2 * kFfnWBytes;
+        uint8_t* w2 = w1 + kFfnWBytes;
+        ptx::mbar_wait(&w1_empty[st], ph, 51);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&w1_full[st], kFfnWBytes);
+          ptx::tma_load_2d(w1, &tm_w1, &w1_full[st], 0, c * 128);
+          ptx::tma_load_2d(w1 + 128 * 128, &tm_w1, &w1_full[st], 64, c * 128);
+        }
+        __syncwarp();
+        ptx::mbar_wait(&w2_empty[st], ph, 52);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&w2_full[st], kFfnWBytes);
+          ptx::tma_load_2d(w2, &tm_w2, &w2_full[st], c * 128, 0);
+          ptx::tma_load_2d(w2 + 128 * 128, &tm_w2, &w2_full[st], c * 128 + 64, 0);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer: G1(g+1) is issued before G2(g) so the tensor core overlaps the E1 epilogue
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 128, 0, 0);
+    const uint64_t dA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024, ptx::kSwz128);
+    const uint64_t dW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024, ptx::kSwz128);
+    const int my_tiles = blockIdx.x < num_m ? (num_m - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total = my_tiles * num_c;
+    auto issue_G1 = [&](int g) {
+      const int tile_it = g / num_c, c = g % num_c, buf = tile_it & 1, st = g & 1, as1 = g & 1;
+      if (c == 0) ptx::mbar_wait(&a_full[buf], (uint32_t)((tile_it >> 1) & 1), 53);
+      ptx::mbar_wait(&w1_full[st], (uint32_t)((g >> 1) & 1), 54);
+      ptx::mbar_wait(&d1_empty[as1], (uint32_t)((g >> 1) & 1) ^ 1, 55);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint64_t da = dA0 + (uint64_t)(buf * (kLnGemmABytes >> 4));
+        const uint64_t dw = dW0 + (uint64_t)(st * ((2 * kFfnWBytes) >> 4));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // K block (kk >> 2) is 16 KB further, 32 bytes per K=16 slice inside it
+          const uint64_t off = (uint64_t)((kk >> 2) * ((128 * 128) >> 4) + (kk & 3) * 2);
+          ptx::umma_bf16(tmem_D1 + as1 * 128, da + off, dw + off, idesc, kk != 0);
+        }
+        ptx::umma_commit(&w1_empty[st]);
+        ptx::umma_commit(&d1_full[as1]);
+        if (c == num_c - 1) ptx::umma_commit(&a_empty[buf]);
+      }
+      __syncwarp();
+    };
+    if (total > 0) issue_G1(0);
+    for (int g = 0; g < total; ++g) {
+      if (g + 1 < total) issue_G1(g + 1);
+      const int tile_it = g / num_c, c = g % num_c, st = g & 1, hs = g & 1;
+      ptx::mbar_wait(&w2_full[st], (uint32_t)((g >> 1) & 1), 56);
+      ptx::mbar_wait(&h_full[hs], (uint32_t)((g >> 1) & 1), 57);
+      if (c == 0 && tile_it > 0) ptx::mbar_wait(d2_empty, (uint32_t)((tile_it - 1) & 1), 58);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint64_t dw = dW0 + (uint64_t)(st * ((2 * kFfnWBytes) >> 4) + (kFfnWBytes >> 4));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t off = (uint64_t)((kk >> 2) * ((128 * 128) >> 4) + (kk & 3) * 2);
+          ptx::umma_bf16_ts(tmem_D2, tmem_H + hs * 64 + kk * 8, dw + off, idesc, (c | kk) != 0);
+        }
+        ptx::umma_commit(&w2_empty[st]);
+        ptx::umma_commit(&h_empty[hs]);
+        if (c == num_c - 1) ptx::umma_commit(d2_full);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue warps: (TMEM lane quarter q) x (64-column half)
+    const int q = warp & 3, half = (warp - 8) >> 2;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    int g = 0, tile_it = 0;
+    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++tile_it) {
+      for (int c = 0; c < num_c; ++c, ++g) {
+        // ---- E1: D1 -> +b1 -> ReLU -> bf16 pairs -> H
+        const int as1 = g & 1, hs = g & 1;
+        const float* bp = b1 + c * 128 + half * 64;
+        float4 bb[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bp) + e);
+        ptx::mbar_wait(&d1_full[as1], (uint32_t)((g >> 1) & 1), 59);
+        ptx::tc_fence_after();
+        uint32_t pk[32];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_D1 + as1 * 128 + half * 64 + cc * 32 + lane_off, v);
+          ptx::tmem_wait_ld();
+          if (cc == 1) {  // D1 fully read by this thread
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&d1_empty[as1]);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 b4 = bb[cc * 8 + e];
+            const float f0 = fmaxf(__uint_as_float(v[e * 4 + 0]) + b4.x, 0.f), f1 = fmaxf(__uint_as_float(v[e * 4 + 1]) + b4.y, 0.f);
+            const float f2 = fmaxf(__uint_as_float(v[e * 4 + 2]) + b4.z, 0.f), f3 = fmaxf(__uint_as_float(v[e * 4 + 3]) + b4.w, 0.f);
+            pk[cc * 16 + e * 2 + 0] = ptx::pack_bf16(f0, f1);
+            pk[cc * 16 + e * 2 + 1] = ptx::pack_bf16(f2, f3);
+          }
+        }
+        ptx::mbar_wait(&h_empty[hs], (uint32_t)((g >> 1) & 1) ^ 1, 60);  // G2 of two chunks ago has consumed H[hs]
+        ptx::tc_fence_after();
+        ptx::tmem_st32(tmem_H + hs * 64 + half * 32 + lane_off, pk);
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&h_full[hs]);
+      }
+      // ---- E2: z += D2 + b2 (row per thread, 64 columns per warp half)
+      ptx::mbar_wait(d2_full, (uint32_t)(tile_it & 1), 61);
+      ptx::tc_fence_after();
+      const int row = mt * 128 + q * 32 + lane;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_D2 + half * 64 + cc * 32 + lane_off, v);
+        ptx::tmem_wait_ld();
+        if (cc == 1) {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(d2_empty);
+        }
+        if (row < M) {
+          float* zp = z + (size_t)row * 128 + half * 64 + cc * 32;
+          const float* b2p = b2 + half * 64 + cc * 32;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float4 o = __ldcg(reinterpret_cast<const float4*>(zp) + e);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2p) + e);
+            o.x += __uint_as_float(v[e * 4 + 0]) + b4.x;
+            o.y += __uint_as_float(v[e * 4 + 1]) + b4.y;
+            o.z += __uint_as_float(v[e * 4 + 2]) + b4.z;
+            o.w += __uint_as_float(v[e * 4 + 3]) + b4.w;
+            reinterpret_cast<float4*>(zp)[e] = o;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 6) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------
 // Flash-style axial attention on tensor cores.  head dim 32, 128-query x 128-key tiles.
 //   qkv viewed through ONE 4-D tensor map {3*H*32, d, n, B}; a work item (s, h, qt) loads its
 //   [128 x 32] Q tile and streams [128 x 32] K / V tiles with a box of {32,128,1,1} (attend over d)

@@ -159,6 +159,9 @@ int avb_test_gemm_bf16(const void* a_bf16_dev, const void* wt_bf16_dev, const fl
 /* out[M,N] bf16 = act(LayerNorm(z[M,128], no affine) @ Wt[N,128]^T + bias), N % 256 == 0, act = ReLU if relu. */
 int avb_test_ln_gemm_bf16(const float* z_dev, const void* wt_bf16_dev, const float* bias_dev, void* out_bf16_dev,
                           int32_t M, int32_t N, int32_t relu, void* stream);
+/* z[M,128] fp32 += relu(LayerNorm(z, no affine) @ W1t[F,128]^T + b1) @ W2t[128,F]^T + b2, in place (F % 128 == 0). */
+int avb_test_ffn_bf16(float* z_dev, const void* w1t_bf16_dev, const void* w2t_bf16_dev, const float* b1_dev,
+                      const float* b2_dev, int32_t M, int32_t F, void* stream);
 /* Axial attention on packed qkv[B,n,d,3*H*32] bf16 (q pre-scaled by log2e/sqrt(32)):
  * out[B,n,d,H*32] bf16. */
 int avb_test_attention_bf16(const void* qkv_bf16_dev, void* out_bf16_dev, int32_t B, int32_t n,

@@ -92,6 +92,27 @@ def test_ln_gemm_tc_against_torch(built_lib, M, N, relu):
     assert err <= 2 ** -7 * max(ref.abs().max().item(), 1.0), f"ln_gemm_tc err {err}"
 
 
+@pytest.mark.parametrize("M", [128, 1000, 333, 70001])
+def test_ffn_tc_against_torch(built_lib, M):
+    F = 512
+    g = torch.Generator(device="cuda").manual_seed(M)
+    z = torch.randn(M, 128, device="cuda", generator=g) * 2 + torch.randn(M, 1, device="cuda", generator=g)
+    w1t = (torch.randn(F, 128, device="cuda", generator=g) / 128 ** 0.5).to(torch.bfloat16)
+    w2t = (torch.randn(128, F, device="cuda", generator=g) / F ** 0.5).to(torch.bfloat16)
+    b1 = torch.randn(F, device="cuda", generator=g) * 0.5
+    b2 = torch.randn(128, device="cuda", generator=g) * 0.5
+    xhat = torch.nn.functional.layer_norm(z, (128,), eps=1e-5).to(torch.bfloat16).float()
+    hid = (xhat @ w1t.float().T + b1).relu().to(torch.bfloat16).float()
+    ref = z + hid @ w2t.float().T + b2
+    out = z.clone()
+    rc = built_lib.avb_test_ffn_bf16(out.data_ptr(), w1t.data_ptr(), w2t.data_ptr(), b1.data_ptr(), b2.data_ptr(), M, F,
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(built_lib, None, rc)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-2, f"ffn_tc err {err}"  # an xhat that rounds differently by one bf16 ulp moves a hidden unit by ~1e-2
+
+
 def attention_reference(qkv, B, n, d, H, axis):
     """fp32 softmax attention over axis `axis` of qkv[B,n,d,3*H*32]; q is pre-scaled by log2e/sqrt(32)."""
     x = qkv.float().reshape(B, n, d, 3, H, 32)
