@@ -36,6 +36,57 @@ __global__ void ln_bf16_kernel(const float* __restrict__ z, size_t ntok, __nv_bf
   }
 }
 
+// Debug timeline: when set (avb_debug_set_trace), block 0 records clock64() stamps of the first steps of each
+// role of stream 0 into trace[role * 4096 + step * 8 + event].
+__device__ long long* g_attn_trace = nullptr;
+#define AVB_TRACE(role, step, ev)                                                      \
+  do {                                                                                 \
+    if (trace && (step) < 500) trace[(role) * 4096 + (step) * 8 + (ev)] = clock64();  \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// Residual update of a [32 rows x 32 cols] fp32 block held row-per-thread in registers (the tcgen05.ld layout):
+//     zblk[r][c] += acc[r][c] + bias[c]
+// A row-per-thread global access touches 32 different 128-byte lines per warp instruction and is bound by L1
+// wavefronts (measured: ~11k cycles per 128x128 tile).  The block is therefore transposed through a 4 KB
+// XOR-swizzled smem stage owned by the warp, after which every warp instruction covers 4 rows x 128 contiguous bytes.
+//   stage: smem address of this warp's 4 KB stage; zblk: &z[row0][col0]; ldz: row pitch in floats;
+//   rows_valid: number of rows of the block that exist (<= 32)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void residual_add_block_32x32(const uint32_t (&acc)[32], const float* __restrict__ bias,
+                                                         uint32_t stage, float* zblk, int ldz, int rows_valid, int lane) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {  // thread = row `lane`: 16-byte chunk c goes to slot c ^ (lane & 7)
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + c);
+    uint4 pk;
+    pk.x = __float_as_uint(__uint_as_float(acc[c * 4 + 0]) + b4.x);
+    pk.y = __float_as_uint(__uint_as_float(acc[c * 4 + 1]) + b4.y);
+    pk.z = __float_as_uint(__uint_as_float(acc[c * 4 + 2]) + b4.z);
+    pk.w = __float_as_uint(__uint_as_float(acc[c * 4 + 3]) + b4.w);
+    ptx::st_shared_v4(stage + (uint32_t)(lane * 128 + ((c ^ (lane & 7)) << 4)), pk);
+  }
+  __syncwarp();
+  const int sub = lane >> 3, l8 = lane & 7;
+  float4 zr[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + sub;
+    zr[i] = row < rows_valid ? __ldcg(reinterpret_cast<const float4*>(zblk + (size_t)row * ldz) + l8) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + sub;
+    uint4 a;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+                 : "r"(stage + (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4))));
+    float4 o = zr[i];
+    o.x += __uint_as_float(a.x); o.y += __uint_as_float(a.y); o.z += __uint_as_float(a.z); o.w += __uint_as_float(a.w);
+    if (row < rows_valid) reinterpret_cast<float4*>(zblk + (size_t)row * ldz)[l8] = o;
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------
 // Persistent warp-specialised GEMM:  C[M,N] = A[M,K] @ Wt[N,K]^T + bias[N]
 //   A, Wt: bf16, K-major, fetched by TMA in 128B-swizzled [rows x 64] boxes.
@@ -49,7 +100,8 @@ template <int BN> struct GemmCfg {
   static constexpr int kABytes = 128 * 64 * 2;
   static constexpr int kBBytes = BN * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiStageBytes = 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN, int EPI>
@@ -60,7 +112,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   constexpr int ST = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST * Cfg::kStageBytes);
+  uint8_t* sEpi = smem + ST * Cfg::kStageBytes;  // [4][4 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + Cfg::kEpiStageBytes);
   uint64_t* full = bars;            // [ST]
   uint64_t* empty = bars + ST;      // [ST]
   uint64_t* tfull = bars + 2 * ST;  // [2]
@@ -149,8 +202,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         ptx::tmem_ld32(taddr + c * 32, r);
         ptx::tmem_wait_ld();
         const int col0 = n_blk * BN + c * 32;
-        if (row < M) {
-          if (EPI == 2) {
+        if (EPI == 2) {
+          // row-per-thread read-modify-write (measured faster here than the smem-transposed variant: with only four
+          // epilogue warps and K >= 256 this kernel is bound by its TMA stream, not by L1 wavefronts)
+          if (row < M) {
             float* op = reinterpret_cast<float*>(out) + (size_t)row * ldo + col0;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -162,7 +217,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               o.w += __uint_as_float(r[e * 4 + 3]) + bb.w;
               *reinterpret_cast<float4*>(op + e * 4) = o;
             }
-          } else {
+          }
+        } else if (row < M) {
+          {
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)row * ldo + col0;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -194,6 +251,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (no affine) of 32 consecutive 128-channel fp32 rows by one warp, written as bf16 into a
+// 128B-swizzled K-major UMMA A tile ([128 rows x 128 ch] = two K blocks of [128 x 64], 16 KB apart).
+// Eight lanes share a row (16 channels each, 3 shuffle steps per statistic) and a warp instruction covers
+// four rows, so the global loads are 128-byte segments and the reductions cost 6 shuffles per 4 rows.
+//   a_tile: smem address of the A tile; row0: first row of this warp inside the tile (multiple of 32)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ln_warp_rows_to_umma_tile(const float* __restrict__ z, int M, int grow0, uint32_t a_tile,
+                                                          int row0, int lane) {
+  const int rs = lane >> 3, j = lane & 7;
+  const float4* zp = reinterpret_cast<const float4*>(z) + j;
+  float4 cur[2][4], nxt[2][4];
+  auto load = [&](float4 (&dst)[2][4], int r0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int grow = grow0 + r0 + u * 4 + rs;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        dst[u][k] = grow < M ? __ldcg(zp + (size_t)grow * 32 + k * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  load(cur, 0);
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 8) {
+    if (r0 + 8 < 32) load(nxt, r0 + 8);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sum += (cur[u][k].x + cur[u][k].y) + (cur[u][k].z + cur[u][k].w);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      const float mean = sum * (1.0f / 128.0f);
+      float sq = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        cur[u][k].x -= mean; cur[u][k].y -= mean; cur[u][k].z -= mean; cur[u][k].w -= mean;
+        sq += (cur[u][k].x * cur[u][k].x + cur[u][k].y * cur[u][k].y) + (cur[u][k].z * cur[u][k].z + cur[u][k].w * cur[u][k].w);
+      }
+      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+      const float rstd = rsqrtf(sq * (1.0f / 128.0f) + kLnEps);
+      const int r = row0 + r0 + u * 4 + rs;
+      const uint32_t rbase = a_tile + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (j & 1) * 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // channels 4(j+8k)..+3: K block (k >> 1), 16-byte chunk (j + 8(k & 1)) >> 1 inside its 128-byte row
+        const int chunk = (j + 8 * (k & 1)) >> 1;
+        const uint32_t addr = rbase + (uint32_t)((k >> 1) * (128 * 128) + ((chunk ^ (r & 7)) << 4));
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ptx::pack_bf16(cur[u][k].x * rstd, cur[u][k].y * rstd)),
+                     "r"(ptx::pack_bf16(cur[u][k].z * rstd, cur[u][k].w * rstd))
+                     : "memory");
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cur[u][k] = nxt[u][k];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -259,47 +379,11 @@ ln_gemm_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorM
 
   if (warp < 4) {
     // ===================== LN producers: warp w normalises rows 32w .. 32w+31 of each tile
-    // lane l owns channels 4l..4l+3: K block (l >> 4), 16-byte chunk ((l & 15) >> 1), 8-byte half (l & 1)
-    const uint32_t lane_col = (uint32_t)((lane >> 4) * (128 * 128));
-    const int chunk = (lane & 15) >> 1;
-    const uint32_t half8 = (uint32_t)((lane & 1) * 8);
     int it = 0;
     for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
       const int buf = it & 1;
       ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 40);
-      const uint32_t abase = ptx::smem_u32(sA + buf * kLnGemmABytes) + lane_col + half8;
-      // software pipeline: the loads of the next 8 rows are in flight while 8 rows are normalised
-      const float4* zrow = reinterpret_cast<const float4*>(z) + lane;
-      const int row_base = mt * 128 + warp * 32;
-      float4 cur[8], nxt[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        cur[u] = row_base + u < M ? __ldg(zrow + (size_t)(row_base + u) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int r0 = 0; r0 < 32; r0 += 8) {
-        if (r0 + 8 < 32) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int row = row_base + r0 + 8 + u;
-            nxt[u] = row < M ? __ldg(zrow + (size_t)row * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float4 v = cur[u];
-          const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / 128.0f);
-          const float4 c = make_float4(v.x - mean, v.y - mean, v.z - mean, v.w - mean);
-          const float var = warp_sum(c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w) * (1.0f / 128.0f);
-          const float rs = rsqrtf(var + kLnEps);
-          const int r = warp * 32 + r0 + u;
-          const uint32_t addr = abase + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ptx::pack_bf16(c.x * rs, c.y * rs)),
-                       "r"(ptx::pack_bf16(c.z * rs, c.w * rs))
-                       : "memory");
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
-      }
+      ln_warp_rows_to_umma_tile(z, M, mt * 128 + warp * 32, ptx::smem_u32(sA + buf * kLnGemmABytes), warp * 32, lane);
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&a_full[buf]);
     }
@@ -435,7 +519,7 @@ ln_gemm_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorM
 // ------------------------------------------------------------------------------------------
 constexpr int kFfnThreads = 512;
 constexpr int kFfnWBytes = 128 * 128 * 2;  // 32 KB: one [128 x 128] bf16 weight chunk = two 128B-swizzled K blocks
-constexpr int kFfnSmemBytes = 2 * kLnGemmABytes + 2 * 2 * kFfnWBytes + 1024 + 256;
+constexpr int kFfnSmemBytes = 2 * kLnGemmABytes + 2 * 2 * kFfnWBytes + 8 * 4096 + 1024 + 256;  // + 8 x 4 KB epilogue stages
 
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
@@ -444,7 +528,8 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                        // [2][32K] xhat
   uint8_t* sW = sA + 2 * kLnGemmABytes;      // [2 stages][W1c 32K | W2c 32K]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 4 * kFfnWBytes);
+  uint8_t* sStage = sW + 4 * kFfnWBytes;     // [8 epilogue warps][4 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 8 * 4096);
   uint64_t* a_full = bars;          // [2] 128 LN threads
   uint64_t* a_empty = bars + 2;     // [2]
   uint64_t* w1_full = bars + 4;     // [2]
@@ -461,6 +546,7 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int num_m = (M + 127) / 128, num_c = F / 128;
+  long long* trace = (blockIdx.x == 0 && (warp == 5 || warp == 8 || warp == 0) && lane == 0) ? g_attn_trace : nullptr;
 
   if (warp == 4 && lane == 0) { ptx::prefetch_tmap(&tm_w1); ptx::prefetch_tmap(&tm_w2); }
   if (warp == 5 && lane == 0) {
@@ -488,47 +574,16 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
 
   if (warp < 4) {
     // ===================== LN producers (same as ln_gemm_tc_kernel)
-    const uint32_t lane_col = (uint32_t)((lane >> 4) * (128 * 128));
-    const int chunk = (lane & 15) >> 1;
-    const uint32_t half8 = (uint32_t)((lane & 1) * 8);
     int it = 0;
     for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
       const int buf = it & 1;
+      AVB_TRACE(0, it, 0);
       ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 50);
-      const uint32_t abase = ptx::smem_u32(sA + buf * kLnGemmABytes) + lane_col + half8;
-      const float4* zrow = reinterpret_cast<const float4*>(z) + lane;
-      const int row_base = mt * 128 + warp * 32;
-      float4 cur[8], nxt[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        cur[u] = row_base + u < M ? __ldcg(zrow + (size_t)(row_base + u) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int r0 = 0; r0 < 32; r0 += 8) {
-        if (r0 + 8 < 32) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int row = row_base + r0 + 8 + u;
-            nxt[u] = row < M ? __ldcg(zrow + (size_t)row * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float4 v = cur[u];
-          const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / 128.0f);
-          const float4 c = make_float4(v.x - mean, v.y - mean, v.z - mean, v.w - mean);
-          const float var = warp_sum(c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w) * (1.0f / 128.0f);
-          const float rs = rsqrtf(var + kLnEps);
-          const int r = warp * 32 + r0 + u;
-          const uint32_t addr = abase + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ptx::pack_bf16(c.x * rs, c.y * rs)),
-                       "r"(ptx::pack_bf16(c.z * rs, c.w * rs))
-                       : "memory");
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
-      }
+      AVB_TRACE(0, it, 1);
+      ln_warp_rows_to_umma_tile(z, M, mt * 128 + warp * 32, ptx::smem_u32(sA + buf * kLnGemmABytes), warp * 32, lane);
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&a_full[buf]);
+      AVB_TRACE(0, it, 2);
     }
   } else if (warp == 4) {
     // ===================== weight TMA producer: per chunk W1c = W1t[128c.., 0..127], W2c = W2t[0..127, 128c..]
@@ -584,10 +639,14 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
     };
     if (total > 0) issue_G1(0);
     for (int g = 0; g < total; ++g) {
+      AVB_TRACE(1, g, 0);
       if (g + 1 < total) issue_G1(g + 1);
+      AVB_TRACE(1, g, 1);
       const int tile_it = g / num_c, c = g % num_c, st = g & 1, hs = g & 1;
       ptx::mbar_wait(&w2_full[st], (uint32_t)((g >> 1) & 1), 56);
+      AVB_TRACE(1, g, 2);
       ptx::mbar_wait(&h_full[hs], (uint32_t)((g >> 1) & 1), 57);
+      AVB_TRACE(1, g, 3);
       if (c == 0 && tile_it > 0) ptx::mbar_wait(d2_empty, (uint32_t)((tile_it - 1) & 1), 58);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
@@ -602,6 +661,7 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
         if (c == num_c - 1) ptx::umma_commit(d2_full);
       }
       __syncwarp();
+      AVB_TRACE(1, g, 4);
     }
   } else if (warp >= 8) {
     // ===================== epilogue warps: (TMEM lane quarter q) x (64-column half)
@@ -616,7 +676,9 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
         float4 bb[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bp) + e);
+        AVB_TRACE(2, g, 0);
         ptx::mbar_wait(&d1_full[as1], (uint32_t)((g >> 1) & 1), 59);
+        AVB_TRACE(2, g, 1);
         ptx::tc_fence_after();
         uint32_t pk[32];
 #pragma unroll
@@ -637,17 +699,23 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
             pk[cc * 16 + e * 2 + 1] = ptx::pack_bf16(f2, f3);
           }
         }
+        AVB_TRACE(2, g, 2);
         ptx::mbar_wait(&h_empty[hs], (uint32_t)((g >> 1) & 1) ^ 1, 60);  // G2 of two chunks ago has consumed H[hs]
+        AVB_TRACE(2, g, 3);
         ptx::tc_fence_after();
         ptx::tmem_st32(tmem_H + hs * 64 + half * 32 + lane_off, pk);
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&h_full[hs]);
+        AVB_TRACE(2, g, 4);
       }
       // ---- E2: z += D2 + b2 (row per thread, 64 columns per warp half)
       ptx::mbar_wait(d2_full, (uint32_t)(tile_it & 1), 61);
+      AVB_TRACE(2, g - 1, 5);
       ptx::tc_fence_after();
-      const int row = mt * 128 + q * 32 + lane;
+      const int row0 = mt * 128 + q * 32;
+      const int rows_valid = M - row0 < 32 ? M - row0 : 32;  // may be <= 0 on the last tile
+      const uint32_t stage = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 4096);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         uint32_t v[32];
@@ -657,21 +725,10 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
           ptx::tc_fence_before();
           ptx::mbar_arrive(d2_empty);
         }
-        if (row < M) {
-          float* zp = z + (size_t)row * 128 + half * 64 + cc * 32;
-          const float* b2p = b2 + half * 64 + cc * 32;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float4 o = __ldcg(reinterpret_cast<const float4*>(zp) + e);
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2p) + e);
-            o.x += __uint_as_float(v[e * 4 + 0]) + b4.x;
-            o.y += __uint_as_float(v[e * 4 + 1]) + b4.y;
-            o.z += __uint_as_float(v[e * 4 + 2]) + b4.z;
-            o.w += __uint_as_float(v[e * 4 + 3]) + b4.w;
-            reinterpret_cast<float4*>(zp)[e] = o;
-          }
-        }
+        residual_add_block_32x32(v, b2 + half * 64 + cc * 32, stage, z + (size_t)row0 * 128 + half * 64 + cc * 32, 128,
+                                 rows_valid, lane);
       }
+      AVB_TRACE(2, g - 1, 6);
     }
   }
   ptx::tc_fence_before();
@@ -714,14 +771,6 @@ constexpr int kAttnXchgBytes = 2 /*parity*/ * kAttnStreams * 2 /*halves*/ * 128 
 constexpr int kAttnSmemBytes = kAttnStreams * kAttnStreamBytes + 1024 + 512 + 512 + kAttnXchgBytes;  // + align slack, barriers, ones tile
 constexpr int kAttnTmemStreamCols = 256;  // S 128 (fp32) | P 64 (bf16 pairs) | O 32 | L 16 | spare
 constexpr float kAttnRescaleThreshold = 8.0f;  // log2 units
-
-// Debug timeline: when set (avb_debug_set_trace), block 0 records clock64() stamps of the first steps of each
-// role of stream 0 into trace[role * 4096 + step * 8 + event].
-__device__ long long* g_attn_trace = nullptr;
-#define AVB_TRACE(role, step, ev)                                                      \
-  do {                                                                                 \
-    if (trace && (step) < 500) trace[(role) * 4096 + (step) * 8 + (ev)] = clock64();  \
-  } while (0)
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
