@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 ( timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "exit=$?" >> gpurun_out/bench.err ); cat gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
 if [ "$1" == "ncu" ]; then
   timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
-  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s 351 -c 240 --csv --log-file gpurun_out/launches.csv \
+  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s 180 -c 170 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
   echo "ncu exit=$?"; tail -n 3 gpurun_out/ncu.log
 fi
