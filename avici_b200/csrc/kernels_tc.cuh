@@ -884,13 +884,13 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       const long long tok0 = axis == 0 ? s * d : (s / d) * (long long)n * d + (s % d);
       const __nv_bfloat16* base = qkv + tok0 * (3 * HD) + h * 32;
       const int qb = it & 1;
-      ptx::mbar_wait(&q_empty[qb], (uint32_t)((it >> 1) & 1) ^ 1, 10);
+      ptx::mbar_wait(&q_empty[qb], (uint32_t)((it >> 1) & 1) ^ 1, 10, 200u);
       load_tile(sQ + qb * kAttnTileBytes, base, qt * 128);
       ptx::cp_async_mbar_arrive(&q_full[qb]);
       for (int j = 0; j < nqt; ++j, ++g) {
         const int st = (int)(g % NS);
         AVB_TRACE(0, g, 0);
-        ptx::mbar_wait(&kv_empty[st], (uint32_t)((g / NS) & 1) ^ 1, 11);
+        ptx::mbar_wait(&kv_empty[st], (uint32_t)((g / NS) & 1) ^ 1, 11, 200u);
         AVB_TRACE(0, g, 1);
         uint8_t* sk = sKV + st * 2 * kAttnTileBytes;
         load_tile(sk, base + HD, j * 128);
@@ -916,9 +916,9 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       constexpr uint32_t idesc_l = ptx::make_idesc_bf16(128, 16, 0, 0);
       constexpr uint64_t kStageStep = (2 * kAttnTileBytes) >> 4;
       auto issue_S = [&](long long g, int it, int j) {
-        if (j == 0) { ptx::mbar_wait(&q_full[it & 1], (uint32_t)((it >> 1) & 1), 20); }
+        if (j == 0) { ptx::mbar_wait(&q_full[it & 1], (uint32_t)((it >> 1) & 1), 20, 40u); }
         const int st = (int)(g % NS);
-        ptx::mbar_wait(&kv_full[st], (uint32_t)((g / NS) & 1), 21);
+        ptx::mbar_wait(&kv_full[st], (uint32_t)((g / NS) & 1), 21, 40u);
         ptx::fence_proxy_async();  // cp.async (generic proxy) writes -> visible to the tensor core's async-proxy reads
         ptx::tc_fence_after();
         const int kc = kcols(j);
@@ -943,15 +943,15 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
           const bool more = (j + 1 < nqt) || (item + item_stride < num_items);
           AVB_TRACE(1, g, 0);
           if (more) {
-            ptx::mbar_wait(s_free, (uint32_t)(g & 1), 24);
+            ptx::mbar_wait(s_free, (uint32_t)(g & 1), 24, 40u);
             AVB_TRACE(1, g, 1);
             ptx::tc_fence_after();
             if (j + 1 < nqt) issue_S(g + 1, it, j + 1);
             else issue_S(g + 1, it + 1, 0);
           }
-          if (j == 0 && it >= 1) { ptx::mbar_wait(o_empty, (uint32_t)((it - 1) & 1), 22); }  // epilogue of the previous item has read O
+          if (j == 0 && it >= 1) { ptx::mbar_wait(o_empty, (uint32_t)((it - 1) & 1), 22, 40u); }  // epilogue of the previous item has read O
           AVB_TRACE(1, g, 2);
-          ptx::mbar_wait(p_full, (uint32_t)(g & 1), 23);
+          ptx::mbar_wait(p_full, (uint32_t)(g & 1), 23, 40u);
           AVB_TRACE(1, g, 3);
           ptx::tc_fence_after();
           const int st = (int)(g % NS);

@@ -44,18 +44,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (and reports) instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+// backoff_ns > 0: sleep between polls.  A polling warp competes for issue slots with the compute warps of its
+// SM sub-partition (measured: one spinning role warp per SMSP took ~1/3 of all issued instructions), so the
+// single-lane role warps (TMA producer, MMA issuer) back off while the latency-critical softmax warps do not.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0, unsigned backoff_ns = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 20000u) {  // each failed try_wait may have slept up to ~1 ms
+    if (backoff_ns) __nanosleep(backoff_ns);
+    if (++spins > 4000000u) {
       printf("avici_b200: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
              (int)threadIdx.x, parity);
       __trap();
