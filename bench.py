@@ -110,8 +110,12 @@ def cpu_forward_timing(n_datasets, threads=None):
     from avici_b200.params import init_params
     from oracle import avici_oracle as O
     from oracle import avici_oracle_torch as OT
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm must still use every host core it can
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(threads or avail)
     P = OT.to_torch(init_params(MODEL_KW, seed=0, perturb=True))
     x = torch.as_tensor(make_batch(n_datasets, 1000))
     with torch.no_grad():
