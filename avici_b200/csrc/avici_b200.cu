@@ -211,6 +211,7 @@ int launch_attention_tc(avb_handle h, const void* qkv, void* out, int B, int n, 
   const int T = axis == 0 ? d : n;
   const long long S = axis == 0 ? (long long)B * n : (long long)B * d;
   const long long items = S * H * ((T + 127) / 128);
+  if (items >= (1LL << 31)) return fail(h, AVB_ERR_INVALID, "attention: too many (sequence, head, tile) items in one call (%lld)", items);
   const int grid = (int)std::min<long long>((items + avb::kAttnStreams - 1) / avb::kAttnStreams, num_sms);
   avb::attention_tc_kernel<<<grid, avb::kAttnThreads, avb::kAttnSmemBytes, st>>>(
       reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis);

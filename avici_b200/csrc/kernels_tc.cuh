@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int n, int d, int H,
                     int axis) {
   constexpr int NS = kAttnKvStages;
-  constexpr int kBarsPerStream = 2 + 2 + NS + NS + 1 + 1 + 1 + 1 + 1;
+  constexpr int kBarsPerStream = 2 + 2 + NS + NS + 1 + 1 + 1 + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars_all = reinterpret_cast<uint64_t*>(smem + kAttnStreams * kAttnStreamBytes);
@@ -796,9 +796,9 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   long long* trace = (blockIdx.x == 0 && (warp == 0 || warp == 2 || warp == 4) && lane == 0) ? g_attn_trace : nullptr;
   const int T = axis == 0 ? d : n;
-  const long long S = axis == 0 ? (long long)B * n : (long long)B * d;
+  const int S = axis == 0 ? B * n : B * d;  // sequences; the host guarantees S * H * nqt < 2^31
   const int nqt = (T + 127) / 128;  // query tiles == kv tiles per sequence
-  const long long num_items = S * H * nqt;
+  const int num_items = S * H * nqt;
   const int HD = H * 32;
 
   if (warp == 1 && lane == 0) {
@@ -810,7 +810,6 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       ptx::mbar_init(&b[4 + 2 * NS + 1], kAttnSoftmaxThreads);  // s_free
       ptx::mbar_init(&b[4 + 2 * NS + 2], kAttnSoftmaxThreads);  // p_full
       ptx::mbar_init(&b[4 + 2 * NS + 3], 1);                    // pv_done
-      ptx::mbar_init(&b[4 + 2 * NS + 4], kAttnSoftmaxThreads);  // o_empty
     }
     ptx::mbar_init(&turn_done[0], kAttnSoftmaxThreads);
     ptx::mbar_init(&turn_done[1], kAttnSoftmaxThreads);
@@ -842,18 +841,24 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   uint64_t* s_free = s_full + 1;
   uint64_t* p_full = s_full + 2;
   uint64_t* pv_done = s_full + 3;
-  uint64_t* o_empty = s_full + 4;
   const uint32_t tmem_S = tmem_base + sid * kAttnTmemStreamCols;
   const uint32_t tmem_P = tmem_S + 128;  // 64 columns: P as packed bf16 pairs, A operand of the PV / L MMAs
   const uint32_t tmem_O = tmem_S + 192;  // O 32 | L 16 columns
-  const long long item0 = (long long)blockIdx.x * kAttnStreams + sid;
-  const long long item_stride = (long long)gridDim.x * kAttnStreams;
+  const int item0 = (int)blockIdx.x * kAttnStreams + sid;
+  const int item_stride = (int)gridDim.x * kAttnStreams;
 
-  auto decode = [&](long long item, long long& s, int& h, int& qt) {
-    qt = (int)(item % nqt);
-    const long long sh = item / nqt;
-    h = (int)(sh % H);
-    s = sh / H;
+  auto decode = [&](int item, int& s, int& h, int& qt) {  // 32-bit divisions: this runs once per item on every role
+    const unsigned u = (unsigned)item;
+    qt = (int)(u % (unsigned)nqt);
+    const unsigned sh = u / (unsigned)nqt;
+    h = (int)(sh % (unsigned)H);
+    s = (int)(sh / (unsigned)H);
+  };
+  // first token of sequence s (token index t = (b*n + i)*d + j)
+  auto seq_tok0 = [&](int s) -> long long {
+    if (axis == 0) return (long long)s * d;
+    const unsigned b = (unsigned)s / (unsigned)d, jj = (unsigned)s % (unsigned)d;
+    return (long long)b * n * d + jj;
   };
 
   if (warp < 2) {
@@ -877,12 +882,10 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
     };
     long long g = 0;
     int it = 0;
-    for (long long item = item0; item < num_items; item += item_stride, ++it) {
-      long long s; int h, qt;
+    for (int item = item0; item < num_items; item += item_stride, ++it) {
+      int s, h, qt;
       decode(item, s, h, qt);
-      // first token of the sequence
-      const long long tok0 = axis == 0 ? s * d : (s / d) * (long long)n * d + (s % d);
-      const __nv_bfloat16* base = qkv + tok0 * (3 * HD) + h * 32;
+      const __nv_bfloat16* base = qkv + seq_tok0(s) * (3 * HD) + h * 32;
       const int qb = it & 1;
       ptx::mbar_wait(&q_empty[qb], (uint32_t)((it >> 1) & 1) ^ 1, 10, 200u);
       load_tile(sQ + qb * kAttnTileBytes, base, qt * 128);
@@ -935,7 +938,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       };
       long long g = 0;
       int it = 0;
-      long long item = item0;
+      int item = item0;
       issue_S(0, 0, 0);
       while (item < num_items) {
         for (int j = 0; j < nqt; ++j, ++g) {
@@ -949,7 +952,6 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
             if (j + 1 < nqt) issue_S(g + 1, it, j + 1);
             else issue_S(g + 1, it + 1, 0);
           }
-          if (j == 0 && it >= 1) { ptx::mbar_wait(o_empty, (uint32_t)((it - 1) & 1), 22, 40u); }  // epilogue of the previous item has read O
           AVB_TRACE(1, g, 2);
           ptx::mbar_wait(p_full, (uint32_t)(g & 1), 23, 40u);
           AVB_TRACE(1, g, 3);
@@ -995,8 +997,35 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
 
     long long g = 0;
     int it = 0;
-    for (long long item = item0; item < num_items; item += item_stride, ++it) {
-      long long s; int h, qt;
+    // The epilogue of an item (O / L -> bf16 -> out) is deferred into the first step of the next item, between the
+    // row-max exchange and the exp phase: by then its last PV MMA has long completed (no exposed MMA latency), and
+    // since the next PV is only issued after every softmax thread has arrived on p_full, O needs no second buffer.
+    bool pend = false;
+    long long pend_row0 = 0;  // token of tile row 0 of the pending item
+    int pend_h = 0, pend_t0 = 0;
+    const long long tstride = axis == 0 ? 1 : d;
+    auto epilogue = [&]() {  // each half writes 16 of the 32 output channels of its rows
+      uint32_t o[16];
+      ptx::tmem_ld16(tO + half * 16, o);
+      const float lsum = __uint_as_float(ptx::tmem_ld1(tO + 32));
+      ptx::tmem_wait_ld();
+      if (pend_t0 + r < T) {
+        const long long tok = pend_row0 + (long long)r * tstride;
+        const float inv = 1.0f / lsum;
+        uint4* op = reinterpret_cast<uint4*>(out + (size_t)tok * HD + pend_h * 32 + half * 16);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          uint4 pk;
+          pk.x = ptx::pack_bf16(__uint_as_float(o[e * 8 + 0]) * inv, __uint_as_float(o[e * 8 + 1]) * inv);
+          pk.y = ptx::pack_bf16(__uint_as_float(o[e * 8 + 2]) * inv, __uint_as_float(o[e * 8 + 3]) * inv);
+          pk.z = ptx::pack_bf16(__uint_as_float(o[e * 8 + 4]) * inv, __uint_as_float(o[e * 8 + 5]) * inv);
+          pk.w = ptx::pack_bf16(__uint_as_float(o[e * 8 + 6]) * inv, __uint_as_float(o[e * 8 + 7]) * inv);
+          op[e] = pk;
+        }
+      }
+    };
+    for (int item = item0; item < num_items; item += item_stride, ++it) {
+      int s, h, qt;
       decode(item, s, h, qt);
       float m = -INFINITY;
       for (int j = 0; j < nqt; ++j, ++g) {
@@ -1049,6 +1078,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
           ptx::mbar_wait(pv_done, (uint32_t)((g - 1) & 1), 31);
           ptx::tc_fence_after();
         }
+        if (j == 0 && pend) { epilogue(); pend = false; }
         AVB_TRACE(2, g, 4);
         if (any_need) {
           const float m_new = need ? mx : m;
@@ -1111,30 +1141,15 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
         ptx::tc_fence_before();
         ptx::mbar_arrive(p_full);
       }
-      // ---- epilogue: O / L -> bf16 -> out[token, h*32 ..]; each half writes 16 of the 32 channels of its rows
+      pend = true;
+      pend_h = h;
+      pend_t0 = qt * 128;
+      pend_row0 = seq_tok0(s) + (long long)(qt * 128) * tstride;
+    }
+    if (pend) {
       ptx::mbar_wait(pv_done, (uint32_t)((g - 1) & 1), 33);
       ptx::tc_fence_after();
-      uint32_t o[16];
-      ptx::tmem_ld16(tO + half * 16, o);
-      const float lsum = __uint_as_float(ptx::tmem_ld1(tO + 32));
-      ptx::tmem_wait_ld();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(o_empty);
-      const int t = qt * 128 + r;
-      if (t < T) {
-        const long long tok = axis == 0 ? s * d + t : (s / d) * (long long)n * d + (long long)t * d + (s % d);
-        const float inv = 1.0f / lsum;
-        uint4* op = reinterpret_cast<uint4*>(out + (size_t)tok * HD + h * 32 + half * 16);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          uint4 pk;
-          pk.x = ptx::pack_bf16(__uint_as_float(o[e * 8 + 0]) * inv, __uint_as_float(o[e * 8 + 1]) * inv);
-          pk.y = ptx::pack_bf16(__uint_as_float(o[e * 8 + 2]) * inv, __uint_as_float(o[e * 8 + 3]) * inv);
-          pk.z = ptx::pack_bf16(__uint_as_float(o[e * 8 + 4]) * inv, __uint_as_float(o[e * 8 + 5]) * inv);
-          pk.w = ptx::pack_bf16(__uint_as_float(o[e * 8 + 6]) * inv, __uint_as_float(o[e * 8 + 7]) * inv);
-          op[e] = pk;
-        }
-      }
+      epilogue();
     }
   }
   ptx::tc_fence_before();

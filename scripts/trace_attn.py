@@ -25,7 +25,7 @@ names = {0: ["wait_kv_empty", "got", "issued"], 1: ["top", "s_free", "S_issued/w
          2: ["top", "s_full", "pass1", "xchg+vote", "pv_done", "turn", "S_loaded", "exps_done"]}
 for role, rn in ((0, "producer"), (1, "mma"), (2, "softmax")):
     print(f"== {rn}: events {names[role]} (cycles since kernel start; deltas within a step)")
-    for step in list(range(40, 56)):
+    for step in list(range(40, 50)):
         row = t[role, step, :len(names[role])]
         if row.max() == 0:
             continue
