@@ -771,6 +771,21 @@ constexpr int kAttnXchgBytes = 2 /*parity*/ * kAttnStreams * 2 /*halves*/ * 128 
 constexpr int kAttnSmemBytes = kAttnStreams * kAttnStreamBytes + 1024 + 512 + 512 + kAttnXchgBytes;  // + align slack, barriers, ones tile
 constexpr int kAttnTmemStreamCols = 256;  // S 128 (fp32) | P 64 (bf16 pairs) | O 32 | L 16 | spare
 constexpr float kAttnRescaleThreshold = 8.0f;  // log2 units
+constexpr int kAttnPolyEvery = 4;  // 1 of every kAttnPolyEvery exponent pairs is evaluated on the FMA pipe
+
+// exp2 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = i + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (max relative error 7.5e-5, far below the bf16 rounding of P) and i added into the exponent.
+// The attention kernel is bound by the 16 ex2/clk/SM MUFU pipe, so a fixed fraction of the exponentials takes
+// this path (the trick FlashAttention-4 uses on Blackwell).
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.055171650f, 0.24261113f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992806f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -1109,8 +1124,13 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
             ptx::mbar_arrive(s_free);  // last read of S: hand the buffer back to the tensor core
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-              pk[e] = ptx::pack_bf16(fast_exp2(__uint_as_float(sa[2 * e]) - m), fast_exp2(__uint_as_float(sa[2 * e + 1]) - m));
-              pk[16 + e] = ptx::pack_bf16(fast_exp2(__uint_as_float(sb[2 * e]) - m), fast_exp2(__uint_as_float(sb[2 * e + 1]) - m));
+              if ((e % kAttnPolyEvery) == kAttnPolyEvery - 1) {  // this pair goes through the FMA-pipe polynomial
+                pk[e] = ptx::pack_bf16(poly_exp2(__uint_as_float(sa[2 * e]) - m), poly_exp2(__uint_as_float(sa[2 * e + 1]) - m));
+                pk[16 + e] = ptx::pack_bf16(poly_exp2(__uint_as_float(sb[2 * e]) - m), poly_exp2(__uint_as_float(sb[2 * e + 1]) - m));
+              } else {
+                pk[e] = ptx::pack_bf16(fast_exp2(__uint_as_float(sa[2 * e]) - m), fast_exp2(__uint_as_float(sa[2 * e + 1]) - m));
+                pk[16 + e] = ptx::pack_bf16(fast_exp2(__uint_as_float(sb[2 * e]) - m), fast_exp2(__uint_as_float(sb[2 * e + 1]) - m));
+              }
             }
           } else {
 #pragma unroll
