@@ -183,6 +183,23 @@ int launch_ln_gemm_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, con
   return AVB_OK;
 }
 
+int launch_outproj_tc(avb_handle h, const CUtensorMap& tm_a, const CUtensorMap& tm_w, const float* bias, float* z, int M,
+                      cudaStream_t st, int num_sms, long long* launches) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(avb::outproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         avb::kOutProjSmemBytes);
+    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(outproj_tc): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = std::min((M + 127) / 128, num_sms);
+  avb::outproj_tc_kernel<<<grid, avb::kOutProjThreads, avb::kOutProjSmemBytes, st>>>(tm_a, tm_w, bias, z, M);
+  if (launches) ++*launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "outproj_tc launch: %s", cudaGetErrorString(e));
+  return AVB_OK;
+}
+
 int launch_ffn_tc(avb_handle h, float* z, const CUtensorMap& tm_w1c, const CUtensorMap& tm_w2, const float* b1,
                   const float* b2, int M, int F, cudaStream_t st, int num_sms, long long* launches) {
   static bool attr_set = false;
@@ -607,7 +624,9 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
     { ProfScope ps(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
       if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches))) return rc; }
     { ProfScope ps(h, AVB_PROF_OUT, st);
-      if ((rc = launch_gemm_tc<128, 2>(h, tm_attn, W.tm_wo, W.bo, z, k, M, k, HD, st, h->num_sms, &h->launches))) return rc; }
+      if (HD == 64 * avb::kOutProjKB) {
+        if ((rc = launch_outproj_tc(h, tm_attn, W.tm_wo, W.bo, z, M, st, h->num_sms, &h->launches))) return rc;
+      } else if ((rc = launch_gemm_tc<128, 2>(h, tm_attn, W.tm_wo, W.bo, z, k, M, k, HD, st, h->num_sms, &h->launches))) return rc; }
     // FFN half: LN -> Linear + ReLU -> Linear + residual
     { ProfScope ps(h, AVB_PROF_FFN1, st);  // whole FFN sub-layer in one kernel (LN, up-projection, ReLU, down-projection, residual)
       if ((rc = launch_ffn_tc(h, z, W.tm_w1c, W.tm_w2, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches))) return rc; }

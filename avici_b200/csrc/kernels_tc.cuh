@@ -254,6 +254,130 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------
+// Attention output projection + residual, in place on the fp32 residual stream (model.py:59-65):
+//     z[M,128] += attn[M,K] @ Wo_t[128,K]^T + bo            (K = heads * 32 = 256)
+//   The [128 x K] weight stays resident in shared memory for the whole (persistent) CTA; only the attention
+//   output streams through a TMA ring.  Accumulators are double-buffered in TMEM; eight epilogue warps
+//   (TMEM lane quarter x 64-column half) do the residual update through smem-transposed, coalesced accesses.
+//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM alloc   warps 4-11: epilogue
+// ------------------------------------------------------------------------------------------
+constexpr int kOutProjThreads = 384;
+constexpr int kOutProjStages = 6;
+constexpr int kOutProjKB = 4;  // K blocks of 64 (K = 256)
+constexpr int kOutProjSmemBytes = kOutProjKB * 128 * 128 + kOutProjStages * 128 * 128 + 8 * 4096 + 1024 + 256;
+
+__global__ void __launch_bounds__(kOutProjThreads, 1)
+outproj_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                  const float* __restrict__ bias, float* __restrict__ z, int M) {
+  constexpr int ST = kOutProjStages, KB = kOutProjKB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW = smem;                          // [KB][128 x 64] bf16, resident
+  uint8_t* sA = sW + KB * 128 * 128;           // [ST][128 x 64]
+  uint8_t* sStage = sA + ST * 128 * 128;       // [8 warps][4 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 8 * 4096);
+  uint64_t* full = bars;            // [ST]
+  uint64_t* empty = bars + ST;      // [ST]
+  uint64_t* tfull = bars + 2 * ST;  // [2]
+  uint64_t* tempty = tfull + 2;     // [2] 256 epilogue threads
+  uint64_t* w_full = tempty + 2;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int num_m = (M + 127) / 128;
+
+  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_a); ptx::prefetch_tmap(&tm_w); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < ST; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 256); }
+    ptx::mbar_init(w_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {  // the weight: once
+      ptx::mbar_expect_tx(w_full, KB * 128 * 128);
+      for (int kb = 0; kb < KB; ++kb) ptx::tma_load_2d(sW + kb * 128 * 128, &tm_w, w_full, kb * 64, 0);
+    }
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
+      for (int kb = 0; kb < KB; ++kb) {
+        ptx::mbar_wait(&empty[stage], phase ^ 1, 70, 100u);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&full[stage], 128 * 128);
+          ptx::tma_load_2d(sA + stage * 128 * 128, &tm_a, &full[stage], kb * 64, mt * 128);
+        }
+        __syncwarp();
+        if (++stage == ST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 128, 0, 0);
+    const uint64_t dA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024, ptx::kSwz128);
+    const uint64_t dW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024, ptx::kSwz128);
+    ptx::mbar_wait(w_full, 0, 71, 40u);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
+      const int as = it & 1;
+      ptx::mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1, 72, 40u);
+      ptx::tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb) {
+        ptx::mbar_wait(&full[stage], phase, 73, 40u);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t da = dA0 + (uint64_t)stage * ((128 * 128) >> 4);
+          const uint64_t dw = dW0 + (uint64_t)kb * ((128 * 128) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16(tmem_base + as * 128, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          ptx::umma_commit(&empty[stage]);
+          if (kb == KB - 1) ptx::umma_commit(&tfull[as]);
+        }
+        __syncwarp();
+        if (++stage == ST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t stage_addr = ptx::smem_u32(sStage) + (uint32_t)((warp - 4) * 4096);
+    int it = 0;
+    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
+      const int as = it & 1;
+      ptx::mbar_wait(&tfull[as], (uint32_t)((it >> 1) & 1), 74);
+      ptx::tc_fence_after();
+      const int row0 = mt * 128 + q * 32;
+      const int rows_valid = M - row0 < 32 ? M - row0 : 32;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + as * 128 + half * 64 + cc * 32 + lane_off, v);
+        ptx::tmem_wait_ld();
+        if (cc == 1) {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tempty[as]);
+        }
+        residual_add_block_32x32(v, bias + half * 64 + cc * 32, stage_addr, z + (size_t)row0 * 128 + half * 64 + cc * 32, 128,
+                                 rows_valid, lane);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------
 // LayerNorm (no affine) of 32 consecutive 128-channel fp32 rows by one warp, written as bf16 into a
 // 128B-swizzled K-major UMMA A tile ([128 rows x 128 ch] = two K blocks of [128 x 64], 16 KB apart).
 // Eight lanes share a row (16 channels each, 3 shuffle steps per statistic) and a warp instruction covers
