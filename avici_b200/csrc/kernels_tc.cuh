@@ -377,6 +377,18 @@ outproj_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 256);
 }
 
+// L2 prefetch of the 32 fp32 rows (16 KB = 128 lines) a LayerNorm warp will normalise in its NEXT tile: the producer
+// warps can only keep ~8 rows of loads in flight in registers, far less than HBM latency x bandwidth needs, so the
+// next tile is pulled into L2 while the current one is processed.
+__device__ __forceinline__ void prefetch_rows_l2(const float* __restrict__ z, int M, int grow0, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int line = i * 32 + lane;           // 128-byte line index inside the 32 x 512 B block
+    const int row = grow0 + (line >> 2);
+    if (row < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(z + (size_t)row * 128 + (line & 3) * 32));
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // LayerNorm (no affine) of 32 consecutive 128-channel fp32 rows by one warp, written as bf16 into a
 // 128B-swizzled K-major UMMA A tile ([128 rows x 128 ch] = two K blocks of [128 x 64], 16 KB apart).
@@ -506,6 +518,7 @@ ln_gemm_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorM
     int it = 0;
     for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
       const int buf = it & 1;
+      prefetch_rows_l2(z, M, (mt + (int)gridDim.x) * 128 + warp * 32, lane);
       ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 40);
       ln_warp_rows_to_umma_tile(z, M, mt * 128 + warp * 32, ptx::smem_u32(sA + buf * kLnGemmABytes), warp * 32, lane);
       ptx::fence_proxy_async();
@@ -702,6 +715,7 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
     for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
       const int buf = it & 1;
       AVB_TRACE(0, it, 0);
+      prefetch_rows_l2(z, M, (mt + (int)gridDim.x) * 128 + warp * 32, lane);
       ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 50);
       AVB_TRACE(0, it, 1);
       ln_warp_rows_to_umma_tile(z, M, mt * 128 + warp * 32, ptx::smem_u32(sA + buf * kLnGemmABytes), warp * 32, lane);
