@@ -649,8 +649,9 @@ ln_gemm_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorM
 //     G1_c : D1[128x128 fp32, TMEM] = xhat[smem, bf16] . W1c^T[smem]            (8 MMAs 128x128x16)
 //     E1_c : D1 -> +b1, ReLU -> bf16 pairs -> H[TMEM]                            (8 epilogue warps)
 //     G2_c : D2[128x128 fp32, TMEM] += H[TMEM, A operand] . W2c[smem]            (8 MMAs, A from TMEM)
-//   and after the fourth chunk  E2 : z += D2 + b2.  D1 and H are double-buffered so the tensor core runs
-//   G1_{c+1} while the epilogue warps turn D1_c into H_c.  TMEM: 2x128 (D1) + 2x64 (H) + 128 (D2) = 512 columns.
+//   and after the fourth chunk  E2 : z += D2 + b2.  H is double-buffered (G1_{c+1} is issued as soon as E1_c has read
+//   D1, so the tensor core works while E1_c packs H_c) and D2 is double-buffered by tile, so E2 of a tile is
+//   deferred behind the first E1 of the next tile.  TMEM: 128 (D1) + 2x64 (H) + 2x128 (D2) = 512 columns.
 //   Weights stream from L2 through a 2-stage TMA ring (64 KB per chunk: W1c and W2c).
 //   warps 0-3: LN producers   warp 4: weight TMA   warp 5: MMA issuer   warp 6: TMEM alloc   warps 8-15: epilogues
 // ------------------------------------------------------------------------------------------
@@ -673,12 +674,12 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
   uint64_t* w1_empty = bars + 6;    // [2]
   uint64_t* w2_full = bars + 8;     // [2]
   uint64_t* w2_empty = bars + 10;   // [2]
-  uint64_t* d1_full = bars + 12;    // [2]
-  uint64_t* d1_empty = bars + 14;   // [2] 256 epilogue threads
-  uint64_t* h_full = bars + 16;     // [2] 256 epilogue threads
-  uint64_t* h_empty = bars + 18;    // [2]
-  uint64_t* d2_full = bars + 20;    // [1]
-  uint64_t* d2_empty = bars + 21;   // [1] 256 epilogue threads
+  uint64_t* d1_full = bars + 12;    // [1]
+  uint64_t* d1_empty = bars + 13;   // [1] 256 epilogue threads
+  uint64_t* h_full = bars + 14;     // [2] 256 epilogue threads
+  uint64_t* h_empty = bars + 16;    // [2]
+  uint64_t* d2_full = bars + 18;    // [2]
+  uint64_t* d2_empty = bars + 20;   // [2] 256 epilogue threads
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -691,10 +692,10 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
       ptx::mbar_init(&a_full[i], 128); ptx::mbar_init(&a_empty[i], 1);
       ptx::mbar_init(&w1_full[i], 1); ptx::mbar_init(&w1_empty[i], 1);
       ptx::mbar_init(&w2_full[i], 1); ptx::mbar_init(&w2_empty[i], 1);
-      ptx::mbar_init(&d1_full[i], 1); ptx::mbar_init(&d1_empty[i], 256);
       ptx::mbar_init(&h_full[i], 256); ptx::mbar_init(&h_empty[i], 1);
+      ptx::mbar_init(&d2_full[i], 1); ptx::mbar_init(&d2_empty[i], 256);
     }
-    ptx::mbar_init(d2_full, 1); ptx::mbar_init(d2_empty, 256);
+    ptx::mbar_init(d1_full, 1); ptx::mbar_init(d1_empty, 256);
     ptx::fence_barrier_init();
   }
   if (warp == 6) {
@@ -705,9 +706,9 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_D1 = tmem_base;        // 2 x 128
-  const uint32_t tmem_H = tmem_base + 256;   // 2 x 64
-  const uint32_t tmem_D2 = tmem_base + 384;  // 128
+  const uint32_t tmem_D1 = tmem_base;        // 128
+  const uint32_t tmem_H = tmem_base + 128;   // 2 x 64
+  const uint32_t tmem_D2 = tmem_base + 256;  // 2 x 128 (by tile parity)
 
   if (warp < 4) {
     // ===================== LN producers (same as ln_gemm_tc_kernel)
@@ -756,10 +757,10 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
     const int my_tiles = blockIdx.x < num_m ? (num_m - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int total = my_tiles * num_c;
     auto issue_G1 = [&](int g) {
-      const int tile_it = g / num_c, c = g % num_c, buf = tile_it & 1, st = g & 1, as1 = g & 1;
+      const int tile_it = g / num_c, c = g % num_c, buf = tile_it & 1, st = g & 1;
       if (c == 0) ptx::mbar_wait(&a_full[buf], (uint32_t)((tile_it >> 1) & 1), 53);
       ptx::mbar_wait(&w1_full[st], (uint32_t)((g >> 1) & 1), 54);
-      ptx::mbar_wait(&d1_empty[as1], (uint32_t)((g >> 1) & 1) ^ 1, 55);
+      ptx::mbar_wait(d1_empty, (uint32_t)(g & 1) ^ 1, 55);  // E1 of the previous chunk has read D1
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint64_t da = dA0 + (uint64_t)(buf * (kLnGemmABytes >> 4));
@@ -767,10 +768,10 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {  // K block (kk >> 2) is 16 KB further, 32 bytes per K=16 slice inside it
           const uint64_t off = (uint64_t)((kk >> 2) * ((128 * 128) >> 4) + (kk & 3) * 2);
-          ptx::umma_bf16(tmem_D1 + as1 * 128, da + off, dw + off, idesc, kk != 0);
+          ptx::umma_bf16(tmem_D1, da + off, dw + off, idesc, kk != 0);
         }
         ptx::umma_commit(&w1_empty[st]);
-        ptx::umma_commit(&d1_full[as1]);
+        ptx::umma_commit(d1_full);
         if (c == num_c - 1) ptx::umma_commit(&a_empty[buf]);
       }
       __syncwarp();
@@ -785,18 +786,18 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
       AVB_TRACE(1, g, 2);
       ptx::mbar_wait(&h_full[hs], (uint32_t)((g >> 1) & 1), 57);
       AVB_TRACE(1, g, 3);
-      if (c == 0 && tile_it > 0) ptx::mbar_wait(d2_empty, (uint32_t)((tile_it - 1) & 1), 58);
+      if (c == 0 && tile_it >= 2) ptx::mbar_wait(&d2_empty[tile_it & 1], (uint32_t)(((tile_it >> 1) - 1) & 1), 58);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint64_t dw = dW0 + (uint64_t)(st * ((2 * kFfnWBytes) >> 4) + (kFfnWBytes >> 4));
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint64_t off = (uint64_t)((kk >> 2) * ((128 * 128) >> 4) + (kk & 3) * 2);
-          ptx::umma_bf16_ts(tmem_D2, tmem_H + hs * 64 + kk * 8, dw + off, idesc, (c | kk) != 0);
+          ptx::umma_bf16_ts(tmem_D2 + (tile_it & 1) * 128, tmem_H + hs * 64 + kk * 8, dw + off, idesc, (c | kk) != 0);
         }
         ptx::umma_commit(&w2_empty[st]);
         ptx::umma_commit(&h_empty[hs]);
-        if (c == num_c - 1) ptx::umma_commit(d2_full);
+        if (c == num_c - 1) ptx::umma_commit(&d2_full[tile_it & 1]);
       }
       __syncwarp();
       AVB_TRACE(1, g, 4);
@@ -805,28 +806,49 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
     // ===================== epilogue warps: (TMEM lane quarter q) x (64-column half)
     const int q = warp & 3, half = (warp - 8) >> 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    int g = 0, tile_it = 0;
+    const uint32_t stage = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 4096);
+    // E2 of a tile (z += D2 + b2) is deferred until after the first E1 of the NEXT tile: D2 is double-buffered by tile
+    // parity, so the wait for the tile's last G2 MMAs and the z round trip overlap the next tile's MMAs.
+    auto E2 = [&](int t_it, int t_mt) {
+      ptx::mbar_wait(&d2_full[t_it & 1], (uint32_t)((t_it >> 1) & 1), 61);
+      ptx::tc_fence_after();
+      const int row0 = t_mt * 128 + q * 32;
+      const int rows_valid = M - row0 < 32 ? M - row0 : 32;  // may be <= 0 on the last tile
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_D2 + (t_it & 1) * 128 + half * 64 + cc * 32 + lane_off, v);
+        ptx::tmem_wait_ld();
+        if (cc == 1) {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&d2_empty[t_it & 1]);
+        }
+        residual_add_block_32x32(v, b2 + half * 64 + cc * 32, stage, z + (size_t)row0 * 128 + half * 64 + cc * 32, 128,
+                                 rows_valid, lane);
+      }
+    };
+    int g = 0, tile_it = 0, prev_mt = -1;
     for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++tile_it) {
       for (int c = 0; c < num_c; ++c, ++g) {
         // ---- E1: D1 -> +b1 -> ReLU -> bf16 pairs -> H
-        const int as1 = g & 1, hs = g & 1;
+        const int hs = g & 1;
         const float* bp = b1 + c * 128 + half * 64;
         float4 bb[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bp) + e);
         AVB_TRACE(2, g, 0);
-        ptx::mbar_wait(&d1_full[as1], (uint32_t)((g >> 1) & 1), 59);
+        ptx::mbar_wait(d1_full, (uint32_t)(g & 1), 59);
         AVB_TRACE(2, g, 1);
         ptx::tc_fence_after();
         uint32_t pk[32];
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           uint32_t v[32];
-          ptx::tmem_ld32(tmem_D1 + as1 * 128 + half * 64 + cc * 32 + lane_off, v);
+          ptx::tmem_ld32(tmem_D1 + half * 64 + cc * 32 + lane_off, v);
           ptx::tmem_wait_ld();
-          if (cc == 1) {  // D1 fully read by this thread
+          if (cc == 1) {  // D1 fully read by this thread: the next chunk's G1 may overwrite it
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&d1_empty[as1]);
+            ptx::mbar_arrive(d1_empty);
           }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -846,28 +868,14 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
         ptx::tc_fence_before();
         ptx::mbar_arrive(&h_full[hs]);
         AVB_TRACE(2, g, 4);
-      }
-      // ---- E2: z += D2 + b2 (row per thread, 64 columns per warp half)
-      ptx::mbar_wait(d2_full, (uint32_t)(tile_it & 1), 61);
-      AVB_TRACE(2, g - 1, 5);
-      ptx::tc_fence_after();
-      const int row0 = mt * 128 + q * 32;
-      const int rows_valid = M - row0 < 32 ? M - row0 : 32;  // may be <= 0 on the last tile
-      const uint32_t stage = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 4096);
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tmem_D2 + half * 64 + cc * 32 + lane_off, v);
-        ptx::tmem_wait_ld();
-        if (cc == 1) {
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(d2_empty);
+        if (c == 0 && prev_mt >= 0) {
+          E2(tile_it - 1, prev_mt);
+          AVB_TRACE(2, g, 6);
         }
-        residual_add_block_32x32(v, b2 + half * 64 + cc * 32, stage, z + (size_t)row0 * 128 + half * 64 + cc * 32, 128,
-                                 rows_valid, lane);
       }
-      AVB_TRACE(2, g - 1, 6);
+      prev_mt = mt;
     }
+    if (prev_mt >= 0) E2(tile_it - 1, prev_mt);
   }
   ptx::tc_fence_before();
   __syncthreads();
