@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libavici_b200.so")
+LIB_PATH = os.environ.get("AVB_LIB") or os.path.join(_HERE, "csrc", "libavici_b200.so")  # AVB_LIB: A/B builds
 SRC_DIR = os.path.join(_HERE, "csrc")
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 
@@ -79,7 +79,8 @@ def build(force=False, verbose=False):
     srcs.append(os.path.join(INCLUDE_DIR, "avici_b200.h"))
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in srcs):
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(SRC_DIR, "avici_b200.cu")]
+    extra = os.environ.get("AVB_NVCC_EXTRA", "").split()  # e.g. -DAVB_ATTN_TURNS=0 for an A/B build
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + ["-o", LIB_PATH, os.path.join(SRC_DIR, "avici_b200.cu")]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True, cwd=SRC_DIR)

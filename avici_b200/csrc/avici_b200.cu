@@ -216,13 +216,25 @@ int launch_ffn_tc(avb_handle h, float* z, const CUtensorMap& tm_w1c, const CUten
   return AVB_OK;
 }
 
+// Axial attention = two launches on the same stream: the fast kernel (stale row maximum) and the exact kernel, which
+// exits at once unless the fast one raised `guard` (a score tile outran the running maximum by > 2^64; never seen on
+// LayerNorm-ed inputs, but the result must not depend on that).  guard: 4 bytes of device memory owned by the caller's
+// workspace, so concurrent forwards on different streams / workspaces stay independent.
+// AVB_ATTN_MODE=exact|fast (debug): run only one of the two.
 int launch_attention_tc(avb_handle h, const void* qkv, void* out, int B, int n, int d, int H, int axis,
-                        cudaStream_t st, int num_sms, long long* launches) {
+                        cudaStream_t st, int num_sms, long long* launches, int* guard) {
   static bool attr_set = false;
+  static int mode = 0;  // 0: fast + guarded exact, 1: exact only, 2: fast only
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(avb::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(avb::attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          avb::kAttnSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(avb::attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               avb::kAttnSmemBytes);
     if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(attention_tc): %s", cudaGetErrorString(e));
+    const char* m = getenv("AVB_ATTN_MODE");
+    if (m && !strcmp(m, "exact")) mode = 1;
+    if (m && !strcmp(m, "fast")) mode = 2;
     attr_set = true;
   }
   const int T = axis == 0 ? d : n;
@@ -230,9 +242,17 @@ int launch_attention_tc(avb_handle h, const void* qkv, void* out, int B, int n, 
   const long long items = S * H * ((T + 127) / 128);
   if (items >= (1LL << 31)) return fail(h, AVB_ERR_INVALID, "attention: too many (sequence, head, tile) items in one call (%lld)", items);
   const int grid = (int)std::min<long long>((items + avb::kAttnStreams - 1) / avb::kAttnStreams, num_sms);
-  avb::attention_tc_kernel<<<grid, avb::kAttnThreads, avb::kAttnSmemBytes, st>>>(
-      reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis);
-  if (launches) ++*launches;
+  if (mode != 1) {
+    if (cudaMemsetAsync(guard, 0, sizeof(int), st) != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention guard reset failed");
+    avb::attention_tc_kernel<true><<<grid, avb::kAttnThreads, avb::kAttnSmemBytes, st>>>(
+        reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis, guard);
+    if (launches) ++*launches;
+  }
+  if (mode != 2) {
+    avb::attention_tc_kernel<false><<<grid, avb::kAttnThreads, avb::kAttnSmemBytes, st>>>(
+        reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis, mode == 1 ? nullptr : guard);
+    if (launches) ++*launches;
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention_tc launch: %s", cudaGetErrorString(e));
   return AVB_OK;
@@ -250,7 +270,7 @@ void launch_sgemm(const float* A, int lda, const float* W, int ldw, const float*
 struct BlockWs {
   // bf16 mode: big (qkv bf16[N,768] aliased with h bf16[N,512]) | attn bf16[N,256]
   // f32 mode:  big (qkv f32[N,768] aliased with h f32[N,512]) | attn f32[N,256]
-  size_t xhat_off, big_off, attn_off, total;
+  size_t xhat_off, big_off, attn_off, guard_off, total;
 };
 BlockWs block_ws_layout(const avb_config& c, size_t ntok) {
   BlockWs w{};
@@ -260,6 +280,7 @@ BlockWs block_ws_layout(const avb_config& c, size_t ntok) {
     w.xhat_off = off;  // (the LayerNorm output lives only in shared memory)
     w.big_off = off;  off = align_up(off + ntok * std::max(3 * HD, F) * 2, 1024);
     w.attn_off = off; off = align_up(off + ntok * HD * 2, 1024);
+    w.guard_off = off; off += 1024;  // overflow guard of the fast attention kernel (launch_attention_tc)
   } else {
     w.big_off = off;  off = align_up(off + ntok * std::max(3 * HD, F) * 4, 1024);
     w.attn_off = off; off = align_up(off + ntok * HD * 4, 1024);
@@ -622,7 +643,8 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
     { ProfScope ps(h, AVB_PROF_QKV, st);  // LayerNorm fused into the projection's prologue
       if ((rc = launch_ln_gemm_tc<0>(h, z, W.tm_wqkv, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, st, h->num_sms, &h->launches))) return rc; }
     { ProfScope ps(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
-      if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches))) return rc; }
+      if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches,
+                                    reinterpret_cast<int*>(w8 + L.guard_off)))) return rc; }
     { ProfScope ps(h, AVB_PROF_OUT, st);
       if (HD == 64 * avb::kOutProjKB) {
         if ((rc = launch_outproj_tc(h, tm_attn, W.tm_wo, W.bo, z, M, st, h->num_sms, &h->launches))) return rc;
@@ -864,7 +886,9 @@ int avb_test_attention_bf16(const void* qkv, void* out, int32_t B, int32_t n, in
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device");
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return launch_attention_tc(nullptr, qkv, out, B, n, d, H, axis, reinterpret_cast<cudaStream_t>(stream), sms, nullptr);
+  static int* guard = nullptr;  // test entry point: one process-wide guard word
+  if (!guard && cudaMalloc(&guard, sizeof(int)) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "cudaMalloc(guard) failed");
+  return launch_attention_tc(nullptr, qkv, out, B, n, d, H, axis, reinterpret_cast<cudaStream_t>(stream), sms, nullptr, guard);
 }
 
 }  // extern "C"

@@ -39,10 +39,14 @@ __global__ void ln_bf16_kernel(const float* __restrict__ z, size_t ntok, __nv_bf
 // Debug timeline: when set (avb_debug_set_trace), block 0 records clock64() stamps of the first steps of each
 // role of stream 0 into trace[role * 4096 + step * 8 + event].
 __device__ long long* g_attn_trace = nullptr;
+#ifdef AVB_TRACE_ENABLE
 #define AVB_TRACE(role, step, ev)                                                      \
   do {                                                                                 \
     if (trace && (step) < 500) trace[(role) * 4096 + (step) * 8 + (ev)] = clock64();  \
   } while (0)
+#else  // production builds carry no tracing code (it costs registers and issue slots in the softmax loop)
+#define AVB_TRACE(role, step, ev) do { (void)trace; } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Residual update of a [32 rows x 32 cols] fp32 block held row-per-thread in registers (the tcgen05.ld layout):
@@ -918,6 +922,10 @@ constexpr int kAttnSmemBytes = kAttnStreams * kAttnStreamBytes + 1024 + 512 + 51
 constexpr int kAttnTmemStreamCols = 256;  // S 128 (fp32) | P 64 (bf16 pairs) | O 32 | L 16 | spare
 constexpr float kAttnRescaleThreshold = 8.0f;  // log2 units
 constexpr int kAttnPolyEvery = 4;  // 1 of every kAttnPolyEvery exponent pairs is evaluated on the FMA pipe
+#ifndef AVB_ATTN_POLY_EVERY
+#define AVB_ATTN_POLY_EVERY 4
+#endif
+constexpr float kAttnOverflowGuard = 64.0f;  // log2 units: a tile exceeding the stale row max by more flags the launch
 
 // exp2 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = i + f, f in [-0.5, 0.5], degree-3 minimax
 // polynomial for 2^f (max relative error 7.5e-5, far below the bf16 rounding of P) and i added into the exponent.
@@ -939,23 +947,96 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// Packed fp32 pairs (sm_100 add/fma.f32x2): two results per issued instruction.  The softmax warps are bound by
+// issue slots and the MUFU pipe together, so everything that is not an ex2 is done two elements at a time.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// 32 scores (one TMEM chunk of a query row) -> 16 packed bf16 pairs of exp2(s - ref).  One pair in
+// kAttnFastPolyEvery goes through the FMA-pipe polynomial (same polynomial as poly_exp2, evaluated on packed
+// pairs), the others through MUFU.  pmax accumulates the maximum of the raw scores on the polynomial lanes: MUFU
+// saturates to +inf when s - ref is out of range (the epilogue sees it in the row sum) but the polynomial's exponent
+// arithmetic wraps, so those lanes are range-checked by the caller.
+constexpr int kAttnFastPolyEvery = AVB_ATTN_POLY_EVERY;
+__device__ __forceinline__ void exp_chunk32(const uint32_t (&s)[32], uint64_t negm2, uint32_t* pk, float& pmax) {
+  const uint64_t magic2 = pack2(12582912.0f, 12582912.0f), nmagic2 = pack2(-12582912.0f, -12582912.0f);
+  const uint64_t c3 = pack2(0.055171650f, 0.055171650f), c2 = pack2(0.24261113f, 0.24261113f);
+  const uint64_t c1 = pack2(0.69326097f, 0.69326097f), c0 = pack2(0.99992806f, 0.99992806f);
+  const uint64_t neg1 = pack2(-1.0f, -1.0f);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const float a = __uint_as_float(s[2 * e]), b = __uint_as_float(s[2 * e + 1]);
+    uint64_t x2 = add2(pack2(a, b), negm2);
+    float x0, x1;
+    unpack2(x2, x0, x1);
+    if ((e % kAttnFastPolyEvery) == kAttnFastPolyEvery - 1) {
+      pmax = max3(pmax, a, b);
+      x2 = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+      const uint64_t t2 = add2(x2, magic2);           // integer part lands in the low mantissa bits
+      const uint64_t f2 = fma2(add2(t2, nmagic2), neg1, x2);  // f = x - round(x), in [-0.5, 0.5]
+      uint64_t p2 = fma2(f2, c3, c2);
+      p2 = fma2(p2, f2, c1);
+      p2 = fma2(p2, f2, c0);
+      float p0, p1, t0, t1;
+      unpack2(p2, p0, p1);
+      unpack2(t2, t0, t1);
+      p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+      p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+      pk[e] = ptx::pack_bf16(p0, p1);
+    } else {
+#ifdef AVB_ATTN_NOEXP  // timing experiment only: everything but the exponentials
+      pk[e] = ptx::pack_bf16(x0, x1);
+#else
+      pk[e] = ptx::pack_bf16(fast_exp2(x0), fast_exp2(x1));
+#endif
+    }
+  }
+}
+
+template <bool kFast>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int n, int d, int H,
-                    int axis) {
+                    int axis, int* __restrict__ guard) {
+  // guard: one int per launch pair.  The fast variant (stale row maximum, see the softmax section) raises it when a
+  // score tile exceeds the running maximum by more than kAttnOverflowGuard; the exact variant, launched right after
+  // it on the same stream, returns immediately unless the guard is up and otherwise recomputes the whole launch.
+  if (!kFast && guard != nullptr && *guard == 0) return;
   constexpr int NS = kAttnKvStages;
   constexpr int kBarsPerStream = 2 + 2 + NS + NS + 1 + 1 + 1 + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars_all = reinterpret_cast<uint64_t*>(smem + kAttnStreams * kAttnStreamBytes);
-  uint64_t* turn_done = bars_all + kAttnStreams * kBarsPerStream;  // [2]: stream s finished the exp phase of a step
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn_done + 2);
+  uint64_t* x_full_all = bars_all + kAttnStreams * kBarsPerStream;  // [2][4]: row-max exchange of (stream, row quarter)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full_all + 8);
   uint32_t* s_ones = reinterpret_cast<uint32_t*>(smem + kAttnStreams * kAttnStreamBytes + 512);  // 512 B of bf16 1.0
   float* s_xchg = reinterpret_cast<float*>(smem + kAttnStreams * kAttnStreamBytes + 1024);      // [2][streams][2][128]
 
   // warp index through a shuffle: the compiler then knows the role branches are warp-uniform and keeps the
   // MMA / TMA operands in uniform registers (no per-instruction R2UR chains on the single issuing thread)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  long long* trace = (blockIdx.x == 0 && (warp == 0 || warp == 2 || warp == 4) && lane == 0) ? g_attn_trace : nullptr;
+  long long* trace = (blockIdx.x == 0 && (warp == 0 || warp == 2 || warp == 4 || warp == 12) && lane == 0) ? g_attn_trace : nullptr;
+  const int trole = warp == 12 ? 3 : 2;
   const int T = axis == 0 ? d : n;
   const int S = axis == 0 ? B * n : B * d;  // sequences; the host guarantees S * H * nqt < 2^31
   const int nqt = (T + 127) / 128;  // query tiles == kv tiles per sequence
@@ -972,8 +1053,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       ptx::mbar_init(&b[4 + 2 * NS + 2], kAttnSoftmaxThreads);  // p_full
       ptx::mbar_init(&b[4 + 2 * NS + 3], 1);                    // pv_done
     }
-    ptx::mbar_init(&turn_done[0], kAttnSoftmaxThreads);
-    ptx::mbar_init(&turn_done[1], kAttnSoftmaxThreads);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(&x_full_all[i], 64);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -1171,6 +1251,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       const float lsum = __uint_as_float(ptx::tmem_ld1(tO + 32));
       ptx::tmem_wait_ld();
       if (pend_t0 + r < T) {
+        if (kFast && !(lsum < 1.8446744e19f)) *guard = 1;  // row sum >= 2^64, inf or NaN: a score outran the reference
         const long long tok = pend_row0 + (long long)r * tstride;
         const float inv = 1.0f / lsum;
         uint4* op = reinterpret_cast<uint4*>(out + (size_t)tok * HD + pend_h * 32 + half * 16);
@@ -1185,14 +1266,103 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
         }
       }
     };
+    if constexpr (kFast) {
+      // ---- single-pass softmax against a FIXED per-row reference.
+      // softmax is invariant to the per-row shift: exp2(s - ref) needs a reference that keeps the values in range,
+      // not the exact running maximum.  The exact variant below pays for the exact one with a second read of S,
+      // a shared-memory exchange + barrier between the two warps of a row quarter on every tile, and O rescales -
+      // a dependent chain as long as the exponentials themselves.  Here the reference of a query row is the largest
+      // score against the first 32 keys of the sequence: both warps of a row quarter read those 32 TMEM columns
+      // themselves (same lanes), so they agree without exchanging anything, and it never changes during the item:
+      // no running maximum, no rescale, S is read once and handed back to the tensor core at once.  P can exceed 1
+      // by 2^(true max - ref) - harmless in bf16 / fp32 - and the row sum is >= 1.  If a score outruns the
+      // reference by more than 2^kAttnOverflowGuard (MUFU lanes: the row sum shows it in the epilogue; polynomial
+      // lanes: range check on the raw scores) the launch is flagged and the exact variant recomputes it.
+      const uint32_t a_sfull = ptx::smem_u32(s_full), a_sfree = ptx::smem_u32(s_free);
+      const uint32_t a_pfull = ptx::smem_u32(p_full), a_pvdone = ptx::smem_u32(pv_done);
+      uint32_t gp = 0;  // parity of the current step (g & 1)
+      for (int item = item0; item < num_items; item += item_stride, ++it) {
+        int s, h, qt;
+        decode(item, s, h, qt);
+        float m = 0.0f, pmax = -INFINITY;
+        uint64_t negm2 = 0;
+        for (int j = 0; j < nqt; ++j, ++g, gp ^= 1u) {
+          AVB_TRACE(trole, g, 0);
+          ptx::mbar_wait_s(a_sfull, gp);
+          AVB_TRACE(trole, g, 1);
+          ptx::tc_fence_after();
+          uint32_t sa[32], sb[32];
+          // reference of the row (first tile only): max over the first 32 keys; the half-1 warp reads those columns too
+          auto rowmax32 = [&](const uint32_t (&v)[32]) {
+            float t0 = -INFINITY, t1 = -INFINITY;
+            if (T >= 32) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                t0 = max3(t0, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+                t1 = max3(t1, __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) t0 = fmaxf(t0, e < T ? __uint_as_float(v[e]) : -INFINITY);
+            }
+            return fmaxf(t0, t1);
+          };
+          if (j == 0 && half != 0) {
+            ptx::tmem_ld32(tmem_S + lane_off, sa);
+            ptx::tmem_wait_ld();
+            m = rowmax32(sa);
+          }
+          ptx::tmem_ld32(tS, sa);
+          ptx::tmem_ld32(tS + 32, sb);
+          ptx::tmem_wait_ld();
+          if (j == 0) {
+            if (half == 0) m = rowmax32(sa);
+            negm2 = pack2(-m, -m);
+            pmax = -INFINITY;
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive_s(a_sfree);  // the only read of S: the tensor core may start the next S right away
+          AVB_TRACE(trole, g, 2);
+          const int nv = T - j * 128 - half * 64;  // valid key columns in this warp's half (may be <= 0)
+          if (nv < 64) {  // keys beyond the sequence end: score -inf, probability 0
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              if (e >= nv) sa[e] = 0xff800000u;
+              if (32 + e >= nv) sb[e] = 0xff800000u;
+            }
+          }
+          // ---- P = exp2(S - ref) -> packed bf16 pairs
+          uint32_t pk[32];
+          exp_chunk32(sa, negm2, pk, pmax);
+          exp_chunk32(sb, negm2, pk + 16, pmax);
+          AVB_TRACE(trole, g, 4);
+          if (g >= 1) {  // P is free and O complete once the PV / L MMAs of the previous step have finished
+            ptx::mbar_wait_s(a_pvdone, gp ^ 1u);
+            ptx::tc_fence_after();
+          }
+          if (j == 0 && pend) { epilogue(); pend = false; }
+          AVB_TRACE(trole, g, 5);
+          ptx::tmem_st32(tP, pk);
+          ptx::tmem_wait_st();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive_s(a_pfull);
+          AVB_TRACE(trole, g, 7);
+        }
+        if (pmax > m + kAttnOverflowGuard) *guard = 1;  // a polynomial lane left the safe exponent range
+        pend = true;
+        pend_h = h;
+        pend_t0 = qt * 128;
+        pend_row0 = seq_tok0(s) + (long long)(qt * 128) * tstride;
+      }
+    } else
     for (int item = item0; item < num_items; item += item_stride, ++it) {
       int s, h, qt;
       decode(item, s, h, qt);
       float m = -INFINITY;
       for (int j = 0; j < nqt; ++j, ++g) {
-        AVB_TRACE(2, g, 0);
+        AVB_TRACE(trole, g, 0);
         ptx::mbar_wait(s_full, (uint32_t)(g & 1), 30);
-        AVB_TRACE(2, g, 1);
+        AVB_TRACE(trole, g, 1);
         ptx::tc_fence_after();
         const int nv = T - j * 128 - half * 64;  // valid key columns in this warp's half (may be <= 0)
         // ---- pass 1: row maximum over this half (S is re-read in pass 2: TMEM reads are cheap, registers are not:
@@ -1225,7 +1395,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
             }
           }
         }
-        AVB_TRACE(2, g, 2);
+        AVB_TRACE(trole, g, 2);
         float* xc = s_xchg + (((g & 1) * kAttnStreams + sid) * 2) * 128;
         xc[half * 128 + r] = mx;
         asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
@@ -1234,13 +1404,13 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
         //      both warps of a row quarter see the same values and take the same decision)
         const bool need = mx > m + kAttnRescaleThreshold;  // true on the first tile (m = -inf)
         const bool any_need = __any_sync(0xffffffffu, need);
-        AVB_TRACE(2, g, 3);
+        AVB_TRACE(trole, g, 3);
         if (g >= 1) {  // P is free and O complete once the PV / L MMAs of the previous step have finished
           ptx::mbar_wait(pv_done, (uint32_t)((g - 1) & 1), 31);
           ptx::tc_fence_after();
         }
         if (j == 0 && pend) { epilogue(); pend = false; }
-        AVB_TRACE(2, g, 4);
+        AVB_TRACE(trole, g, 4);
         if (any_need) {
           const float m_new = need ? mx : m;
           if (j > 0 && half == 0) {  // half 0 rescales O and the denominator column in TMEM
@@ -1300,7 +1470,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
             ptx::tc_fence_before();
             ptx::mbar_arrive(s_free);
           }
-          AVB_TRACE(2, g, 7);
+          AVB_TRACE(trole, g, 7);
           ptx::tmem_st32(tP, pk);
           ptx::tmem_wait_st();
         }

@@ -67,6 +67,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// Hot-loop variants on 32-bit shared-space addresses: no generic-address arithmetic, no bounded-spin bookkeeping
+// (build with -DAVB_SYNC_DEBUG to get the trapping version everywhere).
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity) {
+#ifdef AVB_SYNC_DEBUG
+  uint32_t spins = 0, ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+                 : "=r"(ok) : "r"(bar_saddr), "r"(parity) : "memory");
+    if (++spins > 4000000u) { printf("avici_b200: mbarrier timeout saddr=%u block=%d thread=%d\n", bar_saddr, (int)blockIdx.x, (int)threadIdx.x); __trap(); }
+  }
+#else
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+      "@P bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(bar_saddr), "r"(parity)
+      : "memory");
+#endif
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar_saddr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_saddr) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 reads)
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

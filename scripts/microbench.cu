@@ -44,6 +44,16 @@ __global__ void ex2_bench(int iters, long long* cycles, float* sink) {
     for (int e = 0; e < 8; ++e) {
       if (MODE == 0) {
         asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[e]));
+      } else if (MODE == 2) {
+        uint32_t u = __float_as_uint(x[e]);
+        asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u));
+        x[e] = __uint_as_float(u);
+      } else if (MODE == 3) {  // packed fp32 FMA: 2 FMAs per instruction
+        unsigned long long v = ((unsigned long long)__float_as_uint(x[e]) << 32) | __float_as_uint(x[e]);
+        asm volatile("fma.rn.f32x2 %0, %0, %0, %0;" : "+l"(v));
+        x[e] = __uint_as_float((uint32_t)v);
+      } else if (MODE == 4) {
+        asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(x[e]));
       } else {
         uint32_t u = __float_as_uint(x[e]);
         asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u));
@@ -80,6 +90,19 @@ int main() {
     cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
     printf("ex2.bf16x2: %d threads/CTA: %.2f instr/clk/SM = %.2f exps/clk/SM (%s)\n", threads, (double)threads * 8 * iters / h[0],
            2.0 * threads * 8 * iters / h[0], cudaGetErrorString(e));
+    ex2_bench<2><<<148, threads>>>(iters, cyc, fs);
+    e = cudaDeviceSynchronize();
+    cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
+    printf("ex2.f16x2:  %d threads/CTA: %.2f instr/clk/SM = %.2f exps/clk/SM (%s)\n", threads, (double)threads * 8 * iters / h[0],
+           2.0 * threads * 8 * iters / h[0], cudaGetErrorString(e));
+    ex2_bench<3><<<148, threads>>>(iters, cyc, fs);
+    e = cudaDeviceSynchronize();
+    cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
+    printf("fma.f32x2:  %d threads/CTA: %.2f instr/clk/SM (%s)\n", threads, (double)threads * 8 * iters / h[0], cudaGetErrorString(e));
+    ex2_bench<4><<<148, threads>>>(iters, cyc, fs);
+    e = cudaDeviceSynchronize();
+    cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
+    printf("fma.f32:    %d threads/CTA: %.2f instr/clk/SM (%s)\n", threads, (double)threads * 8 * iters / h[0], cudaGetErrorString(e));
   }
   return 0;
 }

@@ -12,18 +12,19 @@ g = torch.Generator(device="cuda").manual_seed(0)
 qkv = torch.randn(B, n, d, 3 * H * 32, device="cuda", generator=g).to(torch.bfloat16)
 out = torch.zeros(B, n, d, H * 32, device="cuda", dtype=torch.bfloat16)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-trace = torch.zeros(3 * 4096, dtype=torch.int64, device="cuda")
+trace = torch.zeros(4 * 4096, dtype=torch.int64, device="cuda")
 lib.avb_test_attention_bf16(qkv.data_ptr(), out.data_ptr(), B, n, d, H, axis, st)  # warm
 torch.cuda.synchronize()
 lib.avb_debug_set_trace(C.c_void_p(trace.data_ptr()))
 lib.avb_test_attention_bf16(qkv.data_ptr(), out.data_ptr(), B, n, d, H, axis, st)
 torch.cuda.synchronize()
 lib.avb_debug_set_trace(None)
-t = trace.cpu().numpy().reshape(3, 512, 8)
+t = trace.cpu().numpy().reshape(4, 512, 8)
 t0 = t[t > 0].min()
 names = {0: ["wait_kv_empty", "got", "issued"], 1: ["top", "s_free", "S_issued/wait_p", "p_full", "PV_issued"],
-         2: ["top", "s_full", "pass1", "xchg+vote", "pv_done", "turn", "S_loaded", "exps_done"]}
-for role, rn in ((0, "producer"), (1, "mma"), (2, "softmax")):
+         2: ["top", "s_full", "pass1", "xchg+vote", "pv_done", "S_loaded", "turn", "exps_done"]}
+names[3] = names[2]
+for role, rn in ((0, "producer"), (1, "mma"), (2, "softmax s0"), (3, "softmax s1")):
     print(f"== {rn}: events {names[role]} (cycles since kernel start; deltas within a step)")
     for step in list(range(40, 50)):
         row = t[role, step, :len(names[role])]
@@ -31,3 +32,7 @@ for role, rn in ((0, "producer"), (1, "mma"), (2, "softmax")):
             continue
         rel = row - t0
         print(f" step {step:3d} start {rel[0]:8d} deltas {np.diff(rel).tolist()}  next_step_in {t[role, step + 1, 0] - row[0]}")
+print("== exp phases (turn acquired -> exps done), absolute cycles: stream 0 | stream 1")
+for step in range(40, 50):
+    a, b = t[2, step] - t0, t[3, step] - t0
+    print(f" step {step}: s0 [{a[6]}, {a[7]}] len {a[7] - a[6]} | s1 [{b[6]}, {b[7]}] len {b[7] - b[6]}")
