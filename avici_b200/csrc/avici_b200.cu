@@ -166,7 +166,8 @@ int launch_gemm_tc(avb_handle h, const CUtensorMap& tm_a, const CUtensorMap& tm_
 
 template <int EPI>
 int launch_ln_gemm_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, const float* bias, void* out, int ldo,
-                      int M, int N, cudaStream_t st, int num_sms, long long* launches) {
+                      int M, int N, cudaStream_t st, int num_sms, long long* launches, int seq_n = 0, int seq_d = 0,
+                      int seq_axis = 0) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(avb::ln_gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -176,7 +177,7 @@ int launch_ln_gemm_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, con
   }
   const int grid = std::min((M + 127) / 128, num_sms);
   avb::ln_gemm_tc_kernel<EPI><<<grid, avb::kLnGemmThreads, avb::kLnGemmSmemBytes, st>>>(
-      z, tm_b, bias, reinterpret_cast<bf16*>(out), ldo, M, N);
+      z, tm_b, bias, reinterpret_cast<bf16*>(out), ldo, M, N, seq_n, seq_d, seq_axis);
   if (launches) ++*launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ln_gemm_tc launch: %s", cudaGetErrorString(e));
@@ -641,7 +642,9 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
     int rc;
     // attention half: LN -> QKV -> attention -> out-proj + residual
     { ProfScope ps(h, AVB_PROF_QKV, st);  // LayerNorm fused into the projection's prologue
-      if ((rc = launch_ln_gemm_tc<0>(h, z, W.tm_wqkv, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, st, h->num_sms, &h->launches))) return rc; }
+      // rows in sequence-major order of `axis`, output in the attention kernel's operand layout
+      if ((rc = launch_ln_gemm_tc<2>(h, z, W.tm_wqkv, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, st, h->num_sms, &h->launches,
+                                     n, d, axis))) return rc; }
     { ProfScope ps(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
       if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches,
                                     reinterpret_cast<int*>(w8 + L.guard_off)))) return rc; }
@@ -886,9 +889,22 @@ int avb_test_attention_bf16(const void* qkv, void* out, int32_t B, int32_t n, in
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device");
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  static int* guard = nullptr;  // test entry point: one process-wide guard word
+  static int* guard = nullptr;  // test entry point: one process-wide guard word and repack buffer
+  static void* packed = nullptr;
+  static size_t packed_bytes = 0;
   if (!guard && cudaMalloc(&guard, sizeof(int)) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "cudaMalloc(guard) failed");
-  return launch_attention_tc(nullptr, qkv, out, B, n, d, H, axis, reinterpret_cast<cudaStream_t>(stream), sms, nullptr, guard);
+  const size_t need = (size_t)B * n * d * 3 * H * 32 * sizeof(bf16);
+  if (packed_bytes < need) {
+    if (packed) cudaFree(packed);
+    packed = nullptr; packed_bytes = 0;
+    if (cudaMalloc(&packed, need) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "cudaMalloc(repack buffer) failed");
+    packed_bytes = need;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const bool prepacked = getenv("AVB_ATTN_PREPACKED") != nullptr;  // profiling scripts: time the attention alone
+  if (prepacked) return launch_attention_tc(nullptr, qkv, out, B, n, d, H, axis, st, sms, nullptr, guard);
+  avb::repack_qkv_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(packed), B, n, d, H, axis);
+  return launch_attention_tc(nullptr, packed, out, B, n, d, H, axis, st, sms, nullptr, guard);
 }
 
 }  // extern "C"

@@ -384,12 +384,26 @@ outproj_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 // L2 prefetch of the 32 fp32 rows (16 KB = 128 lines) a LayerNorm warp will normalise in its NEXT tile: the producer
 // warps can only keep ~8 rows of loads in flight in registers, far less than HBM latency x bandwidth needs, so the
 // next tile is pulled into L2 while the current one is processed.
-__device__ __forceinline__ void prefetch_rows_l2(const float* __restrict__ z, int M, int grow0, int lane) {
+// Sequence-major row order of the QKV projection (see ln_gemm_tc_kernel<2>): GEMM row m = seq * T + pos, where a
+// sequence is what the following attention attends over.  axis 0 (attend over d): seq = (b, i), pos = j, i.e. m is the
+// token index itself.  axis 1 (attend over n): seq = (b, j), pos = i, token = (b*n + i)*d + j.
+struct RowMap {
+  int n, d, axis;
+  __device__ __forceinline__ int token(int m) const {
+    if (axis == 0) return m;
+    const unsigned nd = (unsigned)n * (unsigned)d, b = (unsigned)m / nd, rem = (unsigned)m - b * nd;
+    const unsigned j = rem / (unsigned)n, i = rem - j * (unsigned)n;
+    return (int)((b * (unsigned)n + i) * (unsigned)d + j);
+  }
+};
+
+__device__ __forceinline__ void prefetch_rows_l2(const float* __restrict__ z, int M, int grow0, int lane,
+                                                 const RowMap rm = RowMap{0, 0, 0}) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int line = i * 32 + lane;           // 128-byte line index inside the 32 x 512 B block
     const int row = grow0 + (line >> 2);
-    if (row < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(z + (size_t)row * 128 + (line & 3) * 32));
+    if (row < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(z + (size_t)rm.token(row) * 128 + (line & 3) * 32));
   }
 }
 
@@ -401,7 +415,7 @@ __device__ __forceinline__ void prefetch_rows_l2(const float* __restrict__ z, in
 //   a_tile: smem address of the A tile; row0: first row of this warp inside the tile (multiple of 32)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ln_warp_rows_to_umma_tile(const float* __restrict__ z, int M, int grow0, uint32_t a_tile,
-                                                          int row0, int lane) {
+                                                          int row0, int lane, const RowMap rm = RowMap{0, 0, 0}) {
   const int rs = lane >> 3, j = lane & 7;
   const float4* zp = reinterpret_cast<const float4*>(z) + j;
   float4 cur[2][4], nxt[2][4];
@@ -409,9 +423,10 @@ __device__ __forceinline__ void ln_warp_rows_to_umma_tile(const float* __restric
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int grow = grow0 + r0 + u * 4 + rs;
+      const int tok = grow < M ? rm.token(grow) : 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        dst[u][k] = grow < M ? __ldcg(zp + (size_t)grow * 32 + k * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[u][k] = grow < M ? __ldcg(zp + (size_t)tok * 32 + k * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   load(cur, 0);
@@ -477,10 +492,20 @@ constexpr int kLnGemmStagePitch = 64 * 2 + 16;             // bytes per staged r
 constexpr int kLnGemmStageBytes = 8 * 32 * kLnGemmStagePitch;  // 8 epilogue warps x 32 rows = 36 KB
 constexpr int kLnGemmSmemBytes = 2 * kLnGemmABytes + kLnGemmBStages * kLnGemmBBytes + kLnGemmStageBytes + 1024 + 256;
 
-template <int EPI>  // 0: store, 1: ReLU + store
+//   EPI 2 (the QKV projection in front of the tensor-core attention): rows are processed in SEQUENCE-MAJOR order
+//   (RowMap: the LN producers gather the fp32 rows, a 512-byte segment each, in whatever order) and the output is
+//   written in the attention kernel's operand layout
+//       out[seq][w = q,k,v][head][pos][32 ch]   with the four 16-byte chunks of a 64-byte (pos, head) row stored at
+//       chunk ^ ((pos >> 1) & 3)                 (the UMMA 64B-swizzle pattern, applied here once)
+//   so that a [128 positions x 32 ch] Q / K / V tile is one contiguous 8 KB block whose byte image IS the swizzled
+//   shared-memory tile: the attention producer fetches it with a single 1-D bulk copy (no gather, no per-row TMA
+//   cost, every DRAM sector used), for both attention axes.  N must be 3 * H * 32 with 32-channel heads.
+template <int EPI>  // 0: store, 1: ReLU + store, 2: store in the attention operand layout
 __global__ void __launch_bounds__(kLnGemmThreads, 1)
 ln_gemm_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorMap tm_b,
-                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int M, int N) {
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int M, int N,
+                  int seq_n, int seq_d, int seq_axis) {
+  const RowMap rm{seq_n, seq_d, EPI == 2 ? seq_axis : 0};
   constexpr int ST = kLnGemmBStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -522,9 +547,9 @@ ln_gemm_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorM
     int it = 0;
     for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
       const int buf = it & 1;
-      prefetch_rows_l2(z, M, (mt + (int)gridDim.x) * 128 + warp * 32, lane);
+      prefetch_rows_l2(z, M, (mt + (int)gridDim.x) * 128 + warp * 32, lane, rm);
       ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 40);
-      ln_warp_rows_to_umma_tile(z, M, mt * 128 + warp * 32, ptx::smem_u32(sA + buf * kLnGemmABytes), warp * 32, lane);
+      ln_warp_rows_to_umma_tile(z, M, mt * 128 + warp * 32, ptx::smem_u32(sA + buf * kLnGemmABytes), warp * 32, lane, rm);
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&a_full[buf]);
     }
@@ -585,6 +610,7 @@ ln_gemm_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorM
     const uint32_t stage_warp = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 32 * kLnGemmStagePitch);
     const uint32_t stage_row = stage_warp + (uint32_t)(lane * kLnGemmStagePitch);
     const int sub = lane >> 3, l8 = lane & 7;  // copy-out: 4 rows per warp store, 8 lanes x 16 B per row
+    const int seq_T = seq_axis == 0 ? seq_d : seq_n, seq_H = N / 96;  // EPI 2: sequence length, heads (N = 3 * H * 32)
     int acc_it = 0;
     for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
       for (int c = 0; c < num_c; ++c, ++acc_it) {
@@ -625,6 +651,27 @@ ln_gemm_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorM
             }
           }
           __syncwarp();  // the 32 staged rows are written and read by this warp only
+          if (EPI == 2) {
+            // 64 staged columns = heads (hd0, hd0 + 1) of q, k or v.  A warp store covers 8 consecutive positions of
+            // one head = 512 contiguous bytes (lane = chunk * 8 + row: conflict-free reads of the padded stage).
+            const int colp = col0 + pc * 64, w = colp >> 8, hd0 = (colp & 255) >> 5;
+            const int r8 = lane & 7, c4 = lane >> 3;
+#pragma unroll
+            for (int rr = 0; rr < 32; rr += 8) {
+              const int row = rr + r8;
+              const int grow = mt * 128 + q * 32 + row;
+              const unsigned sq = (unsigned)grow / (unsigned)seq_T, pos = (unsigned)grow - sq * (unsigned)seq_T;
+              __nv_bfloat16* dst = out + ((((size_t)sq * 3 + w) * seq_H + hd0) * seq_T + pos) * 32 + ((c4 ^ ((pos >> 1) & 3)) << 3);
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                uint4 pk;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w)
+                             : "r"(stage_warp + (uint32_t)(row * kLnGemmStagePitch + hh * 64 + c4 * 16)));
+                if (grow < M) *reinterpret_cast<uint4*>(dst + (size_t)hh * seq_T * 32) = pk;
+              }
+            }
+          } else {
 #pragma unroll
           for (int rr = 0; rr < 32; rr += 4) {
             const int row = rr + sub;
@@ -634,6 +681,7 @@ ln_gemm_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorM
                          : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w)
                          : "r"(stage_warp + (uint32_t)(row * kLnGemmStagePitch + l8 * 16)));
             if (grow < M) *reinterpret_cast<uint4*>(out + (size_t)grow * ldo + col0 + pc * 64 + l8 * 8) = pk;
+          }
           }
           __syncwarp();
         }
@@ -888,10 +936,11 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
 
 // ------------------------------------------------------------------------------------------
 // Flash-style axial attention on tensor cores.  head dim 32, 128-query x 128-key tiles.
-//   qkv viewed through ONE 4-D tensor map {3*H*32, d, n, B}; a work item (s, h, qt) loads its
-//   [128 x 32] Q tile and streams [128 x 32] K / V tiles with a box of {32,128,1,1} (attend over d)
-//   or {32,1,128,1} (attend over n): the attended axis is only a different TMA stride, z is never
-//   transposed.  Rows beyond the sequence end are zero-filled by TMA and masked in the softmax.
+//   qkv comes from ln_gemm_tc_kernel<2> in the operand layout [seq][q,k,v][head][pos][32 ch] (pre-swizzled):
+//   a work item (s, h, qt) fetches its [128 x 32] Q tile and streams the [128 x 32] K / V tiles of its sequence,
+//   each ONE contiguous 1-D bulk copy (<= 8 KB) whose bytes are the 64B-swizzled shared-memory image.  The
+//   attended axis only changes the row order of the projection that wrote qkv; z is never transposed.  A ragged
+//   last tile copies only its valid rows: the rest of the slot holds older (finite) rows, which the softmax masks.
 //   S = Q K^T : M=128, N<=128, K=32   (A,B K-major, 64B swizzle)        -> TMEM S (fp32)
 //   P = exp2(S - m) (q is pre-scaled by log2e/sqrt(32)) -> bf16 pairs in TMEM (A operand from TMEM:
 //              no shared-memory round trip; measured: smem bandwidth was the limiter with P in smem)
@@ -1046,8 +1095,8 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   if (warp == 1 && lane == 0) {
     for (int sid = 0; sid < kAttnStreams; ++sid) {
       uint64_t* b = bars_all + sid * kBarsPerStream;
-      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&b[i], 32); ptx::mbar_init(&b[2 + i], 1); }  // q_full (32 producer lanes), q_empty
-      for (int i = 0; i < NS; ++i) { ptx::mbar_init(&b[4 + i], 32); ptx::mbar_init(&b[4 + NS + i], 1); }  // kv_full, kv_empty
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&b[i], 1); ptx::mbar_init(&b[2 + i], 1); }  // q_full (expect_tx), q_empty
+      for (int i = 0; i < NS; ++i) { ptx::mbar_init(&b[4 + i], 1); ptx::mbar_init(&b[4 + NS + i], 1); }  // kv_full, kv_empty
       ptx::mbar_init(&b[4 + 2 * NS + 0], 1);                    // s_full
       ptx::mbar_init(&b[4 + 2 * NS + 1], kAttnSoftmaxThreads);  // s_free
       ptx::mbar_init(&b[4 + 2 * NS + 2], kAttnSoftmaxThreads);  // p_full
@@ -1060,10 +1109,12 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
-  if (threadIdx.x >= 128 && threadIdx.x < 256) {
-    s_ones[threadIdx.x - 128] = 0x3F803F80u;
-    ptx::fence_proxy_async();
-  }
+  if (threadIdx.x >= 128 && threadIdx.x < 256) s_ones[threadIdx.x - 128] = 0x3F803F80u;
+  // the Q / K / V slots start as zeros: a ragged tile leaves the tail of its slot untouched, and whatever the tensor
+  // core reads there must be finite (0 x NaN would poison O through the masked, zero-probability keys)
+  for (int i = threadIdx.x; i < kAttnStreams * kAttnStreamBytes / 16; i += kAttnThreads)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -1103,43 +1154,39 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   };
 
   if (warp < 2) {
-    // ======================= producer warp of stream `sid`: cp.async gathers of [128 x 32] bf16 tiles
-    // Measured on B200: the TMA unit needs ~3.6 cycles per box ROW whatever its width, i.e. ~450 cycles for a
-    // 128-row x 64-byte tile - more than this kernel can afford per K/V tile.  A warp-wide 16-byte cp.async
-    // moves 8 such rows per instruction, so the producers gather through the LSU path instead and write the
-    // 64B-swizzle pattern the UMMA descriptors expect (16-byte chunk index XOR ((row >> 1) & 3)).
-    const long long row_stride = axis == 0 ? (long long)(3 * HD) : (long long)d * (3 * HD);  // elements between positions
-    const int ch = lane & 3;
-    const uint32_t lane_dst = (uint32_t)((lane >> 2) * 64 + ((ch ^ ((lane >> 3) & 3)) << 4));
-    auto load_tile = [&](uint8_t* tile, const __nv_bfloat16* col0, int t0) {
-      // col0: element (position 0 of the sequence, first channel of the tile); rows t0 .. t0+127
-      const uint32_t dst = ptx::smem_u32(tile) + lane_dst;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int t = t0 + k * 8 + (lane >> 2);
-        const int tc = t < T ? t : T - 1;  // keep the address in range; src_bytes = 0 zero-fills
-        ptx::cp_async_16(dst + k * 512, col0 + (long long)tc * row_stride + ch * 8, t < T ? 16u : 0u);
-      }
-    };
-    long long g = 0;
+    // ======================= producer warp of stream `sid`: one bulk copy per [128 x 32] bf16 tile
+    // (Measured on B200 before the operand layout existed: a tensor-map gather costs the TMA unit ~3.6 cycles per box
+    //  row whatever its width, a warp of 16-byte cp.async ~1600 cycles of issue per K/V stage and 3x the DRAM sectors.)
+    const size_t head_elems = (size_t)T * 32;  // one (sequence, q|k|v, head) block
+    uint32_t g = 0;
     int it = 0;
     for (int item = item0; item < num_items; item += item_stride, ++it) {
       int s, h, qt;
       decode(item, s, h, qt);
-      const __nv_bfloat16* base = qkv + seq_tok0(s) * (3 * HD) + h * 32;
+      const __nv_bfloat16* qsrc = qkv + ((size_t)s * 3 * H + h) * head_elems;
+      const __nv_bfloat16* ksrc = qsrc + (size_t)H * head_elems;
+      const __nv_bfloat16* vsrc = ksrc + (size_t)H * head_elems;
       const int qb = it & 1;
       ptx::mbar_wait(&q_empty[qb], (uint32_t)((it >> 1) & 1) ^ 1, 10, 200u);
-      load_tile(sQ + qb * kAttnTileBytes, base, qt * 128);
-      ptx::cp_async_mbar_arrive(&q_full[qb]);
+      if (ptx::elect_one()) {
+        const uint32_t bytes = (uint32_t)min(128, T - qt * 128) * 64u;
+        ptx::mbar_expect_tx(&q_full[qb], bytes);
+        ptx::bulk_load(sQ + qb * kAttnTileBytes, qsrc + (size_t)qt * 128 * 32, bytes, &q_full[qb]);
+      }
+      __syncwarp();
       for (int j = 0; j < nqt; ++j, ++g) {
         const int st = (int)(g % NS);
         AVB_TRACE(0, g, 0);
         ptx::mbar_wait(&kv_empty[st], (uint32_t)((g / NS) & 1) ^ 1, 11, 200u);
         AVB_TRACE(0, g, 1);
-        uint8_t* sk = sKV + st * 2 * kAttnTileBytes;
-        load_tile(sk, base + HD, j * 128);
-        load_tile(sk + kAttnTileBytes, base + 2 * HD, j * 128);
-        ptx::cp_async_mbar_arrive(&kv_full[st]);
+        if (ptx::elect_one()) {
+          uint8_t* sk = sKV + st * 2 * kAttnTileBytes;
+          const uint32_t bytes = (uint32_t)min(128, T - j * 128) * 64u;
+          ptx::mbar_expect_tx(&kv_full[st], 2 * bytes);
+          ptx::bulk_load(sk, ksrc + (size_t)j * 128 * 32, bytes, &kv_full[st]);
+          ptx::bulk_load(sk + kAttnTileBytes, vsrc + (size_t)j * 128 * 32, bytes, &kv_full[st]);
+        }
+        __syncwarp();
         AVB_TRACE(0, g, 2);
       }
     }
@@ -1163,8 +1210,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
         if (j == 0) { ptx::mbar_wait(&q_full[it & 1], (uint32_t)((it >> 1) & 1), 20, 40u); }
         const int st = (int)(g % NS);
         ptx::mbar_wait(&kv_full[st], (uint32_t)((g / NS) & 1), 21, 40u);
-        ptx::fence_proxy_async();  // cp.async (generic proxy) writes -> visible to the tensor core's async-proxy reads
-        ptx::tc_fence_after();
+        ptx::tc_fence_after();  // bulk copies and the tensor core both work through the async proxy: no proxy fence
         const int kc = kcols(j);
         const uint32_t idesc = kc == 128 ? idesc_s : ptx::make_idesc_bf16(128, kc, 0, 0);
         const uint64_t dk = dK + (uint64_t)st * kStageStep;
@@ -1491,6 +1537,26 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// Test helper: token-major qkv[tok][3*H*32] -> the attention operand layout of ln_gemm_tc_kernel<2> (one thread per
+// 16-byte chunk).  The product path never runs this: its QKV projection writes the operand layout directly.
+__global__ void repack_qkv_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int n, int d,
+                                  int H, int axis) {
+  const size_t chunks = (size_t)B * n * d * 3 * H * 4;
+  const int T = axis == 0 ? d : n;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < chunks; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx & 3);
+    size_t r = idx >> 2;
+    const int h = (int)(r % H); r /= H;
+    const int w = (int)(r % 3); r /= 3;
+    const size_t tok = r;
+    const int j = (int)(tok % d), i = (int)((tok / d) % n), b = (int)(tok / ((size_t)n * d));
+    const size_t seq = axis == 0 ? (size_t)b * n + i : (size_t)b * d + j;
+    const int pos = axis == 0 ? j : i;
+    const uint4 v = *reinterpret_cast<const uint4*>(in + tok * (size_t)(3 * H * 32) + (size_t)(w * H + h) * 32 + c4 * 8);
+    *reinterpret_cast<uint4*>(out + (((seq * 3 + w) * H + h) * T + pos) * 32 + ((c4 ^ ((pos >> 1) & 3)) << 3)) = v;
+  }
 }
 
 }  // namespace avb

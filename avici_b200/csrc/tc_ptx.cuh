@@ -125,6 +125,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (contiguous bytes, 16-byte aligned, size a multiple of 16); completes on `bar`
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---------------------------------------------------------------- cp.async (LDGSTS) gathers
 // 16-byte global -> shared copy, L2-only; src_bytes = 0 zero-fills the destination (row past the end).
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
