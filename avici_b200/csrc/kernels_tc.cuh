@@ -974,6 +974,15 @@ constexpr int kAttnPolyEvery = 4;  // 1 of every kAttnPolyEvery exponent pairs i
 #ifndef AVB_ATTN_POLY_EVERY
 #define AVB_ATTN_POLY_EVERY 4
 #endif
+// Exp-phase turn taking (fast variant).  The MUFU pipe belongs to an SM sub-partition and is shared round-robin, so
+// two streams left alone drift into a convoy: all four softmax warps of a sub-partition run their exponentials
+// together (each at a quarter of the MUFU rate), finish together, and leave the pipe idle together while they wait
+// for S / pv_done and move TMEM.  The streams therefore alternate explicitly, per sub-partition (row quarter q):
+// stream 1 starts the exponentials of its step g once stream 0 has issued those of its step g, stream 0 starts step g
+// once stream 1 is through step g-1; one stream's non-MUFU work then overlaps the other's exponentials.
+#ifndef AVB_ATTN_TURNS
+#define AVB_ATTN_TURNS 0
+#endif
 constexpr float kAttnOverflowGuard = 64.0f;  // log2 units: a tile exceeding the stale row max by more flags the launch
 
 // exp2 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = i + f, f in [-0.5, 0.5], degree-3 minimax
@@ -1327,6 +1336,12 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       const uint32_t a_sfull = ptx::smem_u32(s_full), a_sfree = ptx::smem_u32(s_free);
       const uint32_t a_pfull = ptx::smem_u32(p_full), a_pvdone = ptx::smem_u32(pv_done);
       uint32_t gp = 0;  // parity of the current step (g & 1)
+      const uint32_t a_myturn = ptx::smem_u32(&x_full_all[sid * 4 + q]);
+      const uint32_t a_otherturn = ptx::smem_u32(&x_full_all[(sid ^ 1) * 4 + q]);
+      // steps of the other stream (stream 1 never has more than stream 0: its first item is the later one)
+      const int other_item0 = (int)blockIdx.x * kAttnStreams + (sid ^ 1);
+      const long long other_steps =
+          other_item0 < num_items ? (long long)((num_items - other_item0 + item_stride - 1) / item_stride) * nqt : 0;
       for (int item = item0; item < num_items; item += item_stride, ++it) {
         int s, h, qt;
         decode(item, s, h, qt);
@@ -1378,9 +1393,15 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
             }
           }
           // ---- P = exp2(S - ref) -> packed bf16 pairs
+          if (AVB_ATTN_TURNS) {
+            if (sid == 0) { if (g >= 1 && g - 1 < other_steps) ptx::mbar_wait_s(a_otherturn, gp ^ 1u); }
+            else ptx::mbar_wait_s(a_otherturn, gp);
+          }
+          AVB_TRACE(trole, g, 3);
           uint32_t pk[32];
           exp_chunk32(sa, negm2, pk, pmax);
           exp_chunk32(sb, negm2, pk + 16, pmax);
+          if (AVB_ATTN_TURNS) ptx::mbar_arrive_s(a_myturn);
           AVB_TRACE(trole, g, 4);
           if (g >= 1) {  // P is free and O complete once the PV / L MMAs of the previous step have finished
             ptx::mbar_wait_s(a_pvdone, gp ^ 1u);
