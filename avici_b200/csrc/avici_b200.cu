@@ -184,8 +184,8 @@ int launch_ln_gemm_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, con
   return AVB_OK;
 }
 
-int launch_outproj_tc(avb_handle h, const CUtensorMap& tm_a, const CUtensorMap& tm_w, const float* bias, float* z, int M,
-                      cudaStream_t st, int num_sms, long long* launches) {
+int launch_outproj_tc(avb_handle h, const void* attn, const CUtensorMap& tm_w, const float* bias, float* z, int M,
+                      int n, int d, int axis, cudaStream_t st, int num_sms, long long* launches) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(avb::outproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -194,7 +194,8 @@ int launch_outproj_tc(avb_handle h, const CUtensorMap& tm_a, const CUtensorMap& 
     attr_set = true;
   }
   const int grid = std::min((M + 127) / 128, num_sms);
-  avb::outproj_tc_kernel<<<grid, avb::kOutProjThreads, avb::kOutProjSmemBytes, st>>>(tm_a, tm_w, bias, z, M);
+  avb::outproj_tc_kernel<<<grid, avb::kOutProjThreads, avb::kOutProjSmemBytes, st>>>(
+      reinterpret_cast<const bf16*>(attn), tm_w, bias, z, M, n, d, axis);
   if (launches) ++*launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "outproj_tc launch: %s", cudaGetErrorString(e));
@@ -280,7 +281,7 @@ BlockWs block_ws_layout(const avb_config& c, size_t ntok) {
   if (c.compute_dtype == AVB_DTYPE_BF16) {
     w.xhat_off = off;  // (the LayerNorm output lives only in shared memory)
     w.big_off = off;  off = align_up(off + ntok * std::max(3 * HD, F) * 2, 1024);
-    w.attn_off = off; off = align_up(off + ntok * HD * 2, 1024);
+    w.attn_off = off; off = align_up(off + align_up(ntok, 128) * HD * 2, 1024);  // whole 128-row tiles (A-operand layout)
     w.guard_off = off; off += 1024;  // overflow guard of the fast attention kernel (launch_attention_tc)
   } else {
     w.big_off = off;  off = align_up(off + ntok * std::max(3 * HD, F) * 4, 1024);
@@ -365,8 +366,9 @@ int avb_create(avb_handle* out, const avb_config* cfg) {
   if (cfg->out_dim < 1 || cfg->out_dim > 128) return fail(nullptr, AVB_ERR_INVALID, "unsupported out_dim=%d (1..128)", cfg->out_dim);
   if (cfg->compute_dtype != AVB_DTYPE_F32 && cfg->compute_dtype != AVB_DTYPE_BF16)
     return fail(nullptr, AVB_ERR_INVALID, "unknown compute_dtype=%d", cfg->compute_dtype);
-  if (cfg->compute_dtype == AVB_DTYPE_BF16 && (cfg->num_heads * cfg->key_size * 3) % 256 != 0)
-    return fail(nullptr, AVB_ERR_INVALID, "bf16 path needs 3*num_heads*key_size to be a multiple of 256");
+  if (cfg->compute_dtype == AVB_DTYPE_BF16 && cfg->num_heads != 2 * avb::kOutProjKB)
+    return fail(nullptr, AVB_ERR_INVALID, "the bf16 tensor-core path is built for num_heads=%d (got %d); use compute_dtype fp32",
+                2 * avb::kOutProjKB, cfg->num_heads);
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(e));
@@ -636,9 +638,6 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
   if (c.compute_dtype == AVB_DTYPE_BF16) {
     bf16* qkv = reinterpret_cast<bf16*>(w8 + L.big_off);
     bf16* attn = reinterpret_cast<bf16*>(w8 + L.attn_off);
-    CUtensorMap tm_attn;
-    if (!make_tmap_2d(&tm_attn, attn, ntok, HD, 128))
-      return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for activations");
     int rc;
     // attention half: LN -> QKV -> attention -> out-proj + residual
     { ProfScope ps(h, AVB_PROF_QKV, st);  // LayerNorm fused into the projection's prologue
@@ -649,9 +648,7 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
       if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches,
                                     reinterpret_cast<int*>(w8 + L.guard_off)))) return rc; }
     { ProfScope ps(h, AVB_PROF_OUT, st);
-      if (HD == 64 * avb::kOutProjKB) {
-        if ((rc = launch_outproj_tc(h, tm_attn, W.tm_wo, W.bo, z, M, st, h->num_sms, &h->launches))) return rc;
-      } else if ((rc = launch_gemm_tc<128, 2>(h, tm_attn, W.tm_wo, W.bo, z, k, M, k, HD, st, h->num_sms, &h->launches))) return rc; }
+      if ((rc = launch_outproj_tc(h, attn, W.tm_wo, W.bo, z, M, n, d, axis, st, h->num_sms, &h->launches))) return rc; }
     // FFN half: LN -> Linear + ReLU -> Linear + residual
     { ProfScope ps(h, AVB_PROF_FFN1, st);  // whole FFN sub-layer in one kernel (LN, up-projection, ReLU, down-projection, residual)
       if ((rc = launch_ffn_tc(h, z, W.tm_w1c, W.tm_w2, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches))) return rc; }
@@ -893,7 +890,7 @@ int avb_test_attention_bf16(const void* qkv, void* out, int32_t B, int32_t n, in
   static void* packed = nullptr;
   static size_t packed_bytes = 0;
   if (!guard && cudaMalloc(&guard, sizeof(int)) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "cudaMalloc(guard) failed");
-  const size_t need = (size_t)B * n * d * 3 * H * 32 * sizeof(bf16);
+  const size_t need = ((size_t)B * n * d * 3 + (((size_t)B * n * d + 127) / 128) * 128) * H * 32 * sizeof(bf16);
   if (packed_bytes < need) {
     if (packed) cudaFree(packed);
     packed = nullptr; packed_bytes = 0;
@@ -903,8 +900,15 @@ int avb_test_attention_bf16(const void* qkv, void* out, int32_t B, int32_t n, in
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static const bool prepacked = getenv("AVB_ATTN_PREPACKED") != nullptr;  // profiling scripts: time the attention alone
   if (prepacked) return launch_attention_tc(nullptr, qkv, out, B, n, d, H, axis, st, sms, nullptr, guard);
-  avb::repack_qkv_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(packed), B, n, d, H, axis);
-  return launch_attention_tc(nullptr, packed, out, B, n, d, H, axis, st, sms, nullptr, guard);
+  // token-major test tensors <-> the kernels' operand layouts; `out` must hold whole 128-row tiles in the packed form,
+  // so the packed output lives behind the packed input in the scratch buffer
+  bf16* pin = reinterpret_cast<bf16*>(packed);
+  bf16* pout = pin + (size_t)B * n * d * 3 * H * 32;
+  avb::repack_qkv_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const bf16*>(qkv), pin, B, n, d, H, axis);
+  const int rc = launch_attention_tc(nullptr, pin, pout, B, n, d, H, axis, st, sms, nullptr, guard);
+  if (rc != AVB_OK) return rc;
+  avb::unpack_attn_kernel<<<sms * 8, 256, 0, st>>>(pout, reinterpret_cast<bf16*>(out), B, n, d, H, axis);
+  return cudaGetLastError() == cudaSuccess ? AVB_OK : fail(nullptr, AVB_ERR_CUDA, "unpack_attn launch failed");
 }
 
 }  // extern "C"

@@ -48,6 +48,42 @@ __device__ long long* g_attn_trace = nullptr;
 #define AVB_TRACE(role, step, ev) do { (void)trace; } while (0)
 #endif
 
+// Sequence-major row order of the attention sub-layer (QKV projection ln_gemm_tc_kernel<2>, attention, out-projection): GEMM row m = seq * T + pos, where a
+// sequence is what the following attention attends over.  axis 0 (attend over d): seq = (b, i), pos = j, i.e. m is the
+// token index itself.  axis 1 (attend over n): seq = (b, j), pos = i, token = (b*n + i)*d + j.
+struct RowMap {
+  int n, d, axis;
+  __device__ __forceinline__ int token(int m) const {
+    if (axis == 0) return m;
+    const unsigned nd = (unsigned)n * (unsigned)d, b = (unsigned)m / nd, rem = (unsigned)m - b * nd;
+    const unsigned j = rem / (unsigned)n, i = rem - j * (unsigned)n;
+    return (int)((b * (unsigned)n + i) * (unsigned)d + j);
+  }
+  // tokens of rows m, m + step, m + 2*step, ... (count of them) without a division per row: the position inside the
+  // sequence advances by `step` and carries into (j, b)
+  template <int COUNT>
+  __device__ __forceinline__ void tokens(int m, int step, int M, int (&tok)[COUNT]) const {
+    if (axis == 0) {
+#pragma unroll
+      for (int k = 0; k < COUNT; ++k) tok[k] = m + k * step < M ? m + k * step : -1;
+      return;
+    }
+    const unsigned nd = (unsigned)n * (unsigned)d;
+    unsigned b = (unsigned)m / nd;
+    const unsigned rem = (unsigned)m - b * nd;
+    unsigned j = rem / (unsigned)n, i = rem - j * (unsigned)n;
+#pragma unroll
+    for (int k = 0; k < COUNT; ++k) {
+      tok[k] = m + k * step < M ? (int)((b * (unsigned)n + i) * (unsigned)d + j) : -1;
+      i += (unsigned)step;
+      while (i >= (unsigned)n) {
+        i -= (unsigned)n;
+        if (++j >= (unsigned)d) { j = 0; ++b; }
+      }
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------
 // Residual update of a [32 rows x 32 cols] fp32 block held row-per-thread in registers (the tcgen05.ld layout):
 //     zblk[r][c] += acc[r][c] + bias[c]
@@ -57,6 +93,43 @@ __device__ long long* g_attn_trace = nullptr;
 //   stage: smem address of this warp's 4 KB stage; zblk: &z[row0][col0]; ldz: row pitch in floats;
 //   rows_valid: number of rows of the block that exist (<= 32)
 // ------------------------------------------------------------------------------------------
+template <class RowPtr>  // rowptr(row) -> float* of the block's row `row` (first of its 32 columns), nullptr if absent
+__device__ __forceinline__ void residual_add_block_32x32_rows(const uint32_t (&acc)[32], const float* __restrict__ bias,
+                                                              uint32_t stage, RowPtr rowptr, int lane) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {  // thread = row `lane`: 16-byte chunk c goes to slot c ^ (lane & 7)
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + c);
+    uint4 pk;
+    pk.x = __float_as_uint(__uint_as_float(acc[c * 4 + 0]) + b4.x);
+    pk.y = __float_as_uint(__uint_as_float(acc[c * 4 + 1]) + b4.y);
+    pk.z = __float_as_uint(__uint_as_float(acc[c * 4 + 2]) + b4.z);
+    pk.w = __float_as_uint(__uint_as_float(acc[c * 4 + 3]) + b4.w);
+    ptx::st_shared_v4(stage + (uint32_t)(lane * 128 + ((c ^ (lane & 7)) << 4)), pk);
+  }
+  __syncwarp();
+  const int sub = lane >> 3, l8 = lane & 7;
+  float4 zr[8];
+  float4* zp[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float* rp = rowptr(i * 4 + sub);
+    zp[i] = rp ? reinterpret_cast<float4*>(rp) + l8 : nullptr;
+    zr[i] = zp[i] ? __ldcg(zp[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + sub;
+    uint4 a;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+                 : "r"(stage + (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4))));
+    float4 o = zr[i];
+    o.x += __uint_as_float(a.x); o.y += __uint_as_float(a.y); o.z += __uint_as_float(a.z); o.w += __uint_as_float(a.w);
+    if (zp[i]) *zp[i] = o;
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ void residual_add_block_32x32(const uint32_t (&acc)[32], const float* __restrict__ bias,
                                                          uint32_t stage, float* zblk, int ldz, int rows_valid, int lane) {
 #pragma unroll
@@ -261,7 +334,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 // Attention output projection + residual, in place on the fp32 residual stream (model.py:59-65):
 //     z[M,128] += attn[M,K] @ Wo_t[128,K]^T + bo            (K = heads * 32 = 256)
 //   The [128 x K] weight stays resident in shared memory for the whole (persistent) CTA; only the attention
-//   output streams through a TMA ring.  Accumulators are double-buffered in TMEM; eight epilogue warps
+//   output streams through a ring.  The attention kernel writes it in this kernel's A-operand layout,
+//       attn[tile = m >> 7][head][m & 127][32 ch], 16-byte chunks at chunk ^ ((m >> 1) & 3)   (64B swizzle image)
+//   with m the SEQUENCE-MAJOR row index (RowMap), so a stage (two heads = one K block of 64) is one contiguous
+//   16 KB bulk copy and the attention epilogue's stores are contiguous runs instead of one 64-byte piece per token.
+//   Only the epilogue knows about tokens: row m updates z[token(m)], a 512-byte row each.
+//   Accumulators are double-buffered in TMEM; eight epilogue warps
 //   (TMEM lane quarter x 64-column half) do the residual update through smem-transposed, coalesced accesses.
 //   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM alloc   warps 4-11: epilogue
 // ------------------------------------------------------------------------------------------
@@ -271,8 +349,9 @@ constexpr int kOutProjKB = 4;  // K blocks of 64 (K = 256)
 constexpr int kOutProjSmemBytes = kOutProjKB * 128 * 128 + kOutProjStages * 128 * 128 + 8 * 4096 + 1024 + 256;
 
 __global__ void __launch_bounds__(kOutProjThreads, 1)
-outproj_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
-                  const float* __restrict__ bias, float* __restrict__ z, int M) {
+outproj_tc_kernel(const __nv_bfloat16* __restrict__ attn, const __grid_constant__ CUtensorMap tm_w,
+                  const float* __restrict__ bias, float* __restrict__ z, int M, int seq_n, int seq_d, int seq_axis) {
+  const RowMap rm{seq_n, seq_d, seq_axis};
   constexpr int ST = kOutProjStages, KB = kOutProjKB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -290,7 +369,7 @@ outproj_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int num_m = (M + 127) / 128;
 
-  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_a); ptx::prefetch_tmap(&tm_w); }
+  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tm_w);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < ST; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 256); }
@@ -317,8 +396,8 @@ outproj_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       for (int kb = 0; kb < KB; ++kb) {
         ptx::mbar_wait(&empty[stage], phase ^ 1, 70, 100u);
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(&full[stage], 128 * 128);
-          ptx::tma_load_2d(sA + stage * 128 * 128, &tm_a, &full[stage], kb * 64, mt * 128);
+          ptx::mbar_expect_tx(&full[stage], 128 * 128);  // heads 2kb, 2kb+1 of tile mt: 2 x [128 x 32] = 16 KB contiguous
+          ptx::bulk_load(sA + stage * 128 * 128, attn + ((size_t)mt * (2 * KB) + 2 * kb) * (128 * 32), 128 * 128, &full[stage]);
         }
         __syncwarp();
         if (++stage == ST) { stage = 0; phase ^= 1; }
@@ -326,7 +405,7 @@ outproj_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 128, 0, 0);
-    const uint64_t dA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024, ptx::kSwz128);
+    const uint64_t dA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 512, ptx::kSwz64);  // [128 x 32] head blocks
     const uint64_t dW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024, ptx::kSwz128);
     ptx::mbar_wait(w_full, 0, 71, 40u);
     int stage = 0; uint32_t phase = 0;
@@ -342,8 +421,9 @@ outproj_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           const uint64_t da = dA0 + (uint64_t)stage * ((128 * 128) >> 4);
           const uint64_t dw = dW0 + (uint64_t)kb * ((128 * 128) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16(tmem_base + as * 128, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k)  // K slice k of the block: head block k >> 1 (8 KB apart), 32-byte half k & 1 of its rows
+            ptx::umma_bf16(tmem_base + as * 128, da + (uint64_t)((k >> 1) * (8192 >> 4) + (k & 1) * 2), dw + (uint64_t)(k * 2), idesc,
+                           (kb | k) != 0);
           ptx::umma_commit(&empty[stage]);
           if (kb == KB - 1) ptx::umma_commit(&tfull[as]);
         }
@@ -361,7 +441,9 @@ outproj_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       ptx::mbar_wait(&tfull[as], (uint32_t)((it >> 1) & 1), 74);
       ptx::tc_fence_after();
       const int row0 = mt * 128 + q * 32;
-      const int rows_valid = M - row0 < 32 ? M - row0 : 32;
+      // tokens of the 8 rows this lane copies out (rows i*4 + (lane >> 3)); -1: past the end
+      int tok[8];
+      rm.tokens<8>(row0 + (lane >> 3), 4, M, tok);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         uint32_t v[32];
@@ -371,8 +453,10 @@ outproj_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           ptx::tc_fence_before();
           ptx::mbar_arrive(&tempty[as]);
         }
-        residual_add_block_32x32(v, bias + half * 64 + cc * 32, stage_addr, z + (size_t)row0 * 128 + half * 64 + cc * 32, 128,
-                                 rows_valid, lane);
+        float* zc = z + half * 64 + cc * 32;
+        residual_add_block_32x32_rows(v, bias + half * 64 + cc * 32, stage_addr,
+                                      [&](int row) -> float* { const int t = tok[row >> 2]; return t >= 0 ? zc + (size_t)t * 128 : nullptr; },
+                                      lane);
       }
     }
   }
@@ -384,19 +468,6 @@ outproj_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 // L2 prefetch of the 32 fp32 rows (16 KB = 128 lines) a LayerNorm warp will normalise in its NEXT tile: the producer
 // warps can only keep ~8 rows of loads in flight in registers, far less than HBM latency x bandwidth needs, so the
 // next tile is pulled into L2 while the current one is processed.
-// Sequence-major row order of the QKV projection (see ln_gemm_tc_kernel<2>): GEMM row m = seq * T + pos, where a
-// sequence is what the following attention attends over.  axis 0 (attend over d): seq = (b, i), pos = j, i.e. m is the
-// token index itself.  axis 1 (attend over n): seq = (b, j), pos = i, token = (b*n + i)*d + j.
-struct RowMap {
-  int n, d, axis;
-  __device__ __forceinline__ int token(int m) const {
-    if (axis == 0) return m;
-    const unsigned nd = (unsigned)n * (unsigned)d, b = (unsigned)m / nd, rem = (unsigned)m - b * nd;
-    const unsigned j = rem / (unsigned)n, i = rem - j * (unsigned)n;
-    return (int)((b * (unsigned)n + i) * (unsigned)d + j);
-  }
-};
-
 __device__ __forceinline__ void prefetch_rows_l2(const float* __restrict__ z, int M, int grow0, int lane,
                                                  const RowMap rm = RowMap{0, 0, 0}) {
 #pragma unroll
@@ -1148,20 +1219,30 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   const int item0 = (int)blockIdx.x * kAttnStreams + sid;
   const int item_stride = (int)gridDim.x * kAttnStreams;
 
-  auto decode = [&](int item, int& s, int& h, int& qt) {  // 32-bit divisions: this runs once per item on every role
+  // Work-item coordinates (sequence s, head h, query tile qt; item = (s*H + h)*nqt + qt) are carried incrementally:
+  // consecutive items of a stream are item_stride apart, a fixed (ds, dh, dqt) step in mixed radix.  Divisions by
+  // run-time values cost ~1000 cycles of dependent MUFU.RCP / I2F chains per item on the softmax warps' critical
+  // path (measured), which is every step when the sequence fits one tile (attention over d = 100).
+  struct ItemPos { int s, h, qt; };
+  auto decode = [&](int item) {  // divisions: once per role, at start-up
     const unsigned u = (unsigned)item;
-    qt = (int)(u % (unsigned)nqt);
+    ItemPos p;
+    p.qt = (int)(u % (unsigned)nqt);
     const unsigned sh = u / (unsigned)nqt;
-    h = (int)(sh % (unsigned)H);
-    s = (int)(sh / (unsigned)H);
+    p.h = (int)(sh % (unsigned)H);
+    p.s = (int)(sh / (unsigned)H);
+    return p;
   };
-  // first token of sequence s (token index t = (b*n + i)*d + j)
-  auto seq_tok0 = [&](int s) -> long long {
-    if (axis == 0) return (long long)s * d;
-    const unsigned b = (unsigned)s / (unsigned)d, jj = (unsigned)s % (unsigned)d;
-    return (long long)b * n * d + jj;
+  const ItemPos step_pos = decode(item_stride);
+  auto advance = [&](ItemPos& p) {
+    p.qt += step_pos.qt;
+    int c = p.qt >= nqt;
+    p.qt -= c ? nqt : 0;
+    p.h += step_pos.h + c;
+    c = p.h >= H;
+    p.h -= c ? H : 0;
+    p.s += step_pos.s + c;
   };
-
   if (warp < 2) {
     // ======================= producer warp of stream `sid`: one bulk copy per [128 x 32] bf16 tile
     // (Measured on B200 before the operand layout existed: a tensor-map gather costs the TMA unit ~3.6 cycles per box
@@ -1169,9 +1250,9 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
     const size_t head_elems = (size_t)T * 32;  // one (sequence, q|k|v, head) block
     uint32_t g = 0;
     int it = 0;
-    for (int item = item0; item < num_items; item += item_stride, ++it) {
-      int s, h, qt;
-      decode(item, s, h, qt);
+    ItemPos ip = decode(item0);
+    for (int item = item0; item < num_items; item += item_stride, ++it, advance(ip)) {
+      const int s = ip.s, h = ip.h, qt = ip.qt;
       const __nv_bfloat16* qsrc = qkv + ((size_t)s * 3 * H + h) * head_elems;
       const __nv_bfloat16* ksrc = qsrc + (size_t)H * head_elems;
       const __nv_bfloat16* vsrc = ksrc + (size_t)H * head_elems;
@@ -1293,13 +1374,13 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
 
     long long g = 0;
     int it = 0;
-    // The epilogue of an item (O / L -> bf16 -> out) is deferred into the first step of the next item, between the
-    // row-max exchange and the exp phase: by then its last PV MMA has long completed (no exposed MMA latency), and
-    // since the next PV is only issued after every softmax thread has arrived on p_full, O needs no second buffer.
+    // The epilogue of an item (O / L -> bf16 -> out) is deferred into the first step of the next item, after the
+    // exponentials: by then its last PV MMA has long completed (no exposed MMA latency), and since the next PV is only
+    // issued after every softmax thread has arrived on p_full, O needs no second buffer.
+    // out is the out-projection's A-operand layout (outproj_tc_kernel): row m = s*T + position goes to
+    // out[m >> 7][head][m & 127][32 ch] with the 16-byte chunks XOR-swizzled by (m >> 1) & 3.
     bool pend = false;
-    long long pend_row0 = 0;  // token of tile row 0 of the pending item
-    int pend_h = 0, pend_t0 = 0;
-    const long long tstride = axis == 0 ? 1 : d;
+    int pend_m0 = 0, pend_h = 0, pend_t0 = 0;  // sequence-major index of tile row 0, head, first position of the tile
     auto epilogue = [&]() {  // each half writes 16 of the 32 output channels of its rows
       uint32_t o[16];
       ptx::tmem_ld16(tO + half * 16, o);
@@ -1307,9 +1388,10 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       ptx::tmem_wait_ld();
       if (pend_t0 + r < T) {
         if (kFast && !(lsum < 1.8446744e19f)) *guard = 1;  // row sum >= 2^64, inf or NaN: a score outran the reference
-        const long long tok = pend_row0 + (long long)r * tstride;
+        const unsigned m = (unsigned)(pend_m0 + r);
         const float inv = 1.0f / lsum;
-        uint4* op = reinterpret_cast<uint4*>(out + (size_t)tok * HD + pend_h * 32 + half * 16);
+        __nv_bfloat16* orow = out + (((size_t)(m >> 7) * H + pend_h) * 128 + (m & 127)) * 32;
+        const unsigned swz = (m >> 1) & 3;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           uint4 pk;
@@ -1317,7 +1399,11 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
           pk.y = ptx::pack_bf16(__uint_as_float(o[e * 8 + 2]) * inv, __uint_as_float(o[e * 8 + 3]) * inv);
           pk.z = ptx::pack_bf16(__uint_as_float(o[e * 8 + 4]) * inv, __uint_as_float(o[e * 8 + 5]) * inv);
           pk.w = ptx::pack_bf16(__uint_as_float(o[e * 8 + 6]) * inv, __uint_as_float(o[e * 8 + 7]) * inv);
-          op[e] = pk;
+#ifndef AVB_ATTN_NOSTORE  // timing experiment: epilogue without its global stores
+          *reinterpret_cast<uint4*>(orow + (((unsigned)(half * 2 + e) ^ swz) << 3)) = pk;
+#else
+          if (pk.x == 0x12345678u) *reinterpret_cast<uint4*>(orow + (((unsigned)(half * 2 + e) ^ swz) << 3)) = pk;
+#endif
         }
       }
     };
@@ -1342,9 +1428,9 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       const int other_item0 = (int)blockIdx.x * kAttnStreams + (sid ^ 1);
       const long long other_steps =
           other_item0 < num_items ? (long long)((num_items - other_item0 + item_stride - 1) / item_stride) * nqt : 0;
+      ItemPos ip = decode(item0);
       for (int item = item0; item < num_items; item += item_stride, ++it) {
-        int s, h, qt;
-        decode(item, s, h, qt);
+        const int s = ip.s, h = ip.h, qt = ip.qt;
         float m = 0.0f, pmax = -INFINITY;
         uint64_t negm2 = 0;
         for (int j = 0; j < nqt; ++j, ++g, gp ^= 1u) {
@@ -1419,12 +1505,13 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
         pend = true;
         pend_h = h;
         pend_t0 = qt * 128;
-        pend_row0 = seq_tok0(s) + (long long)(qt * 128) * tstride;
+        pend_m0 = s * T + qt * 128;
+        advance(ip);
       }
-    } else
+    } else {
+    ItemPos ip = decode(item0);
     for (int item = item0; item < num_items; item += item_stride, ++it) {
-      int s, h, qt;
-      decode(item, s, h, qt);
+      const int s = ip.s, h = ip.h, qt = ip.qt;
       float m = -INFINITY;
       for (int j = 0; j < nqt; ++j, ++g) {
         AVB_TRACE(trole, g, 0);
@@ -1547,7 +1634,9 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       pend = true;
       pend_h = h;
       pend_t0 = qt * 128;
-      pend_row0 = seq_tok0(s) + (long long)(qt * 128) * tstride;
+      pend_m0 = s * T + qt * 128;
+      advance(ip);
+    }
     }
     if (pend) {
       ptx::mbar_wait(pv_done, (uint32_t)((g - 1) & 1), 33);
@@ -1577,6 +1666,21 @@ __global__ void repack_qkv_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfl
     const int pos = axis == 0 ? j : i;
     const uint4 v = *reinterpret_cast<const uint4*>(in + tok * (size_t)(3 * H * 32) + (size_t)(w * H + h) * 32 + c4 * 8);
     *reinterpret_cast<uint4*>(out + (((seq * 3 + w) * H + h) * T + pos) * 32 + ((c4 ^ ((pos >> 1) & 3)) << 3)) = v;
+  }
+}
+
+// Test helper: attention output in the out-projection's A-operand layout -> token-major out[tok][H*32].
+__global__ void unpack_attn_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int n, int d,
+                                   int H, int axis) {
+  const size_t chunks = (size_t)B * n * d * H * 4;
+  const RowMap rm{n, d, axis};
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < chunks; idx += (size_t)gridDim.x * blockDim.x) {
+    const unsigned c4 = (unsigned)(idx & 3);
+    size_t r = idx >> 2;
+    const int h = (int)(r % H);
+    const unsigned m = (unsigned)(r / H);
+    const uint4 v = *reinterpret_cast<const uint4*>(in + (((size_t)(m >> 7) * H + h) * 128 + (m & 127)) * 32 + ((c4 ^ ((m >> 1) & 3)) << 3));
+    *reinterpret_cast<uint4*>(out + (size_t)rm.token((int)m) * (H * 32) + h * 32 + c4 * 8) = v;
   }
 }
 
