@@ -243,7 +243,8 @@ int launch_attention_tc(avb_handle h, const void* qkv, void* out, int B, int n, 
   const long long S = axis == 0 ? (long long)B * n : (long long)B * d;
   const long long items = S * H * ((T + 127) / 128);
   if (items >= (1LL << 31)) return fail(h, AVB_ERR_INVALID, "attention: too many (sequence, head, tile) items in one call (%lld)", items);
-  const int grid = (int)std::min<long long>((items + avb::kAttnStreams - 1) / avb::kAttnStreams, num_sms);
+  // a stream owns whole (sequence, head) pairs and walks their query tiles itself
+  const int grid = (int)std::min<long long>((S * H + avb::kAttnStreams - 1) / avb::kAttnStreams, num_sms);
   if (mode != 1) {
     if (cudaMemsetAsync(guard, 0, sizeof(int), st) != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention guard reset failed");
     avb::attention_tc_kernel<true><<<grid, avb::kAttnThreads, avb::kAttnSmemBytes, st>>>(

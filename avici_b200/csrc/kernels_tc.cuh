@@ -1045,14 +1045,8 @@ constexpr int kAttnPolyEvery = 4;  // 1 of every kAttnPolyEvery exponent pairs i
 #ifndef AVB_ATTN_POLY_EVERY
 #define AVB_ATTN_POLY_EVERY 4
 #endif
-// Exp-phase turn taking (fast variant).  The MUFU pipe belongs to an SM sub-partition and is shared round-robin, so
-// two streams left alone drift into a convoy: all four softmax warps of a sub-partition run their exponentials
-// together (each at a quarter of the MUFU rate), finish together, and leave the pipe idle together while they wait
-// for S / pv_done and move TMEM.  The streams therefore alternate explicitly, per sub-partition (row quarter q):
-// stream 1 starts the exponentials of its step g once stream 0 has issued those of its step g, stream 0 starts step g
-// once stream 1 is through step g-1; one stream's non-MUFU work then overlaps the other's exponentials.
-#ifndef AVB_ATTN_TURNS
-#define AVB_ATTN_TURNS 0
+#ifndef AVB_ATTN_KV_POLICY  // L2 eviction priority of the K / V tile loads
+#define AVB_ATTN_KV_POLICY (nqt > 1 ? ptx::kL2EvictLast : ptx::kL2EvictFirst)
 #endif
 constexpr float kAttnOverflowGuard = 64.0f;  // log2 units: a tile exceeding the stale row max by more flags the launch
 
@@ -1216,33 +1210,28 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   const uint32_t tmem_S = tmem_base + sid * kAttnTmemStreamCols;
   const uint32_t tmem_P = tmem_S + 128;  // 64 columns: P as packed bf16 pairs, A operand of the PV / L MMAs
   const uint32_t tmem_O = tmem_S + 192;  // O 32 | L 16 columns
-  const int item0 = (int)blockIdx.x * kAttnStreams + sid;
-  const int item_stride = (int)gridDim.x * kAttnStreams;
-
-  // Work-item coordinates (sequence s, head h, query tile qt; item = (s*H + h)*nqt + qt) are carried incrementally:
-  // consecutive items of a stream are item_stride apart, a fixed (ds, dh, dqt) step in mixed radix.  Divisions by
-  // run-time values cost ~1000 cycles of dependent MUFU.RCP / I2F chains per item on the softmax warps' critical
-  // path (measured), which is every step when the sequence fits one tile (attention over d = 100).
+  // Work items of a stream.  A stream owns whole (sequence, head) pairs - pair = pair0 + i * pair_stride - and walks
+  // the query tiles of a pair back to back, so the pair's K / V (re-read by every query tile) stays in L2 between its
+  // own passes instead of depending on how well eight different streams keep time (measured: 2.2x the algorithmic
+  // DRAM reads with the query tiles spread over streams).  Coordinates are carried incrementally: a division by a
+  // run-time value costs a long dependent MUFU.RCP / I2F chain on the softmax warps' critical path per item.
+  const int num_pairs = S * H;
+  const int pair0 = (int)blockIdx.x * kAttnStreams + sid;
+  const int pair_stride = (int)gridDim.x * kAttnStreams;
+  const int my_items = pair0 < num_pairs ? ((num_pairs - pair0 + pair_stride - 1) / pair_stride) * nqt : 0;
   struct ItemPos { int s, h, qt; };
-  auto decode = [&](int item) {  // divisions: once per role, at start-up
-    const unsigned u = (unsigned)item;
-    ItemPos p;
-    p.qt = (int)(u % (unsigned)nqt);
-    const unsigned sh = u / (unsigned)nqt;
-    p.h = (int)(sh % (unsigned)H);
-    p.s = (int)(sh / (unsigned)H);
-    return p;
+  const int step_h = pair_stride % H, step_s = pair_stride / H;
+  auto first_item = [&]() { ItemPos p; p.s = pair0 / H; p.h = pair0 % H; p.qt = 0; return p; };
+  auto advance = [&](ItemPos& p) {  // branch-free: next query tile, or first tile of the stream's next pair
+    p.qt += 1;
+    const int c = p.qt >= nqt;
+    p.qt = c ? 0 : p.qt;
+    p.h += c ? step_h : 0;
+    const int c2 = p.h >= H;
+    p.h -= c2 ? H : 0;
+    p.s += (c ? step_s : 0) + c2;
   };
-  const ItemPos step_pos = decode(item_stride);
-  auto advance = [&](ItemPos& p) {
-    p.qt += step_pos.qt;
-    int c = p.qt >= nqt;
-    p.qt -= c ? nqt : 0;
-    p.h += step_pos.h + c;
-    c = p.h >= H;
-    p.h -= c ? H : 0;
-    p.s += step_pos.s + c;
-  };
+
   if (warp < 2) {
     // ======================= producer warp of stream `sid`: one bulk copy per [128 x 32] bf16 tile
     // (Measured on B200 before the operand layout existed: a tensor-map gather costs the TMA unit ~3.6 cycles per box
@@ -1250,8 +1239,8 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
     const size_t head_elems = (size_t)T * 32;  // one (sequence, q|k|v, head) block
     uint32_t g = 0;
     int it = 0;
-    ItemPos ip = decode(item0);
-    for (int item = item0; item < num_items; item += item_stride, ++it, advance(ip)) {
+    ItemPos ip = first_item();
+    for (int item = 0; item < my_items; ++item, ++it, advance(ip)) {
       const int s = ip.s, h = ip.h, qt = ip.qt;
       const __nv_bfloat16* qsrc = qkv + ((size_t)s * 3 * H + h) * head_elems;
       const __nv_bfloat16* ksrc = qsrc + (size_t)H * head_elems;
@@ -1261,7 +1250,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       if (ptx::elect_one()) {
         const uint32_t bytes = (uint32_t)min(128, T - qt * 128) * 64u;
         ptx::mbar_expect_tx(&q_full[qb], bytes);
-        ptx::bulk_load(sQ + qb * kAttnTileBytes, qsrc + (size_t)qt * 128 * 32, bytes, &q_full[qb]);
+        ptx::bulk_load_hint(sQ + qb * kAttnTileBytes, qsrc + (size_t)qt * 128 * 32, bytes, &q_full[qb], ptx::kL2EvictFirst);
       }
       __syncwarp();
       for (int j = 0; j < nqt; ++j, ++g) {
@@ -1273,8 +1262,10 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
           uint8_t* sk = sKV + st * 2 * kAttnTileBytes;
           const uint32_t bytes = (uint32_t)min(128, T - j * 128) * 64u;
           ptx::mbar_expect_tx(&kv_full[st], 2 * bytes);
-          ptx::bulk_load(sk, ksrc + (size_t)j * 128 * 32, bytes, &kv_full[st]);
-          ptx::bulk_load(sk + kAttnTileBytes, vsrc + (size_t)j * 128 * 32, bytes, &kv_full[st]);
+          // every query tile of the (sequence, head) streams the same K / V: keep them in L2 (Q is read once)
+          const uint64_t pol = AVB_ATTN_KV_POLICY;
+          ptx::bulk_load_hint(sk, ksrc + (size_t)j * 128 * 32, bytes, &kv_full[st], pol);
+          ptx::bulk_load_hint(sk + kAttnTileBytes, vsrc + (size_t)j * 128 * 32, bytes, &kv_full[st], pol);
         }
         __syncwarp();
         AVB_TRACE(0, g, 2);
@@ -1284,7 +1275,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
     // ======================= MMA issuer of stream `sid`
     // One thread issues every tcgen05.mma of the stream, so per-MMA scalar work is on the critical path:
     // all shared-memory descriptors are built once and advanced by adding (byte offset >> 4) to them.
-    if (item0 < num_items) {  // all 32 lanes run the control flow; one elected lane issues the tcgen05 instructions
+    if (my_items > 0) {  // all 32 lanes run the control flow; one elected lane issues the tcgen05 instructions
       // number of key columns the MMAs of kv tile j touch (multiple of 16)
       auto kcols = [&](int j) { int v = T - j * 128; v = v > 128 ? 128 : v; return (v + 15) & ~15; };
       const uint64_t dQ = ptx::make_smem_desc(ptx::smem_u32(sQ), 16, 512, ptx::kSwz64);
@@ -1315,12 +1306,12 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       };
       long long g = 0;
       int it = 0;
-      int item = item0;
+      int item = 0;
       issue_S(0, 0, 0);
-      while (item < num_items) {
+      while (item < my_items) {
         for (int j = 0; j < nqt; ++j, ++g) {
           // S of the next step goes to the tensor core as soon as this step's softmax has read S
-          const bool more = (j + 1 < nqt) || (item + item_stride < num_items);
+          const bool more = (j + 1 < nqt) || (item + 1 < my_items);
           AVB_TRACE(1, g, 0);
           if (more) {
             ptx::mbar_wait(s_free, (uint32_t)(g & 1), 24, 40u);
@@ -1356,7 +1347,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
           __syncwarp();
           AVB_TRACE(1, g, 4);
         }
-        item += item_stride;
+        ++item;
         ++it;
       }
     }
@@ -1422,14 +1413,8 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       const uint32_t a_sfull = ptx::smem_u32(s_full), a_sfree = ptx::smem_u32(s_free);
       const uint32_t a_pfull = ptx::smem_u32(p_full), a_pvdone = ptx::smem_u32(pv_done);
       uint32_t gp = 0;  // parity of the current step (g & 1)
-      const uint32_t a_myturn = ptx::smem_u32(&x_full_all[sid * 4 + q]);
-      const uint32_t a_otherturn = ptx::smem_u32(&x_full_all[(sid ^ 1) * 4 + q]);
-      // steps of the other stream (stream 1 never has more than stream 0: its first item is the later one)
-      const int other_item0 = (int)blockIdx.x * kAttnStreams + (sid ^ 1);
-      const long long other_steps =
-          other_item0 < num_items ? (long long)((num_items - other_item0 + item_stride - 1) / item_stride) * nqt : 0;
-      ItemPos ip = decode(item0);
-      for (int item = item0; item < num_items; item += item_stride, ++it) {
+      ItemPos ip = first_item();
+      for (int item = 0; item < my_items; ++item, ++it) {
         const int s = ip.s, h = ip.h, qt = ip.qt;
         float m = 0.0f, pmax = -INFINITY;
         uint64_t negm2 = 0;
@@ -1479,15 +1464,10 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
             }
           }
           // ---- P = exp2(S - ref) -> packed bf16 pairs
-          if (AVB_ATTN_TURNS) {
-            if (sid == 0) { if (g >= 1 && g - 1 < other_steps) ptx::mbar_wait_s(a_otherturn, gp ^ 1u); }
-            else ptx::mbar_wait_s(a_otherturn, gp);
-          }
           AVB_TRACE(trole, g, 3);
           uint32_t pk[32];
           exp_chunk32(sa, negm2, pk, pmax);
           exp_chunk32(sb, negm2, pk + 16, pmax);
-          if (AVB_ATTN_TURNS) ptx::mbar_arrive_s(a_myturn);
           AVB_TRACE(trole, g, 4);
           if (g >= 1) {  // P is free and O complete once the PV / L MMAs of the previous step have finished
             ptx::mbar_wait_s(a_pvdone, gp ^ 1u);
@@ -1509,8 +1489,8 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
         advance(ip);
       }
     } else {
-    ItemPos ip = decode(item0);
-    for (int item = item0; item < num_items; item += item_stride, ++it) {
+    ItemPos ip = first_item();
+    for (int item = 0; item < my_items; ++item, ++it) {
       const int s = ip.s, h = ip.h, qt = ip.qt;
       float m = -INFINITY;
       for (int j = 0; j < nqt; ++j, ++g) {

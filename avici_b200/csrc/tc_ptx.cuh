@@ -132,6 +132,18 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                : "memory");
 }
 
+// same with an L2 eviction-priority hint (createpolicy encodings): tiles that several CTAs re-read keep their lines
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull, kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void bulk_load_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+#ifdef AVB_NO_L2_HINTS
+  bulk_load(smem_dst, gsrc, bytes, bar);
+  return;
+#endif
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- cp.async (LDGSTS) gathers
 // 16-byte global -> shared copy, L2-only; src_bytes = 0 zero-fills the destination (row past the end).
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
