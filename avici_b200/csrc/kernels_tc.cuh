@@ -1048,7 +1048,7 @@ constexpr int kAttnPolyEvery = 4;  // 1 of every kAttnPolyEvery exponent pairs i
 #ifndef AVB_ATTN_KV_POLICY  // L2 eviction priority of the K / V tile loads
 #define AVB_ATTN_KV_POLICY (nqt > 1 ? ptx::kL2EvictLast : ptx::kL2EvictFirst)
 #endif
-constexpr float kAttnOverflowGuard = 64.0f;  // log2 units: a tile exceeding the stale row max by more flags the launch
+constexpr float kAttnOverflowGuard = 100.0f;  // log2 units: scores beyond this on a polynomial lane flag the launch
 
 // exp2 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = i + f, f in [-0.5, 0.5], degree-3 minimax
 // polynomial for 2^f (max relative error 7.5e-5, far below the bf16 rounding of P) and i added into the exponent.
@@ -1096,13 +1096,13 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   return r;
 }
 
-// 32 scores (one TMEM chunk of a query row) -> 16 packed bf16 pairs of exp2(s - ref).  One pair in
-// kAttnFastPolyEvery goes through the FMA-pipe polynomial (same polynomial as poly_exp2, evaluated on packed
-// pairs), the others through MUFU.  pmax accumulates the maximum of the raw scores on the polynomial lanes: MUFU
-// saturates to +inf when s - ref is out of range (the epilogue sees it in the row sum) but the polynomial's exponent
-// arithmetic wraps, so those lanes are range-checked by the caller.
+// 32 scores (one TMEM chunk of a query row) -> 16 packed bf16 pairs of exp2(s).  No reference is subtracted (see the
+// fast softmax section).  One pair in kAttnFastPolyEvery goes through the FMA-pipe polynomial (same polynomial as
+// poly_exp2, evaluated on packed pairs), the others through MUFU.  pmax accumulates the maximum of the raw scores on
+// the polynomial lanes: MUFU saturates to +inf when a score is out of range (the epilogue sees it in the row sum) but
+// the polynomial's exponent arithmetic wraps, so those lanes are range-checked by the caller.
 constexpr int kAttnFastPolyEvery = AVB_ATTN_POLY_EVERY;
-__device__ __forceinline__ void exp_chunk32(const uint32_t (&s)[32], uint64_t negm2, uint32_t* pk, float& pmax) {
+__device__ __forceinline__ void exp_chunk32(const uint32_t (&s)[32], uint32_t* pk, float& pmax) {
   const uint64_t magic2 = pack2(12582912.0f, 12582912.0f), nmagic2 = pack2(-12582912.0f, -12582912.0f);
   const uint64_t c3 = pack2(0.055171650f, 0.055171650f), c2 = pack2(0.24261113f, 0.24261113f);
   const uint64_t c1 = pack2(0.69326097f, 0.69326097f), c0 = pack2(0.99992806f, 0.99992806f);
@@ -1110,12 +1110,9 @@ __device__ __forceinline__ void exp_chunk32(const uint32_t (&s)[32], uint64_t ne
 #pragma unroll
   for (int e = 0; e < 16; ++e) {
     const float a = __uint_as_float(s[2 * e]), b = __uint_as_float(s[2 * e + 1]);
-    uint64_t x2 = add2(pack2(a, b), negm2);
-    float x0, x1;
-    unpack2(x2, x0, x1);
     if ((e % kAttnFastPolyEvery) == kAttnFastPolyEvery - 1) {
       pmax = max3(pmax, a, b);
-      x2 = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+      const uint64_t x2 = pack2(fmaxf(a, -126.0f), fmaxf(b, -126.0f));
       const uint64_t t2 = add2(x2, magic2);           // integer part lands in the low mantissa bits
       const uint64_t f2 = fma2(add2(t2, nmagic2), neg1, x2);  // f = x - round(x), in [-0.5, 0.5]
       uint64_t p2 = fma2(f2, c3, c2);
@@ -1129,9 +1126,9 @@ __device__ __forceinline__ void exp_chunk32(const uint32_t (&s)[32], uint64_t ne
       pk[e] = ptx::pack_bf16(p0, p1);
     } else {
 #ifdef AVB_ATTN_NOEXP  // timing experiment only: everything but the exponentials
-      pk[e] = ptx::pack_bf16(x0, x1);
+      pk[e] = ptx::pack_bf16(a, b);
 #else
-      pk[e] = ptx::pack_bf16(fast_exp2(x0), fast_exp2(x1));
+      pk[e] = ptx::pack_bf16(fast_exp2(a), fast_exp2(b));
 #endif
     }
   }
@@ -1378,7 +1375,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       const float lsum = __uint_as_float(ptx::tmem_ld1(tO + 32));
       ptx::tmem_wait_ld();
       if (pend_t0 + r < T) {
-        if (kFast && !(lsum < 1.8446744e19f)) *guard = 1;  // row sum >= 2^64, inf or NaN: a score outran the reference
+        if (kFast && !(lsum < 1.2676506e30f && lsum > 7.8886091e-31f)) *guard = 1;  // outside (2^-100, 2^100), inf or NaN
         const unsigned m = (unsigned)(pend_m0 + r);
         const float inv = 1.0f / lsum;
         __nv_bfloat16* orow = out + (((size_t)(m >> 7) * H + pend_h) * 128 + (m & 127)) * 32;
@@ -1399,59 +1396,33 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       }
     };
     if constexpr (kFast) {
-      // ---- single-pass softmax against a FIXED per-row reference.
-      // softmax is invariant to the per-row shift: exp2(s - ref) needs a reference that keeps the values in range,
-      // not the exact running maximum.  The exact variant below pays for the exact one with a second read of S,
-      // a shared-memory exchange + barrier between the two warps of a row quarter on every tile, and O rescales -
-      // a dependent chain as long as the exponentials themselves.  Here the reference of a query row is the largest
-      // score against the first 32 keys of the sequence: both warps of a row quarter read those 32 TMEM columns
-      // themselves (same lanes), so they agree without exchanging anything, and it never changes during the item:
-      // no running maximum, no rescale, S is read once and handed back to the tensor core at once.  P can exceed 1
-      // by 2^(true max - ref) - harmless in bf16 / fp32 - and the row sum is >= 1.  If a score outruns the
-      // reference by more than 2^kAttnOverflowGuard (MUFU lanes: the row sum shows it in the epilogue; polynomial
-      // lanes: range check on the raw scores) the launch is flagged and the exact variant recomputes it.
+      // ---- single-pass softmax WITHOUT a running maximum.
+      // softmax is invariant to a per-row shift of the scores; implementations subtract the running row maximum only
+      // to keep exp2 in range.  bf16 P and the fp32 accumulators have the full 8-bit exponent, so for scores within
+      // +-100 (log2 units, i.e. +-69 nats - far beyond what LayerNorm-ed activations produce) exp2(s) itself is in
+      // range and the normalisation O / L cancels the missing shift exactly, with no loss of precision.  That removes
+      // everything the exact variant below pays for: the second read of S, the row-max reduction, the shared-memory
+      // exchange + barrier between the two warps of a row quarter on every tile, the subtraction, and the O rescales -
+      // a dependent chain as long as the exponentials themselves.  S is read once and handed back to the tensor core
+      // at once.  Out-of-range scores cannot go unnoticed: on the MUFU lanes they give P = inf or a row sum of 0, which
+      // the epilogue checks (2^-100 < L < 2^100); the polynomial lanes (whose exponent arithmetic would wrap) are
+      // range-checked on the raw scores.  Either raises `guard`, and the exact variant recomputes the launch.
       const uint32_t a_sfull = ptx::smem_u32(s_full), a_sfree = ptx::smem_u32(s_free);
       const uint32_t a_pfull = ptx::smem_u32(p_full), a_pvdone = ptx::smem_u32(pv_done);
       uint32_t gp = 0;  // parity of the current step (g & 1)
+      float pmax = -INFINITY;
       ItemPos ip = first_item();
       for (int item = 0; item < my_items; ++item, ++it) {
         const int s = ip.s, h = ip.h, qt = ip.qt;
-        float m = 0.0f, pmax = -INFINITY;
-        uint64_t negm2 = 0;
         for (int j = 0; j < nqt; ++j, ++g, gp ^= 1u) {
           AVB_TRACE(trole, g, 0);
           ptx::mbar_wait_s(a_sfull, gp);
           AVB_TRACE(trole, g, 1);
           ptx::tc_fence_after();
           uint32_t sa[32], sb[32];
-          // reference of the row (first tile only): max over the first 32 keys; the half-1 warp reads those columns too
-          auto rowmax32 = [&](const uint32_t (&v)[32]) {
-            float t0 = -INFINITY, t1 = -INFINITY;
-            if (T >= 32) {
-#pragma unroll
-              for (int e = 0; e < 32; e += 4) {
-                t0 = max3(t0, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-                t1 = max3(t1, __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) t0 = fmaxf(t0, e < T ? __uint_as_float(v[e]) : -INFINITY);
-            }
-            return fmaxf(t0, t1);
-          };
-          if (j == 0 && half != 0) {
-            ptx::tmem_ld32(tmem_S + lane_off, sa);
-            ptx::tmem_wait_ld();
-            m = rowmax32(sa);
-          }
           ptx::tmem_ld32(tS, sa);
           ptx::tmem_ld32(tS + 32, sb);
           ptx::tmem_wait_ld();
-          if (j == 0) {
-            if (half == 0) m = rowmax32(sa);
-            negm2 = pack2(-m, -m);
-            pmax = -INFINITY;
-          }
           ptx::tc_fence_before();
           ptx::mbar_arrive_s(a_sfree);  // the only read of S: the tensor core may start the next S right away
           AVB_TRACE(trole, g, 2);
@@ -1463,11 +1434,10 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
               if (32 + e >= nv) sb[e] = 0xff800000u;
             }
           }
-          // ---- P = exp2(S - ref) -> packed bf16 pairs
-          AVB_TRACE(trole, g, 3);
+          // ---- P = exp2(S) -> packed bf16 pairs
           uint32_t pk[32];
-          exp_chunk32(sa, negm2, pk, pmax);
-          exp_chunk32(sb, negm2, pk + 16, pmax);
+          exp_chunk32(sa, pk, pmax);
+          exp_chunk32(sb, pk + 16, pmax);
           AVB_TRACE(trole, g, 4);
           if (g >= 1) {  // P is free and O complete once the PV / L MMAs of the previous step have finished
             ptx::mbar_wait_s(a_pvdone, gp ^ 1u);
@@ -1481,13 +1451,13 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
           ptx::mbar_arrive_s(a_pfull);
           AVB_TRACE(trole, g, 7);
         }
-        if (pmax > m + kAttnOverflowGuard) *guard = 1;  // a polynomial lane left the safe exponent range
         pend = true;
         pend_h = h;
         pend_t0 = qt * 128;
         pend_m0 = s * T + qt * 128;
         advance(ip);
       }
+      if (pmax > kAttnOverflowGuard) *guard = 1;  // a polynomial lane left the safe exponent range
     } else {
     ItemPos ip = first_item();
     for (int item = 0; item < my_items; ++item, ++it) {

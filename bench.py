@@ -153,6 +153,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (None if absent)."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            e = json.load(f)[key]
+        return e["dram_read_bytes"] + e["dram_write_bytes"]
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -251,7 +261,10 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"kernel": "attention_tc_kernel (attend over n)", "bound": "tensor", "achieved": achieved,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                         "traffic": None, "peak_source": peaks["source"] + " bf16_tflops_sustained",
+                         "traffic": ncu_traffic("attention_tc_kernel<1>:axis_n:B64") if B == 64 else None,
+                         "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                         "algorithmic_bytes": B * N_OBS * N_VARS * 2048,
+                         "peak_source": peaks["source"] + " bf16_tflops_sustained",
                          "ms_per_launch": ms_attn / max(cnt_attn, 1), "launches_timed": cnt_attn},
             "kernel_ms_per_step": breakdown, "profiled_ms_per_step": ms_prof / args.steps,
             "cpu_baseline": None if cpu_val is None else {

@@ -142,6 +142,27 @@ def test_attention_tc_against_torch(built_lib, B, n, d, H, axis):
     assert err <= 3e-2, f"attention_tc err {err}"  # bf16 P and output rounding on |v| ~ 4
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("axis", [0, 1])
+def test_attention_tc_out_of_range_scores_fall_back_to_exact(built_lib, axis):
+    """The fast attention kernel exponentiates raw scores (no running maximum); scores beyond +-100 (log2 units) must
+    raise its guard so that the exact kernel recomputes the launch.  |q.k| reaches several hundred here."""
+    B, n, d, H = 1, 300, 130, 8
+    g = torch.Generator(device="cuda").manual_seed(7)
+    qkv = torch.randn(B, n, d, 3 * H * 32, device="cuda", generator=g)
+    qkv[..., :2 * H * 32] *= 4.0  # q and k: score std ~ 90, tails far beyond the guard
+    qkv = qkv.to(torch.bfloat16)
+    out = torch.zeros(B, n, d, H * 32, device="cuda", dtype=torch.bfloat16)
+    rc = built_lib.avb_test_attention_bf16(qkv.data_ptr(), out.data_ptr(), B, n, d, H, axis,
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(built_lib, None, rc)
+    torch.cuda.synchronize()
+    ref = attention_reference(qkv, B, n, d, H, axis)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 3e-2, f"attention_tc (guarded) err {err}"
+
+
 # ------------------------------------------------------------------------------ end-to-end parity
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))))
