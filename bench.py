@@ -265,7 +265,13 @@ def run_ours(args):
                          "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                          "algorithmic_bytes": B * N_OBS * N_VARS * 2048,
                          "peak_source": peaks["source"] + " bf16_tflops_sustained",
-                         "ms_per_launch": ms_attn / max(cnt_attn, 1), "launches_timed": cnt_attn},
+                         "ms_per_launch": ms_attn / max(cnt_attn, 1), "launches_timed": cnt_attn,
+                         # head dim 32: the softmax, not the MMA, is the floor of this kernel
+                         "co_limit": {"what": "exp2 per launch on MUFU (16/clk/SM) + FMA-pipe polynomial (25%)",
+                                      "exps_per_launch": B * N_OBS * N_VARS * 8 * N_OBS,
+                                      "achieved_Texp_s": B * N_OBS * N_VARS * 8 * N_OBS / (ms_attn / max(cnt_attn, 1) * 1e-3) / 1e12
+                                      if ms_attn > 0 else 0.0,
+                                      "mufu_peak_Texp_s": 16 * 148 * 1.965e9 / 1e12}},
             "kernel_ms_per_step": breakdown, "profiled_ms_per_step": ms_prof / args.steps,
             "cpu_baseline": None if cpu_val is None else {
                 "value": cpu_val, "unit": "datasets/s", "cores": cores, "kind": "port",
