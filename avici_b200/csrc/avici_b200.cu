@@ -863,6 +863,59 @@ int avb_test_ln_gemm_bf16(const float* z, const void* wt, const float* bias, voi
               : launch_ln_gemm_tc<0>(nullptr, z, tb, bias, out, N, M, N, st, sms, nullptr);
 }
 
+namespace {
+// scratch of the layout test hooks (grown on demand, process lifetime)
+void* test_scratch(size_t bytes) {
+  static void* buf = nullptr;
+  static size_t cap = 0;
+  if (cap < bytes) {
+    if (buf) cudaFree(buf);
+    buf = nullptr; cap = 0;
+    if (cudaMalloc(&buf, bytes) != cudaSuccess) return nullptr;
+    cap = bytes;
+  }
+  return buf;
+}
+}  // namespace
+
+int avb_test_qkv_layout_bf16(const float* z, const void* wt, const float* bias, void* out, int32_t B, int32_t n, int32_t d,
+                             int32_t H, int32_t axis, void* stream) {
+  if (!z || !wt || !bias || !out || B < 1 || n < 1 || d < 1 || H != 8 || (axis != 0 && axis != 1))
+    return fail(nullptr, AVB_ERR_INVALID, "avb_test_qkv_layout_bf16: bad argument (H must be 8)");
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device");
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t ntok = (size_t)B * n * d;
+  const int N = 3 * H * 32;
+  void* packed = test_scratch(ntok * N * sizeof(bf16));
+  if (!packed) return fail(nullptr, AVB_ERR_CUDA, "cudaMalloc(test scratch) failed");
+  CUtensorMap tb;
+  if (!make_tmap_2d(&tb, wt, N, 128, 256)) return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rc = launch_ln_gemm_tc<2>(nullptr, z, tb, bias, packed, N, (int)ntok, N, st, sms, nullptr, n, d, axis);
+  if (rc != AVB_OK) return rc;
+  avb::unpack_qkv_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const bf16*>(packed), reinterpret_cast<bf16*>(out), B, n, d, H, axis);
+  return cudaGetLastError() == cudaSuccess ? AVB_OK : fail(nullptr, AVB_ERR_CUDA, "unpack_qkv launch failed");
+}
+
+int avb_test_outproj_bf16(const void* attn, const void* wot, const float* bias, float* z, int32_t B, int32_t n, int32_t d,
+                          int32_t axis, void* stream) {
+  if (!attn || !wot || !bias || !z || B < 1 || n < 1 || d < 1 || (axis != 0 && axis != 1))
+    return fail(nullptr, AVB_ERR_INVALID, "avb_test_outproj_bf16: bad argument");
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device");
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t ntok = (size_t)B * n * d;
+  const int H = 2 * avb::kOutProjKB, HD = H * 32;
+  void* packed = test_scratch(((ntok + 127) / 128) * 128 * HD * sizeof(bf16));
+  if (!packed) return fail(nullptr, AVB_ERR_CUDA, "cudaMalloc(test scratch) failed");
+  CUtensorMap tw;
+  if (!make_tmap_2d(&tw, wot, 128, HD, 128)) return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  avb::pack_attn_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const bf16*>(attn), reinterpret_cast<bf16*>(packed), B, n, d, H, axis);
+  return launch_outproj_tc(nullptr, packed, tw, bias, z, (int)ntok, n, d, axis, st, sms, nullptr);
+}
+
 int avb_test_ffn_bf16(float* z, const void* w1t, const void* w2t, const float* b1, const float* b2, int32_t M, int32_t F,
                       void* stream) {
   if (!z || !w1t || !w2t || !b1 || !b2 || M < 1 || F % 128) return fail(nullptr, AVB_ERR_INVALID, "avb_test_ffn_bf16: bad shape");

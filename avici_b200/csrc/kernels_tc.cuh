@@ -1634,4 +1634,36 @@ __global__ void unpack_attn_kernel(const __nv_bfloat16* __restrict__ in, __nv_bf
   }
 }
 
+// Test helpers (inverse directions of the two above).
+__global__ void unpack_qkv_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int n, int d,
+                                  int H, int axis) {
+  const size_t chunks = (size_t)B * n * d * 3 * H * 4;
+  const int T = axis == 0 ? d : n;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < chunks; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx & 3);
+    size_t r = idx >> 2;
+    const int h = (int)(r % H); r /= H;
+    const int w = (int)(r % 3); r /= 3;
+    const size_t tok = r;
+    const int j = (int)(tok % d), i = (int)((tok / d) % n), b = (int)(tok / ((size_t)n * d));
+    const size_t seq = axis == 0 ? (size_t)b * n + i : (size_t)b * d + j;
+    const int pos = axis == 0 ? j : i;
+    const uint4 v = *reinterpret_cast<const uint4*>(in + (((seq * 3 + w) * H + h) * T + pos) * 32 + ((c4 ^ ((pos >> 1) & 3)) << 3));
+    *reinterpret_cast<uint4*>(out + tok * (size_t)(3 * H * 32) + (size_t)(w * H + h) * 32 + c4 * 8) = v;
+  }
+}
+__global__ void pack_attn_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int n, int d,
+                                 int H, int axis) {
+  const size_t chunks = (size_t)B * n * d * H * 4;
+  const RowMap rm{n, d, axis};
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < chunks; idx += (size_t)gridDim.x * blockDim.x) {
+    const unsigned c4 = (unsigned)(idx & 3);
+    size_t r = idx >> 2;
+    const int h = (int)(r % H);
+    const unsigned m = (unsigned)(r / H);
+    const uint4 v = *reinterpret_cast<const uint4*>(in + (size_t)rm.token((int)m) * (H * 32) + h * 32 + c4 * 8);
+    *reinterpret_cast<uint4*>(out + (((size_t)(m >> 7) * H + h) * 128 + (m & 127)) * 32 + ((c4 ^ ((m >> 1) & 3)) << 3)) = v;
+  }
+}
+
 }  // namespace avb

@@ -167,6 +167,18 @@ int avb_test_ffn_bf16(float* z_dev, const void* w1t_bf16_dev, const void* w2t_bf
 int avb_test_attention_bf16(const void* qkv_bf16_dev, void* out_bf16_dev, int32_t B, int32_t n,
                             int32_t d, int32_t H, int32_t axis, void* stream);
 
+/* The QKV projection as the block runs it (ln_gemm_tc_kernel<2>): LayerNorm + projection of z[B*n*d,128] with rows taken
+ * in the sequence-major order of `axis` and the result written in the attention operand layout; the hook converts
+ * that layout back to token-major out[B,n,d,3*H*32] bf16 so a test can compare it with a plain reference. */
+int avb_test_qkv_layout_bf16(const float* z_dev, const void* wt_bf16_dev, const float* bias_dev,
+                             void* out_tokmajor_bf16_dev, int32_t B, int32_t n, int32_t d, int32_t H,
+                             int32_t axis, void* stream);
+/* The out-projection as the block runs it (outproj_tc_kernel): z[B*n*d,128] fp32 += attn @ Wot[128,256]^T + bias in
+ * place, with attn given token-major [B,n,d,256] bf16 and packed by the hook into the kernel's A-operand layout
+ * (sequence-major rows of `axis`). */
+int avb_test_outproj_bf16(const void* attn_tokmajor_bf16_dev, const void* wot_bf16_dev, const float* bias_dev,
+                          float* z_dev, int32_t B, int32_t n, int32_t d, int32_t axis, void* stream);
+
 /* Debug: device buffer of 3*4096 int64 that block 0 of the attention kernel fills with clock64() stamps of
  * its producer / MMA / softmax roles (NULL switches tracing off). */
 int avb_debug_set_trace(void* trace_dev);

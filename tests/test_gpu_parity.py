@@ -92,6 +92,48 @@ def test_ln_gemm_tc_against_torch(built_lib, M, N, relu):
     assert err <= 2 ** -7 * max(ref.abs().max().item(), 1.0), f"ln_gemm_tc err {err}"
 
 
+@pytest.mark.parametrize("B,n,d,axis", [(1, 8, 100, 0), (2, 200, 50, 0), (2, 200, 50, 1), (1, 300, 130, 1),
+                                        (3, 1000, 7, 1), (1, 1, 1, 0), (1, 5, 3, 1)])
+def test_qkv_projection_operand_layout(built_lib, B, n, d, axis):
+    """ln_gemm_tc_kernel<2>: rows gathered in sequence-major order of `axis`, output in the attention operand layout
+    (the hook converts it back to token-major): must equal the plain LayerNorm + projection of every token."""
+    H, N, M = 8, 768, B * n * d
+    g = torch.Generator(device="cuda").manual_seed(M + axis)
+    z = torch.randn(M, 128, device="cuda", generator=g) * 3 + torch.randn(M, 1, device="cuda", generator=g)
+    wt = (torch.randn(N, 128, device="cuda", generator=g) / 128 ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    rc = built_lib.avb_test_qkv_layout_bf16(z.data_ptr(), wt.data_ptr(), bias.data_ptr(), out.data_ptr(), B, n, d, H, axis,
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(built_lib, None, rc)
+    torch.cuda.synchronize()
+    xhat = torch.nn.functional.layer_norm(z, (128,), eps=1e-5).to(torch.bfloat16).float()
+    ref = xhat @ wt.float().T + bias
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2 ** -7 * max(ref.abs().max().item(), 1.0), f"qkv layout err {err}"
+
+
+@pytest.mark.parametrize("B,n,d,axis", [(1, 8, 100, 0), (2, 200, 50, 0), (2, 200, 50, 1), (1, 300, 130, 1),
+                                        (3, 1000, 7, 1), (1, 1, 1, 0), (1, 5, 3, 1)])
+def test_outproj_operand_layout_and_row_map(built_lib, B, n, d, axis):
+    """outproj_tc_kernel: A operand in the tile-major head-split layout, z rows updated through the sequence-major row
+    map: z += attn @ Wo^T + bo for every token, exactly once."""
+    M = B * n * d
+    g = torch.Generator(device="cuda").manual_seed(M * 3 + axis)
+    attn = torch.randn(M, 256, device="cuda", generator=g).to(torch.bfloat16)
+    wot = (torch.randn(128, 256, device="cuda", generator=g) / 16).to(torch.bfloat16)
+    bias = torch.randn(128, device="cuda", generator=g)
+    z0 = torch.randn(M, 128, device="cuda", generator=g)
+    z = z0.clone()
+    rc = built_lib.avb_test_outproj_bf16(attn.data_ptr(), wot.data_ptr(), bias.data_ptr(), z.data_ptr(), B, n, d, axis,
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(built_lib, None, rc)
+    torch.cuda.synchronize()
+    ref = z0 + attn.float() @ wot.float().T + bias
+    err = (z - ref).abs().max().item()
+    assert err <= 2e-4 * max(ref.abs().max().item(), 1.0), f"outproj err {err}"
+
+
 @pytest.mark.parametrize("M", [128, 1000, 333, 70001])
 def test_ffn_tc_against_torch(built_lib, M):
     F = 512
