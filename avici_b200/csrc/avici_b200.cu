@@ -35,7 +35,7 @@ struct Block {
   // bf16 tensor-core copies: K-major [N,K], LayerNorm affine and softmax scale folded in
   const bf16 *wqkv_t, *wo_t, *w1_t, *w2_t;
   const float *bqkv_f, *b1_f;
-  CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2, tm_w1c;  // tm_w1c: W1t in [128 x 64] boxes for the fused FFN kernel
+  CUtensorMap tm_wqkv, tm_wqkv_h, tm_wo, tm_w1, tm_w2, tm_w1c;  // tm_wqkv_h: [128 x 64] boxes for the CTA-pair kernel  // tm_w1c: W1t in [128 x 64] boxes for the fused FFN kernel
 };
 
 }  // namespace
@@ -181,6 +181,27 @@ int launch_ln_gemm_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, con
   if (launches) ++*launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ln_gemm_tc launch: %s", cudaGetErrorString(e));
+  return AVB_OK;
+}
+
+// CTA-pair (cluster of 2, cta_group::2) version; tm_b must have [128 x 64] boxes.
+template <int EPI>
+int launch_ln_gemm2_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, const float* bias, void* out, int ldo,
+                       int M, int N, cudaStream_t st, int num_sms, long long* launches, int seq_n, int seq_d, int seq_axis) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(avb::ln_gemm2_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         avb::kLnGemmSmemBytes);
+    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(ln_gemm2_tc): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int num_pairs = ((M + 127) / 128 + 1) / 2;
+  const int grid = 2 * std::min(num_pairs, num_sms / 2);
+  avb::ln_gemm2_tc_kernel<EPI><<<grid, avb::kLnGemmThreads, avb::kLnGemmSmemBytes, st>>>(
+      z, tm_b, bias, reinterpret_cast<bf16*>(out), ldo, M, N, seq_n, seq_d, seq_axis);
+  if (launches) ++*launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ln_gemm2_tc launch: %s", cudaGetErrorString(e));
   return AVB_OK;
 }
 
@@ -561,7 +582,8 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
     B.bqkv_f = df + o.bqkv_f; B.b1_f = df + o.b1_f;
     if (c.compute_dtype == AVB_DTYPE_BF16) {
       B.wqkv_t = db + o.wqkv_t; B.wo_t = db + o.wo_t; B.w1_t = db + o.w1_t; B.w2_t = db + o.w2_t;
-      bool ok = make_tmap_2d(&B.tm_wqkv, B.wqkv_t, 3 * HD, k, 256) && make_tmap_2d(&B.tm_wo, B.wo_t, k, HD, 128) &&
+      bool ok = make_tmap_2d(&B.tm_wqkv, B.wqkv_t, 3 * HD, k, 256) && make_tmap_2d(&B.tm_wqkv_h, B.wqkv_t, 3 * HD, k, 128) &&
+                make_tmap_2d(&B.tm_wo, B.wo_t, k, HD, 128) &&
                 make_tmap_2d(&B.tm_w1, B.w1_t, F, k, 256) && make_tmap_2d(&B.tm_w2, B.w2_t, k, F, 128) &&
                 make_tmap_2d(&B.tm_w1c, B.w1_t, F, k, 128);
       if (!ok) return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for block %d weights", i);
@@ -643,8 +665,12 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
     // attention half: LN -> QKV -> attention -> out-proj + residual
     { ProfScope ps(h, AVB_PROF_QKV, st);  // LayerNorm fused into the projection's prologue
       // rows in sequence-major order of `axis`, output in the attention kernel's operand layout
-      if ((rc = launch_ln_gemm_tc<2>(h, z, W.tm_wqkv, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, st, h->num_sms, &h->launches,
-                                     n, d, axis))) return rc; }
+      static const bool pair = !(getenv("AVB_QKV_2CTA") && getenv("AVB_QKV_2CTA")[0] == '0');  // A/B switch (debug)
+      if (pair) {
+        if ((rc = launch_ln_gemm2_tc<2>(h, z, W.tm_wqkv_h, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, st, h->num_sms, &h->launches,
+                                        n, d, axis))) return rc;
+      } else if ((rc = launch_ln_gemm_tc<2>(h, z, W.tm_wqkv, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, st, h->num_sms, &h->launches,
+                                            n, d, axis))) return rc; }
     { ProfScope ps(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
       if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches,
                                     reinterpret_cast<int*>(w8 + L.guard_off)))) return rc; }
@@ -889,10 +915,12 @@ int avb_test_qkv_layout_bf16(const float* z, const void* wt, const float* bias, 
   const int N = 3 * H * 32;
   void* packed = test_scratch(ntok * N * sizeof(bf16));
   if (!packed) return fail(nullptr, AVB_ERR_CUDA, "cudaMalloc(test scratch) failed");
+  static const bool pair = !(getenv("AVB_QKV_2CTA") && getenv("AVB_QKV_2CTA")[0] == '0');
   CUtensorMap tb;
-  if (!make_tmap_2d(&tb, wt, N, 128, 256)) return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  if (!make_tmap_2d(&tb, wt, N, 128, pair ? 128 : 256)) return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int rc = launch_ln_gemm_tc<2>(nullptr, z, tb, bias, packed, N, (int)ntok, N, st, sms, nullptr, n, d, axis);
+  const int rc = pair ? launch_ln_gemm2_tc<2>(nullptr, z, tb, bias, packed, N, (int)ntok, N, st, sms, nullptr, n, d, axis)
+                      : launch_ln_gemm_tc<2>(nullptr, z, tb, bias, packed, N, (int)ntok, N, st, sms, nullptr, n, d, axis);
   if (rc != AVB_OK) return rc;
   avb::unpack_qkv_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const bf16*>(packed), reinterpret_cast<bf16*>(out), B, n, d, H, axis);
   return cudaGetLastError() == cudaSuccess ? AVB_OK : fail(nullptr, AVB_ERR_CUDA, "unpack_qkv launch failed");

@@ -765,6 +765,209 @@ ln_gemm_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorM
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA-pair version of ln_gemm_tc_kernel (cluster of 2, tcgen05 cta_group::2): the pair works on 256 rows, each CTA
+// LayerNorm-s its own 128-row A tile and runs its own epilogue exactly as above, but every weight stage is fetched
+// half by each CTA ([128 of the 256 N-rows] x 64 K, 16 KB instead of 32 KB) and ONE M = 256 MMA issued by the leader
+// feeds both SMs.  The single-CTA kernel re-streams all 192 KB of QKV weights out of L2 for every 128 tokens and is
+// bound by the L2 -> SM fabric (measured ~29 B/clk/SM, reads + writes); the pair halves the weight share.
+// tm_b: tensor map of Wt with [128 rows x 64] boxes.
+// ------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLnGemmThreads, 1)
+ln_gemm2_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorMap tm_b,
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int M, int N,
+                  int seq_n, int seq_d, int seq_axis) {
+  const RowMap rm{seq_n, seq_d, EPI == 2 ? seq_axis : 0};
+  constexpr int ST = kLnGemmBStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                   // [2][32K]
+  uint8_t* sB = sA + 2 * kLnGemmABytes;                 // [ST][32K]
+  uint8_t* sStage = sB + ST * kLnGemmBBytes;            // [128][pitch]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + kLnGemmStageBytes);
+  uint64_t* a_full = bars;             // [2] leader: 2 x 128 LN threads
+  uint64_t* a_empty = bars + 2;        // [2] per CTA (multicast commit)
+  uint64_t* b_full = bars + 4;         // [ST]
+  uint64_t* b_empty = bars + 4 + ST;   // [ST]
+  uint64_t* t_full = bars + 4 + 2 * ST;  // [2]
+  uint64_t* t_empty = t_full + 2;      // [2] leader: 2 x 256 epilogue threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int num_m = (M + 127) / 128, num_c = N / 256;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int num_pairs = (num_m + 1) / 2, pair0 = (int)blockIdx.x >> 1, pair_stride = (int)gridDim.x >> 1;
+
+  if (warp == 4 && lane == 0) ptx::prefetch_tmap(&tm_b);
+  if (warp == 5 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&a_full[i], 256); ptx::mbar_init(&a_empty[i], 1);
+      ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 512);
+    }
+    for (int i = 0; i < ST; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 6) {
+    ptx::tmem_alloc_2sm(tmem_slot, 512);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();  // barriers of both CTAs initialised before anyone arrives on the peer's
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== LN producers: warp w normalises rows 32w .. 32w+31 of each tile
+    int it = 0;
+    for (int pr = pair0, mt = 2 * pair0 + (int)rank; pr < num_pairs; pr += pair_stride, mt += 2 * pair_stride, ++it) {
+      const int buf = it & 1;
+      prefetch_rows_l2(z, M, (mt + 2 * pair_stride) * 128 + warp * 32, lane, rm);
+      ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 40);
+      ln_warp_rows_to_umma_tile(z, M, mt * 128 + warp * 32, ptx::smem_u32(sA + buf * kLnGemmABytes), warp * 32, lane, rm);
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive_cluster(&a_full[buf], 0);
+    }
+  } else if (warp == 4) {
+    // ===================== weight TMA producer: for every m tile, N/256 chunks x 2 K blocks of [256 x 64]
+    int stage = 0; uint32_t phase = 0;
+    for (int pr = pair0, mt = 2 * pair0 + (int)rank; pr < num_pairs; pr += pair_stride, mt += 2 * pair_stride) {
+      for (int c = 0; c < num_c; ++c) {
+        for (int kb = 0; kb < 2; ++kb) {
+          ptx::mbar_wait(&b_empty[stage], phase ^ 1, 41);
+          if (ptx::elect_one()) {  // this CTA's half of the stage: N-rows [c*256 + rank*128, +128)
+            if (rank == 0) ptx::mbar_expect_tx(&b_full[stage], kLnGemmBBytes);  // both halves complete on the leader's barrier
+            ptx::tma_load_2d_2sm(sB + stage * kLnGemmBBytes, &tm_b, &b_full[stage], kb * 64, c * 256 + (int)rank * 128);
+          }
+          __syncwarp();
+          if (++stage == ST) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only): M = 256 over the pair
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(256, 256, 0, 0);
+    const uint64_t dA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024, ptx::kSwz128);
+    const uint64_t dB0 = ptx::make_smem_desc(ptx::smem_u32(sB), 16, 1024, ptx::kSwz128);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0, acc_it = 0;
+    for (int pr = pair0, mt = 2 * pair0 + (int)rank; pr < num_pairs; pr += pair_stride, mt += 2 * pair_stride, ++it) {
+      const int buf = it & 1;
+      ptx::mbar_wait(&a_full[buf], (it >> 1) & 1, 42);
+      for (int c = 0; c < num_c; ++c, ++acc_it) {
+        const int as = acc_it & 1;
+        ptx::mbar_wait(&t_empty[as], ((acc_it >> 1) & 1) ^ 1, 43);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int kb = 0; kb < 2; ++kb) {
+          ptx::mbar_wait(&b_full[stage], phase, 44);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint64_t da = dA0 + (uint64_t)(buf * (kLnGemmABytes >> 4) + kb * ((128 * 128) >> 4));
+            const uint64_t db = dB0 + (uint64_t)stage * (kLnGemmBBytes >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            ptx::umma_commit_2sm(&b_empty[stage], 3u);
+            if (kb == 1) {
+              ptx::umma_commit_2sm(&t_full[as], 3u);
+              if (c == num_c - 1) ptx::umma_commit_2sm(&a_empty[buf], 3u);
+            }
+          }
+          __syncwarp();
+          if (++stage == ST) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue: TMEM -> +bias (ReLU) -> bf16 -> smem stage -> coalesced global stores
+    const int q = warp & 3, hf = (warp - 8) >> 2;
+    const uint32_t stage_warp = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 32 * kLnGemmStagePitch);
+    const uint32_t stage_row = stage_warp + (uint32_t)(lane * kLnGemmStagePitch);
+    const int sub = lane >> 3, l8 = lane & 7;  // copy-out: 4 rows per warp store, 8 lanes x 16 B per row
+    const int seq_T = seq_axis == 0 ? seq_d : seq_n, seq_H = N / 96;  // EPI 2: sequence length, heads (N = 3 * H * 32)
+    int acc_it = 0;
+    for (int pr = pair0, mt = 2 * pair0 + (int)rank; pr < num_pairs; pr += pair_stride, mt += 2 * pair_stride) {
+      for (int c = 0; c < num_c; ++c, ++acc_it) {
+        const int as = acc_it & 1;
+        ptx::mbar_wait(&t_full[as], (acc_it >> 1) & 1, 45);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + as * 256 + hf * 128 + ((uint32_t)(q * 32) << 16);
+        const int col0 = c * 256 + hf * 128;
+#pragma unroll 1
+        for (int pc = 0; pc < 2; ++pc) {  // two pieces of 64 columns
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            float4 bb[8];  // bias of these 32 columns, requested before the TMEM load so the latencies overlap
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bias + col0 + pc * 64 + cc * 32) + e);
+            uint32_t v[32];
+            ptx::tmem_ld32(taddr + pc * 64 + cc * 32, v);
+            ptx::tmem_wait_ld();
+            if (pc == 1 && cc == 1) {  // accumulator fully read by this warp: hand it back to the MMA warp
+              ptx::tc_fence_before();
+              ptx::mbar_arrive_cluster(&t_empty[as], 0);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float f[8];
+              f[0] = __uint_as_float(v[e * 8 + 0]) + bb[e * 2].x;     f[1] = __uint_as_float(v[e * 8 + 1]) + bb[e * 2].y;
+              f[2] = __uint_as_float(v[e * 8 + 2]) + bb[e * 2].z;     f[3] = __uint_as_float(v[e * 8 + 3]) + bb[e * 2].w;
+              f[4] = __uint_as_float(v[e * 8 + 4]) + bb[e * 2 + 1].x; f[5] = __uint_as_float(v[e * 8 + 5]) + bb[e * 2 + 1].y;
+              f[6] = __uint_as_float(v[e * 8 + 6]) + bb[e * 2 + 1].z; f[7] = __uint_as_float(v[e * 8 + 7]) + bb[e * 2 + 1].w;
+              if (EPI == 1) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], 0.f);
+              }
+              uint4 pk;
+              pk.x = ptx::pack_bf16(f[0], f[1]); pk.y = ptx::pack_bf16(f[2], f[3]);
+              pk.z = ptx::pack_bf16(f[4], f[5]); pk.w = ptx::pack_bf16(f[6], f[7]);
+              ptx::st_shared_v4(stage_row + (uint32_t)(cc * 64 + e * 16), pk);
+            }
+          }
+          __syncwarp();  // the 32 staged rows are written and read by this warp only
+          if (EPI == 2) {
+            // 64 staged columns = heads (hd0, hd0 + 1) of q, k or v.  A warp store covers 8 consecutive positions of
+            // one head = 512 contiguous bytes (lane = chunk * 8 + row: conflict-free reads of the padded stage).
+            const int colp = col0 + pc * 64, w = colp >> 8, hd0 = (colp & 255) >> 5;
+            const int r8 = lane & 7, c4 = lane >> 3;
+#pragma unroll
+            for (int rr = 0; rr < 32; rr += 8) {
+              const int row = rr + r8;
+              const int grow = mt * 128 + q * 32 + row;
+              const unsigned sq = (unsigned)grow / (unsigned)seq_T, pos = (unsigned)grow - sq * (unsigned)seq_T;
+              __nv_bfloat16* dst = out + ((((size_t)sq * 3 + w) * seq_H + hd0) * seq_T + pos) * 32 + ((c4 ^ ((pos >> 1) & 3)) << 3);
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                uint4 pk;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w)
+                             : "r"(stage_warp + (uint32_t)(row * kLnGemmStagePitch + hh * 64 + c4 * 16)));
+                if (grow < M) *reinterpret_cast<uint4*>(dst + (size_t)hh * seq_T * 32) = pk;
+              }
+            }
+          } else {
+#pragma unroll
+          for (int rr = 0; rr < 32; rr += 4) {
+            const int row = rr + sub;
+            const int grow = mt * 128 + q * 32 + row;
+            uint4 pk;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w)
+                         : "r"(stage_warp + (uint32_t)(row * kLnGemmStagePitch + l8 * 16)));
+            if (grow < M) *reinterpret_cast<uint4*>(out + (size_t)grow * ldo + col0 + pc * 64 + l8 * 8) = pk;
+          }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();  // the peer's shared memory and barriers stay valid until both CTAs are done
+  if (warp == 6) ptx::tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------
 // Fused FFN sub-layer, in place on the fp32 residual stream (model.py:67-75):
 //     z += relu( LN(z) @ W1' + b1' ) @ W2 + b2          (LayerNorm affine folded into W1' / b1')
 //   Neither the LayerNorm output nor the 512-wide hidden activation ever touch HBM: per 128-token tile the
