@@ -35,7 +35,7 @@ struct Block {
   // bf16 tensor-core copies: K-major [N,K], LayerNorm affine and softmax scale folded in
   const bf16 *wqkv_t, *wo_t, *w1_t, *w2_t;
   const float *bqkv_f, *b1_f;
-  CUtensorMap tm_wqkv, tm_wqkv_h, tm_wo, tm_w1, tm_w2, tm_w1c;  // tm_wqkv_h: [128 x 64] boxes for the CTA-pair kernel  // tm_w1c: W1t in [128 x 64] boxes for the fused FFN kernel
+  CUtensorMap tm_wqkv, tm_wqkv_h, tm_wo, tm_w1, tm_w2, tm_w1c, tm_w1q, tm_w2q;  // *q: [64 x 64] boxes (CTA-pair FFN)  // tm_wqkv_h: [128 x 64] boxes for the CTA-pair kernel  // tm_w1c: W1t in [128 x 64] boxes for the fused FFN kernel
 };
 
 }  // namespace
@@ -236,6 +236,24 @@ int launch_ffn_tc(avb_handle h, float* z, const CUtensorMap& tm_w1c, const CUten
   if (launches) ++*launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ffn_tc launch: %s", cudaGetErrorString(e));
+  return AVB_OK;
+}
+
+// CTA-pair (cluster of 2, cta_group::2) fused FFN; tensor maps with [64 x 64] boxes.
+int launch_ffn2_tc(avb_handle h, float* z, const CUtensorMap& tm_w1q, const CUtensorMap& tm_w2q, const float* b1,
+                   const float* b2, int M, int F, cudaStream_t st, int num_sms, long long* launches) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(avb::ffn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kFfnSmemBytes);
+    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(ffn2_tc): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int num_pairs = ((M + 127) / 128 + 1) / 2;
+  const int grid = 2 * std::min(num_pairs, num_sms / 2);
+  avb::ffn2_tc_kernel<<<grid, avb::kFfnThreads, avb::kFfnSmemBytes, st>>>(z, tm_w1q, tm_w2q, b1, b2, M, F);
+  if (launches) ++*launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ffn2_tc launch: %s", cudaGetErrorString(e));
   return AVB_OK;
 }
 
@@ -585,7 +603,8 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
       bool ok = make_tmap_2d(&B.tm_wqkv, B.wqkv_t, 3 * HD, k, 256) && make_tmap_2d(&B.tm_wqkv_h, B.wqkv_t, 3 * HD, k, 128) &&
                 make_tmap_2d(&B.tm_wo, B.wo_t, k, HD, 128) &&
                 make_tmap_2d(&B.tm_w1, B.w1_t, F, k, 256) && make_tmap_2d(&B.tm_w2, B.w2_t, k, F, 128) &&
-                make_tmap_2d(&B.tm_w1c, B.w1_t, F, k, 128);
+                make_tmap_2d(&B.tm_w1c, B.w1_t, F, k, 128) && make_tmap_2d(&B.tm_w1q, B.w1_t, F, k, 64) &&
+                make_tmap_2d(&B.tm_w2q, B.w2_t, k, F, 64);
       if (!ok) return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for block %d weights", i);
     }
   }
@@ -678,7 +697,9 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
       if ((rc = launch_outproj_tc(h, attn, W.tm_wo, W.bo, z, M, n, d, axis, st, h->num_sms, &h->launches))) return rc; }
     // FFN half: LN -> Linear + ReLU -> Linear + residual
     { ProfScope ps(h, AVB_PROF_FFN1, st);  // whole FFN sub-layer in one kernel (LN, up-projection, ReLU, down-projection, residual)
-      if ((rc = launch_ffn_tc(h, z, W.tm_w1c, W.tm_w2, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches))) return rc; }
+      static const bool pair = !(getenv("AVB_FFN_2CTA") && getenv("AVB_FFN_2CTA")[0] == '0');  // A/B switch (debug)
+      if (pair) { if ((rc = launch_ffn2_tc(h, z, W.tm_w1q, W.tm_w2q, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches))) return rc; }
+      else if ((rc = launch_ffn_tc(h, z, W.tm_w1c, W.tm_w2, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches))) return rc; }
   } else {
     float* qkv = reinterpret_cast<float*>(w8 + L.big_off);
     float* hid = qkv;
@@ -950,10 +971,12 @@ int avb_test_ffn_bf16(float* z, const void* w1t, const void* w2t, const float* b
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device");
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static const bool pair = !(getenv("AVB_FFN_2CTA") && getenv("AVB_FFN_2CTA")[0] == '0');
   CUtensorMap t1, t2;
-  if (!make_tmap_2d(&t1, w1t, F, 128, 128) || !make_tmap_2d(&t2, w2t, 128, F, 128))
+  if (!make_tmap_2d(&t1, w1t, F, 128, pair ? 64 : 128) || !make_tmap_2d(&t2, w2t, 128, F, pair ? 64 : 128))
     return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-  return launch_ffn_tc(nullptr, z, t1, t2, b1, b2, M, F, reinterpret_cast<cudaStream_t>(stream), sms, nullptr);
+  return pair ? launch_ffn2_tc(nullptr, z, t1, t2, b1, b2, M, F, reinterpret_cast<cudaStream_t>(stream), sms, nullptr)
+              : launch_ffn_tc(nullptr, z, t1, t2, b1, b2, M, F, reinterpret_cast<cudaStream_t>(stream), sms, nullptr);
 }
 
 int avb_debug_set_trace(void* trace_dev) {

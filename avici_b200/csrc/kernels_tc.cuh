@@ -1209,6 +1209,239 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA-pair version of ffn_tc_kernel (cluster of 2, tcgen05 cta_group::2).  Each CTA keeps its own 128-token tile,
+// LayerNorm, E1 / E2 epilogues and TMEM exactly as above; the pair shares every weight chunk: each CTA fetches 64 of
+// the 128 N-rows of W1c and of W2c (half the L2 -> SM weight traffic, which is 2/3 of this kernel's reads and what
+// bounds it) and the leader issues M = 256 MMAs for both SMs.  Barriers the MMA issuer waits on live in the leader
+// and count the arrivals of both CTAs; its commits are multicast to both.
+// tm_w1 / tm_w2: tensor maps with [64 rows x 64] boxes.
+// ------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFfnThreads, 1)
+ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
+              const float* __restrict__ b1, const float* __restrict__ b2, int M, int F) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                        // [2][32K] xhat
+  uint8_t* sW = sA + 2 * kLnGemmABytes;      // [2 stages][W1c 32K | W2c 32K]
+  uint8_t* sStage = sW + 4 * kFfnWBytes;     // [8 epilogue warps][4 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 8 * 4096);
+  uint64_t* a_full = bars;          // [2] 128 LN threads
+  uint64_t* a_empty = bars + 2;     // [2]
+  uint64_t* w1_full = bars + 4;     // [2]
+  uint64_t* w1_empty = bars + 6;    // [2]
+  uint64_t* w2_full = bars + 8;     // [2]
+  uint64_t* w2_empty = bars + 10;   // [2]
+  uint64_t* d1_full = bars + 12;    // [1]
+  uint64_t* d1_empty = bars + 13;   // [1] 256 epilogue threads
+  uint64_t* h_full = bars + 14;     // [2] 256 epilogue threads
+  uint64_t* h_empty = bars + 16;    // [2]
+  uint64_t* d2_full = bars + 18;    // [2]
+  uint64_t* d2_empty = bars + 20;   // [2] 256 epilogue threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int num_m = (M + 127) / 128, num_c = F / 128;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int num_pairs = (num_m + 1) / 2, pair0 = (int)blockIdx.x >> 1, pair_stride = (int)gridDim.x >> 1;
+  long long* trace = (blockIdx.x == 0 && (warp == 5 || warp == 8 || warp == 0) && lane == 0) ? g_attn_trace : nullptr;
+
+  if (warp == 4 && lane == 0) { ptx::prefetch_tmap(&tm_w1); ptx::prefetch_tmap(&tm_w2); }
+  if (warp == 5 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&a_full[i], 256); ptx::mbar_init(&a_empty[i], 1);
+      ptx::mbar_init(&w1_full[i], 1); ptx::mbar_init(&w1_empty[i], 1);
+      ptx::mbar_init(&w2_full[i], 1); ptx::mbar_init(&w2_empty[i], 1);
+      ptx::mbar_init(&h_full[i], 512); ptx::mbar_init(&h_empty[i], 1);
+      ptx::mbar_init(&d2_full[i], 1); ptx::mbar_init(&d2_empty[i], 512);
+    }
+    ptx::mbar_init(d1_full, 1); ptx::mbar_init(d1_empty, 512);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 6) {
+    ptx::tmem_alloc_2sm(tmem_slot, 512);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_D1 = tmem_base;        // 128
+  const uint32_t tmem_H = tmem_base + 128;   // 2 x 64
+  const uint32_t tmem_D2 = tmem_base + 256;  // 2 x 128 (by tile parity)
+
+  if (warp < 4) {
+    // ===================== LN producers (same as ln_gemm_tc_kernel)
+    int it = 0;
+    for (int pr = pair0, mt = 2 * pair0 + (int)rank; pr < num_pairs; pr += pair_stride, mt += 2 * pair_stride, ++it) {
+      const int buf = it & 1;
+      AVB_TRACE(0, it, 0);
+      prefetch_rows_l2(z, M, (mt + 2 * pair_stride) * 128 + warp * 32, lane);
+      ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 50);
+      AVB_TRACE(0, it, 1);
+      ln_warp_rows_to_umma_tile(z, M, mt * 128 + warp * 32, ptx::smem_u32(sA + buf * kLnGemmABytes), warp * 32, lane);
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive_cluster(&a_full[buf], 0);
+      AVB_TRACE(0, it, 2);
+    }
+  } else if (warp == 4) {
+    // ===================== weight TMA producer: per chunk W1c = W1t[128c.., 0..127], W2c = W2t[0..127, 128c..]
+    int g = 0;
+    for (int pr = pair0, mt = 2 * pair0 + (int)rank; pr < num_pairs; pr += pair_stride, mt += 2 * pair_stride) {
+      for (int c = 0; c < num_c; ++c, ++g) {
+        const int st = g & 1;
+        const uint32_t ph = (uint32_t)((g >> 1) & 1) ^ 1;
+        uint8_t* w1 = sW + st * 2 * kFfnWBytes;
+        uint8_t* w2 = w1 + kFfnWBytes;
+        ptx::mbar_wait(&w1_empty[st], ph, 51);
+        if (ptx::elect_one()) {  // this CTA's 64 of the chunk's 128 N-rows (hidden units), both K blocks
+          if (rank == 0) ptx::mbar_expect_tx(&w1_full[st], kFfnWBytes);  // both halves complete on the leader's barrier
+          ptx::tma_load_2d_2sm(w1, &tm_w1, &w1_full[st], 0, c * 128 + (int)rank * 64);
+          ptx::tma_load_2d_2sm(w1 + 128 * 128, &tm_w1, &w1_full[st], 64, c * 128 + (int)rank * 64);
+        }
+        __syncwarp();
+        ptx::mbar_wait(&w2_empty[st], ph, 52);
+        if (ptx::elect_one()) {  // this CTA's 64 of the 128 N-rows (output channels)
+          if (rank == 0) ptx::mbar_expect_tx(&w2_full[st], kFfnWBytes);
+          ptx::tma_load_2d_2sm(w2, &tm_w2, &w2_full[st], c * 128, (int)rank * 64);
+          ptx::tma_load_2d_2sm(w2 + 128 * 128, &tm_w2, &w2_full[st], c * 128 + 64, (int)rank * 64);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 5 && rank == 0) {
+    // ===================== MMA issuer (leader CTA): G1(g+1) is issued before G2(g) so the tensor core overlaps E1
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(256, 128, 0, 0);
+    const uint64_t dA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024, ptx::kSwz128);
+    const uint64_t dW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024, ptx::kSwz128);
+    const int my_tiles = pair0 < num_pairs ? (num_pairs - 1 - pair0) / pair_stride + 1 : 0;
+    const int total = my_tiles * num_c;
+    auto issue_G1 = [&](int g) {
+      const int tile_it = g / num_c, c = g % num_c, buf = tile_it & 1, st = g & 1;
+      if (c == 0) ptx::mbar_wait(&a_full[buf], (uint32_t)((tile_it >> 1) & 1), 53);
+      ptx::mbar_wait(&w1_full[st], (uint32_t)((g >> 1) & 1), 54);
+      ptx::mbar_wait(d1_empty, (uint32_t)(g & 1) ^ 1, 55);  // E1 of the previous chunk has read D1
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint64_t da = dA0 + (uint64_t)(buf * (kLnGemmABytes >> 4));
+        const uint64_t dw = dW0 + (uint64_t)(st * ((2 * kFfnWBytes) >> 4));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // K block (kk >> 2) is 16 KB further, 32 bytes per K=16 slice inside it
+          const uint64_t off = (uint64_t)((kk >> 2) * ((128 * 128) >> 4) + (kk & 3) * 2);
+          ptx::umma_bf16_2sm(tmem_D1, da + off, dw + off, idesc, kk != 0);
+        }
+        ptx::umma_commit_2sm(&w1_empty[st], 3u);
+        ptx::umma_commit_2sm(d1_full, 3u);
+        if (c == num_c - 1) ptx::umma_commit_2sm(&a_empty[buf], 3u);
+      }
+      __syncwarp();
+    };
+    if (total > 0) issue_G1(0);
+    for (int g = 0; g < total; ++g) {
+      AVB_TRACE(1, g, 0);
+      if (g + 1 < total) issue_G1(g + 1);
+      AVB_TRACE(1, g, 1);
+      const int tile_it = g / num_c, c = g % num_c, st = g & 1, hs = g & 1;
+      ptx::mbar_wait(&w2_full[st], (uint32_t)((g >> 1) & 1), 56);
+      AVB_TRACE(1, g, 2);
+      ptx::mbar_wait(&h_full[hs], (uint32_t)((g >> 1) & 1), 57);
+      AVB_TRACE(1, g, 3);
+      if (c == 0 && tile_it >= 2) ptx::mbar_wait(&d2_empty[tile_it & 1], (uint32_t)(((tile_it >> 1) - 1) & 1), 58);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint64_t dw = dW0 + (uint64_t)(st * ((2 * kFfnWBytes) >> 4) + (kFfnWBytes >> 4));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t off = (uint64_t)((kk >> 2) * ((128 * 128) >> 4) + (kk & 3) * 2);
+          ptx::umma_bf16_ts_2sm(tmem_D2 + (tile_it & 1) * 128, tmem_H + hs * 64 + kk * 8, dw + off, idesc, (c | kk) != 0);
+        }
+        ptx::umma_commit_2sm(&w2_empty[st], 3u);
+        ptx::umma_commit_2sm(&h_empty[hs], 3u);
+        if (c == num_c - 1) ptx::umma_commit_2sm(&d2_full[tile_it & 1], 3u);
+      }
+      __syncwarp();
+      AVB_TRACE(1, g, 4);
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue warps: (TMEM lane quarter q) x (64-column half)
+    const int q = warp & 3, half = (warp - 8) >> 2;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t stage = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 4096);
+    // E2 of a tile (z += D2 + b2) is deferred until after the first E1 of the NEXT tile: D2 is double-buffered by tile
+    // parity, so the wait for the tile's last G2 MMAs and the z round trip overlap the next tile's MMAs.
+    auto E2 = [&](int t_it, int t_mt) {
+      ptx::mbar_wait(&d2_full[t_it & 1], (uint32_t)((t_it >> 1) & 1), 61);
+      ptx::tc_fence_after();
+      const int row0 = t_mt * 128 + q * 32;
+      const int rows_valid = M - row0 < 32 ? M - row0 : 32;  // may be <= 0 on the last tile
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_D2 + (t_it & 1) * 128 + half * 64 + cc * 32 + lane_off, v);
+        ptx::tmem_wait_ld();
+        if (cc == 1) {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive_cluster(&d2_empty[t_it & 1], 0);
+        }
+        residual_add_block_32x32(v, b2 + half * 64 + cc * 32, stage, z + (size_t)row0 * 128 + half * 64 + cc * 32, 128,
+                                 rows_valid, lane);
+      }
+    };
+    int g = 0, tile_it = 0, prev_mt = -1;
+    for (int pr = pair0, mt = 2 * pair0 + (int)rank; pr < num_pairs; pr += pair_stride, mt += 2 * pair_stride, ++tile_it) {
+      for (int c = 0; c < num_c; ++c, ++g) {
+        // ---- E1: D1 -> +b1 -> ReLU -> bf16 pairs -> H
+        const int hs = g & 1;
+        const float* bp = b1 + c * 128 + half * 64;
+        float4 bb[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bp) + e);
+        AVB_TRACE(2, g, 0);
+        ptx::mbar_wait(d1_full, (uint32_t)(g & 1), 59);
+        AVB_TRACE(2, g, 1);
+        ptx::tc_fence_after();
+        uint32_t pk[32];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_D1 + half * 64 + cc * 32 + lane_off, v);
+          ptx::tmem_wait_ld();
+          if (cc == 1) {  // D1 fully read by this thread: the next chunk's G1 may overwrite it
+            ptx::tc_fence_before();
+            ptx::mbar_arrive_cluster(d1_empty, 0);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 b4 = bb[cc * 8 + e];
+            const float f0 = fmaxf(__uint_as_float(v[e * 4 + 0]) + b4.x, 0.f), f1 = fmaxf(__uint_as_float(v[e * 4 + 1]) + b4.y, 0.f);
+            const float f2 = fmaxf(__uint_as_float(v[e * 4 + 2]) + b4.z, 0.f), f3 = fmaxf(__uint_as_float(v[e * 4 + 3]) + b4.w, 0.f);
+            pk[cc * 16 + e * 2 + 0] = ptx::pack_bf16(f0, f1);
+            pk[cc * 16 + e * 2 + 1] = ptx::pack_bf16(f2, f3);
+          }
+        }
+        AVB_TRACE(2, g, 2);
+        ptx::mbar_wait(&h_empty[hs], (uint32_t)((g >> 1) & 1) ^ 1, 60);  // G2 of two chunks ago has consumed H[hs]
+        AVB_TRACE(2, g, 3);
+        ptx::tc_fence_after();
+        ptx::tmem_st32(tmem_H + hs * 64 + half * 32 + lane_off, pk);
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive_cluster(&h_full[hs], 0);
+        AVB_TRACE(2, g, 4);
+        if (c == 0 && prev_mt >= 0) {
+          E2(tile_it - 1, prev_mt);
+          AVB_TRACE(2, g, 6);
+        }
+      }
+      prev_mt = mt;
+    }
+    if (prev_mt >= 0) E2(tile_it - 1, prev_mt);
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 6) ptx::tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------
 // Flash-style axial attention on tensor cores.  head dim 32, 128-query x 128-key tiles.
 //   qkv comes from ln_gemm_tc_kernel<2> in the operand layout [seq][q,k,v][head][pos][32 ch] (pre-swizzled):
 //   a work item (s, h, qt) fetches its [128 x 32] Q tile and streams the [128 x 32] K / V tiles of its sequence,

@@ -304,6 +304,16 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, 
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
+// same with the A operand in TMEM (each CTA's own 128 lanes)
+__device__ __forceinline__ void umma_bf16_ts_2sm(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
 // arrive on the barrier at this offset in every CTA of `cta_mask` once all MMAs issued so far have completed
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint32_t cta_mask) {
   asm volatile(
