@@ -1222,22 +1222,23 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                        // [2][32K] xhat
-  uint8_t* sW = sA + 2 * kLnGemmABytes;      // [2 stages][W1c 32K | W2c 32K]
+  uint8_t* sW = sA + 2 * kLnGemmABytes;      // [4 stages][W1c half 16K | W2c half 16K]: 64 N-rows per CTA, twice the ring depth
   uint8_t* sStage = sW + 4 * kFfnWBytes;     // [8 epilogue warps][4 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 8 * 4096);
   uint64_t* a_full = bars;          // [2] 128 LN threads
   uint64_t* a_empty = bars + 2;     // [2]
-  uint64_t* w1_full = bars + 4;     // [2]
-  uint64_t* w1_empty = bars + 6;    // [2]
-  uint64_t* w2_full = bars + 8;     // [2]
-  uint64_t* w2_empty = bars + 10;   // [2]
-  uint64_t* d1_full = bars + 12;    // [1]
-  uint64_t* d1_empty = bars + 13;   // [1] 256 epilogue threads
-  uint64_t* h_full = bars + 14;     // [2] 256 epilogue threads
-  uint64_t* h_empty = bars + 16;    // [2]
-  uint64_t* d2_full = bars + 18;    // [2]
-  uint64_t* d2_empty = bars + 20;   // [2] 256 epilogue threads
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  constexpr int WS = 4;             // weight ring stages
+  uint64_t* w1_full = bars + 4;     // [WS] leader
+  uint64_t* w1_empty = bars + 8;    // [WS]
+  uint64_t* w2_full = bars + 12;    // [WS] leader
+  uint64_t* w2_empty = bars + 16;   // [WS]
+  uint64_t* d1_full = bars + 20;    // [1]
+  uint64_t* d1_empty = bars + 21;   // [1] leader: 2 x 256 epilogue threads
+  uint64_t* h_full = bars + 22;     // [2] leader: 2 x 256 epilogue threads
+  uint64_t* h_empty = bars + 24;    // [2]
+  uint64_t* d2_full = bars + 26;    // [2]
+  uint64_t* d2_empty = bars + 28;   // [2] leader: 2 x 256 epilogue threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int num_m = (M + 127) / 128, num_c = F / 128;
@@ -1247,10 +1248,12 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
 
   if (warp == 4 && lane == 0) { ptx::prefetch_tmap(&tm_w1); ptx::prefetch_tmap(&tm_w2); }
   if (warp == 5 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&a_full[i], 256); ptx::mbar_init(&a_empty[i], 1);
+    for (int i = 0; i < WS; ++i) {
       ptx::mbar_init(&w1_full[i], 1); ptx::mbar_init(&w1_empty[i], 1);
       ptx::mbar_init(&w2_full[i], 1); ptx::mbar_init(&w2_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&a_full[i], 256); ptx::mbar_init(&a_empty[i], 1);
       ptx::mbar_init(&h_full[i], 512); ptx::mbar_init(&h_empty[i], 1);
       ptx::mbar_init(&d2_full[i], 1); ptx::mbar_init(&d2_empty[i], 512);
     }
@@ -1288,22 +1291,22 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
     int g = 0;
     for (int pr = pair0, mt = 2 * pair0 + (int)rank; pr < num_pairs; pr += pair_stride, mt += 2 * pair_stride) {
       for (int c = 0; c < num_c; ++c, ++g) {
-        const int st = g & 1;
-        const uint32_t ph = (uint32_t)((g >> 1) & 1) ^ 1;
-        uint8_t* w1 = sW + st * 2 * kFfnWBytes;
-        uint8_t* w2 = w1 + kFfnWBytes;
+        const int st = g & 3;
+        const uint32_t ph = (uint32_t)((g >> 2) & 1) ^ 1;
+        uint8_t* w1 = sW + st * kFfnWBytes;       // 32 KB per stage: W1c half | W2c half
+        uint8_t* w2 = w1 + kFfnWBytes / 2;
         ptx::mbar_wait(&w1_empty[st], ph, 51);
         if (ptx::elect_one()) {  // this CTA's 64 of the chunk's 128 N-rows (hidden units), both K blocks
           if (rank == 0) ptx::mbar_expect_tx(&w1_full[st], kFfnWBytes);  // both halves complete on the leader's barrier
           ptx::tma_load_2d_2sm(w1, &tm_w1, &w1_full[st], 0, c * 128 + (int)rank * 64);
-          ptx::tma_load_2d_2sm(w1 + 128 * 128, &tm_w1, &w1_full[st], 64, c * 128 + (int)rank * 64);
+          ptx::tma_load_2d_2sm(w1 + 64 * 128, &tm_w1, &w1_full[st], 64, c * 128 + (int)rank * 64);
         }
         __syncwarp();
         ptx::mbar_wait(&w2_empty[st], ph, 52);
         if (ptx::elect_one()) {  // this CTA's 64 of the 128 N-rows (output channels)
           if (rank == 0) ptx::mbar_expect_tx(&w2_full[st], kFfnWBytes);
           ptx::tma_load_2d_2sm(w2, &tm_w2, &w2_full[st], c * 128, (int)rank * 64);
-          ptx::tma_load_2d_2sm(w2 + 128 * 128, &tm_w2, &w2_full[st], c * 128 + 64, (int)rank * 64);
+          ptx::tma_load_2d_2sm(w2 + 64 * 128, &tm_w2, &w2_full[st], c * 128 + 64, (int)rank * 64);
         }
         __syncwarp();
       }
@@ -1316,18 +1319,19 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
     const int my_tiles = pair0 < num_pairs ? (num_pairs - 1 - pair0) / pair_stride + 1 : 0;
     const int total = my_tiles * num_c;
     auto issue_G1 = [&](int g) {
-      const int tile_it = g / num_c, c = g % num_c, buf = tile_it & 1, st = g & 1;
+      const int tile_it = g / num_c, c = g % num_c, buf = tile_it & 1, st = g & 3;
       if (c == 0) ptx::mbar_wait(&a_full[buf], (uint32_t)((tile_it >> 1) & 1), 53);
-      ptx::mbar_wait(&w1_full[st], (uint32_t)((g >> 1) & 1), 54);
+      ptx::mbar_wait(&w1_full[st], (uint32_t)((g >> 2) & 1), 54);
       ptx::mbar_wait(d1_empty, (uint32_t)(g & 1) ^ 1, 55);  // E1 of the previous chunk has read D1
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint64_t da = dA0 + (uint64_t)(buf * (kLnGemmABytes >> 4));
-        const uint64_t dw = dW0 + (uint64_t)(st * ((2 * kFfnWBytes) >> 4));
+        const uint64_t dw = dW0 + (uint64_t)(st * (kFfnWBytes >> 4));
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {  // K block (kk >> 2) is 16 KB further, 32 bytes per K=16 slice inside it
-          const uint64_t off = (uint64_t)((kk >> 2) * ((128 * 128) >> 4) + (kk & 3) * 2);
-          ptx::umma_bf16_2sm(tmem_D1, da + off, dw + off, idesc, kk != 0);
+        for (int kk = 0; kk < 8; ++kk) {  // K block (kk >> 2): 16 KB further in A (128 rows), 8 KB in the 64-row W half
+          const uint64_t offa = (uint64_t)((kk >> 2) * ((128 * 128) >> 4) + (kk & 3) * 2);
+          const uint64_t offw = (uint64_t)((kk >> 2) * ((64 * 128) >> 4) + (kk & 3) * 2);
+          ptx::umma_bf16_2sm(tmem_D1, da + offa, dw + offw, idesc, kk != 0);
         }
         ptx::umma_commit_2sm(&w1_empty[st], 3u);
         ptx::umma_commit_2sm(d1_full, 3u);
@@ -1340,18 +1344,18 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
       AVB_TRACE(1, g, 0);
       if (g + 1 < total) issue_G1(g + 1);
       AVB_TRACE(1, g, 1);
-      const int tile_it = g / num_c, c = g % num_c, st = g & 1, hs = g & 1;
-      ptx::mbar_wait(&w2_full[st], (uint32_t)((g >> 1) & 1), 56);
+      const int tile_it = g / num_c, c = g % num_c, st = g & 3, hs = g & 1;
+      ptx::mbar_wait(&w2_full[st], (uint32_t)((g >> 2) & 1), 56);
       AVB_TRACE(1, g, 2);
       ptx::mbar_wait(&h_full[hs], (uint32_t)((g >> 1) & 1), 57);
       AVB_TRACE(1, g, 3);
       if (c == 0 && tile_it >= 2) ptx::mbar_wait(&d2_empty[tile_it & 1], (uint32_t)(((tile_it >> 1) - 1) & 1), 58);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        const uint64_t dw = dW0 + (uint64_t)(st * ((2 * kFfnWBytes) >> 4) + (kFfnWBytes >> 4));
+        const uint64_t dw = dW0 + (uint64_t)(st * (kFfnWBytes >> 4) + ((kFfnWBytes / 2) >> 4));
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t off = (uint64_t)((kk >> 2) * ((128 * 128) >> 4) + (kk & 3) * 2);
+          const uint64_t off = (uint64_t)((kk >> 2) * ((64 * 128) >> 4) + (kk & 3) * 2);
           ptx::umma_bf16_ts_2sm(tmem_D2 + (tile_it & 1) * 128, tmem_H + hs * 64 + kk * 8, dw + off, idesc, (c | kk) != 0);
         }
         ptx::umma_commit_2sm(&w2_empty[st], 3u);
