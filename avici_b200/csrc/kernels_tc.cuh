@@ -542,6 +542,70 @@ __device__ __forceinline__ void ln_warp_rows_to_umma_tile(const float* __restric
   }
 }
 
+// Same, and the RAW fp32 rows are also parked in a per-warp 16 KB shared-memory stage ([32 rows][32 x 16-byte chunks],
+// chunk index XOR-ed with row & 7) from which the warp reads them back one row per thread - the tcgen05.st layout.
+// Used by the CTA-pair FFN kernel to preload its residual accumulator with z (see ffn2_tc_kernel).
+__device__ __forceinline__ void ln_warp_rows_to_umma_tile_stash(const float* __restrict__ z, int M, int grow0, uint32_t a_tile,
+                                                                int row0, int lane, uint32_t stash) {
+  const int rs = lane >> 3, j = lane & 7;
+  const float4* zp = reinterpret_cast<const float4*>(z) + j;
+  float4 cur[2][4], nxt[2][4];
+  auto load = [&](float4 (&dst)[2][4], int r0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int grow = grow0 + r0 + u * 4 + rs;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        dst[u][k] = grow < M ? __ldcg(zp + (size_t)grow * 32 + k * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  load(cur, 0);
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 8) {
+    if (r0 + 8 < 32) load(nxt, r0 + 8);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int rl = r0 + u * 4 + rs;  // row inside the warp's 32
+#pragma unroll
+      for (int k = 0; k < 4; ++k)  // raw values: chunk (j + 8k) of row rl
+        ptx::st_shared_v4(stash + (uint32_t)(rl * 512 + (((j + 8 * k) ^ (rl & 7)) << 4)),
+                          make_uint4(__float_as_uint(cur[u][k].x), __float_as_uint(cur[u][k].y), __float_as_uint(cur[u][k].z),
+                                     __float_as_uint(cur[u][k].w)));
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sum += (cur[u][k].x + cur[u][k].y) + (cur[u][k].z + cur[u][k].w);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      const float mean = sum * (1.0f / 128.0f);
+      float sq = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        cur[u][k].x -= mean; cur[u][k].y -= mean; cur[u][k].z -= mean; cur[u][k].w -= mean;
+        sq += (cur[u][k].x * cur[u][k].x + cur[u][k].y * cur[u][k].y) + (cur[u][k].z * cur[u][k].z + cur[u][k].w * cur[u][k].w);
+      }
+      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+      const float rstd = rsqrtf(sq * (1.0f / 128.0f) + kLnEps);
+      const int r = row0 + rl;
+      const uint32_t rbase = a_tile + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (j & 1) * 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int chunk = (j + 8 * (k & 1)) >> 1;
+        const uint32_t addr = rbase + (uint32_t)((k >> 1) * (128 * 128) + ((chunk ^ (r & 7)) << 4));
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ptx::pack_bf16(cur[u][k].x * rstd, cur[u][k].y * rstd)),
+                     "r"(ptx::pack_bf16(cur[u][k].z * rstd, cur[u][k].w * rstd))
+                     : "memory");
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cur[u][k] = nxt[u][k];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Fused LayerNorm -> GEMM:  out[M, N] = act( LN(z)[M,128] @ Wt[N,128]^T + bias[N] ),  bf16 out.
 //   (QKV projection: N = 768, act = id;  FFN up-projection: N = 512, act = ReLU.  LayerNorm gamma/beta
@@ -1214,6 +1278,8 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
 // the 128 N-rows of W1c and of W2c (half the L2 -> SM weight traffic, which is 2/3 of this kernel's reads and what
 // bounds it) and the leader issues M = 256 MMAs for both SMs.  Barriers the MMA issuer waits on live in the leader
 // and count the arrivals of both CTAs; its commits are multicast to both.
+// The shared memory the halved weight ring frees carries the raw z rows from the LayerNorm warps into TMEM: D2 starts
+// as the residual, G2 accumulates onto it, and the final epilogue is write-only (no second read of z).
 // tm_w1 / tm_w2: tensor maps with [64 rows x 64] boxes.
 // ------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFfnThreads, 1)
@@ -1222,12 +1288,14 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                        // [2][32K] xhat
-  uint8_t* sW = sA + 2 * kLnGemmABytes;      // [4 stages][W1c half 16K | W2c half 16K]: 64 N-rows per CTA, twice the ring depth
+  uint8_t* sW = sA + 2 * kLnGemmABytes;      // [2 stages][W1c half 16K | W2c half 16K]: 64 N-rows per CTA
+  uint8_t* sZ = sW + 2 * kFfnWBytes;         // [4 LN warps][16 KB]: raw z rows on their way into TMEM (the half of the
+                                             // weight ring the pair does not need)
   uint8_t* sStage = sW + 4 * kFfnWBytes;     // [8 epilogue warps][4 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 8 * 4096);
   uint64_t* a_full = bars;          // [2] 128 LN threads
   uint64_t* a_empty = bars + 2;     // [2]
-  constexpr int WS = 4;             // weight ring stages
+  constexpr int WS = 2;             // weight ring stages
   uint64_t* w1_full = bars + 4;     // [WS] leader
   uint64_t* w1_empty = bars + 8;    // [WS]
   uint64_t* w2_full = bars + 12;    // [WS] leader
@@ -1237,7 +1305,7 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
   uint64_t* h_full = bars + 22;     // [2] leader: 2 x 256 epilogue threads
   uint64_t* h_empty = bars + 24;    // [2]
   uint64_t* d2_full = bars + 26;    // [2]
-  uint64_t* d2_empty = bars + 28;   // [2] leader: 2 x 256 epilogue threads
+  uint64_t* d2_empty = bars + 28;   // [2] local: 256 epilogue threads have read D2[i] (the LN warps may preload it again)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -1255,7 +1323,7 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&a_full[i], 256); ptx::mbar_init(&a_empty[i], 1);
       ptx::mbar_init(&h_full[i], 512); ptx::mbar_init(&h_empty[i], 1);
-      ptx::mbar_init(&d2_full[i], 1); ptx::mbar_init(&d2_empty[i], 512);
+      ptx::mbar_init(&d2_full[i], 1); ptx::mbar_init(&d2_empty[i], 256);
     }
     ptx::mbar_init(d1_full, 1); ptx::mbar_init(d1_empty, 512);
     ptx::fence_barrier_init();
@@ -1281,7 +1349,29 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
       prefetch_rows_l2(z, M, (mt + 2 * pair_stride) * 128 + warp * 32, lane);
       ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 50);
       AVB_TRACE(0, it, 1);
-      ln_warp_rows_to_umma_tile(z, M, mt * 128 + warp * 32, ptx::smem_u32(sA + buf * kLnGemmABytes), warp * 32, lane);
+      const uint32_t stash = ptx::smem_u32(sZ) + (uint32_t)(warp * 16384);
+      ln_warp_rows_to_umma_tile_stash(z, M, mt * 128 + warp * 32, ptx::smem_u32(sA + buf * kLnGemmABytes), warp * 32, lane, stash);
+      // D2[buf] := z rows of this tile (fp32, exact): the down-projection then accumulates onto the residual and the
+      // final epilogue only adds b2 and stores - the second read of z (64 KB per tile through L2) is gone.
+      if (it >= 2) ptx::mbar_wait(&d2_empty[buf], (uint32_t)(((it >> 1) - 1) & 1), 62);  // E2 of tile it-2 has read D2[buf]
+      ptx::tc_fence_after();
+      __syncwarp();
+#pragma unroll
+      for (int blk = 0; blk < 4; ++blk) {
+        uint32_t v[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 q4;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(q4.x), "=r"(q4.y), "=r"(q4.z), "=r"(q4.w)
+                       : "r"(stash + (uint32_t)(lane * 512 + (((blk * 8 + c) ^ (lane & 7)) << 4))));
+          v[c * 4 + 0] = q4.x; v[c * 4 + 1] = q4.y; v[c * 4 + 2] = q4.z; v[c * 4 + 3] = q4.w;
+        }
+        ptx::tmem_st32(tmem_D2 + buf * 128 + blk * 32 + ((uint32_t)(warp * 32) << 16), v);
+      }
+      ptx::tmem_wait_st();
+      __syncwarp();  // the stash is rewritten by the next tile
+      ptx::tc_fence_before();
       ptx::fence_proxy_async();
       ptx::mbar_arrive_cluster(&a_full[buf], 0);
       AVB_TRACE(0, it, 2);
@@ -1291,8 +1381,8 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
     int g = 0;
     for (int pr = pair0, mt = 2 * pair0 + (int)rank; pr < num_pairs; pr += pair_stride, mt += 2 * pair_stride) {
       for (int c = 0; c < num_c; ++c, ++g) {
-        const int st = g & 3;
-        const uint32_t ph = (uint32_t)((g >> 2) & 1) ^ 1;
+        const int st = g & 1;
+        const uint32_t ph = (uint32_t)((g >> 1) & 1) ^ 1;
         uint8_t* w1 = sW + st * kFfnWBytes;       // 32 KB per stage: W1c half | W2c half
         uint8_t* w2 = w1 + kFfnWBytes / 2;
         ptx::mbar_wait(&w1_empty[st], ph, 51);
@@ -1319,9 +1409,9 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
     const int my_tiles = pair0 < num_pairs ? (num_pairs - 1 - pair0) / pair_stride + 1 : 0;
     const int total = my_tiles * num_c;
     auto issue_G1 = [&](int g) {
-      const int tile_it = g / num_c, c = g % num_c, buf = tile_it & 1, st = g & 3;
+      const int tile_it = g / num_c, c = g % num_c, buf = tile_it & 1, st = g & 1;
       if (c == 0) ptx::mbar_wait(&a_full[buf], (uint32_t)((tile_it >> 1) & 1), 53);
-      ptx::mbar_wait(&w1_full[st], (uint32_t)((g >> 2) & 1), 54);
+      ptx::mbar_wait(&w1_full[st], (uint32_t)((g >> 1) & 1), 54);
       ptx::mbar_wait(d1_empty, (uint32_t)(g & 1) ^ 1, 55);  // E1 of the previous chunk has read D1
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
@@ -1344,19 +1434,19 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
       AVB_TRACE(1, g, 0);
       if (g + 1 < total) issue_G1(g + 1);
       AVB_TRACE(1, g, 1);
-      const int tile_it = g / num_c, c = g % num_c, st = g & 3, hs = g & 1;
-      ptx::mbar_wait(&w2_full[st], (uint32_t)((g >> 2) & 1), 56);
+      const int tile_it = g / num_c, c = g % num_c, st = g & 1, hs = g & 1;
+      ptx::mbar_wait(&w2_full[st], (uint32_t)((g >> 1) & 1), 56);
       AVB_TRACE(1, g, 2);
       ptx::mbar_wait(&h_full[hs], (uint32_t)((g >> 1) & 1), 57);
       AVB_TRACE(1, g, 3);
-      if (c == 0 && tile_it >= 2) ptx::mbar_wait(&d2_empty[tile_it & 1], (uint32_t)(((tile_it >> 1) - 1) & 1), 58);
+      // D2[tile_it & 1] already holds the tile's residual rows (LN warps, ordered by a_full): always accumulate
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint64_t dw = dW0 + (uint64_t)(st * (kFfnWBytes >> 4) + ((kFfnWBytes / 2) >> 4));
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint64_t off = (uint64_t)((kk >> 2) * ((64 * 128) >> 4) + (kk & 3) * 2);
-          ptx::umma_bf16_ts_2sm(tmem_D2 + (tile_it & 1) * 128, tmem_H + hs * 64 + kk * 8, dw + off, idesc, (c | kk) != 0);
+          ptx::umma_bf16_ts_2sm(tmem_D2 + (tile_it & 1) * 128, tmem_H + hs * 64 + kk * 8, dw + off, idesc, 1u);
         }
         ptx::umma_commit_2sm(&w2_empty[st], 3u);
         ptx::umma_commit_2sm(&h_empty[hs], 3u);
@@ -1372,11 +1462,12 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
     const uint32_t stage = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 4096);
     // E2 of a tile (z += D2 + b2) is deferred until after the first E1 of the NEXT tile: D2 is double-buffered by tile
     // parity, so the wait for the tile's last G2 MMAs and the z round trip overlap the next tile's MMAs.
-    auto E2 = [&](int t_it, int t_mt) {
+    auto E2 = [&](int t_it, int t_mt) {  // z_new = D2 + b2 (D2 = z + FFN already): write-only, coalesced through the stage
       ptx::mbar_wait(&d2_full[t_it & 1], (uint32_t)((t_it >> 1) & 1), 61);
       ptx::tc_fence_after();
       const int row0 = t_mt * 128 + q * 32;
       const int rows_valid = M - row0 < 32 ? M - row0 : 32;  // may be <= 0 on the last tile
+      const int sub = lane >> 3, l8 = lane & 7;
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         uint32_t v[32];
@@ -1384,10 +1475,31 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
         ptx::tmem_wait_ld();
         if (cc == 1) {
           ptx::tc_fence_before();
-          ptx::mbar_arrive_cluster(&d2_empty[t_it & 1], 0);
+          ptx::mbar_arrive(&d2_empty[t_it & 1]);
         }
-        residual_add_block_32x32(v, b2 + half * 64 + cc * 32, stage, z + (size_t)row0 * 128 + half * 64 + cc * 32, 128,
-                                 rows_valid, lane);
+        const float* bias = b2 + half * 64 + cc * 32;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {  // thread = row `lane`: 16-byte chunk c goes to slot c ^ (lane & 7)
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + c);
+          uint4 pk;
+          pk.x = __float_as_uint(__uint_as_float(v[c * 4 + 0]) + b4.x);
+          pk.y = __float_as_uint(__uint_as_float(v[c * 4 + 1]) + b4.y);
+          pk.z = __float_as_uint(__uint_as_float(v[c * 4 + 2]) + b4.z);
+          pk.w = __float_as_uint(__uint_as_float(v[c * 4 + 3]) + b4.w);
+          ptx::st_shared_v4(stage + (uint32_t)(lane * 128 + ((c ^ (lane & 7)) << 4)), pk);
+        }
+        __syncwarp();
+        float* zblk = z + (size_t)row0 * 128 + half * 64 + cc * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + sub;
+          uint4 a;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+                       : "r"(stage + (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4))));
+          if (row < rows_valid) reinterpret_cast<uint4*>(zblk + (size_t)row * 128)[l8] = a;
+        }
+        __syncwarp();
       }
     };
     int g = 0, tile_it = 0, prev_mt = -1;
