@@ -624,7 +624,8 @@ constexpr int kLnGemmBStages = 3;
 constexpr int kLnGemmABytes = 128 * 128 * 2;               // 32 KB: two 128B-swizzled K blocks of 64
 constexpr int kLnGemmBBytes = 256 * 64 * 2;                // 32 KB per (256-column chunk, K block)
 constexpr int kLnGemmStagePitch = 64 * 2 + 16;             // bytes per staged row (64 bf16 + pad)
-constexpr int kLnGemmStageBytes = 8 * 32 * kLnGemmStagePitch;  // 8 epilogue warps x 32 rows = 36 KB
+constexpr int kLnGemmStageBytes = 8 * 2 * 4096;  // 8 epilogue warps x 2 buffers x 4 KB (pair kernel); the single-CTA kernel
+                                                 // uses 8 x 32 rows x pitch = 36 KB of it
 constexpr int kLnGemmSmemBytes = 2 * kLnGemmABytes + kLnGemmBStages * kLnGemmBBytes + kLnGemmStageBytes + 1024 + 256;
 
 //   EPI 2 (the QKV projection in front of the tensor-core attention): rows are processed in SEQUENCE-MAJOR order
@@ -943,14 +944,24 @@ ln_gemm2_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensor
       }
     }
   } else if (warp >= 8) {
-    // ===================== epilogue: TMEM -> +bias (ReLU) -> bf16 -> smem stage -> coalesced global stores
+    // ===================== epilogue: TMEM -> +bias -> bf16 -> smem stage -> bulk stores (attention operand layout)
+    // A piece of 64 accumulator columns = heads (hd0, hd0+1) of q, k or v for this warp's 32 rows.  It is staged as
+    // [2 heads][32 rows][64 B] with the 16-byte chunks already at chunk ^ ((pos >> 1) & 3): that is both the byte image
+    // of the output (each head's rows are one contiguous run per sequence) and a conflict-free shared-memory pattern
+    // for the row-per-thread writes.  One lane then issues a bulk copy per head and run: the LSU / L1 path, which the
+    // ld.shared + st.global copy-out kept ~80 % busy (ncu l1tex throughput), only sees the staging writes.
+    static_assert(EPI == 2, "the CTA-pair kernel is built for the QKV projection");
     const int q = warp & 3, hf = (warp - 8) >> 2;
-    const uint32_t stage_warp = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 32 * kLnGemmStagePitch);
-    const uint32_t stage_row = stage_warp + (uint32_t)(lane * kLnGemmStagePitch);
-    const int sub = lane >> 3, l8 = lane & 7;  // copy-out: 4 rows per warp store, 8 lanes x 16 B per row
-    const int seq_T = seq_axis == 0 ? seq_d : seq_n, seq_H = N / 96;  // EPI 2: sequence length, heads (N = 3 * H * 32)
+    const uint32_t stage_warp = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 2 * 4096);
+    const int seq_T = seq_axis == 0 ? seq_d : seq_n, seq_H = N / 96;  // sequence length, heads (N = 3 * H * 32)
     int acc_it = 0;
+    uint32_t piece = 0;  // stage buffer parity
     for (int pr = pair0, mt = 2 * pair0 + (int)rank; pr < num_pairs; pr += pair_stride, mt += 2 * pair_stride) {
+      const int grow0 = mt * 128 + q * 32;                    // first row (sequence-major index) of this warp
+      const int rows_valid = M - grow0 < 32 ? M - grow0 : 32;  // may be <= 0
+      const unsigned my_m = (unsigned)(grow0 + lane);
+      const unsigned my_pos = my_m % (unsigned)seq_T;
+      const uint32_t my_swz = (my_pos >> 1) & 3;
       for (int c = 0; c < num_c; ++c, ++acc_it) {
         const int as = acc_it & 1;
         ptx::mbar_wait(&t_full[as], (acc_it >> 1) & 1, 45);
@@ -958,7 +969,11 @@ ln_gemm2_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensor
         const uint32_t taddr = tmem_base + as * 256 + hf * 128 + ((uint32_t)(q * 32) << 16);
         const int col0 = c * 256 + hf * 128;
 #pragma unroll 1
-        for (int pc = 0; pc < 2; ++pc) {  // two pieces of 64 columns
+        for (int pc = 0; pc < 2; ++pc, piece ^= 1u) {  // two pieces of 64 columns
+          const uint32_t stage = stage_warp + piece * 4096;
+          // the bulk stores that read this buffer two pieces ago must be done with it
+          if (lane == 0) ptx::bulk_wait_read<1>();
+          __syncwarp();
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             float4 bb[8];  // bias of these 32 columns, requested before the TMEM load so the latencies overlap
@@ -978,53 +993,33 @@ ln_gemm2_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensor
               f[2] = __uint_as_float(v[e * 8 + 2]) + bb[e * 2].z;     f[3] = __uint_as_float(v[e * 8 + 3]) + bb[e * 2].w;
               f[4] = __uint_as_float(v[e * 8 + 4]) + bb[e * 2 + 1].x; f[5] = __uint_as_float(v[e * 8 + 5]) + bb[e * 2 + 1].y;
               f[6] = __uint_as_float(v[e * 8 + 6]) + bb[e * 2 + 1].z; f[7] = __uint_as_float(v[e * 8 + 7]) + bb[e * 2 + 1].w;
-              if (EPI == 1) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], 0.f);
-              }
               uint4 pk;
               pk.x = ptx::pack_bf16(f[0], f[1]); pk.y = ptx::pack_bf16(f[2], f[3]);
               pk.z = ptx::pack_bf16(f[4], f[5]); pk.w = ptx::pack_bf16(f[6], f[7]);
-              ptx::st_shared_v4(stage_row + (uint32_t)(cc * 64 + e * 16), pk);
+              ptx::st_shared_v4(stage + (uint32_t)(cc * 2048 + lane * 64 + (((uint32_t)e ^ my_swz) << 4)), pk);
             }
           }
-          __syncwarp();  // the 32 staged rows are written and read by this warp only
-          if (EPI == 2) {
-            // 64 staged columns = heads (hd0, hd0 + 1) of q, k or v.  A warp store covers 8 consecutive positions of
-            // one head = 512 contiguous bytes (lane = chunk * 8 + row: conflict-free reads of the padded stage).
-            const int colp = col0 + pc * 64, w = colp >> 8, hd0 = (colp & 255) >> 5;
-            const int r8 = lane & 7, c4 = lane >> 3;
-#pragma unroll
-            for (int rr = 0; rr < 32; rr += 8) {
-              const int row = rr + r8;
-              const int grow = mt * 128 + q * 32 + row;
-              const unsigned sq = (unsigned)grow / (unsigned)seq_T, pos = (unsigned)grow - sq * (unsigned)seq_T;
-              __nv_bfloat16* dst = out + ((((size_t)sq * 3 + w) * seq_H + hd0) * seq_T + pos) * 32 + ((c4 ^ ((pos >> 1) & 3)) << 3);
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                uint4 pk;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w)
-                             : "r"(stage_warp + (uint32_t)(row * kLnGemmStagePitch + hh * 64 + c4 * 16)));
-                if (grow < M) *reinterpret_cast<uint4*>(dst + (size_t)hh * seq_T * 32) = pk;
-              }
-            }
-          } else {
-#pragma unroll
-          for (int rr = 0; rr < 32; rr += 4) {
-            const int row = rr + sub;
-            const int grow = mt * 128 + q * 32 + row;
-            uint4 pk;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w)
-                         : "r"(stage_warp + (uint32_t)(row * kLnGemmStagePitch + l8 * 16)));
-            if (grow < M) *reinterpret_cast<uint4*>(out + (size_t)grow * ldo + col0 + pc * 64 + l8 * 8) = pk;
-          }
-          }
+          ptx::fence_proxy_async();  // staging writes (generic proxy) -> visible to the bulk copy engine
           __syncwarp();
+          if (lane == 0 && rows_valid > 0) {
+            const int colp = col0 + pc * 64, w = colp >> 8, hd0 = (colp & 255) >> 5;
+            int r = 0;
+            while (r < rows_valid) {  // one run per sequence the 32 rows touch (usually one)
+              const unsigned m = (unsigned)(grow0 + r);
+              const unsigned sq = m / (unsigned)seq_T, pos = m - sq * (unsigned)seq_T;
+              const int len = min(rows_valid - r, seq_T - (int)pos);
+              __nv_bfloat16* dst = out + ((((size_t)sq * 3 + w) * seq_H + hd0) * seq_T + pos) * 32;
+              ptx::bulk_store(dst, stage + (uint32_t)(r * 64), (uint32_t)len * 64u);
+              ptx::bulk_store(dst + (size_t)seq_T * 32, stage + 2048u + (uint32_t)(r * 64), (uint32_t)len * 64u);
+              r += len;
+            }
+          }
+          if (lane == 0) ptx::bulk_commit();
         }
       }
     }
+    if (lane == 0) ptx::bulk_wait_all();
+    __syncwarp();
   }
   ptx::tc_fence_before();
   ptx::cluster_sync_all();  // the peer's shared memory and barriers stay valid until both CTAs are done

@@ -144,6 +144,19 @@ __device__ __forceinline__ void bulk_load_hint(void* smem_dst, const void* gsrc,
                : "memory");
 }
 
+// 1-D bulk copy shared -> global (bulk async-group completion); the issuing thread commits the group and later waits
+// until the shared-memory source of all but the `keep` most recent groups has been read
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int KEEP>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(KEEP) : "memory");
+}
+
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }  // writes done
+
 // ---------------------------------------------------------------- cp.async (LDGSTS) gathers
 // 16-byte global -> shared copy, L2-only; src_bytes = 0 zero-fills the destination (row past the end).
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
