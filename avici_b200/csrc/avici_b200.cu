@@ -131,6 +131,19 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // [rows, cols] bf16 row-major, box [box_rows x 64 cols], 128B swizzle
+// fp32 [rows x cols] matrix in [box_rows x 32 cols] boxes (128-byte rows, 128B swizzle): the z tiles the FFN stores
+bool make_tmap_2d_f32(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {cols * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
@@ -250,7 +263,9 @@ int launch_ffn2_tc(avb_handle h, float* z, const CUtensorMap& tm_w1q, const CUte
   }
   const int num_pairs = ((M + 127) / 128 + 1) / 2;
   const int grid = 2 * std::min(num_pairs, num_sms / 2);
-  avb::ffn2_tc_kernel<<<grid, avb::kFfnThreads, avb::kFfnSmemBytes, st>>>(z, tm_w1q, tm_w2q, b1, b2, M, F);
+  CUtensorMap tm_z;  // the residual stream of this call, for the final epilogue's tensor-map stores
+  if (!make_tmap_2d_f32(&tm_z, z, (uint64_t)M, 128, 32)) return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for z");
+  avb::ffn2_tc_kernel<<<grid, avb::kFfnThreads, avb::kFfnSmemBytes, st>>>(z, tm_z, tm_w1q, tm_w2q, b1, b2, M, F);
   if (launches) ++*launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ffn2_tc launch: %s", cudaGetErrorString(e));

@@ -1278,7 +1278,8 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
 // tm_w1 / tm_w2: tensor maps with [64 rows x 64] boxes.
 // ------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFfnThreads, 1)
-ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
+ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_w1,
+               const __grid_constant__ CUtensorMap tm_w2,
               const float* __restrict__ b1, const float* __restrict__ b2, int M, int F) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1457,12 +1458,12 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
     const uint32_t stage = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 4096);
     // E2 of a tile (z += D2 + b2) is deferred until after the first E1 of the NEXT tile: D2 is double-buffered by tile
     // parity, so the wait for the tile's last G2 MMAs and the z round trip overlap the next tile's MMAs.
-    auto E2 = [&](int t_it, int t_mt) {  // z_new = D2 + b2 (D2 = z + FFN already): write-only, coalesced through the stage
+    auto E2 = [&](int t_it, int t_mt) {  // z_new = D2 + b2 (D2 = z + FFN already): write-only
+      // Each [32 rows x 32 cols] fp32 block is staged with the 128B-swizzle pattern (chunk ^ (row & 7): conflict-free
+      // for the row-per-thread writes) and leaves through ONE tensor-map store; rows past M are clipped by the TMA.
       ptx::mbar_wait(&d2_full[t_it & 1], (uint32_t)((t_it >> 1) & 1), 61);
       ptx::tc_fence_after();
       const int row0 = t_mt * 128 + q * 32;
-      const int rows_valid = M - row0 < 32 ? M - row0 : 32;  // may be <= 0 on the last tile
-      const int sub = lane >> 3, l8 = lane & 7;
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         uint32_t v[32];
@@ -1472,6 +1473,8 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
           ptx::tc_fence_before();
           ptx::mbar_arrive(&d2_empty[t_it & 1]);
         }
+        if (lane == 0) ptx::bulk_wait_read<0>();  // the previous block's store has read the stage
+        __syncwarp();
         const float* bias = b2 + half * 64 + cc * 32;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {  // thread = row `lane`: 16-byte chunk c goes to slot c ^ (lane & 7)
@@ -1483,18 +1486,12 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
           pk.w = __float_as_uint(__uint_as_float(v[c * 4 + 3]) + b4.w);
           ptx::st_shared_v4(stage + (uint32_t)(lane * 128 + ((c ^ (lane & 7)) << 4)), pk);
         }
+        ptx::fence_proxy_async();
         __syncwarp();
-        float* zblk = z + (size_t)row0 * 128 + half * 64 + cc * 32;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = i * 4 + sub;
-          uint4 a;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
-                       : "r"(stage + (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4))));
-          if (row < rows_valid) reinterpret_cast<uint4*>(zblk + (size_t)row * 128)[l8] = a;
+        if (lane == 0) {
+          ptx::tma_store_2d(&tm_z, stage, half * 64 + cc * 32, row0);
+          ptx::bulk_commit();
         }
-        __syncwarp();
       }
     };
     int g = 0, tile_it = 0, prev_mt = -1;
@@ -1546,6 +1543,7 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1,
       prev_mt = mt;
     }
     if (prev_mt >= 0) E2(tile_it - 1, prev_mt);
+    if (lane == 0) ptx::bulk_wait_all();
   }
   ptx::tc_fence_before();
   ptx::cluster_sync_all();

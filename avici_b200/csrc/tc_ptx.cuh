@@ -149,6 +149,12 @@ __device__ __forceinline__ void bulk_load_hint(void* smem_dst, const void* gsrc,
 __device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
 }
+// 2-D tensor-map store shared -> global (same bulk async-group completion); out-of-range rows / columns are clipped
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int KEEP>
 __device__ __forceinline__ void bulk_wait_read() {
