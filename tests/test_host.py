@@ -149,3 +149,31 @@ def test_axial_reshard_world2_gloo():
     ret = mp.Manager().dict()
     mp.spawn(_reshard_worker, args=(world, port, 8, 6, 4, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def test_operand_layout_index_maps_are_bijections():
+    """RowMap and the two operand layouts: every (row, head, channel) lands on its own element,
+    inside the buffer the workspace reserves, for both attention axes and ragged shapes."""
+    from avici_b200 import layouts as L
+    for B, n, d in ((1, 5, 3), (2, 130, 7), (1, 50, 100), (3, 1, 4)):
+        N = B * n * d
+        for axis in (0, 1):
+            m = np.arange(N)
+            t = L.seq_major_to_token(m, n, d, axis)
+            assert sorted(t.tolist()) == list(range(N))
+            assert np.array_equal(L.token_to_seq_major(t, n, d, axis), m)
+            # consecutive rows of one sequence are the tokens the block attends over
+            T = d if axis == 0 else n
+            step = 1 if axis == 0 else d
+            first = t.reshape(-1, T)
+            assert np.all(np.diff(first, axis=1) == step)
+            mm, w, h, c = np.meshgrid(m, np.arange(3), np.arange(8), np.arange(32), indexing="ij")
+            off = L.qkv_operand_offset(mm, w, h, c, n, d, axis).ravel()
+            assert off.min() == 0 and off.max() == N * 768 - 1 and len(np.unique(off)) == off.size
+            # a (sequence, q|k|v, head) block is contiguous: [T positions x 32 channels]
+            blk = L.qkv_operand_offset(np.arange(T), 1, 3, 0, n, d, axis) // 32
+            assert np.array_equal(blk, blk[0] + np.arange(T))
+            mm, h, c = np.meshgrid(m, np.arange(8), np.arange(32), indexing="ij")
+            off = L.attn_operand_offset(mm, h, c).ravel()
+            tiles = (N + 127) // 128
+            assert off.min() == 0 and off.max() < tiles * 128 * 256 and len(np.unique(off)) == off.size
