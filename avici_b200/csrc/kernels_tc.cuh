@@ -1774,6 +1774,14 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
     p.s += (c ? step_s : 0) + c2;
   };
 
+  // Register budget per role (warpgroup-wide, setmaxnreg): 640 threads leave 96 registers each, and the softmax loop
+  // (64 scores + 32 packed results + its loop state) spilled a handful of them - ncu attributed ~20 % of the d-axis
+  // launch's stall samples to the reloads.  The four role warps give registers up, the softmax warpgroups take them.
+#ifndef AVB_ATTN_NO_SETMAXNREG
+  // (the pool only holds what this CTA released: 128 x (96 - 64) == 512 x (104 - 96))
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+#endif
   if (warp < 2) {
     // ======================= producer warp of stream `sid`: one bulk copy per [128 x 32] bf16 tile
     // (Measured on B200 before the operand layout existed: a tensor-map gather costs the TMA unit ~3.6 cycles per box
