@@ -1588,7 +1588,10 @@ constexpr int kAttnTmemStreamCols = 256;  // S 128 (fp32) | P 64 (bf16 pairs) | 
 constexpr float kAttnRescaleThreshold = 8.0f;  // log2 units
 constexpr int kAttnPolyEvery = 4;  // 1 of every kAttnPolyEvery exponent pairs is evaluated on the FMA pipe
 #ifndef AVB_ATTN_POLY_EVERY
-#define AVB_ATTN_POLY_EVERY 4
+#define AVB_ATTN_POLY_EVERY 3
+#endif
+#ifndef AVB_ATTN_POLY_MASK  // which of the 16 pairs of a 32-score chunk take the polynomial (default: every 3rd, 5 of 16)
+#define AVB_ATTN_POLY_MASK 0
 #endif
 #ifndef AVB_ATTN_KV_POLICY  // L2 eviction priority of the K / V tile loads
 #define AVB_ATTN_KV_POLICY (nqt > 1 ? ptx::kL2EvictLast : ptx::kL2EvictFirst)
@@ -1655,7 +1658,7 @@ __device__ __forceinline__ void exp_chunk32(const uint32_t (&s)[32], uint32_t* p
 #pragma unroll
   for (int e = 0; e < 16; ++e) {
     const float a = __uint_as_float(s[2 * e]), b = __uint_as_float(s[2 * e + 1]);
-    if ((e % kAttnFastPolyEvery) == kAttnFastPolyEvery - 1) {
+    if (AVB_ATTN_POLY_MASK ? ((AVB_ATTN_POLY_MASK >> e) & 1) : ((e % kAttnFastPolyEvery) == kAttnFastPolyEvery - 1)) {
       pmax = max3(pmax, a, b);
       const uint64_t x2 = pack2(fmaxf(a, -126.0f), fmaxf(b, -126.0f));
       const uint64_t t2 = add2(x2, magic2);           // integer part lands in the low mantissa bits
