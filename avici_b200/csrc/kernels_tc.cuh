@@ -444,6 +444,17 @@ outproj_tc_kernel(const __nv_bfloat16* __restrict__ attn, const __grid_constant_
       // tokens of the 8 rows this lane copies out (rows i*4 + (lane >> 3)); -1: past the end
       int tok[8];
       rm.tokens<8>(row0 + (lane >> 3), 4, M, tok);
+      // the z round trip is the long pole (HBM, scattered 512-byte rows on the n-axis blocks): all 16 loads of the
+      // lane (both 32-column blocks) are in flight before the accumulator is even read
+      const int l8 = lane & 7;
+      float4* zp[8];
+      float4 zr[2][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        zp[i] = tok[i] >= 0 ? reinterpret_cast<float4*>(z + (size_t)tok[i] * 128 + half * 64) + l8 : nullptr;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) zr[cc][i] = zp[i] ? __ldcg(zp[i] + cc * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         uint32_t v[32];
@@ -451,12 +462,32 @@ outproj_tc_kernel(const __nv_bfloat16* __restrict__ attn, const __grid_constant_
         ptx::tmem_wait_ld();
         if (cc == 1) {
           ptx::tc_fence_before();
-          ptx::mbar_arrive(&tempty[as]);
+          ptx::mbar_arrive_relaxed(&tempty[as]);  // relaxed: a release-arrive would first drain the z loads in flight
         }
-        float* zc = z + half * 64 + cc * 32;
-        residual_add_block_32x32_rows(v, bias + half * 64 + cc * 32, stage_addr,
-                                      [&](int row) -> float* { const int t = tok[row >> 2]; return t >= 0 ? zc + (size_t)t * 128 : nullptr; },
-                                      lane);
+        const float* bp = bias + half * 64 + cc * 32;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {  // thread = row `lane`: 16-byte chunk c goes to slot c ^ (lane & 7)
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + c);
+          uint4 pk;
+          pk.x = __float_as_uint(__uint_as_float(v[c * 4 + 0]) + b4.x);
+          pk.y = __float_as_uint(__uint_as_float(v[c * 4 + 1]) + b4.y);
+          pk.z = __float_as_uint(__uint_as_float(v[c * 4 + 2]) + b4.z);
+          pk.w = __float_as_uint(__uint_as_float(v[c * 4 + 3]) + b4.w);
+          ptx::st_shared_v4(stage_addr + (uint32_t)(lane * 128 + ((c ^ (lane & 7)) << 4)), pk);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + (lane >> 3);
+          uint4 a;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+                       : "r"(stage_addr + (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4))));
+          float4 o = zr[cc][i];
+          o.x += __uint_as_float(a.x); o.y += __uint_as_float(a.y); o.z += __uint_as_float(a.z); o.w += __uint_as_float(a.w);
+          if (zp[i]) zp[i][cc * 8] = o;
+        }
+        __syncwarp();
       }
     }
   }

@@ -38,6 +38,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive without release semantics: a release-arrive first drains the thread's outstanding global loads.  For handing
+// a TMEM buffer back, the ordering that matters is tcgen05.wait::ld + tcgen05.fence::before_thread_sync (the caller's).
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the
 // hint expires) instead of burning issue slots in a polling loop.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
