@@ -1327,8 +1327,7 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_z, 
   uint64_t* w1_empty = bars + 8;    // [WS]
   uint64_t* w2_full = bars + 12;    // [WS] leader
   uint64_t* w2_empty = bars + 16;   // [WS]
-  uint64_t* d1_full = bars + 20;    // [1]
-  uint64_t* d1_empty = bars + 21;   // [1] leader: 2 x 256 epilogue threads
+  uint64_t* d1_full = bars + 20;    // [2] by chunk parity
   uint64_t* h_full = bars + 22;     // [2] leader: 2 x 256 epilogue threads
   uint64_t* h_empty = bars + 24;    // [2]
   uint64_t* d2_full = bars + 26;    // [2]
@@ -1352,7 +1351,7 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_z, 
       ptx::mbar_init(&h_full[i], 512); ptx::mbar_init(&h_empty[i], 1);
       ptx::mbar_init(&d2_full[i], 1); ptx::mbar_init(&d2_empty[i], 256);
     }
-    ptx::mbar_init(d1_full, 1); ptx::mbar_init(d1_empty, 512);
+    ptx::mbar_init(&d1_full[0], 1); ptx::mbar_init(&d1_full[1], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 6) {
@@ -1363,8 +1362,11 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_z, 
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_D1 = tmem_base;        // 128
-  const uint32_t tmem_H = tmem_base + 128;   // 2 x 64
+  // D1 is double-buffered by chunk parity and the packed hidden activation H is written IN PLACE over the columns its
+  // warp has just read (half 0: D1 columns 0-31, half 1: columns 64-95), so G1 of the next chunk runs while E1 is
+  // still reading / packing this one, without a separate H buffer.  MMAs execute in issue order, which is all the
+  // reuse of a D1 buffer (G1 of chunk g+2 after G2 of chunk g) needs.
+  const uint32_t tmem_D1 = tmem_base;        // 2 x 128 (by chunk parity); H inside
   const uint32_t tmem_D2 = tmem_base + 256;  // 2 x 128 (by tile parity)
 
   if (warp < 4) {
@@ -1439,7 +1441,6 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_z, 
       const int tile_it = g / num_c, c = g % num_c, buf = tile_it & 1, st = g & 1;
       if (c == 0) ptx::mbar_wait(&a_full[buf], (uint32_t)((tile_it >> 1) & 1), 53);
       ptx::mbar_wait(&w1_full[st], (uint32_t)((g >> 1) & 1), 54);
-      ptx::mbar_wait(d1_empty, (uint32_t)(g & 1) ^ 1, 55);  // E1 of the previous chunk has read D1
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint64_t da = dA0 + (uint64_t)(buf * (kLnGemmABytes >> 4));
@@ -1448,18 +1449,18 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_z, 
         for (int kk = 0; kk < 8; ++kk) {  // K block (kk >> 2): 16 KB further in A (128 rows), 8 KB in the 64-row W half
           const uint64_t offa = (uint64_t)((kk >> 2) * ((128 * 128) >> 4) + (kk & 3) * 2);
           const uint64_t offw = (uint64_t)((kk >> 2) * ((64 * 128) >> 4) + (kk & 3) * 2);
-          ptx::umma_bf16_2sm(tmem_D1, da + offa, dw + offw, idesc, kk != 0);
+          ptx::umma_bf16_2sm(tmem_D1 + (g & 1) * 128, da + offa, dw + offw, idesc, kk != 0);
         }
         ptx::umma_commit_2sm(&w1_empty[st], 3u);
-        ptx::umma_commit_2sm(d1_full, 3u);
+        ptx::umma_commit_2sm(&d1_full[g & 1], 3u);
         if (c == num_c - 1) ptx::umma_commit_2sm(&a_empty[buf], 3u);
       }
       __syncwarp();
     };
     if (total > 0) issue_G1(0);
+    if (total > 1) issue_G1(1);
     for (int g = 0; g < total; ++g) {
       AVB_TRACE(1, g, 0);
-      if (g + 1 < total) issue_G1(g + 1);
       AVB_TRACE(1, g, 1);
       const int tile_it = g / num_c, c = g % num_c, st = g & 1, hs = g & 1;
       ptx::mbar_wait(&w2_full[st], (uint32_t)((g >> 1) & 1), 56);
@@ -1473,14 +1474,16 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_z, 
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint64_t off = (uint64_t)((kk >> 2) * ((64 * 128) >> 4) + (kk & 3) * 2);
-          ptx::umma_bf16_ts_2sm(tmem_D2 + (tile_it & 1) * 128, tmem_H + hs * 64 + kk * 8, dw + off, idesc, 1u);
+          // H of this chunk: 16 hidden units (8 packed columns) per K slice; slices 0-3 at D1 columns 0-31, 4-7 at 64-95
+          const uint32_t ah = tmem_D1 + hs * 128 + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8);
+          ptx::umma_bf16_ts_2sm(tmem_D2 + (tile_it & 1) * 128, ah, dw + off, idesc, 1u);
         }
         ptx::umma_commit_2sm(&w2_empty[st], 3u);
-        ptx::umma_commit_2sm(&h_empty[hs], 3u);
         if (c == num_c - 1) ptx::umma_commit_2sm(&d2_full[tile_it & 1], 3u);
       }
       __syncwarp();
       AVB_TRACE(1, g, 4);
+      if (g + 2 < total) issue_G1(g + 2);  // into the D1 buffer G2(g) has just been issued on (MMAs run in issue order)
     }
   } else if (warp >= 8) {
     // ===================== epilogue warps: (TMEM lane quarter q) x (64-column half)
@@ -1535,19 +1538,15 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_z, 
 #pragma unroll
         for (int e = 0; e < 16; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bp) + e);
         AVB_TRACE(2, g, 0);
-        ptx::mbar_wait(d1_full, (uint32_t)(g & 1), 59);
+        ptx::mbar_wait(&d1_full[g & 1], (uint32_t)((g >> 1) & 1), 59);
         AVB_TRACE(2, g, 1);
         ptx::tc_fence_after();
         uint32_t pk[32];
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           uint32_t v[32];
-          ptx::tmem_ld32(tmem_D1 + half * 64 + cc * 32 + lane_off, v);
+          ptx::tmem_ld32(tmem_D1 + hs * 128 + half * 64 + cc * 32 + lane_off, v);
           ptx::tmem_wait_ld();
-          if (cc == 1) {  // D1 fully read by this thread: the next chunk's G1 may overwrite it
-            ptx::tc_fence_before();
-            ptx::mbar_arrive_cluster(d1_empty, 0);
-          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float4 b4 = bb[cc * 8 + e];
@@ -1558,10 +1557,8 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_z, 
           }
         }
         AVB_TRACE(2, g, 2);
-        ptx::mbar_wait(&h_empty[hs], (uint32_t)((g >> 1) & 1) ^ 1, 60);  // G2 of two chunks ago has consumed H[hs]
         AVB_TRACE(2, g, 3);
-        ptx::tc_fence_after();
-        ptx::tmem_st32(tmem_H + hs * 64 + half * 32 + lane_off, pk);
+        ptx::tmem_st32(tmem_D1 + hs * 128 + half * 64 + lane_off, pk);  // in place: the first 32 of this warp's own 64 columns
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive_cluster(&h_full[hs], 0);
