@@ -1304,9 +1304,13 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
 // the 128 N-rows of W1c and of W2c (half the L2 -> SM weight traffic, which is 2/3 of this kernel's reads and what
 // bounds it) and the leader issues M = 256 MMAs for both SMs.  Barriers the MMA issuer waits on live in the leader
 // and count the arrivals of both CTAs; its commits are multicast to both.
-// The shared memory the halved weight ring frees carries the raw z rows from the LayerNorm warps into TMEM: D2 starts
-// as the residual, G2 accumulates onto it, and the final epilogue is write-only (no second read of z).
-// tm_w1 / tm_w2: tensor maps with [64 rows x 64] boxes.
+// Differences from the single-CTA schedule above (each measured, profiles/r1f_summary.md, r1g_summary.md):
+//  * the shared memory the halved weight ring frees carries the raw z rows from the LayerNorm warps into TMEM: D2 starts
+//    as the residual, G2 always accumulates, and the final epilogue is write-only (no second read of z) and leaves
+//    through 128B-swizzled tensor-map stores;
+//  * D1 is double-buffered by chunk and H is packed IN PLACE over the D1 columns its warp has just read, so G1 of the
+//    next chunk overlaps E1 entirely.  TMEM: 2x128 (D1, H inside) + 2x128 (D2) = 512 columns.
+// tm_w1 / tm_w2: tensor maps with [64 rows x 64] boxes; tm_z: the residual stream, [32 rows x 32 cols] fp32 boxes.
 // ------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFfnThreads, 1)
 ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_w1,
