@@ -2016,11 +2016,14 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
           AVB_TRACE(trole, g, 2);
           const int nv = T - j * 128 - half * 64;  // valid key columns in this warp's half (may be <= 0)
           if (nv < 64) {  // keys beyond the sequence end: score -inf, probability 0
+            if (nv < 32) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              if (e >= nv) sa[e] = 0xff800000u;
-              if (32 + e >= nv) sb[e] = 0xff800000u;
+              for (int e = 0; e < 32; ++e)
+                if (e >= nv) sa[e] = 0xff800000u;
             }
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (32 + e >= nv) sb[e] = 0xff800000u;
           }
           // ---- P = exp2(S) -> packed bf16 pairs
           uint32_t pk[32];
