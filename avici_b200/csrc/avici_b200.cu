@@ -218,18 +218,25 @@ int launch_ln_gemm2_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, co
   return AVB_OK;
 }
 
+// delta == nullptr: z += attn . Wo^T + bo in place; otherwise the update is written to delta (bf16, sequence-major rows)
 int launch_outproj_tc(avb_handle h, const void* attn, const CUtensorMap& tm_w, const float* bias, float* z, int M,
-                      int n, int d, int axis, cudaStream_t st, int num_sms, long long* launches) {
+                      int n, int d, int axis, cudaStream_t st, int num_sms, long long* launches, void* delta = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(avb::outproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(avb::outproj_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          avb::kOutProjSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(avb::outproj_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kOutProjSmemBytes);
     if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(outproj_tc): %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int grid = std::min((M + 127) / 128, num_sms);
-  avb::outproj_tc_kernel<<<grid, avb::kOutProjThreads, avb::kOutProjSmemBytes, st>>>(
-      reinterpret_cast<const bf16*>(attn), tm_w, bias, z, M, n, d, axis);
+  if (delta)
+    avb::outproj_tc_kernel<true><<<grid, avb::kOutProjThreads, avb::kOutProjSmemBytes, st>>>(
+        reinterpret_cast<const bf16*>(attn), tm_w, bias, z, reinterpret_cast<bf16*>(delta), M, n, d, axis);
+  else
+    avb::outproj_tc_kernel<false><<<grid, avb::kOutProjThreads, avb::kOutProjSmemBytes, st>>>(
+        reinterpret_cast<const bf16*>(attn), tm_w, bias, z, nullptr, M, n, d, axis);
   if (launches) ++*launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "outproj_tc launch: %s", cudaGetErrorString(e));
@@ -254,7 +261,8 @@ int launch_ffn_tc(avb_handle h, float* z, const CUtensorMap& tm_w1c, const CUten
 
 // CTA-pair (cluster of 2, cta_group::2) fused FFN; tensor maps with [64 x 64] boxes.
 int launch_ffn2_tc(avb_handle h, float* z, const CUtensorMap& tm_w1q, const CUtensorMap& tm_w2q, const float* b1,
-                   const float* b2, int M, int F, cudaStream_t st, int num_sms, long long* launches) {
+                   const float* b2, int M, int F, cudaStream_t st, int num_sms, long long* launches,
+                   const void* delta = nullptr, int n = 0, int d = 0, int axis = 0) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(avb::ffn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kFfnSmemBytes);
@@ -265,7 +273,8 @@ int launch_ffn2_tc(avb_handle h, float* z, const CUtensorMap& tm_w1q, const CUte
   const int grid = 2 * std::min(num_pairs, num_sms / 2);
   CUtensorMap tm_z;  // the residual stream of this call, for the final epilogue's tensor-map stores
   if (!make_tmap_2d_f32(&tm_z, z, (uint64_t)M, 128, 32)) return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for z");
-  avb::ffn2_tc_kernel<<<grid, avb::kFfnThreads, avb::kFfnSmemBytes, st>>>(z, tm_z, tm_w1q, tm_w2q, b1, b2, M, F);
+  avb::ffn2_tc_kernel<<<grid, avb::kFfnThreads, avb::kFfnSmemBytes, st>>>(z, reinterpret_cast<const bf16*>(delta), n, d, axis,
+                                                                           tm_z, tm_w1q, tm_w2q, b1, b2, M, F);
   if (launches) ++*launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ffn2_tc launch: %s", cudaGetErrorString(e));
@@ -696,6 +705,8 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
     bf16* qkv = reinterpret_cast<bf16*>(w8 + L.big_off);
     bf16* attn = reinterpret_cast<bf16*>(w8 + L.attn_off);
     int rc;
+    static const bool ffn_pair = !(getenv("AVB_FFN_2CTA") && getenv("AVB_FFN_2CTA")[0] == '0');
+    static const bool use_delta = ffn_pair && !(getenv("AVB_OUT_DELTA") && getenv("AVB_OUT_DELTA")[0] == '0');  // A/B switch (debug)
     // attention half: LN -> QKV -> attention -> out-proj + residual
     { ProfScope ps(h, AVB_PROF_QKV, st);  // LayerNorm fused into the projection's prologue
       // rows in sequence-major order of `axis`, output in the attention kernel's operand layout
@@ -709,11 +720,14 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
       if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches,
                                     reinterpret_cast<int*>(w8 + L.guard_off)))) return rc; }
     { ProfScope ps(h, AVB_PROF_OUT, st);
-      if ((rc = launch_outproj_tc(h, attn, W.tm_wo, W.bo, z, M, n, d, axis, st, h->num_sms, &h->launches))) return rc; }
+      // with the CTA-pair FFN the update goes to `delta` (the dead qkv buffer) and is added to z by the FFN's LN warps
+      if ((rc = launch_outproj_tc(h, attn, W.tm_wo, W.bo, z, M, n, d, axis, st, h->num_sms, &h->launches,
+                                  use_delta ? qkv : nullptr))) return rc; }
     // FFN half: LN -> Linear + ReLU -> Linear + residual
     { ProfScope ps(h, AVB_PROF_FFN1, st);  // whole FFN sub-layer in one kernel (LN, up-projection, ReLU, down-projection, residual)
       static const bool pair = !(getenv("AVB_FFN_2CTA") && getenv("AVB_FFN_2CTA")[0] == '0');  // A/B switch (debug)
-      if (pair) { if ((rc = launch_ffn2_tc(h, z, W.tm_w1q, W.tm_w2q, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches))) return rc; }
+      if (pair) { if ((rc = launch_ffn2_tc(h, z, W.tm_w1q, W.tm_w2q, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches,
+                                           use_delta ? qkv : nullptr, n, d, axis))) return rc; }
       else if ((rc = launch_ffn_tc(h, z, W.tm_w1c, W.tm_w2, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches))) return rc; }
   } else {
     float* qkv = reinterpret_cast<float*>(w8 + L.big_off);

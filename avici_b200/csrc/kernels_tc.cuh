@@ -59,6 +59,35 @@ struct RowMap {
     const unsigned j = rem / (unsigned)n, i = rem - j * (unsigned)n;
     return (int)((b * (unsigned)n + i) * (unsigned)d + j);
   }
+  // inverse: token index -> sequence-major row
+  __device__ __forceinline__ int seq_row(int t) const {
+    if (axis == 0) return t;
+    const unsigned nd = (unsigned)n * (unsigned)d, b = (unsigned)t / nd, rem = (unsigned)t - b * nd;
+    const unsigned i = rem / (unsigned)d, jj = rem - i * (unsigned)d;
+    return (int)((b * (unsigned)d + jj) * (unsigned)n + i);
+  }
+  // sequence-major rows of tokens t, t + step, ... (count of them) without a division per token; -1 past the end
+  template <int COUNT>
+  __device__ __forceinline__ void seq_rows(int t, int step, int M, int (&out)[COUNT]) const {
+    if (axis == 0) {
+#pragma unroll
+      for (int k = 0; k < COUNT; ++k) out[k] = t + k * step < M ? t + k * step : -1;
+      return;
+    }
+    const unsigned nd = (unsigned)n * (unsigned)d;
+    unsigned b = (unsigned)t / nd;
+    const unsigned rem = (unsigned)t - b * nd;
+    unsigned i = rem / (unsigned)d, j = rem - i * (unsigned)d;
+#pragma unroll
+    for (int k = 0; k < COUNT; ++k) {
+      out[k] = t + k * step < M ? (int)((b * (unsigned)d + j) * (unsigned)n + i) : -1;
+      j += (unsigned)step;
+      while (j >= (unsigned)d) {
+        j -= (unsigned)d;
+        if (++i >= (unsigned)n) { i = 0; ++b; }
+      }
+    }
+  }
   // tokens of rows m, m + step, m + 2*step, ... (count of them) without a division per row: the position inside the
   // sequence advances by `step` and carries into (j, b)
   template <int COUNT>
@@ -348,9 +377,16 @@ constexpr int kOutProjStages = 6;
 constexpr int kOutProjKB = 4;  // K blocks of 64 (K = 256)
 constexpr int kOutProjSmemBytes = kOutProjKB * 128 * 128 + kOutProjStages * 128 * 128 + 8 * 4096 + 1024 + 256;
 
+//   kDelta: instead of updating z in place, write the update  delta[m][128] = attn . Wo^T + bo  as bf16 rows in
+//   sequence-major order (contiguous, 256 B per row); the FFN kernel that follows adds it to z while it reads z for
+//   its LayerNorm anyway (ffn2_tc_kernel).  The out-projection then moves 768 B/token instead of 1536 and the residual
+//   stream makes one HBM round trip per block half instead of two.  The update is rounded to bf16 (2^-9 relative, the
+//   same size as the bf16 rounding of the attention output that feeds it); z itself stays fp32.
+template <bool kDelta>
 __global__ void __launch_bounds__(kOutProjThreads, 1)
 outproj_tc_kernel(const __nv_bfloat16* __restrict__ attn, const __grid_constant__ CUtensorMap tm_w,
-                  const float* __restrict__ bias, float* __restrict__ z, int M, int seq_n, int seq_d, int seq_axis) {
+                  const float* __restrict__ bias, float* __restrict__ z, __nv_bfloat16* __restrict__ delta, int M, int seq_n,
+                  int seq_d, int seq_axis) {
   const RowMap rm{seq_n, seq_d, seq_axis};
   constexpr int ST = kOutProjStages, KB = kOutProjKB;
   extern __shared__ uint8_t smem_raw[];
@@ -441,6 +477,44 @@ outproj_tc_kernel(const __nv_bfloat16* __restrict__ attn, const __grid_constant_
       ptx::mbar_wait(&tfull[as], (uint32_t)((it >> 1) & 1), 74);
       ptx::tc_fence_after();
       const int row0 = mt * 128 + q * 32;
+      if constexpr (kDelta) {
+        // ---- delta rows: this warp's 32 rows x 64 columns -> bf16 -> [32 rows x 128 B] stage -> 4 rows per store
+        uint32_t pk[32];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_base + as * 128 + half * 64 + cc * 32 + lane_off, v);
+          ptx::tmem_wait_ld();
+          if (cc == 1) {
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty[as]);
+          }
+          const float* bp = bias + half * 64 + cc * 32;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + c);
+            pk[cc * 16 + c * 2 + 0] = ptx::pack_bf16(__uint_as_float(v[c * 4 + 0]) + b4.x, __uint_as_float(v[c * 4 + 1]) + b4.y);
+            pk[cc * 16 + c * 2 + 1] = ptx::pack_bf16(__uint_as_float(v[c * 4 + 2]) + b4.z, __uint_as_float(v[c * 4 + 3]) + b4.w);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)  // thread = row `lane`: 16-byte chunk c (8 bf16) goes to slot c ^ (lane & 7)
+          ptx::st_shared_v4(stage_addr + (uint32_t)(lane * 128 + ((c ^ (lane & 7)) << 4)),
+                            make_uint4(pk[c * 4 + 0], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]));
+        __syncwarp();
+        const int l8 = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + (lane >> 3);
+          uint4 a;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+                       : "r"(stage_addr + (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4))));
+          if (row0 + row < M) *reinterpret_cast<uint4*>(delta + (size_t)(row0 + row) * 128 + half * 64 + l8 * 8) = a;
+        }
+        __syncwarp();
+        continue;
+      }
       // tokens of the 8 rows this lane copies out (rows i*4 + (lane >> 3)); -1: past the end
       int tok[8];
       rm.tokens<8>(row0 + (lane >> 3), 4, M, tok);
@@ -577,26 +651,45 @@ __device__ __forceinline__ void ln_warp_rows_to_umma_tile(const float* __restric
 // chunk index XOR-ed with row & 7) from which the warp reads them back one row per thread - the tcgen05.st layout.
 // Used by the CTA-pair FFN kernel to preload its residual accumulator with z (see ffn2_tc_kernel).
 __device__ __forceinline__ void ln_warp_rows_to_umma_tile_stash(const float* __restrict__ z, int M, int grow0, uint32_t a_tile,
-                                                                int row0, int lane, uint32_t stash) {
+                                                                int row0, int lane, uint32_t stash,
+                                                                const __nv_bfloat16* __restrict__ delta = nullptr,
+                                                                const RowMap rm = RowMap{0, 0, 0}) {
   const int rs = lane >> 3, j = lane & 7;
   const float4* zp = reinterpret_cast<const float4*>(z) + j;
   float4 cur[2][4], nxt[2][4];
-  auto load = [&](float4 (&dst)[2][4], int r0) {
+  uint2 dcur[2][4], dnxt[2][4];  // the out-projection's update of the same rows (bf16), added when the row is processed
+  int mrow[8];                    // its sequence-major row for each of this lane's 8 rows (grow0 + rs + 4q)
+  if (delta != nullptr) rm.seq_rows<8>(grow0 + rs, 4, M, mrow);
+  auto load = [&](float4 (&dst)[2][4], uint2 (&ddst)[2][4], int r0) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int grow = grow0 + r0 + u * 4 + rs;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         dst[u][k] = grow < M ? __ldcg(zp + (size_t)grow * 32 + k * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ddst[u][k] = make_uint2(0u, 0u);
+      if (delta != nullptr && grow < M) {
+        // z1 = z + delta is formed here so that the residual stream is read once for both sub-layers; the loads are
+        // only consumed one row group later, like the z loads
+        const uint2* dp = reinterpret_cast<const uint2*>(delta + (size_t)mrow[(r0 >> 2) + u] * 128) + j;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ddst[u][k] = __ldcg(dp + k * 8);
+      }
     }
   };
-  load(cur, 0);
+  load(cur, dcur, 0);
 #pragma unroll
   for (int r0 = 0; r0 < 32; r0 += 8) {
-    if (r0 + 8 < 32) load(nxt, r0 + 8);
+    if (r0 + 8 < 32) load(nxt, dnxt, r0 + 8);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int rl = r0 + u * 4 + rs;  // row inside the warp's 32
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        cur[u][k].x += __uint_as_float(dcur[u][k].x << 16); cur[u][k].y += __uint_as_float(dcur[u][k].x & 0xffff0000u);
+        cur[u][k].z += __uint_as_float(dcur[u][k].y << 16); cur[u][k].w += __uint_as_float(dcur[u][k].y & 0xffff0000u);
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k)  // raw values: chunk (j + 8k) of row rl
         ptx::st_shared_v4(stash + (uint32_t)(rl * 512 + (((j + 8 * k) ^ (rl & 7)) << 4)),
@@ -633,7 +726,7 @@ __device__ __forceinline__ void ln_warp_rows_to_umma_tile_stash(const float* __r
 #pragma unroll
     for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) cur[u][k] = nxt[u][k];
+      for (int k = 0; k < 4; ++k) { cur[u][k] = nxt[u][k]; dcur[u][k] = dnxt[u][k]; }
   }
 }
 
@@ -1313,7 +1406,8 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
 // tm_w1 / tm_w2: tensor maps with [64 rows x 64] boxes; tm_z: the residual stream, [32 rows x 32 cols] fp32 boxes.
 // ------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFfnThreads, 1)
-ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_w1,
+ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, int seq_n, int seq_d, int seq_axis,
+               const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_w1,
                const __grid_constant__ CUtensorMap tm_w2,
               const float* __restrict__ b1, const float* __restrict__ b2, int M, int F) {
   extern __shared__ uint8_t smem_raw[];
@@ -1383,7 +1477,8 @@ ffn2_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_z, 
       ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 50);
       AVB_TRACE(0, it, 1);
       const uint32_t stash = ptx::smem_u32(sZ) + (uint32_t)(warp * 16384);
-      ln_warp_rows_to_umma_tile_stash(z, M, mt * 128 + warp * 32, ptx::smem_u32(sA + buf * kLnGemmABytes), warp * 32, lane, stash);
+      ln_warp_rows_to_umma_tile_stash(z, M, mt * 128 + warp * 32, ptx::smem_u32(sA + buf * kLnGemmABytes), warp * 32, lane, stash,
+                                      delta, RowMap{seq_n, seq_d, seq_axis});
       // D2[buf] := z rows of this tile (fp32, exact): the down-projection then accumulates onto the residual and the
       // final epilogue only adds b2 and stores - the second read of z (64 KB per tile through L2) is gone.
       if (it >= 2) ptx::mbar_wait(&d2_empty[buf], (uint32_t)(((it >> 1) - 1) & 1), 62);  // E2 of tile it-2 has read D2[buf]
