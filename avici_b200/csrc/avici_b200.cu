@@ -218,7 +218,7 @@ int launch_ln_gemm2_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, co
   return AVB_OK;
 }
 
-// delta == nullptr: z += attn . Wo^T + bo in place; otherwise the update is written to delta (bf16, sequence-major rows)
+// delta == nullptr: z += attn . Wo^T + bo in place; otherwise the update is written to delta (bf16 rows, token order)
 int launch_outproj_tc(avb_handle h, const void* attn, const CUtensorMap& tm_w, const float* bias, float* z, int M,
                       int n, int d, int axis, cudaStream_t st, int num_sms, long long* launches, void* delta = nullptr) {
   static bool attr_set = false;
