@@ -21,6 +21,7 @@
 
 #include "kernels_f32.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_metrics.cuh"
 
 namespace {
 
@@ -1006,6 +1007,63 @@ int avb_test_ffn_bf16(float* z, const void* w1t, const void* w2t, const float* b
     return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   return pair ? launch_ffn2_tc(nullptr, z, t1, t2, b1, b2, M, F, reinterpret_cast<cudaStream_t>(stream), sms, nullptr)
               : launch_ffn_tc(nullptr, z, t1, t2, b1, b2, M, F, reinterpret_cast<cudaStream_t>(stream), sms, nullptr);
+}
+
+// ----------------------------------------------------------------------------------- graph metrics (8(f) row 4)
+size_t avb_graph_metrics_workspace_bytes(int32_t B, int32_t d) {
+  if (B < 1 || d < 1) return 0;
+  return (size_t)4 * B * d * d * sizeof(double);
+}
+
+int avb_graph_metrics(const float* probs, const int32_t* g_true, float threshold, int32_t B, int32_t d, int64_t* out,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (!probs || !out || B < 1 || d < 1) return fail(nullptr, AVB_ERR_INVALID, "avb_graph_metrics: bad argument");
+  if ((size_t)d * d > (size_t)1 << 30) return fail(nullptr, AVB_ERR_INVALID, "avb_graph_metrics: d too large");
+  const size_t need = avb_graph_metrics_workspace_bytes(B, d);
+  if (!workspace || workspace_bytes < need)
+    return fail(nullptr, AVB_ERR_WORKSPACE, "avb_graph_metrics: workspace %zu < %zu", workspace_bytes, need);
+  if (B > 65535) return fail(nullptr, AVB_ERR_INVALID, "avb_graph_metrics: B > 65535");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  long long* o = reinterpret_cast<long long*>(out);
+  avb::graph_counts_kernel<<<B, 256, 0, st>>>(probs, g_true, threshold, d, o);
+  const size_t per = (size_t)B * d * d;
+  double* zb[2] = {reinterpret_cast<double*>(workspace), reinterpret_cast<double*>(workspace) + per};  // z ping/pong
+  double* rb[2] = {zb[1] + per, zb[1] + 2 * per};                                                      // result ping/pong
+  avb::acyc_init_kernel<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(probs, threshold, d, per, zb[0]);  // mat = I + G/d
+  const dim3 grid((d + 15) / 16, (d + 15) / 16, B);
+  auto mm = [&](const double* x, const double* y, double* c) { avb::bmm_f64_kernel<<<grid, 256, 0, st>>>(x, y, c, d); };
+  // numpy.linalg.matrix_power(mat, d): the multiplication order decides the fp64 rounding, so it is numpy's
+  const double* result = nullptr;
+  if (d == 1) {
+    result = zb[0];
+  } else if (d == 2) {
+    mm(zb[0], zb[0], rb[0]); result = rb[0];
+  } else if (d == 3) {
+    mm(zb[0], zb[0], zb[1]); mm(zb[1], zb[0], rb[0]); result = rb[0];
+  } else {
+    // binary decomposition: z = a, a^2, a^4, ...; result = product of the z whose bit is set, low bit first
+    int zi = 0, ri = 0, n = d;
+    bool first_z = true;
+    while (n > 0) {
+      if (first_z) first_z = false;
+      else { mm(zb[zi], zb[zi], zb[zi ^ 1]); zi ^= 1; }
+      const int bit = n & 1;
+      n >>= 1;
+      if (bit) {
+        if (!result) {
+          if (cudaMemcpyAsync(rb[ri], zb[zi], per * sizeof(double), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            return fail(nullptr, AVB_ERR_CUDA, "avb_graph_metrics: copy failed");
+        } else {
+          mm(rb[ri], zb[zi], rb[ri ^ 1]); ri ^= 1;
+        }
+        result = rb[ri];
+      }
+    }
+  }
+  avb::acyc_trace_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(result, d, B, o);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "avb_graph_metrics: launch failed: %s", cudaGetErrorString(e));
+  return AVB_OK;
 }
 
 int avb_debug_set_trace(void* trace_dev) {

@@ -130,6 +130,26 @@ int avb_pool(avb_handle h, const float* z_dev, int32_t B, int32_t n, int32_t d, 
 int avb_head(avb_handle h, const float* pooled_dev, int32_t B, int32_t d, float* probs_dev,
              void* scratch_dev, size_t scratch_bytes, void* stream);
 
+/* ---- graph metrics on the device: replaces the per-dataset numpy calls of the eval loop
+ * avici/train.py:125-151 -> avici/metrics.py:5-24 (shd), :27-32 (n_edges), :35-51 (is_acyclic / is_cyclic),
+ * :54-87 (classification_metrics: precision / recall / f1 follow from tp, fp, fn).
+ * probs_dev[B,d,d] f32; the predicted graph is probs > threshold (train.py:63).  g_true_dev[B,d,d] int32 0/1 or NULL
+ * (then shd / n_edges_true / tp / fp / fn are computed against the empty graph).  out_dev[B][AVB_GM_FIELDS] int64.
+ * `cyclic` is the REFERENCE's test, trace((I + G/d)^d) - d not isclose 0 in fp64 with numpy's matrix_power
+ * multiplication order, not a graph search: cycles too long to reach its 1e-8 tolerance count as acyclic there too.
+ * No handle: the call needs no weights; errors are reported through avb_last_error(NULL). ---- */
+#define AVB_GM_SHD 0
+#define AVB_GM_EDGES_PRED 1
+#define AVB_GM_EDGES_TRUE 2
+#define AVB_GM_TP 3
+#define AVB_GM_FP 4
+#define AVB_GM_FN 5
+#define AVB_GM_CYCLIC 6
+#define AVB_GM_FIELDS 8
+size_t avb_graph_metrics_workspace_bytes(int32_t B, int32_t d);
+int avb_graph_metrics(const float* probs_dev, const int32_t* g_true_dev, float threshold, int32_t B, int32_t d,
+                      int64_t* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Kernel launches issued by this handle since creation (bench.py's `gpu_launches`). */
 int64_t avb_launch_count(avb_handle h);
 

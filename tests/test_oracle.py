@@ -134,3 +134,44 @@ def test_golden_vectors(path):
     p = O.avici_call(params, d["x"], cfg, interv=None if interv is None else interv.copy(),
                      expects_counts=bool(d["expects_counts"]), experimental_chunk_size=chunk, dtype=np.float64)
     assert np.abs(p - d["p"]).max() < 1e-12
+
+
+# ---------------------------------------------------------------------------- graph metrics
+def _metrics_cases():
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics", "metrics_cases.npz")
+    z = np.load(path)
+    return [(str(n), z[f"{n}__probs"], z[f"{n}__true"], z[f"{n}__ref"]) for n in z["names"]]
+
+
+def test_metrics_oracle_matches_reference_outputs():
+    """PINNED: tests/golden/metrics/metrics_cases.npz holds outputs of the reference's own avici/metrics.py
+    (tests/golden/metrics/make_metrics_golden.py); the numpy restatement must reproduce every one of them."""
+    from oracle import metrics_oracle as MO
+    cases = _metrics_cases()
+    assert len(cases) >= 70
+    seen_missed_cycle = False
+    for name, probs, true, ref in cases:
+        pred = (probs > 0.5).astype(np.int32)
+        assert int(MO.shd(true, pred)) == int(ref[0]), name
+        assert int(MO.n_edges(pred)) == int(ref[1]), name
+        assert int(MO.is_cyclic(pred)) == int(ref[2]), name
+        cm = MO.classification_metrics(true, pred)
+        assert (cm["precision"], cm["recall"], cm["f1"]) == pytest.approx(tuple(ref[3:6]), abs=1e-15), name
+        if name.startswith("cycle_d100_L13"):
+            seen_missed_cycle = int(ref[2]) == 0
+    # the reference's matrix-power test does not see a lone 13-cycle at d = 100: the oracle (and the CUDA path) must
+    # return the reference's answer, not the graph-theoretic one
+    assert seen_missed_cycle
+
+
+def test_metrics_oracle_shd_properties():
+    from oracle import metrics_oracle as MO
+    rng = np.random.default_rng(0)
+    g = (rng.random((5, 12, 12)) < 0.2).astype(np.int32)
+    h = (rng.random((5, 12, 12)) < 0.2).astype(np.int32)
+    assert (MO.shd(g, g) == 0).all()
+    assert (MO.shd(g, h) == MO.shd(h, g)).all()
+    # a reversed edge counts once (metrics.py:8-9)
+    a = np.zeros((4, 4), np.int32); a[0, 1] = 1
+    assert MO.shd(a, a.T) == 1
