@@ -265,17 +265,30 @@ int launch_ffn2_tc(avb_handle h, float* z, const CUtensorMap& tm_w1q, const CUte
                    const float* b2, int M, int F, cudaStream_t st, int num_sms, long long* launches,
                    const void* delta = nullptr, int n = 0, int d = 0, int axis = 0) {
   static bool attr_set = false;
+  static bool resident = true;  // AVB_FFN_RESIDENT=0: the weight-ring version (A/B reference)
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(avb::ffn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kFfnSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(avb::ffn2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kFfnSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(avb::ffn2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kFfnSmemBytes);
     if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(ffn2_tc): %s", cudaGetErrorString(e));
+    const char* r = getenv("AVB_FFN_RESIDENT");
+    if (r && r[0] == '0') resident = false;
     attr_set = true;
   }
+#if !AVB_DELTA_TOKENS
+  resident = false;  // the resident version reads delta next to z: token order only
+#endif
+  const bool use_resident = resident && F == 512;  // four resident chunks
   const int num_pairs = ((M + 127) / 128 + 1) / 2;
   const int grid = 2 * std::min(num_pairs, num_sms / 2);
   CUtensorMap tm_z;  // the residual stream of this call, for the final epilogue's tensor-map stores
   if (!make_tmap_2d_f32(&tm_z, z, (uint64_t)M, 128, 32)) return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for z");
-  avb::ffn2_tc_kernel<<<grid, avb::kFfnThreads, avb::kFfnSmemBytes, st>>>(z, reinterpret_cast<const bf16*>(delta), n, d, axis,
-                                                                           tm_z, tm_w1q, tm_w2q, b1, b2, M, F);
+  if (use_resident)
+    avb::ffn2_tc_kernel<true><<<grid, avb::kFfnThreads, avb::kFfnSmemBytes, st>>>(z, reinterpret_cast<const bf16*>(delta), n, d, axis,
+                                                                                   tm_z, tm_w1q, tm_w2q, b1, b2, M, F);
+  else
+    avb::ffn2_tc_kernel<false><<<grid, avb::kFfnThreads, avb::kFfnSmemBytes, st>>>(z, reinterpret_cast<const bf16*>(delta), n, d, axis,
+                                                                                    tm_z, tm_w1q, tm_w2q, b1, b2, M, F);
   if (launches) ++*launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ffn2_tc launch: %s", cudaGetErrorString(e));

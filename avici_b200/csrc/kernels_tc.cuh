@@ -1424,6 +1424,14 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
 //    next chunk overlaps E1 entirely.  TMEM: 2x128 (D1, H inside) + 2x128 (D2) = 512 columns.
 // tm_w1 / tm_w2: tensor maps with [64 rows x 64] boxes; tm_z: the residual stream, [32 rows x 32 cols] fp32 boxes.
 // ------------------------------------------------------------------------------------------
+// kResident (the default, AVB_FFN_RESIDENT=0 selects the ring version): ALL of this CTA's weight halves (4 chunks x
+// [W1c half 16K | W2c half 16K] = 128 KB) are fetched ONCE and stay in shared memory, so the only per-tile traffic
+// through the L2 -> SM fabric (what bounds the ring version) is the tile's own z and delta rows.  The 64 KB this needs
+// is the stash: the LayerNorm warps instead read their rows one ROW PER THREAD (256-bit loads, a full sector per
+// lane), write z1 = z + delta straight into the D2 accumulator (tcgen05.st: the thread's row is its TMEM lane) while
+// accumulating sum and sum of squares, then read the row back from TMEM to normalise it into the A tile: TMEM is the
+// stash.  No shuffles, no shared-memory round trip.
+template <bool kResident>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFfnThreads, 1)
 ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, int seq_n, int seq_d, int seq_axis,
                const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_w1,
@@ -1439,7 +1447,7 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 8 * 4096);
   uint64_t* a_full = bars;          // [2] 128 LN threads
   uint64_t* a_empty = bars + 2;     // [2]
-  constexpr int WS = 2;             // weight ring stages
+  constexpr int WS = kResident ? 4 : 2;  // weight stages: ring of 2, or the four chunks resident
   uint64_t* w1_full = bars + 4;     // [WS] leader
   uint64_t* w1_empty = bars + 8;    // [WS]
   uint64_t* w2_full = bars + 12;    // [WS] leader
@@ -1493,6 +1501,88 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
       const int buf = it & 1;
       AVB_TRACE(0, it, 0);
       prefetch_rows_l2(z, M, (mt + 2 * pair_stride) * 128 + warp * 32, lane);
+      if constexpr (kResident) {
+        // ---- row per thread: lane = row = TMEM lane
+        const int r = warp * 32 + lane, grow = mt * 128 + r;
+        const bool valid = grow < M;
+        const float* zr = z + (size_t)(valid ? grow : 0) * 128;
+        const __nv_bfloat16* dr = delta ? delta + (size_t)(valid ? grow : 0) * 128 : nullptr;
+        if (delta != nullptr) {  // next tile's delta rows towards L2 (z: prefetch_rows_l2 above)
+          const int nrow = (mt + 2 * pair_stride) * 128 + warp * 32 + (lane >> 1);  // 16 rows x 2 lines per pass
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            if (nrow + i * 16 < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(delta + (size_t)(nrow + i * 16) * 128 + (lane & 1) * 64));
+        }
+        // 8 blocks of 16 columns, loads two blocks ahead in a rotating 3-slot register buffer (72 registers):
+        // ~6 KB per warp in flight, enough for L2-latency x the 10 B/clk/SM this stream needs
+        float zb[3][2][8];
+        uint32_t db[3][8];
+        auto load = [&](int slot, int blk) {
+          if (valid) {
+            ptx::ldg_v8_f32(zr + blk * 16, zb[slot][0]);
+            ptx::ldg_v8_f32(zr + blk * 16 + 8, zb[slot][1]);
+            if (dr != nullptr) ptx::ldg_v8_b32(dr + blk * 16, db[slot]);
+          }
+        };
+#pragma unroll
+        for (int sl = 0; sl < 3; ++sl)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { zb[sl][0][e] = 0.f; zb[sl][1][e] = 0.f; db[sl][e] = 0u; }
+        load(0, 0);
+        load(1, 1);
+        if (it >= 2) ptx::mbar_wait(&d2_empty[buf], (uint32_t)(((it >> 1) - 1) & 1), 62);  // E2 of tile it-2 has read D2[buf]
+        AVB_TRACE(0, it, 1);
+        ptx::tc_fence_after();
+        const uint32_t trow = tmem_D2 + buf * 128 + ((uint32_t)(warp * 32) << 16);
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int blk = 0; blk < 8; ++blk) {
+          const int sl = blk % 3;
+          if (blk + 2 < 8) load((blk + 2) % 3, blk + 2);
+          uint32_t v[16];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {  // columns 2e, 2e+1 of this 16-column block; delta word e holds both
+            const uint32_t dw = db[sl][e];
+            const float x0 = zb[sl][e >> 2][(e & 3) * 2] + __uint_as_float(dw << 16);
+            const float x1 = zb[sl][e >> 2][(e & 3) * 2 + 1] + __uint_as_float(dw & 0xffff0000u);
+            sum += x0 + x1;
+            sq = fmaf(x0, x0, sq);
+            sq = fmaf(x1, x1, sq);
+            v[2 * e] = __float_as_uint(x0);
+            v[2 * e + 1] = __float_as_uint(x1);
+          }
+          ptx::tmem_st16(trow + blk * 16, v);
+        }
+        ptx::tmem_wait_st();
+        const float mean = sum * (1.0f / 128.0f);
+        const float rstd = rsqrtf(fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f) + kLnEps);
+        const float shift = -mean * rstd;
+        AVB_TRACE(0, it, 3);
+        ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 50);  // G1 of tile it-2 has read this A tile
+        AVB_TRACE(0, it, 4);
+        const uint32_t rbase = ptx::smem_u32(sA + buf * kLnGemmABytes) + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk) {
+          uint32_t v[32];
+          ptx::tmem_ld32(trow + blk * 32, v);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {  // 16-byte chunk (blk & 1) * 4 + c4 of K block blk >> 1
+            uint4 pk;
+            pk.x = ptx::pack_bf16(fmaf(__uint_as_float(v[c4 * 8 + 0]), rstd, shift), fmaf(__uint_as_float(v[c4 * 8 + 1]), rstd, shift));
+            pk.y = ptx::pack_bf16(fmaf(__uint_as_float(v[c4 * 8 + 2]), rstd, shift), fmaf(__uint_as_float(v[c4 * 8 + 3]), rstd, shift));
+            pk.z = ptx::pack_bf16(fmaf(__uint_as_float(v[c4 * 8 + 4]), rstd, shift), fmaf(__uint_as_float(v[c4 * 8 + 5]), rstd, shift));
+            pk.w = ptx::pack_bf16(fmaf(__uint_as_float(v[c4 * 8 + 6]), rstd, shift), fmaf(__uint_as_float(v[c4 * 8 + 7]), rstd, shift));
+            const int chunk = (blk & 1) * 4 + c4;
+            ptx::st_shared_v4(rbase + (uint32_t)((blk >> 1) * (128 * 128) + ((chunk ^ (r & 7)) << 4)), pk);
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async();
+        ptx::mbar_arrive_cluster(&a_full[buf], 0);
+        AVB_TRACE(0, it, 2);
+        continue;
+      }
       ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 50);
       AVB_TRACE(0, it, 1);
       const uint32_t stash = ptx::smem_u32(sZ) + (uint32_t)(warp * 16384);
@@ -1527,9 +1617,10 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
     // ===================== weight TMA producer: per chunk W1c = W1t[128c.., 0..127], W2c = W2t[0..127, 128c..]
     int g = 0;
     for (int pr = pair0, mt = 2 * pair0 + (int)rank; pr < num_pairs; pr += pair_stride, mt += 2 * pair_stride) {
+      if (kResident && g >= num_c) break;  // resident: the four chunks are fetched once, stage = chunk
       for (int c = 0; c < num_c; ++c, ++g) {
-        const int st = g & 1;
-        const uint32_t ph = (uint32_t)((g >> 1) & 1) ^ 1;
+        const int st = kResident ? c : (g & 1);
+        const uint32_t ph = (uint32_t)(((kResident ? 0 : g >> 1)) & 1) ^ 1;
         uint8_t* w1 = sW + st * kFfnWBytes;       // 32 KB per stage: W1c half | W2c half
         uint8_t* w2 = w1 + kFfnWBytes / 2;
         ptx::mbar_wait(&w1_empty[st], ph, 51);
@@ -1556,9 +1647,9 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
     const int my_tiles = pair0 < num_pairs ? (num_pairs - 1 - pair0) / pair_stride + 1 : 0;
     const int total = my_tiles * num_c;
     auto issue_G1 = [&](int g) {
-      const int tile_it = g / num_c, c = g % num_c, buf = tile_it & 1, st = g & 1;
+      const int tile_it = g / num_c, c = g % num_c, buf = tile_it & 1, st = kResident ? c : (g & 1);
       if (c == 0) ptx::mbar_wait(&a_full[buf], (uint32_t)((tile_it >> 1) & 1), 53);
-      ptx::mbar_wait(&w1_full[st], (uint32_t)((g >> 1) & 1), 54);
+      ptx::mbar_wait(&w1_full[st], kResident ? 0u : (uint32_t)((g >> 1) & 1), 54);  // resident: completes once, stays complete
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint64_t da = dA0 + (uint64_t)(buf * (kLnGemmABytes >> 4));
@@ -1569,7 +1660,7 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
           const uint64_t offw = (uint64_t)((kk >> 2) * ((64 * 128) >> 4) + (kk & 3) * 2);
           ptx::umma_bf16_2sm(tmem_D1 + (g & 1) * 128, da + offa, dw + offw, idesc, kk != 0);
         }
-        ptx::umma_commit_2sm(&w1_empty[st], 3u);
+        if (!kResident) ptx::umma_commit_2sm(&w1_empty[st], 3u);
         ptx::umma_commit_2sm(&d1_full[g & 1], 3u);
         if (c == num_c - 1) ptx::umma_commit_2sm(&a_empty[buf], 3u);
       }
@@ -1580,8 +1671,8 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
     for (int g = 0; g < total; ++g) {
       AVB_TRACE(1, g, 0);
       AVB_TRACE(1, g, 1);
-      const int tile_it = g / num_c, c = g % num_c, st = g & 1, hs = g & 1;
-      ptx::mbar_wait(&w2_full[st], (uint32_t)((g >> 1) & 1), 56);
+      const int tile_it = g / num_c, c = g % num_c, st = kResident ? c : (g & 1), hs = g & 1;
+      ptx::mbar_wait(&w2_full[st], kResident ? 0u : (uint32_t)((g >> 1) & 1), 56);
       AVB_TRACE(1, g, 2);
       ptx::mbar_wait(&h_full[hs], (uint32_t)((g >> 1) & 1), 57);
       AVB_TRACE(1, g, 3);
@@ -1596,7 +1687,7 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
           const uint32_t ah = tmem_D1 + hs * 128 + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8);
           ptx::umma_bf16_ts_2sm(tmem_D2 + (tile_it & 1) * 128, ah, dw + off, idesc, 1u);
         }
-        ptx::umma_commit_2sm(&w2_empty[st], 3u);
+        if (!kResident) ptx::umma_commit_2sm(&w2_empty[st], 3u);
         if (c == num_c - 1) ptx::umma_commit_2sm(&d2_full[tile_it & 1], 3u);
       }
       __syncwarp();

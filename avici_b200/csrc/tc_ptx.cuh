@@ -97,6 +97,17 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity)
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar_saddr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_saddr) : "memory");
 }
+// 256-bit global loads (sm_100: LDG.E.256): one full 32-byte sector per lane, for row-per-thread access patterns
+__device__ __forceinline__ void ldg_v8_f32(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ldg_v8_b32(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
 __device__ __forceinline__ float ld_shared_f32(uint32_t saddr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
