@@ -59,6 +59,7 @@ SIGNATURES = {
     "avb_graph_metrics_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "avb_graph_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_size_t, C.c_void_p]),
+    "avb_threshold_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "avb_launch_count": (C.c_int64, [C.c_void_p]),
     "avb_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "avb_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),

@@ -1079,6 +1079,21 @@ int avb_graph_metrics(const float* probs, const int32_t* g_true, float threshold
   return AVB_OK;
 }
 
+int avb_threshold_metrics(const float* probs, const int32_t* g_true, int32_t B, int32_t d, double* out, void* stream) {
+  if (!probs || !g_true || !out || B < 1 || d < 1) return fail(nullptr, AVB_ERR_INVALID, "avb_threshold_metrics: bad argument");
+  if ((size_t)d * d > (size_t)1 << 30) return fail(nullptr, AVB_ERR_INVALID, "avb_threshold_metrics: d too large");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int threads = d * d >= 1024 ? 1024 : 256;
+  for (int b0 = 0; b0 < B; b0 += 65535) {
+    const int bc = std::min(65535, B - b0);
+    const size_t off = (size_t)b0 * d * d;
+    avb::threshold_metrics_kernel<<<bc, threads, 0, st>>>(probs + off, g_true + off, d, out + (size_t)b0 * 4);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "avb_threshold_metrics: launch failed: %s", cudaGetErrorString(e));
+  return AVB_OK;
+}
+
 int avb_debug_set_trace(void* trace_dev) {
   long long* p = reinterpret_cast<long long*>(trace_dev);
   return cudaMemcpyToSymbol(avb::g_attn_trace, &p, sizeof p) == cudaSuccess ? AVB_OK : AVB_ERR_CUDA;

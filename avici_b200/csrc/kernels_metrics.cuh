@@ -105,4 +105,85 @@ __global__ void acyc_trace_kernel(const double* __restrict__ mat_pow, int d, int
   }
 }
 
+// Threshold-free metrics of one prediction against the truth: auroc, auprc (trapezoid over the precision-recall curve)
+// and average precision, as avici/metrics.py:90-127 computes them with sklearn (roc_curve + auc,
+// precision_recall_curve + auc, average_precision_score), including its three corner cases.
+// sklearn sorts the scores; here every quantity is written as a sum over the POSITIVE entries of counts over all
+// entries, which needs no sort and no workspace (ties included; checked against sklearn 1.9.0 to 3e-15):
+//   with, for a positive with score s:  TP>= / TP> = positives with score >= s / > s,  N>= / N> the same for negatives,
+//   auroc = 1/(P N) sum_pos [ (N - N>=) + (N>= - N>)/2 ]                      (Mann-Whitney = trapezoid under the ROC curve)
+//   ap    = 1/P     sum_pos  TP>=/(TP>= + N>=)                                (precision at the positive's own threshold)
+//   auprc = 1/P     sum_pos [ TP>=/(TP>= + N>=) + prec> ]/2,  prec> = TP>/(TP> + N>) or 1 when nothing scores higher
+//                                                                           (the curve's previous point; (0, 1) at the start)
+// One CTA per dataset; thread t owns entries t, t + blockDim, ...; fp64 sums, fixed reduction order (deterministic).
+// out[b] = {auroc, auprc, ap, 0}.
+__global__ void __launch_bounds__(1024) threshold_metrics_kernel(const float* __restrict__ probs, const int32_t* __restrict__ g_true,
+                                                                 int d, double* __restrict__ out) {
+  const int b = blockIdx.x, total = d * d;
+  const float* p = probs + (size_t)b * total;
+  const int32_t* g = g_true + (size_t)b * total;
+  __shared__ double red[3][32];
+  __shared__ double tot[3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  auto block_sum3 = [&](double a0, double a1, double a2) {
+    double v[3] = {a0, a1, a2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+      if (lane == 0) red[k][warp] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double acc = 0.0;
+      for (int w = 0; w < nwarp; ++w) acc += red[threadIdx.x][w];
+      tot[threadIdx.x] = acc;
+    }
+    __syncthreads();
+  };
+  double npos = 0.0, psum = 0.0;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    npos += g[e] != 0 ? 1.0 : 0.0;
+    psum += (double)p[e];
+  }
+  block_sum3(npos, psum, 0.0);
+  const double P = tot[0], S = tot[1], N = (double)total - P;
+  __syncthreads();
+  if (!(S > 0.0 && P > 0.0)) {  // metrics.py:112-127
+    if (threadIdx.x == 0) {
+      const bool none = (S == 0.0 && P == 0.0);
+      out[(size_t)b * 4 + 0] = none ? 1.0 : 0.5;
+      out[(size_t)b * 4 + 1] = none ? 1.0 : 0.0;
+      out[(size_t)b * 4 + 2] = none ? 1.0 : 0.0;
+      out[(size_t)b * 4 + 3] = 0.0;
+    }
+    return;
+  }
+  double au = 0.0, pr = 0.0, ap = 0.0;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    if (g[e] == 0) continue;
+    const float s = p[e];
+    int tpge = 0, tpgt = 0, nge = 0, ngt = 0;
+    for (int f = 0; f < total; ++f) {
+      const float sf = __ldg(p + f);
+      const int lab = __ldg(g + f) != 0;
+      const int ge = sf >= s, gt = sf > s;
+      tpge += ge & lab; tpgt += gt & lab;
+      nge += ge & (lab ^ 1); ngt += gt & (lab ^ 1);
+    }
+    au += (N - (double)nge) + 0.5 * (double)(nge - ngt);
+    const double pge = (double)tpge / (double)(tpge + nge);
+    const double pgt = (tpgt + ngt) > 0 ? (double)tpgt / (double)(tpgt + ngt) : 1.0;
+    ap += pge;
+    pr += 0.5 * (pge + pgt);
+  }
+  block_sum3(au, pr, ap);
+  if (threadIdx.x == 0) {
+    out[(size_t)b * 4 + 0] = tot[0] / (P * N);  // N = 0: nan, as sklearn's 0/0 false-positive rate
+    out[(size_t)b * 4 + 1] = tot[1] / P;
+    out[(size_t)b * 4 + 2] = tot[2] / P;
+    out[(size_t)b * 4 + 3] = 0.0;
+  }
+}
+
 }  // namespace avb

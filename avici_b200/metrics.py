@@ -6,8 +6,9 @@ Host-side mirror of `avici/metrics.py` for the metrics the eval loop computes pe
 call (`graph_metrics`) covers the whole `[B, d, d]` batch with four kinds of kernel launches through the C-ABI entry point
 `avb_graph_metrics`; nothing is computed on the host except turning tp / fp / fn counts into precision / recall / f1.
 
-Not here: `threshold_metrics` (auroc / auprc / ap, metrics.py:90-127) and the calibration statistics (:130-220) -
-they are sklearn curve computations over sorted scores and stay on the CPU.
+`threshold_metrics` (auroc / auprc / ap, metrics.py:90-127: sklearn's roc_curve, precision_recall_curve, auc,
+average_precision_score) runs on the device too (`avb_threshold_metrics`), written as sort-free sums over the positive
+entries; it agrees with sklearn to ~1e-14 (fp64 sums), not bit for bit.  Not here: the calibration statistics (:130-220).
 
 There is no CPU fallback: every function needs the in-tree CUDA extension and an sm_100 device.
 """
@@ -116,3 +117,38 @@ def classification_metrics(true, pred):
     pp[:d2] = onp.asarray(pred.cpu() if hasattr(pred, "cpu") else pred).reshape(-1)
     m = graph_metrics(pp.reshape(side, side), tt.reshape(side, side))
     return {"precision": float(m["precision"]), "recall": float(m["recall"]), "f1": float(m["f1"])}
+
+
+def threshold_metrics_batch(true, pred):
+    """auroc / auprc / ap per dataset for `[..., d, d]` batches: dict of float64 arrays of shape `[...]`."""
+    torch = _torch()
+    lib = _lib.load()
+    p = _as_cuda(pred, torch.float32)
+    g = _as_cuda(true, torch.int32)
+    assert p.ndim >= 2 and p.shape[-1] == p.shape[-2], "pred must be [..., d, d]"
+    assert tuple(g.shape) == tuple(p.shape), "true and pred must have the same shape"
+    lead, d = tuple(p.shape[:-2]), int(p.shape[-1])
+    B = int(onp.prod(lead)) if lead else 1
+    out = torch.empty((max(B, 1), 4), dtype=torch.float64, device="cuda")
+    if B > 0:
+        rc = lib.avb_threshold_metrics(p.data_ptr(), g.data_ptr(), B, d, out.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib, None, rc)
+    host = out[:B].cpu().numpy()
+    return {"auroc": host[:, 0].reshape(lead).copy(), "auprc": host[:, 1].reshape(lead).copy(),
+            "ap": host[:, 2].reshape(lead).copy()}
+
+
+def threshold_metrics(true, pred):
+    """auroc / auprc / ap of ONE flattened prediction (metrics.py:90-127)."""
+    t = onp.asarray(true.cpu() if hasattr(true, "cpu") else true).reshape(-1)
+    s = onp.asarray(pred.cpu() if hasattr(pred, "cpu") else pred).reshape(-1)
+    n = int(t.size)
+    side = int(onp.ceil(onp.sqrt(max(n, 1))))
+    if side * side != n:
+        # the C-ABI takes square [d, d] inputs; a flattened array of another length is padded with entries that are
+        # neither positives nor able to outrank anything: label 0, score -inf.  They would still count as negatives,
+        # so only exact squares are accepted instead of silently changing the metric.
+        raise AssertionError("threshold_metrics: input must have d*d entries")
+    m = threshold_metrics_batch(t.reshape(side, side), s.reshape(side, side))
+    return {"auroc": float(m["auroc"]), "auprc": float(m["auprc"]), "ap": float(m["ap"])}

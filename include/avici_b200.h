@@ -150,6 +150,13 @@ size_t avb_graph_metrics_workspace_bytes(int32_t B, int32_t d);
 int avb_graph_metrics(const float* probs_dev, const int32_t* g_true_dev, float threshold, int32_t B, int32_t d,
                       int64_t* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Threshold-free metrics per dataset: out_dev[B][4] f64 = {auroc, auprc, average precision, 0}, the values
+ * avici/metrics.py:90-127 (`threshold_metrics`) gets from sklearn's roc_curve/auc, precision_recall_curve/auc and
+ * average_precision_score on the flattened [d*d] scores, with the same corner cases (no positives and no predicted
+ * mass -> 1, 1, 1; exactly one of them -> 0.5, 0, 0).  fp64 sums: agreement with sklearn to ~1e-14, not bit-exact. */
+int avb_threshold_metrics(const float* probs_dev, const int32_t* g_true_dev, int32_t B, int32_t d, double* out_dev,
+                          void* stream);
+
 /* Kernel launches issued by this handle since creation (bench.py's `gpu_launches`). */
 int64_t avb_launch_count(avb_handle h);
 

@@ -65,3 +65,36 @@ def graph_metrics(probs, true, threshold=0.5):
         for k in ("precision", "recall", "f1"):
             out[k].append(m[k])
     return {k: onp.asarray(v) for k, v in out.items()}
+
+
+def _binary_clf_curve(t, s):
+    """sklearn.metrics._ranking._binary_clf_curve (scikit-learn 1.9.0, the version in this image; un-vendored
+    dependency of avici/metrics.py:101-104): stable descending sort, one point per distinct score."""
+    order = onp.argsort(-s, kind="stable")  # sklearn: argsort(kind="mergesort")[::-1]; ties inside a score do not matter
+    s, t = s[order], t[order]
+    distinct = onp.where(onp.diff(s))[0]
+    idx = onp.r_[distinct, t.size - 1]
+    tps = onp.cumsum(t, dtype=onp.float64)[idx]
+    fps = 1.0 + idx - tps
+    return fps, tps
+
+
+def threshold_metrics(true, pred):
+    """avici/metrics.py:90-127: auroc = auc(roc_curve), auprc = auc(recall, precision), ap = average_precision_score."""
+    t = (onp.asarray(true).reshape(-1) != 0).astype(onp.float64)
+    s = onp.asarray(pred).reshape(-1).astype(onp.float64)
+    if s.sum() > 0 and t.sum() > 0:
+        fps, tps = _binary_clf_curve(t, s)
+        # roc_curve: origin prepended; dropping collinear points (drop_intermediate) does not change the trapezoid area
+        fpr = onp.r_[0.0, fps] / fps[-1] if fps[-1] > 0 else onp.full(fps.size + 1, onp.nan)
+        tpr = onp.r_[0.0, tps] / tps[-1]
+        auroc = float(onp.trapezoid(tpr, fpr))
+        # precision_recall_curve: precision = tps / (tps + fps), recall = tps / P, reversed, (recall 0, precision 1) appended
+        precision = onp.r_[(tps / (tps + fps))[::-1], 1.0]
+        recall = onp.r_[(tps / tps[-1])[::-1], 0.0]
+        auprc = float(-onp.trapezoid(precision, recall))  # auc() on a decreasing x
+        ap = float(-onp.sum(onp.diff(recall) * precision[:-1]))
+        return {"auroc": auroc, "auprc": auprc, "ap": ap}
+    if s.sum() == 0 and t.sum() == 0:
+        return {"auroc": 1.0, "auprc": 1.0, "ap": 1.0}
+    return {"auroc": 0.5, "auprc": 0.0, "ap": 0.0}

@@ -63,6 +63,12 @@ def cases():
             out.append((f"cycle_d{d}_L{L}", single_cycle(d, L, rng).astype(np.float32), random_dag(rng, d, 2.0 / d)))
             out.append((f"cycle_dag_d{d}_L{L}", single_cycle(d, L, rng, extra_dag_p=0.05).astype(np.float32),
                         random_dag(rng, d, 2.0 / d)))
+    # heavy score ties (probabilities on a coarse grid): the curve has one point per DISTINCT score
+    for d in (12, 40):
+        true = random_dag(rng, d, 3.0 / d)
+        probs = (np.round(rng.random((d, d)) * 6) / 6).astype(np.float32)
+        out.append((f"ties_d{d}", probs, true))
+        out.append((f"ties_informative_d{d}", np.clip(np.round((0.5 * true + 0.6 * rng.random((d, d))) * 5) / 5, 0, 1).astype(np.float32), true))
     # self loops and bidirected edges (shd's diagonal / double-edge rules)
     d = 6
     g = np.zeros((d, d), np.int32); g[0, 1] = g[1, 0] = 1; g[2, 2] = 1; g[3, 4] = 1
@@ -82,6 +88,8 @@ def main():
         store[f"{name}__true"] = true.astype(np.int32)
         store[f"{name}__ref"] = np.array([float(ref.shd(true, pred)), float(ref.n_edges(pred)), float(ref.is_cyclic(pred)),
                                           cm["precision"], cm["recall"], cm["f1"]], dtype=np.float64)
+        tm = ref.threshold_metrics(true, probs)  # avici/metrics.py:90-127 (sklearn curves)
+        store[f"{name}__thr"] = np.array([tm["auroc"], tm["auprc"], tm["ap"]], dtype=np.float64)
         names.append(name)
     store["names"] = np.array(names)
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "metrics_cases.npz")

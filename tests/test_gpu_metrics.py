@@ -84,6 +84,33 @@ def test_other_thresholds_and_reference_named_functions(built_lib):
     assert np.array_equal(GM.shd(g, h), MO.shd(g, h))
 
 
+def test_threshold_metrics_reference_golden_and_oracle(built_lib):
+    """auroc / auprc / ap (metrics.py:90-127): fp64 sums, tolerance 1e-12 against the reference's outputs."""
+    z = np.load(GOLDEN)
+    for n in z["names"]:
+        n = str(n)
+        m = GM.threshold_metrics(z[f"{n}__true"], z[f"{n}__probs"])
+        np.testing.assert_allclose([m["auroc"], m["auprc"], m["ap"]], z[f"{n}__thr"], rtol=0, atol=1e-12, err_msg=n)
+    rng = np.random.default_rng(11)
+    for B, d, grid in ((64, 100, 0), (5, 33, 7), (3, 2, 3), (2, 130, 0)):
+        true = (rng.random((B, d, d)) < 3.0 / max(d, 3)).astype(np.int32)
+        probs = (0.3 * true + 0.7 * rng.random((B, d, d))).astype(np.float32)
+        if grid:
+            probs = (np.round(probs * grid) / grid).astype(np.float32)  # heavy ties
+        true[0] = 0                       # no positives, predicted mass > 0 -> 0.5, 0, 0
+        if B > 2:
+            true[1] = 0; probs[1] = 0.0   # neither -> 1, 1, 1
+        got = GM.threshold_metrics_batch(torch.from_numpy(true).cuda(), torch.from_numpy(probs).cuda())
+        for b in range(B):
+            want = MO.threshold_metrics(true[b], probs[b])
+            for k in ("auroc", "auprc", "ap"):  # an all-positive truth has no ROC curve: nan on both sides (sklearn warns)
+                np.testing.assert_allclose(got[k][b], want[k], rtol=0, atol=1e-12, equal_nan=True, err_msg=f"{B} {d} {b} {k}")
+    # a perfect ranking: every positive above every negative
+    true = (rng.random((20, 20)) < 0.1).astype(np.int32)
+    m = GM.threshold_metrics(true, np.where(true, 0.9, 0.1).astype(np.float32))
+    assert m == pytest.approx({"auroc": 1.0, "auprc": 1.0, "ap": 1.0}, abs=1e-15)
+
+
 def test_c_abi_errors(built_lib):
     lib = built_lib
     p = torch.zeros((2, 4, 4), device="cuda")
@@ -95,3 +122,5 @@ def test_c_abi_errors(built_lib):
     assert lib.avb_graph_metrics(p.data_ptr(), None, C.c_float(0.5), 2, 4, out.data_ptr(), ws.data_ptr(), ws.numel(), None) == _lib.AVB_OK
     torch.cuda.synchronize()
     assert out[:, :7].abs().sum().item() == 0  # empty prediction, no truth: every count 0, acyclic
+    tout = torch.zeros((2, 4), dtype=torch.float64, device="cuda")
+    assert lib.avb_threshold_metrics(p.data_ptr(), None, 2, 4, tout.data_ptr(), None) == _lib.AVB_ERR_INVALID

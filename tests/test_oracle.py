@@ -144,6 +144,23 @@ def _metrics_cases():
     return [(str(n), z[f"{n}__probs"], z[f"{n}__true"], z[f"{n}__ref"]) for n in z["names"]]
 
 
+def test_threshold_metrics_oracle_matches_reference_outputs():
+    """auroc / auprc / ap: the sort-based numpy restatement of sklearn's curves against the reference's own
+    threshold_metrics outputs (metrics.py:90-127, sklearn 1.9.0), corner cases included."""
+    import os
+    from oracle import metrics_oracle as MO
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics", "metrics_cases.npz"))
+    corner = set()
+    for n in z["names"]:
+        n = str(n)
+        m = MO.threshold_metrics(z[f"{n}__true"], z[f"{n}__probs"])
+        got, want = np.array([m["auroc"], m["auprc"], m["ap"]]), z[f"{n}__thr"]
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-13, err_msg=n)
+        if tuple(want) in ((1.0, 1.0, 1.0), (0.5, 0.0, 0.0)):
+            corner.add(tuple(want))
+    assert len(corner) == 2  # both corner-case branches of metrics.py:112-127 are in the golden set
+
+
 def test_metrics_oracle_matches_reference_outputs():
     """PINNED: tests/golden/metrics/metrics_cases.npz holds outputs of the reference's own avici/metrics.py
     (tests/golden/metrics/make_metrics_golden.py); the numpy restatement must reproduce every one of them."""
