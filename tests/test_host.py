@@ -177,3 +177,19 @@ def test_operand_layout_index_maps_are_bijections():
             off = L.attn_operand_offset(mm, h, c).ravel()
             tiles = (N + 127) // 128
             assert off.min() == 0 and off.max() < tiles * 128 * 256 and len(np.unique(off)) == off.size
+
+
+def test_device_metrics_fail_loudly_without_a_gpu():
+    """avici_b200.metrics has no CPU fallback: without a CUDA device every entry point raises (it never routes
+    through the numpy oracle)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine WITHOUT a GPU")
+    from avici_b200 import metrics as GM
+    g = np.zeros((4, 4), np.int32)
+    for call in (lambda: GM.graph_metrics(g.astype(np.float32), g), lambda: GM.shd(g, g), lambda: GM.is_cyclic(g),
+                 lambda: GM.threshold_metrics(g, g.astype(np.float32))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+    import inspect
+    assert "oracle" not in "".join(l for l in inspect.getsource(GM).splitlines() if "import" in l)
