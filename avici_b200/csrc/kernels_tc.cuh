@@ -1431,6 +1431,9 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
 // lane), write z1 = z + delta straight into the D2 accumulator (tcgen05.st: the thread's row is its TMEM lane) while
 // accumulating sum and sum of squares, then read the row back from TMEM to normalise it into the A tile: TMEM is the
 // stash.  No shuffles, no shared-memory round trip.
+#ifndef AVB_FFN_E2_PLAIN
+#define AVB_FFN_E2_PLAIN 0  // 1: final epilogue leaves through plain coalesced stores instead of tensor-map stores (A/B build)
+#endif
 template <bool kResident>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFfnThreads, 1)
 ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, int seq_n, int seq_d, int seq_axis,
@@ -1716,7 +1719,9 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
           ptx::tc_fence_before();
           ptx::mbar_arrive(&d2_empty[t_it & 1]);
         }
+#if !AVB_FFN_E2_PLAIN
         if (lane == 0) ptx::bulk_wait_read<0>();  // the previous block's store has read the stage
+#endif
         __syncwarp();
         const float* bias = b2 + half * 64 + cc * 32;
 #pragma unroll
@@ -1729,12 +1734,31 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
           pk.w = __float_as_uint(__uint_as_float(v[c * 4 + 3]) + b4.w);
           ptx::st_shared_v4(stage + (uint32_t)(lane * 128 + ((c ^ (lane & 7)) << 4)), pk);
         }
+#if AVB_FFN_E2_PLAIN
+        // no async proxy: fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC (it drains every outstanding memory
+        // operation of the thread) and sits in front of each tensor-map store.  Read the staged block back 8 lanes per
+        // row and leave with plain coalesced 16-byte stores.
+        __syncwarp();
+        {
+          const int l8 = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + (lane >> 3);
+            uint4 a;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+                         : "r"(stage + (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4))));
+            if (row0 + row < M) *reinterpret_cast<uint4*>(z + (size_t)(row0 + row) * 128 + half * 64 + cc * 32 + l8 * 4) = a;
+          }
+        }
+#else
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
           ptx::tma_store_2d(&tm_z, stage, half * 64 + cc * 32, row0);
           ptx::bulk_commit();
         }
+#endif
       }
     };
     int g = 0, tile_it = 0, prev_mt = -1;
