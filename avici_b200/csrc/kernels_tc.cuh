@@ -1704,10 +1704,12 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
     const uint32_t stage = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 4096);
     // E2 of a tile (z += D2 + b2) is deferred until after the first E1 of the NEXT tile: D2 is double-buffered by tile
     // parity, so the wait for the tile's last G2 MMAs and the z round trip overlap the next tile's MMAs.
+    [[maybe_unused]] int e2_g = 0;       // chunk index the trace stamps of E2 are filed under
     auto E2 = [&](int t_it, int t_mt) {  // z_new = D2 + b2 (D2 = z + FFN already): write-only
       // Each [32 rows x 32 cols] fp32 block is staged with the 128B-swizzle pattern (chunk ^ (row & 7): conflict-free
       // for the row-per-thread writes) and leaves through ONE tensor-map store; rows past M are clipped by the TMA.
       ptx::mbar_wait(&d2_full[t_it & 1], (uint32_t)((t_it >> 1) & 1), 61);
+      AVB_TRACE(2, e2_g, 5);
       ptx::tc_fence_after();
       const int row0 = t_mt * 128 + q * 32;
 #pragma unroll
@@ -1715,6 +1717,7 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
         uint32_t v[32];
         ptx::tmem_ld32(tmem_D2 + (t_it & 1) * 128 + half * 64 + cc * 32 + lane_off, v);
         ptx::tmem_wait_ld();
+        if (cc == 0) AVB_TRACE(2, e2_g, 7);
         if (cc == 1) {
           ptx::tc_fence_before();
           ptx::mbar_arrive(&d2_empty[t_it & 1]);
@@ -1797,6 +1800,7 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
         ptx::mbar_arrive_cluster(&h_full[hs], 0);
         AVB_TRACE(2, g, 4);
         if (c == 0 && prev_mt >= 0) {
+          e2_g = g;
           E2(tile_it - 1, prev_mt);
           AVB_TRACE(2, g, 6);
         }
@@ -1965,12 +1969,10 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   // MMA / TMA operands in uniform registers (no per-instruction R2UR chains on the single issuing thread)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   long long* trace = (blockIdx.x == 0 && (warp == 0 || warp == 2 || warp == 4 || warp == 12) && lane == 0) ? g_attn_trace : nullptr;
-  const int trole = warp == 12 ? 3 : 2;
+  [[maybe_unused]] const int trole = warp == 12 ? 3 : 2;  // trace builds only
   const int T = axis == 0 ? d : n;
   const int S = axis == 0 ? B * n : B * d;  // sequences; the host guarantees S * H * nqt < 2^31
   const int nqt = (T + 127) / 128;  // query tiles == kv tiles per sequence
-  const int num_items = S * H * nqt;
-  const int HD = H * 32;
 
   if (warp == 1 && lane == 0) {
     for (int sid = 0; sid < kAttnStreams; ++sid) {

@@ -28,7 +28,7 @@ lib.avb_debug_set_trace(None)
 t = trace.cpu().numpy().reshape(3, 512, 8)
 t0 = t[t > 0].min()
 names = {0: ["top", "d2_empty", "arrived", "pass1_done", "a_empty"], 1: ["top", "G1next", "w2_full", "h_full", "G2_issued"],
-         2: ["top", "d1_full", "math", "h_empty", "h_full_arr", "d2_full", "E2_done"]}
+         2: ["top", "d1_full", "math", "h_empty", "h_full_arr", "E2:d2_full", "E2_done", "E2:first_tmem_ld"]}
 for role, rn in ((0, "ln"), (1, "mma"), (2, "epilogue")):
     print(f"== {rn}: {names[role]}")
     for step in range(16, 28):
