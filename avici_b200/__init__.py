@@ -10,6 +10,7 @@ from .params import init_params, param_count
 from .pretrain import load_checkpoint, load_pretrained, random_init_model, save_checkpoint
 from .synthetic import simulate_data
 from . import metrics  # noqa: F401  (graph metrics on the device, avici/metrics.py mirror)
+from .evaluate import eval_batch  # noqa: F401  (train.py:51-69,125-151 on the device)
 
 __all__ = ["load_pretrained", "AVICIModel", "simulate_data", "InferenceModel", "BaseModel", "init_params",
            "param_count", "load_checkpoint", "save_checkpoint", "random_init_model"]

@@ -193,3 +193,49 @@ def test_device_metrics_fail_loudly_without_a_gpu():
             call()
     import inspect
     assert "oracle" not in "".join(l for l in inspect.getsource(GM).splitlines() if "import" in l)
+
+
+def test_eval_batch_composition_matches_the_reference_loop(monkeypatch):
+    """avici_b200.evaluate.eval_batch (train.py:51-69,125-151): scalar names and batch means, checked on the CPU with
+    the device entry points replaced by the numpy oracle (the real ones are exercised in tests/test_zz_gpu_eval.py)."""
+    from avici_b200 import evaluate, metrics as GM
+    from oracle import metrics_oracle as MO
+    rng = np.random.default_rng(3)
+    B, n, d = 5, 11, 7
+    probs = rng.random((B, d, d)).astype(np.float32)
+    g = (rng.random((B, d, d)) < 0.2).astype(np.int32)
+
+    class FakeModel:
+        def infer_batch(self, x, interv=None, return_probs=True, experimental_chunk_size=None):
+            assert x.shape == (B, n, d) and return_probs
+            return probs
+
+    def fake_graph_metrics(pred, true, threshold=0.5):
+        m = MO.graph_metrics(pred, true, threshold)
+        return dict(m, tp=None)
+
+    def fake_threshold_batch(true, pred):
+        rows = [MO.threshold_metrics(true[b], pred[b]) for b in range(len(pred))]
+        return {k: np.array([r[k] for r in rows]) for k in ("auroc", "auprc", "ap")}
+
+    monkeypatch.setattr(GM, "graph_metrics", fake_graph_metrics)
+    monkeypatch.setattr(GM, "threshold_metrics_batch", fake_threshold_batch)
+    scalars, out = evaluate.eval_batch(FakeModel(), np.zeros((B, n, d), np.float32), g, decision_thresholds=(0.5, 0.25))
+    assert out is probs
+    # the reference's accumulation: scalars[name] += value / batch_size for every dataset j (train.py:125-151)
+    want = {}
+    for thres in (0.5, 0.25):
+        key = f"{thres}".replace(".", "_")
+        pred = (probs > thres).astype(np.int32)
+        for j in range(B):
+            want[f"shd_{key}"] = want.get(f"shd_{key}", 0.0) + MO.shd(g[j], pred[j]) / B
+            want[f"edges_{key}"] = want.get(f"edges_{key}", 0.0) + MO.n_edges(pred[j]) / B
+            want[f"cyclic_{key}"] = want.get(f"cyclic_{key}", 0.0) + float(MO.is_cyclic(pred[j])) / B
+            for k, v in MO.classification_metrics(g[j], pred[j]).items():
+                want[f"{k}_{key}"] = want.get(f"{k}_{key}", 0.0) + v / B
+    for j in range(B):
+        for k, v in MO.threshold_metrics(g[j], probs[j]).items():
+            want[k] = want.get(k, 0.0) + v / B
+    assert set(scalars) == set(want) and "f1_0_25" in scalars and "cyclic_0_5" in scalars
+    for k in want:
+        assert scalars[k] == pytest.approx(want[k], abs=1e-12), k
