@@ -1431,6 +1431,9 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
 // lane), write z1 = z + delta straight into the D2 accumulator (tcgen05.st: the thread's row is its TMEM lane) while
 // accumulating sum and sum of squares, then read the row back from TMEM to normalise it into the A tile: TMEM is the
 // stash.  No shuffles, no shared-memory round trip.
+#ifndef AVB_FFN_E1_X64
+#define AVB_FFN_E1_X64 0  // 1: E1 reads its 64 D1 columns with one tcgen05.ld.x64 (A/B build, not measured yet)
+#endif
 #ifndef AVB_FFN_E2_PLAIN
 #define AVB_FFN_E2_PLAIN 0  // 1: final epilogue leaves through plain coalesced stores instead of tensor-map stores (A/B build)
 #endif
@@ -1769,6 +1772,29 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
       for (int c = 0; c < num_c; ++c, ++g) {
         // ---- E1: D1 -> +b1 -> ReLU -> bf16 pairs -> H
         const int hs = g & 1;
+#if AVB_FFN_E1_X64
+        // A/B build: the warp's 64 D1 columns in ONE tcgen05.ld (one TMEM round trip instead of two serial ones); the
+        // bias then comes from L1 (b1 is 2 KB and hot) instead of 64 preloaded registers
+        const float* bp = b1 + c * 128 + half * 64;
+        AVB_TRACE(2, g, 0);
+        ptx::mbar_wait(&d1_full[g & 1], (uint32_t)((g >> 1) & 1), 59);
+        AVB_TRACE(2, g, 1);
+        ptx::tc_fence_after();
+        uint32_t pk[32];
+        {
+          uint32_t v[64];
+          ptx::tmem_ld64(tmem_D1 + hs * 128 + half * 64 + lane_off, v);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + e);
+            const float f0 = fmaxf(__uint_as_float(v[e * 4 + 0]) + b4.x, 0.f), f1 = fmaxf(__uint_as_float(v[e * 4 + 1]) + b4.y, 0.f);
+            const float f2 = fmaxf(__uint_as_float(v[e * 4 + 2]) + b4.z, 0.f), f3 = fmaxf(__uint_as_float(v[e * 4 + 3]) + b4.w, 0.f);
+            pk[e * 2 + 0] = ptx::pack_bf16(f0, f1);
+            pk[e * 2 + 1] = ptx::pack_bf16(f2, f3);
+          }
+        }
+#else
         const float* bp = b1 + c * 128 + half * 64;
         float4 bb[16];
 #pragma unroll
@@ -1792,6 +1818,7 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
             pk[cc * 16 + e * 2 + 1] = ptx::pack_bf16(f2, f3);
           }
         }
+#endif
         AVB_TRACE(2, g, 2);
         AVB_TRACE(2, g, 3);
         ptx::tmem_st32(tmem_D1 + hs * 128 + half * 64 + lane_off, pk);  // in place: the first 32 of this warp's own 64 columns
