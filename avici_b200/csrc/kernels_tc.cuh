@@ -1431,6 +1431,14 @@ ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, 
 // lane), write z1 = z + delta straight into the D2 accumulator (tcgen05.st: the thread's row is its TMEM lane) while
 // accumulating sum and sum of squares, then read the row back from TMEM to normalise it into the A tile: TMEM is the
 // stash.  No shuffles, no shared-memory round trip.
+// AVB_FFN_DECOUPLE=1 (A/B build, not measured yet): breaks the serial chain LN(t) -> G1(t,0) -> E1(t,0) -> E2(t-1) ->
+// LN(t+1) found by the trace (profiles/r1j_summary.md) at both ends: the MMA issuer never blocks on the next tile's
+// LayerNorm while down-projections of the current tile are still unissued, and the epilogue warps run E2 of the
+// previous tile first whenever the current tile's first D1 is not ready.  (E2-first alone was measured slower: with the
+// blocking issuer, d2_full of the previous tile itself waited for the LayerNorm.)
+#ifndef AVB_FFN_DECOUPLE
+#define AVB_FFN_DECOUPLE 0
+#endif
 #ifndef AVB_FFN_E1_X64
 #define AVB_FFN_E1_X64 0  // 1: E1 reads its 64 D1 columns with one tcgen05.ld.x64 (A/B build, not measured yet)
 #endif
@@ -1652,9 +1660,12 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
     const uint64_t dW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024, ptx::kSwz128);
     const int my_tiles = pair0 < num_pairs ? (num_pairs - 1 - pair0) / pair_stride + 1 : 0;
     const int total = my_tiles * num_c;
-    auto issue_G1 = [&](int g) {
+    auto issue_G1 = [&](int g, bool block = true) -> bool {
       const int tile_it = g / num_c, c = g % num_c, buf = tile_it & 1, st = kResident ? c : (g & 1);
-      if (c == 0) ptx::mbar_wait(&a_full[buf], (uint32_t)((tile_it >> 1) & 1), 53);
+      if (c == 0) {
+        if (block) ptx::mbar_wait(&a_full[buf], (uint32_t)((tile_it >> 1) & 1), 53);
+        else if (!ptx::mbar_test_warp(&a_full[buf], (uint32_t)((tile_it >> 1) & 1))) return false;
+      }
       ptx::mbar_wait(&w1_full[st], kResident ? 0u : (uint32_t)((g >> 1) & 1), 54);  // resident: completes once, stays complete
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
@@ -1671,10 +1682,15 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
         if (c == num_c - 1) ptx::umma_commit_2sm(&a_empty[buf], 3u);
       }
       __syncwarp();
+      return true;
     };
     if (total > 0) issue_G1(0);
     if (total > 1) issue_G1(1);
+    [[maybe_unused]] int next_g1 = 2;  // AVB_FFN_DECOUPLE: first up-projection not issued yet
     for (int g = 0; g < total; ++g) {
+#if AVB_FFN_DECOUPLE
+      while (next_g1 <= g) { issue_G1(next_g1, true); ++next_g1; }  // this chunk's own up-projection is due now
+#endif
       AVB_TRACE(1, g, 0);
       AVB_TRACE(1, g, 1);
       const int tile_it = g / num_c, c = g % num_c, st = kResident ? c : (g & 1), hs = g & 1;
@@ -1698,7 +1714,16 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
       }
       __syncwarp();
       AVB_TRACE(1, g, 4);
+#if AVB_FFN_DECOUPLE
+      // up to two chunks ahead, but never WAITING for the next tile's LayerNorm here: the remaining down-projections of
+      // this tile (and with them d2_full -> E2 -> the D2 buffer the LayerNorm warps need) must not queue behind it
+      while (next_g1 <= g + 2 && next_g1 < total) {
+        if (!issue_G1(next_g1, false)) break;
+        ++next_g1;
+      }
+#else
       if (g + 2 < total) issue_G1(g + 2);  // into the D1 buffer G2(g) has just been issued on (MMAs run in issue order)
+#endif
     }
   } else if (warp >= 8) {
     // ===================== epilogue warps: (TMEM lane quarter q) x (64-column half)
@@ -1800,6 +1825,16 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
 #pragma unroll
         for (int e = 0; e < 16; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bp) + e);
         AVB_TRACE(2, g, 0);
+#if AVB_FFN_DECOUPLE
+        // E2 of the previous tile goes FIRST when this tile's first D1 is not there yet (the issuer is waiting for the
+        // LayerNorm warps, which in turn wait for the D2 buffer E2 releases)
+        bool e2_early = false;
+        if (c == 0 && prev_mt >= 0 && !ptx::mbar_test_warp(&d1_full[g & 1], (uint32_t)((g >> 1) & 1))) {
+          e2_g = g;
+          E2(tile_it - 1, prev_mt);
+          e2_early = true;
+        }
+#endif
         ptx::mbar_wait(&d1_full[g & 1], (uint32_t)((g >> 1) & 1), 59);
         AVB_TRACE(2, g, 1);
         ptx::tc_fence_after();
@@ -1826,7 +1861,11 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
         ptx::tc_fence_before();
         ptx::mbar_arrive_cluster(&h_full[hs], 0);
         AVB_TRACE(2, g, 4);
+#if AVB_FFN_DECOUPLE
+        if (c == 0 && prev_mt >= 0 && !e2_early) {
+#else
         if (c == 0 && prev_mt >= 0) {
+#endif
           e2_g = g;
           E2(tile_it - 1, prev_mt);
           AVB_TRACE(2, g, 6);

@@ -60,6 +60,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // backoff_ns > 0: sleep between polls.  A polling warp competes for issue slots with the compute warps of its
 // SM sub-partition (measured: one spinning role warp per SMSP took ~1/3 of all issued instructions), so the
 // single-lane role warps (TMA producer, MMA issuer) back off while the latency-critical softmax warps do not.
+// non-blocking, warp-uniform: has the phase with this parity completed?  (lane 0 tests, the warp agrees)
+__device__ __forceinline__ bool mbar_test_warp(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  if ((threadIdx.x & 31) == 0)
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0, unsigned backoff_ns = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
