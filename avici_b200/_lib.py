@@ -17,7 +17,7 @@ AVB_OK, AVB_ERR_INVALID, AVB_ERR_CUDA, AVB_ERR_MISSING, AVB_ERR_WORKSPACE = 0, 1
 AVB_DTYPE_F32, AVB_DTYPE_BF16 = 0, 1
 AVB_STANDARDIZE_NONE, AVB_STANDARDIZE_DEFAULT, AVB_STANDARDIZE_COUNT = 0, 1, 2
 AVB_AXIS_D, AVB_AXIS_N = 0, 1
-PROF_CATEGORIES = ("prologue", "ln", "qkv", "attn_d", "attn_n", "out", "ffn1", "ffn2", "pool_head")
+PROF_CATEGORIES = ("prologue", "qkv", "attn_d", "attn_n", "out", "ffn", "pool_head", "dattn")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -44,6 +44,8 @@ SIGNATURES = {
     "avb_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "avb_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                               C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "avb_forward_logprobs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "avb_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_void_p]),
     "avb_standardize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -56,6 +58,8 @@ SIGNATURES = {
                            C.c_void_p]),
     "avb_head": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t,
                            C.c_void_p]),
+    "avb_head_logprobs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t,
+                                    C.c_void_p]),
     "avb_graph_metrics_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "avb_graph_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_size_t, C.c_void_p]),
@@ -64,10 +68,6 @@ SIGNATURES = {
     "avb_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "avb_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "avb_debug_set_trace": (C.c_int, [C.c_void_p]),
-    "avb_test_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
-                                     C.c_int32, C.c_int32, C.c_void_p]),
-    "avb_test_ln_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                                        C.c_void_p]),
     "avb_test_ffn_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_void_p]),
     "avb_test_qkv_layout_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

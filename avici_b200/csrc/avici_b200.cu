@@ -10,12 +10,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -36,7 +38,7 @@ struct Block {
   // bf16 tensor-core copies: K-major [N,K], LayerNorm affine and softmax scale folded in
   const bf16 *wqkv_t, *wo_t, *w1_t, *w2_t;
   const float *bqkv_f, *b1_f;
-  CUtensorMap tm_wqkv, tm_wqkv_h, tm_wo, tm_w1, tm_w2, tm_w1c, tm_w1q, tm_w2q;  // *q: [64 x 64] boxes (CTA-pair FFN)  // tm_wqkv_h: [128 x 64] boxes for the CTA-pair kernel  // tm_w1c: W1t in [128 x 64] boxes for the fused FFN kernel
+  CUtensorMap tm_wqkv_h, tm_wo, tm_w1q, tm_w2q;  // wqkv: [128 x 64] boxes (CTA-pair QKV), wo: [128 x 64], w1 / w2: [64 x 64] (CTA-pair FFN)
 };
 
 }  // namespace
@@ -54,8 +56,10 @@ struct avb_model_s {
   const float *lnu_g = nullptr, *lnu_b = nullptr, *wu = nullptr, *bu = nullptr;
   const float *lnv_g = nullptr, *lnv_b = nullptr, *wv = nullptr, *bv = nullptr;
   const float *temp = nullptr, *bias = nullptr;
-  void* host_ws = nullptr;  // internal workspace of avb_forward_host
+  void* host_ws = nullptr;  // internal workspace of avb_forward_host (one host-buffer call at a time per handle)
   size_t host_ws_bytes = 0;
+  cudaStream_t host_stream = nullptr;
+  std::mutex host_mu;
   long long launches = 0;
   // optional per-kernel-category CUDA-event timing (avb_profile_*)
   bool prof = false;
@@ -92,6 +96,17 @@ struct ProfScope {
   ~ProfScope() {
     if (a) { cudaEventRecord(b, st); h->prof_recs.push_back({cat, a, b}); }
   }
+};
+
+// Every entry point that takes a handle runs on the handle's device (one process may hold one handle per GPU):
+// switch to it for the duration of the call and restore the caller's current device afterwards.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
 #define AVB_CUDA(h, expr)                                                                          \
@@ -158,127 +173,88 @@ bool make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols
 }
 
 // ------------------------------------------------------------------ kernel launchers
-template <int BN, int EPI>
-int launch_gemm_tc(avb_handle h, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const float* bias, void* out,
-                   int ldo, int M, int N, int K, cudaStream_t st, int num_sms, long long* launches) {
-  using Cfg = avb::GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(avb::gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
-    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(gemm_tc): %s", cudaGetErrorString(e));
-    attr_set = true;
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: every launcher remembers which devices
+// it has prepared (one process may hold one handle per GPU).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  template <class F> cudaError_t run(F&& f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = f();
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
   }
-  const int tiles = ((M + 127) / 128) * (N / BN);
-  const int grid = std::min(tiles, num_sms);
-  avb::gemm_tc_kernel<BN, EPI><<<grid, avb::kGemmThreads, Cfg::kSmemBytes, st>>>(tm_a, tm_b, bias, out, ldo, M, N, K);
-  if (launches) ++*launches;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "gemm_tc launch: %s", cudaGetErrorString(e));
-  return AVB_OK;
+};
+
+// Debug / A-B switches read from the environment exist only in -DAVB_AB_BUILD builds (scripts/ab_run.sh); the
+// production library never calls getenv.
+inline const char* ab_env(const char* name) {
+#ifdef AVB_AB_BUILD
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
 }
 
-template <int EPI>
-int launch_ln_gemm_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, const float* bias, void* out, int ldo,
-                      int M, int N, cudaStream_t st, int num_sms, long long* launches, int seq_n = 0, int seq_d = 0,
-                      int seq_axis = 0) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(avb::ln_gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         avb::kLnGemmSmemBytes);
-    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(ln_gemm_tc): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  const int grid = std::min((M + 127) / 128, num_sms);
-  avb::ln_gemm_tc_kernel<EPI><<<grid, avb::kLnGemmThreads, avb::kLnGemmSmemBytes, st>>>(
-      z, tm_b, bias, reinterpret_cast<bf16*>(out), ldo, M, N, seq_n, seq_d, seq_axis);
-  if (launches) ++*launches;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ln_gemm_tc launch: %s", cudaGetErrorString(e));
-  return AVB_OK;
-}
-
-// CTA-pair (cluster of 2, cta_group::2) version; tm_b must have [128 x 64] boxes.
-template <int EPI>
+// LayerNorm + QKV projection, CTA pairs (cluster of 2, cta_group::2); tm_b must have [128 x 64] boxes.
+// run_if: see ln_gemm2_tc_kernel.
 int launch_ln_gemm2_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, const float* bias, void* out, int ldo,
-                       int M, int N, cudaStream_t st, int num_sms, long long* launches, int seq_n, int seq_d, int seq_axis) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(avb::ln_gemm2_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         avb::kLnGemmSmemBytes);
-    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(ln_gemm2_tc): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+                       int M, int N, cudaStream_t st, int num_sms, long long* launches, int seq_n, int seq_d, int seq_axis,
+                       const int* run_if = nullptr) {
+  static PerDeviceOnce once;
+  cudaError_t e = once.run([] {
+    return cudaFuncSetAttribute(avb::ln_gemm2_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kLnGemmSmemBytes);
+  });
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(ln_gemm2_tc): %s", cudaGetErrorString(e));
   const int num_pairs = ((M + 127) / 128 + 1) / 2;
   const int grid = 2 * std::min(num_pairs, num_sms / 2);
-  avb::ln_gemm2_tc_kernel<EPI><<<grid, avb::kLnGemmThreads, avb::kLnGemmSmemBytes, st>>>(
-      z, tm_b, bias, reinterpret_cast<bf16*>(out), ldo, M, N, seq_n, seq_d, seq_axis);
+  avb::ln_gemm2_tc_kernel<2><<<grid, avb::kLnGemmThreads, avb::kLnGemmSmemBytes, st>>>(
+      z, tm_b, bias, reinterpret_cast<bf16*>(out), ldo, M, N, seq_n, seq_d, seq_axis, run_if);
   if (launches) ++*launches;
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ln_gemm2_tc launch: %s", cudaGetErrorString(e));
   return AVB_OK;
 }
 
-// delta == nullptr: z += attn . Wo^T + bo in place; otherwise the update is written to delta (bf16 rows, token order)
-int launch_outproj_tc(avb_handle h, const void* attn, const CUtensorMap& tm_w, const float* bias, float* z, int M,
-                      int n, int d, int axis, cudaStream_t st, int num_sms, long long* launches, void* delta = nullptr) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(avb::outproj_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         avb::kOutProjSmemBytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(avb::outproj_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kOutProjSmemBytes);
-    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(outproj_tc): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+// delta[token][128] (bf16) = attn . Wo^T + bo
+int launch_outproj_tc(avb_handle h, const void* attn, const CUtensorMap& tm_w, const float* bias, void* delta, int M,
+                      int n, int d, int axis, cudaStream_t st, int num_sms, long long* launches, const int* run_if = nullptr) {
+  static PerDeviceOnce once;
+  cudaError_t e = once.run([] {
+    return cudaFuncSetAttribute(avb::outproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kOutProjSmemBytes);
+  });
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(outproj_tc): %s", cudaGetErrorString(e));
   const int grid = std::min((M + 127) / 128, num_sms);
-  if (delta)
-    avb::outproj_tc_kernel<true><<<grid, avb::kOutProjThreads, avb::kOutProjSmemBytes, st>>>(
-        reinterpret_cast<const bf16*>(attn), tm_w, bias, z, reinterpret_cast<bf16*>(delta), M, n, d, axis);
-  else
-    avb::outproj_tc_kernel<false><<<grid, avb::kOutProjThreads, avb::kOutProjSmemBytes, st>>>(
-        reinterpret_cast<const bf16*>(attn), tm_w, bias, z, nullptr, M, n, d, axis);
+  avb::outproj_tc_kernel<<<grid, avb::kOutProjThreads, avb::kOutProjSmemBytes, st>>>(
+      reinterpret_cast<const bf16*>(attn), tm_w, bias, reinterpret_cast<bf16*>(delta), M, n, d, axis, run_if);
   if (launches) ++*launches;
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "outproj_tc launch: %s", cudaGetErrorString(e));
   return AVB_OK;
 }
 
-int launch_ffn_tc(avb_handle h, float* z, const CUtensorMap& tm_w1c, const CUtensorMap& tm_w2, const float* b1,
-                  const float* b2, int M, int F, cudaStream_t st, int num_sms, long long* launches) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(avb::ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kFfnSmemBytes);
-    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(ffn_tc): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  const int grid = std::min((M + 127) / 128, num_sms);
-  avb::ffn_tc_kernel<<<grid, avb::kFfnThreads, avb::kFfnSmemBytes, st>>>(z, tm_w1c, tm_w2, b1, b2, M, F);
-  if (launches) ++*launches;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ffn_tc launch: %s", cudaGetErrorString(e));
-  return AVB_OK;
-}
-
-// CTA-pair (cluster of 2, cta_group::2) fused FFN; tensor maps with [64 x 64] boxes.
+// CTA-pair (cluster of 2, cta_group::2) fused FFN; tensor maps with [64 x 64] boxes.  The resident-weight variant
+// serves the published width (F = 512, four resident chunks), the weight-ring variant every other multiple of 256.
 int launch_ffn2_tc(avb_handle h, float* z, const CUtensorMap& tm_w1q, const CUtensorMap& tm_w2q, const float* b1,
                    const float* b2, int M, int F, cudaStream_t st, int num_sms, long long* launches,
                    const void* delta = nullptr, int n = 0, int d = 0, int axis = 0) {
-  static bool attr_set = false;
-  static bool resident = true;  // AVB_FFN_RESIDENT=0: the weight-ring version (A/B reference)
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(avb::ffn2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kFfnSmemBytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(avb::ffn2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kFfnSmemBytes);
-    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(ffn2_tc): %s", cudaGetErrorString(e));
-    const char* r = getenv("AVB_FFN_RESIDENT");
-    if (r && r[0] == '0') resident = false;
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  cudaError_t e = once.run([] {
+    cudaError_t r = cudaFuncSetAttribute(avb::ffn2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kFfnSmemBytes);
+    if (r == cudaSuccess)
+      r = cudaFuncSetAttribute(avb::ffn2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kFfnSmemBytes);
+    return r;
+  });
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(ffn2_tc): %s", cudaGetErrorString(e));
+  bool use_resident = F == 512;
 #if !AVB_DELTA_TOKENS
-  resident = false;  // the resident version reads delta next to z: token order only
+  use_resident = false;  // the resident version reads delta next to z: token order only
 #endif
-  const bool use_resident = resident && F == 512;  // four resident chunks
+  if (const char* r = ab_env("AVB_FFN_RESIDENT")) use_resident = use_resident && r[0] != '0';
   const int num_pairs = ((M + 127) / 128 + 1) / 2;
   const int grid = 2 * std::min(num_pairs, num_sms / 2);
   CUtensorMap tm_z;  // the residual stream of this call, for the final epilogue's tensor-map stores
@@ -290,31 +266,29 @@ int launch_ffn2_tc(avb_handle h, float* z, const CUtensorMap& tm_w1q, const CUte
     avb::ffn2_tc_kernel<false><<<grid, avb::kFfnThreads, avb::kFfnSmemBytes, st>>>(z, reinterpret_cast<const bf16*>(delta), n, d, axis,
                                                                                     tm_z, tm_w1q, tm_w2q, b1, b2, M, F);
   if (launches) ++*launches;
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ffn2_tc launch: %s", cudaGetErrorString(e));
   return AVB_OK;
 }
 
-// Axial attention = two launches on the same stream: the fast kernel (stale row maximum) and the exact kernel, which
-// exits at once unless the fast one raised `guard` (a score tile outran the running maximum by > 2^64; never seen on
-// LayerNorm-ed inputs, but the result must not depend on that).  guard: 4 bytes of device memory owned by the caller's
-// workspace, so concurrent forwards on different streams / workspaces stay independent.
-// AVB_ATTN_MODE=exact|fast (debug): run only one of the two.
+// Axial attention = two launches on the same stream: the fast kernel (no running maximum) and the exact kernel, which
+// exits at once unless the fast one raised `guard` (scores outside +-100 log2 units; never seen on LayerNorm-ed inputs,
+// but the result must not depend on that).  guard: 4 bytes of device memory owned by the caller's workspace, so
+// concurrent forwards on different streams / workspaces stay independent.
+// mode 0: fast + guarded exact (reset_guard: clear the guard first); 1: the exact kernel alone, unconditionally;
+// 3: the exact kernel alone, only if the guard is already up (fallback behind dattn_tc_kernel).
 int launch_attention_tc(avb_handle h, const void* qkv, void* out, int B, int n, int d, int H, int axis,
-                        cudaStream_t st, int num_sms, long long* launches, int* guard) {
-  static bool attr_set = false;
-  static int mode = 0;  // 0: fast + guarded exact, 1: exact only, 2: fast only
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(avb::attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         avb::kAttnSmemBytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(avb::attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               avb::kAttnSmemBytes);
-    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(attention_tc): %s", cudaGetErrorString(e));
-    const char* m = getenv("AVB_ATTN_MODE");
-    if (m && !strcmp(m, "exact")) mode = 1;
-    if (m && !strcmp(m, "fast")) mode = 2;
-    attr_set = true;
+                        cudaStream_t st, int num_sms, long long* launches, int* guard, int mode = 0) {
+  static PerDeviceOnce once;
+  cudaError_t e = once.run([] {
+    cudaError_t r = cudaFuncSetAttribute(avb::attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kAttnSmemBytes);
+    if (r == cudaSuccess)
+      r = cudaFuncSetAttribute(avb::attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kAttnSmemBytes);
+    return r;
+  });
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(attention_tc): %s", cudaGetErrorString(e));
+  if (mode == 0) {
+    if (const char* m = ab_env("AVB_ATTN_MODE")) mode = !strcmp(m, "exact") ? 1 : (!strcmp(m, "fast") ? 2 : 0);
   }
   const int T = axis == 0 ? d : n;
   const long long S = axis == 0 ? (long long)B * n : (long long)B * d;
@@ -322,7 +296,7 @@ int launch_attention_tc(avb_handle h, const void* qkv, void* out, int B, int n, 
   if (items >= (1LL << 31)) return fail(h, AVB_ERR_INVALID, "attention: too many (sequence, head, tile) items in one call (%lld)", items);
   // a stream owns whole (sequence, head) pairs and walks their query tiles itself
   const int grid = (int)std::min<long long>((S * H + avb::kAttnStreams - 1) / avb::kAttnStreams, num_sms);
-  if (mode != 1) {
+  if (mode == 0 || mode == 2) {
     if (cudaMemsetAsync(guard, 0, sizeof(int), st) != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention guard reset failed");
     avb::attention_tc_kernel<true><<<grid, avb::kAttnThreads, avb::kAttnSmemBytes, st>>>(
         reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis, guard);
@@ -333,7 +307,7 @@ int launch_attention_tc(avb_handle h, const void* qkv, void* out, int B, int n, 
         reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis, mode == 1 ? nullptr : guard);
     if (launches) ++*launches;
   }
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention_tc launch: %s", cudaGetErrorString(e));
   return AVB_OK;
 }
@@ -370,7 +344,7 @@ BlockWs block_ws_layout(const avb_config& c, size_t ntok) {
 }
 
 struct FwdWs {
-  size_t xs_off, iv_off, stat_off, pooled_off, pooled_c_off, uv_off, z_off, blk_off, total;
+  size_t xs_off, xtmp_off, iv_off, stat_off, pooled_off, pooled_c_off, uv_off, z_off, blk_off, total;
   int Bc;  // datasets (after chunk expansion) processed per pass
 };
 constexpr size_t kWsBudget = (size_t)40 << 30;  // cap on the per-pass activation working set
@@ -381,6 +355,7 @@ FwdWs fwd_ws_layout(const avb_config& c, int B, int n, int d, int chunks) {
   const size_t cells = (size_t)B * n * d;
   size_t off = 0;
   w.xs_off = off; off = align_up(off + cells * 4, 1024);
+  w.xtmp_off = off; off = align_up(off + (chunks > 1 ? cells * 4 : 0), 1024);  // standardizer output before the chunk gather
   w.iv_off = off; off = align_up(off + (chunks > 1 ? cells * 4 : 0), 1024);
   w.stat_off = off; off = align_up(off + (size_t)B * (n + d + 8) * 8, 1024);
   w.pooled_off = off; off = align_up(off + (size_t)B * d * c.dim * 4, 1024);
@@ -458,14 +433,18 @@ int avb_create(avb_handle* out, const avb_config* cfg) {
   h->cfg = *cfg;
   h->device = dev;
   h->num_sms = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete h; return fail(nullptr, AVB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   *out = h;
   return AVB_OK;
 }
 
 void avb_destroy(avb_handle h) {
   if (!h) return;
+  DeviceGuard dg(h->device);
   if (h->arena) cudaFree(h->arena);
   if (h->host_ws) cudaFree(h->host_ws);
+  if (h->host_stream) cudaStreamDestroy(h->host_stream);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
@@ -488,6 +467,7 @@ int avb_profile_enable(avb_handle h, int32_t on) {
 
 int avb_profile_read(avb_handle h, double* ms_out, int64_t* count_out, int32_t reset) {
   if (!h) return AVB_ERR_INVALID;
+  DeviceGuard dg(h->device);
   AVB_CUDA(h, cudaDeviceSynchronize());
   for (const auto& r : h->prof_recs) {
     float ms = 0.f;
@@ -505,6 +485,7 @@ int avb_profile_read(avb_handle h, double* ms_out, int64_t* count_out, int32_t r
 
 int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count) {
   if (!h || !tensors) return fail(h, AVB_ERR_INVALID, "avb_load_weights: null argument");
+  DeviceGuard dg(h->device);
   const avb_config& c = h->cfg;
   const int k = c.dim, HD = c.num_heads * c.key_size, F = c.widening_factor * c.dim, nb = 2 * c.layers;
   std::map<std::string, std::pair<const float*, int64_t>> tab;
@@ -638,11 +619,8 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
     B.bqkv_f = df + o.bqkv_f; B.b1_f = df + o.b1_f;
     if (c.compute_dtype == AVB_DTYPE_BF16) {
       B.wqkv_t = db + o.wqkv_t; B.wo_t = db + o.wo_t; B.w1_t = db + o.w1_t; B.w2_t = db + o.w2_t;
-      bool ok = make_tmap_2d(&B.tm_wqkv, B.wqkv_t, 3 * HD, k, 256) && make_tmap_2d(&B.tm_wqkv_h, B.wqkv_t, 3 * HD, k, 128) &&
-                make_tmap_2d(&B.tm_wo, B.wo_t, k, HD, 128) &&
-                make_tmap_2d(&B.tm_w1, B.w1_t, F, k, 256) && make_tmap_2d(&B.tm_w2, B.w2_t, k, F, 128) &&
-                make_tmap_2d(&B.tm_w1c, B.w1_t, F, k, 128) && make_tmap_2d(&B.tm_w1q, B.w1_t, F, k, 64) &&
-                make_tmap_2d(&B.tm_w2q, B.w2_t, k, F, 64);
+      bool ok = make_tmap_2d(&B.tm_wqkv_h, B.wqkv_t, 3 * HD, k, 128) && make_tmap_2d(&B.tm_wo, B.wo_t, k, HD, 128) &&
+                make_tmap_2d(&B.tm_w1q, B.w1_t, F, k, 64) && make_tmap_2d(&B.tm_w2q, B.w2_t, k, F, 64);
       if (!ok) return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for block %d weights", i);
     }
   }
@@ -654,6 +632,7 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
 int avb_standardize(avb_handle h, const float* x, int32_t B, int32_t n, int32_t d, int32_t mode, float* xs,
                     void* scratch, size_t scratch_bytes, void* stream) {
   if (!shape_ok(h, B, n, d) || !x || !xs) return fail(h, AVB_ERR_INVALID, "avb_standardize: bad argument");
+  DeviceGuard dg(h->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t total = (size_t)B * n * d;
   ProfScope ps(h, AVB_PROF_PROLOGUE, st);
@@ -686,6 +665,7 @@ int avb_standardize(avb_handle h, const float* x, int32_t B, int32_t n, int32_t 
 int avb_embed(avb_handle h, const float* xs, const float* interv, int64_t ntok, float* z, void* stream) {
   if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_embed: weights not loaded");
   if (!xs || !z || ntok < 1) return fail(h, AVB_ERR_INVALID, "avb_embed: bad argument");
+  DeviceGuard dg(h->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = (int)std::min<int64_t>((ntok + 7) / 8, (int64_t)h->num_sms * 16);
   ProfScope ps(h, AVB_PROF_PROLOGUE, st);
@@ -704,6 +684,7 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
   if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_block: weights not loaded");
   if (!shape_ok(h, B, n, d) || !z || (axis != 0 && axis != 1) || bi < 0 || bi >= (int)h->blocks.size())
     return fail(h, AVB_ERR_INVALID, "avb_block: bad argument");
+  DeviceGuard dg(h->device);
   const avb_config& c = h->cfg;
   const size_t ntok = (size_t)B * n * d;
   if (ntok > (size_t)0x7fffff00) return fail(h, AVB_ERR_INVALID, "avb_block: too many tokens per call (%zu)", ntok);
@@ -719,30 +700,21 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
     bf16* qkv = reinterpret_cast<bf16*>(w8 + L.big_off);
     bf16* attn = reinterpret_cast<bf16*>(w8 + L.attn_off);
     int rc;
-    static const bool ffn_pair = !(getenv("AVB_FFN_2CTA") && getenv("AVB_FFN_2CTA")[0] == '0');
-    static const bool use_delta = ffn_pair && !(getenv("AVB_OUT_DELTA") && getenv("AVB_OUT_DELTA")[0] == '0');  // A/B switch (debug)
-    // attention half: LN -> QKV -> attention -> out-proj + residual
-    { ProfScope ps(h, AVB_PROF_QKV, st);  // LayerNorm fused into the projection's prologue
+    int* guard = reinterpret_cast<int*>(w8 + L.guard_off);
+    // attention half: LN -> QKV -> attention -> out-projection, leaving the sub-layer's update as bf16 `delta` rows in
+    // the qkv buffer (dead once the attention has run); the FFN's LayerNorm warps add it to z.
+    { ProfScope ps(h, AVB_PROF_QKV, st);  // LayerNorm fused into the projection's prologue;
       // rows in sequence-major order of `axis`, output in the attention kernel's operand layout
-      static const bool pair = !(getenv("AVB_QKV_2CTA") && getenv("AVB_QKV_2CTA")[0] == '0');  // A/B switch (debug)
-      if (pair) {
-        if ((rc = launch_ln_gemm2_tc<2>(h, z, W.tm_wqkv_h, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, st, h->num_sms, &h->launches,
-                                        n, d, axis))) return rc;
-      } else if ((rc = launch_ln_gemm_tc<2>(h, z, W.tm_wqkv, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, st, h->num_sms, &h->launches,
-                                            n, d, axis))) return rc; }
+      if ((rc = launch_ln_gemm2_tc(h, z, W.tm_wqkv_h, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, st, h->num_sms, &h->launches,
+                                   n, d, axis))) return rc; }
     { ProfScope ps(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
-      if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches,
-                                    reinterpret_cast<int*>(w8 + L.guard_off)))) return rc; }
+      if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches, guard))) return rc; }
     { ProfScope ps(h, AVB_PROF_OUT, st);
-      // with the CTA-pair FFN the update goes to `delta` (the dead qkv buffer) and is added to z by the FFN's LN warps
-      if ((rc = launch_outproj_tc(h, attn, W.tm_wo, W.bo, z, M, n, d, axis, st, h->num_sms, &h->launches,
-                                  use_delta ? qkv : nullptr))) return rc; }
-    // FFN half: LN -> Linear + ReLU -> Linear + residual
-    { ProfScope ps(h, AVB_PROF_FFN1, st);  // whole FFN sub-layer in one kernel (LN, up-projection, ReLU, down-projection, residual)
-      static const bool pair = !(getenv("AVB_FFN_2CTA") && getenv("AVB_FFN_2CTA")[0] == '0');  // A/B switch (debug)
-      if (pair) { if ((rc = launch_ffn2_tc(h, z, W.tm_w1q, W.tm_w2q, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches,
-                                           use_delta ? qkv : nullptr, n, d, axis))) return rc; }
-      else if ((rc = launch_ffn_tc(h, z, W.tm_w1c, W.tm_w2, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches))) return rc; }
+      if ((rc = launch_outproj_tc(h, attn, W.tm_wo, W.bo, qkv, M, n, d, axis, st, h->num_sms, &h->launches))) return rc; }
+    // FFN half: z += delta; LN -> Linear + ReLU -> Linear + residual, one kernel
+    { ProfScope ps(h, AVB_PROF_FFN, st);
+      if ((rc = launch_ffn2_tc(h, z, W.tm_w1q, W.tm_w2q, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches, qkv, n, d, axis)))
+        return rc; }
   } else {
     float* qkv = reinterpret_cast<float*>(w8 + L.big_off);
     float* hid = qkv;
@@ -760,23 +732,21 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
     const long long outer_stride = axis == 0 ? d : (long long)n * d;
     const long long inner_stride = axis == 0 ? 0 : 1;
     const long long tok_stride = axis == 0 ? 1 : d;
-    ProfScope* pa = new ProfScope(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
-    for (long long s0 = 0; s0 < S; s0 += 65535) {  // grid.z is limited to 65535
-      const int sz = (int)std::min<long long>(65535, S - s0);
-      avb::attention_f32_kernel<<<dim3((T + 127) / 128, H, sz), 128, 0, st>>>(
-          qkv, attn, T, H, s0, inner, outer_stride, inner_stride, tok_stride, 1.0f / sqrtf((float)c.key_size));
-      h->launches++;
-    }
-    delete pa;
+    { ProfScope ps(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
+      for (long long s0 = 0; s0 < S; s0 += 65535) {  // grid.z is limited to 65535
+        const int sz = (int)std::min<long long>(65535, S - s0);
+        avb::attention_f32_kernel<<<dim3((T + 127) / 128, H, sz), 128, 0, st>>>(
+            qkv, attn, T, H, s0, inner, outer_stride, inner_stride, tok_stride, 1.0f / sqrtf((float)c.key_size));
+        h->launches++;
+      } }
     { cudaError_t e__ = cudaGetLastError();
       if (e__ != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention_f32 launch failed: %s", cudaGetErrorString(e__)); }
     { ProfScope ps(h, AVB_PROF_OUT, st);
       launch_sgemm<2, false>(attn, HD, W.wo, k, W.bo, nullptr, nullptr, z, k, z, k, ntok, k, HD, st);
       AVB_LAUNCH_CHECK(h); }
-    { ProfScope ps(h, AVB_PROF_FFN1, st);
+    { ProfScope ps(h, AVB_PROF_FFN, st);
       launch_sgemm<1, true>(z, k, W.w1, F, W.b1, W.ln_g[3], W.ln_b[3], nullptr, 0, hid, F, ntok, F, k, st);
-      AVB_LAUNCH_CHECK(h); }
-    { ProfScope ps(h, AVB_PROF_FFN2, st);
+      AVB_LAUNCH_CHECK(h);
       launch_sgemm<2, false>(hid, F, W.w2, k, W.b2, nullptr, nullptr, z, k, z, k, ntok, k, F, st);
       AVB_LAUNCH_CHECK(h); }
   }
@@ -787,6 +757,7 @@ int avb_pool(avb_handle h, const float* z, int32_t B, int32_t n, int32_t d, floa
              void* stream) {
   if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_pool: weights not loaded");
   if (!shape_ok(h, B, n, d) || !z || !pooled) return fail(h, AVB_ERR_INVALID, "avb_pool: bad argument");
+  DeviceGuard dg(h->device);
   if (B > 65535) return fail(h, AVB_ERR_INVALID, "avb_pool: B > 65535");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ProfScope ps(h, AVB_PROF_POOL_HEAD, st);
@@ -795,10 +766,11 @@ int avb_pool(avb_handle h, const float* z, int32_t B, int32_t n, int32_t d, floa
   return AVB_OK;
 }
 
-int avb_head(avb_handle h, const float* pooled, int32_t B, int32_t d, float* probs, void* scratch,
-             size_t scratch_bytes, void* stream) {
+static int head_impl(avb_handle h, const float* pooled, int32_t B, int32_t d, float* probs, void* scratch,
+                     size_t scratch_bytes, void* stream, int log_probs) {
   if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_head: weights not loaded");
-  if (!h || B < 1 || d < 1 || !pooled || !probs) return fail(h, AVB_ERR_INVALID, "avb_head: bad argument");
+  if (B < 1 || d < 1 || !pooled || !probs) return fail(h, AVB_ERR_INVALID, "avb_head: bad argument");
+  DeviceGuard dg(h->device);
   const avb_config& c = h->cfg;
   const size_t need = (size_t)2 * B * d * c.out_dim * 4;
   if (!scratch || scratch_bytes < need) return fail(h, AVB_ERR_WORKSPACE, "avb_head: scratch %zu < %zu", scratch_bytes, need);
@@ -811,9 +783,19 @@ int avb_head(avb_handle h, const float* pooled, int32_t B, int32_t d, float* pro
                                                                h->lnv_b, h->wv, h->bv, c.out_dim, u, v);
   AVB_LAUNCH_CHECK(h);
   avb::head_logits_kernel<<<dim3((d + 15) / 16, (d + 15) / 16, B), dim3(16, 16), 0, st>>>(
-      u, v, d, c.out_dim, h->temp, h->bias, c.mask_diag, probs);
+      u, v, d, c.out_dim, h->temp, h->bias, c.mask_diag, log_probs, probs);
   AVB_LAUNCH_CHECK(h);
   return AVB_OK;
+}
+
+int avb_head(avb_handle h, const float* pooled, int32_t B, int32_t d, float* probs, void* scratch, size_t scratch_bytes,
+             void* stream) {
+  return head_impl(h, pooled, B, d, probs, scratch, scratch_bytes, stream, 0);
+}
+
+int avb_head_logprobs(avb_handle h, const float* pooled, int32_t B, int32_t d, float* logprobs, void* scratch,
+                      size_t scratch_bytes, void* stream) {
+  return head_impl(h, pooled, B, d, logprobs, scratch, scratch_bytes, stream, 1);
 }
 
 // ----------------------------------------------------------------------------------- forward
@@ -833,10 +815,12 @@ size_t avb_workspace_bytes(avb_handle h, int32_t B, int32_t n, int32_t d, int32_
   return fwd_ws_layout(h->cfg, B, n, d, chunks).total;
 }
 
-int avb_forward(avb_handle h, const float* x, const float* interv, int32_t B, int32_t n, int32_t d,
-                int32_t standardize, int32_t chunk_size, float* probs, void* ws, size_t ws_bytes, void* stream) {
+static int forward_impl(avb_handle h, const float* x, const float* interv, int32_t B, int32_t n, int32_t d,
+                        int32_t standardize, int32_t chunk_size, float* probs, void* ws, size_t ws_bytes, void* stream,
+                        int log_probs) {
   if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_forward: weights not loaded");
   if (!shape_ok(h, B, n, d) || !x || !probs) return fail(h, AVB_ERR_INVALID, "avb_forward: bad argument");
+  DeviceGuard dg(h->device);
   int chunks = 1, rc;
   if ((rc = resolve_chunks(h, n, chunk_size, &chunks))) return rc;
   const avb_config& c = h->cfg;
@@ -849,15 +833,15 @@ int avb_forward(avb_handle h, const float* x, const float* interv, int32_t B, in
   float* z = reinterpret_cast<float*>(w8 + L.z_off);
   const size_t cells = (size_t)B * n * d;
 
-  if ((rc = avb_standardize(h, x, B, n, d, standardize, xs, w8 + L.stat_off, (size_t)B * (n + d + 8) * 8, stream))) return rc;
+  // with chunking the standardizer writes to its own staging buffer and the gather below produces xs
+  float* xstd = chunks > 1 ? reinterpret_cast<float*>(w8 + L.xtmp_off) : xs;
+  if ((rc = avb_standardize(h, x, B, n, d, standardize, xstd, w8 + L.stat_off, (size_t)B * (n + d + 8) * 8, stream))) return rc;
   const float* iv = interv;
   float* pool_dst = pooled;
   int Be = B, ne = n;
   if (chunks > 1) {
     // chunk c of dataset b becomes dataset b*chunks + c with n/chunks rows (model.py:105-106)
-    float* tmp = reinterpret_cast<float*>(w8 + L.z_off);  // z region is free until embed
-    AVB_CUDA(h, cudaMemcpyAsync(tmp, xs, cells * 4, cudaMemcpyDeviceToDevice, st));
-    chunk_gather_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(tmp, xs, B, n, d, chunks);
+    chunk_gather_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(xstd, xs, B, n, d, chunks);
     AVB_LAUNCH_CHECK(h);
     if (interv) {
       float* ivp = reinterpret_cast<float*>(w8 + L.iv_off);
@@ -884,13 +868,25 @@ int avb_forward(avb_handle h, const float* x, const float* interv, int32_t B, in
     chunk_max_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pool_dst, pooled, per_ds, chunks, total);
     AVB_LAUNCH_CHECK(h);
   }
-  return avb_head(h, pooled, B, d, probs, w8 + L.uv_off, (size_t)2 * B * d * c.out_dim * 4, stream);
+  return head_impl(h, pooled, B, d, probs, w8 + L.uv_off, (size_t)2 * B * d * c.out_dim * 4, stream, log_probs);
+}
+
+int avb_forward(avb_handle h, const float* x, const float* interv, int32_t B, int32_t n, int32_t d, int32_t standardize,
+                int32_t chunk_size, float* probs, void* ws, size_t ws_bytes, void* stream) {
+  return forward_impl(h, x, interv, B, n, d, standardize, chunk_size, probs, ws, ws_bytes, stream, 0);
+}
+
+int avb_forward_logprobs(avb_handle h, const float* x, const float* interv, int32_t B, int32_t n, int32_t d,
+                         int32_t standardize, int32_t chunk_size, float* logprobs, void* ws, size_t ws_bytes, void* stream) {
+  return forward_impl(h, x, interv, B, n, d, standardize, chunk_size, logprobs, ws, ws_bytes, stream, 1);
 }
 
 int avb_forward_host(avb_handle h, const float* x_host, const float* interv_host, int32_t B, int32_t n, int32_t d,
                      int32_t standardize, int32_t chunk_size, float* probs_host) {
   if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_forward_host: weights not loaded");
   if (!shape_ok(h, B, n, d) || !x_host || !probs_host) return fail(h, AVB_ERR_INVALID, "avb_forward_host: bad argument");
+  DeviceGuard dg(h->device);
+  std::lock_guard<std::mutex> lock(h->host_mu);  // the internal workspace and stream are per handle
   int chunks = 1, rc;
   if ((rc = resolve_chunks(h, n, chunk_size, &chunks))) return rc;
   const size_t cells = (size_t)B * n * d, pbytes = (size_t)B * d * d * 4;
@@ -906,11 +902,11 @@ int avb_forward_host(avb_handle h, const float* x_host, const float* interv_host
   float* dx = reinterpret_cast<float*>(w8);
   float* di = reinterpret_cast<float*>(w8 + align_up(cells * 4, 1024));
   float* dp = reinterpret_cast<float*>(w8 + 2 * align_up(cells * 4, 1024));
-  cudaStream_t st = 0;
+  cudaStream_t st = h->host_stream;  // the handle's own non-blocking stream (not the legacy default stream)
   AVB_CUDA(h, cudaMemcpyAsync(dx, x_host, cells * 4, cudaMemcpyHostToDevice, st));
   if (interv_host) AVB_CUDA(h, cudaMemcpyAsync(di, interv_host, cells * 4, cudaMemcpyHostToDevice, st));
   if ((rc = avb_forward(h, dx, interv_host ? di : nullptr, B, n, d, standardize, chunk_size, dp, w8 + io,
-                        h->host_ws_bytes - io, nullptr)))
+                        h->host_ws_bytes - io, st)))
     return rc;
   AVB_CUDA(h, cudaMemcpyAsync(probs_host, dp, pbytes, cudaMemcpyDeviceToHost, st));
   AVB_CUDA(h, cudaStreamSynchronize(st));
@@ -918,41 +914,6 @@ int avb_forward_host(avb_handle h, const float* x_host, const float* interv_host
 }
 
 // ----------------------------------------------------------------------------------- test hooks
-int avb_test_gemm_bf16(const void* a, const void* wt, const float* bias, void* out, int32_t M, int32_t N, int32_t K,
-                       int32_t epilogue, void* stream) {
-  if (!a || !wt || !bias || !out || M < 1 || K % 64 || (N != 128 && N % 256)) return fail(nullptr, AVB_ERR_INVALID, "avb_test_gemm_bf16: bad shape");
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device");
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  CUtensorMap ta, tb;
-  if (!make_tmap_2d(&ta, a, M, K, 128) || !make_tmap_2d(&tb, wt, N, K, N == 128 ? 128 : 256))
-    return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-  if (N == 128) {
-    if (epilogue == 0) return launch_gemm_tc<128, 0>(nullptr, ta, tb, bias, out, N, M, N, K, st, sms, nullptr);
-    if (epilogue == 1) return launch_gemm_tc<128, 1>(nullptr, ta, tb, bias, out, N, M, N, K, st, sms, nullptr);
-    if (epilogue == 2) return launch_gemm_tc<128, 2>(nullptr, ta, tb, bias, out, N, M, N, K, st, sms, nullptr);
-  } else {
-    if (epilogue == 0) return launch_gemm_tc<256, 0>(nullptr, ta, tb, bias, out, N, M, N, K, st, sms, nullptr);
-    if (epilogue == 1) return launch_gemm_tc<256, 1>(nullptr, ta, tb, bias, out, N, M, N, K, st, sms, nullptr);
-    if (epilogue == 2) return launch_gemm_tc<256, 2>(nullptr, ta, tb, bias, out, N, M, N, K, st, sms, nullptr);
-  }
-  return fail(nullptr, AVB_ERR_INVALID, "avb_test_gemm_bf16: bad epilogue");
-}
-
-int avb_test_ln_gemm_bf16(const float* z, const void* wt, const float* bias, void* out, int32_t M, int32_t N, int32_t relu,
-                          void* stream) {
-  if (!z || !wt || !bias || !out || M < 1 || N % 256) return fail(nullptr, AVB_ERR_INVALID, "avb_test_ln_gemm_bf16: bad shape");
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device");
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  CUtensorMap tb;
-  if (!make_tmap_2d(&tb, wt, N, 128, 256)) return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return relu ? launch_ln_gemm_tc<1>(nullptr, z, tb, bias, out, N, M, N, st, sms, nullptr)
-              : launch_ln_gemm_tc<0>(nullptr, z, tb, bias, out, N, M, N, st, sms, nullptr);
-}
-
 namespace {
 // scratch of the layout test hooks (grown on demand, process lifetime)
 void* test_scratch(size_t bytes) {
@@ -979,20 +940,18 @@ int avb_test_qkv_layout_bf16(const float* z, const void* wt, const float* bias, 
   const int N = 3 * H * 32;
   void* packed = test_scratch(ntok * N * sizeof(bf16));
   if (!packed) return fail(nullptr, AVB_ERR_CUDA, "cudaMalloc(test scratch) failed");
-  static const bool pair = !(getenv("AVB_QKV_2CTA") && getenv("AVB_QKV_2CTA")[0] == '0');
   CUtensorMap tb;
-  if (!make_tmap_2d(&tb, wt, N, 128, pair ? 128 : 256)) return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  if (!make_tmap_2d(&tb, wt, N, 128, 128)) return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int rc = pair ? launch_ln_gemm2_tc<2>(nullptr, z, tb, bias, packed, N, (int)ntok, N, st, sms, nullptr, n, d, axis)
-                      : launch_ln_gemm_tc<2>(nullptr, z, tb, bias, packed, N, (int)ntok, N, st, sms, nullptr, n, d, axis);
+  const int rc = launch_ln_gemm2_tc(nullptr, z, tb, bias, packed, N, (int)ntok, N, st, sms, nullptr, n, d, axis);
   if (rc != AVB_OK) return rc;
   avb::unpack_qkv_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const bf16*>(packed), reinterpret_cast<bf16*>(out), B, n, d, H, axis);
   return cudaGetLastError() == cudaSuccess ? AVB_OK : fail(nullptr, AVB_ERR_CUDA, "unpack_qkv launch failed");
 }
 
-int avb_test_outproj_bf16(const void* attn, const void* wot, const float* bias, float* z, int32_t B, int32_t n, int32_t d,
+int avb_test_outproj_bf16(const void* attn, const void* wot, const float* bias, void* delta, int32_t B, int32_t n, int32_t d,
                           int32_t axis, void* stream) {
-  if (!attn || !wot || !bias || !z || B < 1 || n < 1 || d < 1 || (axis != 0 && axis != 1))
+  if (!attn || !wot || !bias || !delta || B < 1 || n < 1 || d < 1 || (axis != 0 && axis != 1))
     return fail(nullptr, AVB_ERR_INVALID, "avb_test_outproj_bf16: bad argument");
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device");
@@ -1005,21 +964,19 @@ int avb_test_outproj_bf16(const void* attn, const void* wot, const float* bias, 
   if (!make_tmap_2d(&tw, wot, 128, HD, 128)) return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   avb::pack_attn_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const bf16*>(attn), reinterpret_cast<bf16*>(packed), B, n, d, H, axis);
-  return launch_outproj_tc(nullptr, packed, tw, bias, z, (int)ntok, n, d, axis, st, sms, nullptr);
+  return launch_outproj_tc(nullptr, packed, tw, bias, delta, (int)ntok, n, d, axis, st, sms, nullptr);
 }
 
 int avb_test_ffn_bf16(float* z, const void* w1t, const void* w2t, const float* b1, const float* b2, int32_t M, int32_t F,
                       void* stream) {
-  if (!z || !w1t || !w2t || !b1 || !b2 || M < 1 || F % 128) return fail(nullptr, AVB_ERR_INVALID, "avb_test_ffn_bf16: bad shape");
+  if (!z || !w1t || !w2t || !b1 || !b2 || M < 1 || F % 256) return fail(nullptr, AVB_ERR_INVALID, "avb_test_ffn_bf16: bad shape");
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device");
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  static const bool pair = !(getenv("AVB_FFN_2CTA") && getenv("AVB_FFN_2CTA")[0] == '0');
   CUtensorMap t1, t2;
-  if (!make_tmap_2d(&t1, w1t, F, 128, pair ? 64 : 128) || !make_tmap_2d(&t2, w2t, 128, F, pair ? 64 : 128))
+  if (!make_tmap_2d(&t1, w1t, F, 128, 64) || !make_tmap_2d(&t2, w2t, 128, F, 64))
     return fail(nullptr, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-  return pair ? launch_ffn2_tc(nullptr, z, t1, t2, b1, b2, M, F, reinterpret_cast<cudaStream_t>(stream), sms, nullptr)
-              : launch_ffn_tc(nullptr, z, t1, t2, b1, b2, M, F, reinterpret_cast<cudaStream_t>(stream), sms, nullptr);
+  return launch_ffn2_tc(nullptr, z, t1, t2, b1, b2, M, F, reinterpret_cast<cudaStream_t>(stream), sms, nullptr);
 }
 
 // ----------------------------------------------------------------------------------- graph metrics (8(f) row 4)
@@ -1118,7 +1075,7 @@ int avb_test_attention_bf16(const void* qkv, void* out, int32_t B, int32_t n, in
     packed_bytes = need;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static const bool prepacked = getenv("AVB_ATTN_PREPACKED") != nullptr;  // profiling scripts: time the attention alone
+  static const bool prepacked = ab_env("AVB_ATTN_PREPACKED") != nullptr;  // profiling scripts: time the attention alone
   if (prepacked) return launch_attention_tc(nullptr, qkv, out, B, n, d, H, axis, st, sms, nullptr, guard);
   // token-major test tensors <-> the kernels' operand layouts; `out` must hold whole 128-row tiles in the packed form,
   // so the packed output lives behind the packed input in the scratch buffer

@@ -262,11 +262,12 @@ __global__ void head_uv_kernel(const float* __restrict__ pooled,
   }
 }
 
-// p[b,i,j] = exp(log_sigmoid(<u_i,v_j> * exp(temp) + bias)), diag = 0 (model.py:135-141,218-239).
+// p[b,i,j] = exp(log_sigmoid(<u_i,v_j> * exp(temp) + bias)), diag = 0 (model.py:135-141,218-239); with log_probs the
+// log_sigmoid itself, diag = -inf (infer_edge_logprobs, model.py:218-220).
 // grid (ceil(d/16), ceil(d/16), B), block (16,16).
 __global__ void head_logits_kernel(const float* __restrict__ u, const float* __restrict__ v, int d,
                                    int out_dim, const float* __restrict__ temp,
-                                   const float* __restrict__ bias, int mask_diag,
+                                   const float* __restrict__ bias, int mask_diag, int log_probs,
                                    float* __restrict__ probs) {
   __shared__ float s_u[16][129], s_v[16][129];
   const int b = blockIdx.z;
@@ -284,8 +285,9 @@ __global__ void head_logits_kernel(const float* __restrict__ u, const float* __r
   for (int c = 0; c < out_dim; ++c) acc = fmaf(s_u[threadIdx.y][c], s_v[threadIdx.x][c], acc);
   const float l = acc * expf(temp[0]) + bias[0];
   // exp(log_sigmoid(l)) with log_sigmoid(l) = -(max(-l,0) + log1p(exp(-|l|)))
-  float p = expf(-(fmaxf(-l, 0.f) + log1pf(expf(-fabsf(l)))));
-  if (mask_diag && i == j) p = 0.f;
+  const float logp = -(fmaxf(-l, 0.f) + log1pf(expf(-fabsf(l))));
+  float p = log_probs ? logp : expf(logp);
+  if (mask_diag && i == j) p = log_probs ? -INFINITY : 0.f;
   probs[((size_t)b * d + i) * d + j] = p;
 }
 

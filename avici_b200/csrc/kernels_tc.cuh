@@ -16,25 +16,6 @@
 
 namespace avb {
 
-// ------------------------------------------------------------------------------------------
-// LayerNorm (no affine) fp32 -> bf16, one warp per token of 128 channels.
-// ------------------------------------------------------------------------------------------
-__global__ void ln_bf16_kernel(const float* __restrict__ z, size_t ntok, __nv_bfloat16* __restrict__ xhat) {
-  const int lane = threadIdx.x & 31;
-  size_t warp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
-  for (size_t t = warp; t < ntok; t += nwarps) {
-    const float4 v = reinterpret_cast<const float4*>(z + t * 128)[lane];
-    const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / 128.0f);
-    const float4 c = make_float4(v.x - mean, v.y - mean, v.z - mean, v.w - mean);
-    const float var = warp_sum(c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w) * (1.0f / 128.0f);
-    const float r = rsqrtf(var + kLnEps);
-    uint2 o;
-    o.x = ptx::pack_bf16(c.x * r, c.y * r);
-    o.y = ptx::pack_bf16(c.z * r, c.w * r);
-    reinterpret_cast<uint2*>(xhat + t * 128)[lane] = o;
-  }
-}
 
 // Debug timeline: when set (avb_debug_set_trace), block 0 records clock64() stamps of the first steps of each
 // role of stream 0 into trace[role * 4096 + step * 8 + event].
@@ -199,183 +180,21 @@ __device__ __forceinline__ void residual_add_block_32x32(const uint32_t (&acc)[3
   __syncwarp();
 }
 
-// ------------------------------------------------------------------------------------------
-// Persistent warp-specialised GEMM:  C[M,N] = A[M,K] @ Wt[N,K]^T + bias[N]
-//   A, Wt: bf16, K-major, fetched by TMA in 128B-swizzled [rows x 64] boxes.
-//   tile 128 x BN, BK = 64; accumulators double-buffered in TMEM (2 x BN columns).
-//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM alloc   warps 4-7: epilogue
-//   EPI 0: bf16 store   1: ReLU + bf16 store   2: fp32 residual add in place (out += acc + bias)
-// ------------------------------------------------------------------------------------------
-constexpr int kGemmThreads = 256;
-template <int BN> struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
-  static constexpr int kABytes = 128 * 64 * 2;
-  static constexpr int kBBytes = BN * 64 * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiStageBytes = 0;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-};
-
-template <int BN, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-               const float* __restrict__ bias, void* __restrict__ out, int ldo, int M, int N, int K) {
-  using Cfg = GemmCfg<BN>;
-  constexpr int ST = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sEpi = smem + ST * Cfg::kStageBytes;  // [4][4 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + Cfg::kEpiStageBytes);
-  uint64_t* full = bars;            // [ST]
-  uint64_t* empty = bars + ST;      // [ST]
-  uint64_t* tfull = bars + 2 * ST;  // [2]
-  uint64_t* tempty = tfull + 2;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform roles
-  const int num_m = (M + 127) / 128, num_n = N / BN, num_k = K / 64;
-  const int num_tiles = num_m * num_n;
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tm_a);
-    ptx::prefetch_tmap(&tm_b);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < ST; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 128); }
-    ptx::fence_barrier_init();
-  }
-  if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, 2 * BN);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // all 32 lanes run the loop (warp-uniform control flow keeps descriptors in uniform registers);
-    // one elected lane issues the TMA instructions
-    int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
-      for (int kb = 0; kb < num_k; ++kb) {
-        ptx::mbar_wait(&empty[stage], phase ^ 1, 1);
-        uint8_t* sa = smem + stage * Cfg::kStageBytes;
-        if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-          ptx::tma_load_2d(sa, &tm_a, &full[stage], kb * 64, m_blk * 128);
-          ptx::tma_load_2d(sa + Cfg::kABytes, &tm_b, &full[stage], kb * 64, n_blk * BN);
-        }
-        __syncwarp();
-        if (++stage == ST) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN, 0, 0);
-    const uint64_t dA0 = ptx::make_smem_desc(ptx::smem_u32(smem), 16, 1024, ptx::kSwz128);
-    const uint64_t dB0 = ptx::make_smem_desc(ptx::smem_u32(smem) + Cfg::kABytes, 16, 1024, ptx::kSwz128);
-    int stage = 0; uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      ptx::mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1, 2);
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * BN;
-      for (int kb = 0; kb < num_k; ++kb) {
-        ptx::mbar_wait(&full[stage], phase, 3);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint64_t so = (uint64_t)stage * (Cfg::kStageBytes >> 4);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)  // +32 bytes per K=16 slice inside the 128-byte swizzled rows
-            ptx::umma_bf16(d_tmem, dA0 + so + (uint64_t)(k * 2), dB0 + so + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-          ptx::umma_commit(&empty[stage]);
-          if (kb == num_k - 1) ptx::umma_commit(&tfull[as]);
-        }
-        __syncwarp();
-        if (++stage == ST) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp >= 4) {
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
-      const int as = it & 1;
-      ptx::mbar_wait(&tfull[as], (it >> 1) & 1, 4);
-      ptx::tc_fence_after();
-      const int row = m_blk * 128 + q * 32 + lane;
-      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld32(taddr + c * 32, r);
-        ptx::tmem_wait_ld();
-        const int col0 = n_blk * BN + c * 32;
-        if (EPI == 2) {
-          // row-per-thread read-modify-write (measured faster here than the smem-transposed variant: with only four
-          // epilogue warps and K >= 256 this kernel is bound by its TMA stream, not by L1 wavefronts)
-          if (row < M) {
-            float* op = reinterpret_cast<float*>(out) + (size_t)row * ldo + col0;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float4 o = *reinterpret_cast<float4*>(op + e * 4);
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0) + e);
-              o.x += __uint_as_float(r[e * 4 + 0]) + bb.x;
-              o.y += __uint_as_float(r[e * 4 + 1]) + bb.y;
-              o.z += __uint_as_float(r[e * 4 + 2]) + bb.z;
-              o.w += __uint_as_float(r[e * 4 + 3]) + bb.w;
-              *reinterpret_cast<float4*>(op + e * 4) = o;
-            }
-          }
-        } else if (row < M) {
-          {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)row * ldo + col0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float v[8];
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0) + e * 2 + u);
-                v[u * 4 + 0] = __uint_as_float(r[e * 8 + u * 4 + 0]) + bb.x;
-                v[u * 4 + 1] = __uint_as_float(r[e * 8 + u * 4 + 1]) + bb.y;
-                v[u * 4 + 2] = __uint_as_float(r[e * 8 + u * 4 + 2]) + bb.z;
-                v[u * 4 + 3] = __uint_as_float(r[e * 8 + u * 4 + 3]) + bb.w;
-              }
-              if (EPI == 1) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
-              }
-              uint4 o;
-              o.x = ptx::pack_bf16(v[0], v[1]); o.y = ptx::pack_bf16(v[2], v[3]);
-              o.z = ptx::pack_bf16(v[4], v[5]); o.w = ptx::pack_bf16(v[6], v[7]);
-              *reinterpret_cast<uint4*>(op + e * 8) = o;
-            }
-          }
-        }
-      }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty[as]);
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc(tmem_base, 2 * BN);
-}
 
 // ------------------------------------------------------------------------------------------
-// Attention output projection + residual, in place on the fp32 residual stream (model.py:59-65):
-//     z[M,128] += attn[M,K] @ Wo_t[128,K]^T + bo            (K = heads * 32 = 256)
+// Attention output projection (model.py:59-65) as a bf16 update of the residual stream:
+//     delta[token][128] = attn[M,K] @ Wo_t[128,K]^T + bo            (K = heads * 32 = 256)
+//   The FFN kernel that follows adds delta to z while it reads z for its LayerNorm anyway (ffn2_tc_kernel), so this
+//   kernel moves 768 B/token and the residual stream makes one HBM round trip per block.  The update is rounded to
+//   bf16 (2^-9 relative, the same size as the bf16 rounding of the attention output that feeds it); z itself stays fp32.
 //   The [128 x K] weight stays resident in shared memory for the whole (persistent) CTA; only the attention
 //   output streams through a ring.  The attention kernel writes it in this kernel's A-operand layout,
 //       attn[tile = m >> 7][head][m & 127][32 ch], 16-byte chunks at chunk ^ ((m >> 1) & 3)   (64B swizzle image)
 //   with m the SEQUENCE-MAJOR row index (RowMap), so a stage (two heads = one K block of 64) is one contiguous
-//   16 KB bulk copy and the attention epilogue's stores are contiguous runs instead of one 64-byte piece per token.
-//   Only the epilogue knows about tokens: row m updates z[token(m)], a 512-byte row each.
-//   Accumulators are double-buffered in TMEM; eight epilogue warps
-//   (TMEM lane quarter x 64-column half) do the residual update through smem-transposed, coalesced accesses.
+//   16 KB bulk copy.  Only the epilogue knows about tokens: row m writes the 256-byte row delta[token(m)]
+//   (AVB_DELTA_TOKENS; scattered when the block attends over n).  Accumulators are double-buffered in TMEM; eight
+//   epilogue warps (TMEM lane quarter x 64-column half) pack them through a per-warp 4 KB shared-memory stage.
+//   run_if: when not null the kernel returns at once unless *run_if != 0 (the guarded fallback behind dattn_tc_kernel).
 //   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM alloc   warps 4-11: epilogue
 // ------------------------------------------------------------------------------------------
 constexpr int kOutProjThreads = 384;
@@ -383,16 +202,11 @@ constexpr int kOutProjStages = 6;
 constexpr int kOutProjKB = 4;  // K blocks of 64 (K = 256)
 constexpr int kOutProjSmemBytes = kOutProjKB * 128 * 128 + kOutProjStages * 128 * 128 + 8 * 4096 + 1024 + 256;
 
-//   kDelta: instead of updating z in place, write the update  delta[token][128] = attn . Wo^T + bo  as bf16 rows
-//   (256 B per row, scattered to the row's token when the block attends over n: AVB_DELTA_TOKENS); the FFN kernel that follows adds it to z while it reads z for
-//   its LayerNorm anyway (ffn2_tc_kernel).  The out-projection then moves 768 B/token instead of 1536 and the residual
-//   stream makes one HBM round trip per block half instead of two.  The update is rounded to bf16 (2^-9 relative, the
-//   same size as the bf16 rounding of the attention output that feeds it); z itself stays fp32.
-template <bool kDelta>
 __global__ void __launch_bounds__(kOutProjThreads, 1)
 outproj_tc_kernel(const __nv_bfloat16* __restrict__ attn, const __grid_constant__ CUtensorMap tm_w,
-                  const float* __restrict__ bias, float* __restrict__ z, __nv_bfloat16* __restrict__ delta, int M, int seq_n,
-                  int seq_d, int seq_axis) {
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ delta, int M, int seq_n,
+                  int seq_d, int seq_axis, const int* __restrict__ run_if) {
+  if (run_if != nullptr && *run_if == 0) return;
   const RowMap rm{seq_n, seq_d, seq_axis};
   constexpr int ST = kOutProjStages, KB = kOutProjKB;
   extern __shared__ uint8_t smem_raw[];
@@ -483,7 +297,7 @@ outproj_tc_kernel(const __nv_bfloat16* __restrict__ attn, const __grid_constant_
       ptx::mbar_wait(&tfull[as], (uint32_t)((it >> 1) & 1), 74);
       ptx::tc_fence_after();
       const int row0 = mt * 128 + q * 32;
-      if constexpr (kDelta) {
+      {
         // ---- delta rows: this warp's 32 rows x 64 columns -> bf16 -> [32 rows x 128 B] stage -> 4 rows per store
         uint32_t pk[32];
 #pragma unroll
@@ -525,55 +339,6 @@ outproj_tc_kernel(const __nv_bfloat16* __restrict__ attn, const __grid_constant_
 #else
           if (row0 + row < M) *reinterpret_cast<uint4*>(delta + (size_t)(row0 + row) * 128 + half * 64 + l8 * 8) = a;
 #endif
-        }
-        __syncwarp();
-        continue;
-      }
-      // tokens of the 8 rows this lane copies out (rows i*4 + (lane >> 3)); -1: past the end
-      int tok[8];
-      rm.tokens<8>(row0 + (lane >> 3), 4, M, tok);
-      // the z round trip is the long pole (HBM, scattered 512-byte rows on the n-axis blocks): all 16 loads of the
-      // lane (both 32-column blocks) are in flight before the accumulator is even read
-      const int l8 = lane & 7;
-      float4* zp[8];
-      float4 zr[2][8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        zp[i] = tok[i] >= 0 ? reinterpret_cast<float4*>(z + (size_t)tok[i] * 128 + half * 64) + l8 : nullptr;
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) zr[cc][i] = zp[i] ? __ldcg(zp[i] + cc * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tmem_base + as * 128 + half * 64 + cc * 32 + lane_off, v);
-        ptx::tmem_wait_ld();
-        if (cc == 1) {
-          ptx::tc_fence_before();
-          ptx::mbar_arrive_relaxed(&tempty[as]);  // relaxed: a release-arrive would first drain the z loads in flight
-        }
-        const float* bp = bias + half * 64 + cc * 32;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {  // thread = row `lane`: 16-byte chunk c goes to slot c ^ (lane & 7)
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + c);
-          uint4 pk;
-          pk.x = __float_as_uint(__uint_as_float(v[c * 4 + 0]) + b4.x);
-          pk.y = __float_as_uint(__uint_as_float(v[c * 4 + 1]) + b4.y);
-          pk.z = __float_as_uint(__uint_as_float(v[c * 4 + 2]) + b4.z);
-          pk.w = __float_as_uint(__uint_as_float(v[c * 4 + 3]) + b4.w);
-          ptx::st_shared_v4(stage_addr + (uint32_t)(lane * 128 + ((c ^ (lane & 7)) << 4)), pk);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = i * 4 + (lane >> 3);
-          uint4 a;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
-                       : "r"(stage_addr + (uint32_t)(row * 128 + ((l8 ^ (row & 7)) << 4))));
-          float4 o = zr[cc][i];
-          o.x += __uint_as_float(a.x); o.y += __uint_as_float(a.y); o.z += __uint_as_float(a.z); o.w += __uint_as_float(a.w);
-          if (zp[i]) zp[i][cc * 8] = o;
         }
         __syncwarp();
       }
@@ -779,198 +544,6 @@ constexpr int kLnGemmSmemBytes = 2 * kLnGemmABytes + kLnGemmBStages * kLnGemmBBy
 //   so that a [128 positions x 32 ch] Q / K / V tile is one contiguous 8 KB block whose byte image IS the swizzled
 //   shared-memory tile: the attention producer fetches it with a single 1-D bulk copy (no gather, no per-row TMA
 //   cost, every DRAM sector used), for both attention axes.  N must be 3 * H * 32 with 32-channel heads.
-template <int EPI>  // 0: store, 1: ReLU + store, 2: store in the attention operand layout
-__global__ void __launch_bounds__(kLnGemmThreads, 1)
-ln_gemm_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorMap tm_b,
-                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int M, int N,
-                  int seq_n, int seq_d, int seq_axis) {
-  const RowMap rm{seq_n, seq_d, EPI == 2 ? seq_axis : 0};
-  constexpr int ST = kLnGemmBStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                                   // [2][32K]
-  uint8_t* sB = sA + 2 * kLnGemmABytes;                 // [ST][32K]
-  uint8_t* sStage = sB + ST * kLnGemmBBytes;            // [128][pitch]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + kLnGemmStageBytes);
-  uint64_t* a_full = bars;             // [2] 128 LN threads
-  uint64_t* a_empty = bars + 2;        // [2]
-  uint64_t* b_full = bars + 4;         // [ST]
-  uint64_t* b_empty = bars + 4 + ST;   // [ST]
-  uint64_t* t_full = bars + 4 + 2 * ST;  // [2]
-  uint64_t* t_empty = t_full + 2;      // [2] 128 epilogue threads
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int num_m = (M + 127) / 128, num_c = N / 256;
-
-  if (warp == 4 && lane == 0) ptx::prefetch_tmap(&tm_b);
-  if (warp == 5 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&a_full[i], 128); ptx::mbar_init(&a_empty[i], 1);
-      ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 256);
-    }
-    for (int i = 0; i < ST; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
-    ptx::fence_barrier_init();
-  }
-  if (warp == 6) {
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-    // ===================== LN producers: warp w normalises rows 32w .. 32w+31 of each tile
-    int it = 0;
-    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
-      const int buf = it & 1;
-      prefetch_rows_l2(z, M, (mt + (int)gridDim.x) * 128 + warp * 32, lane, rm);
-      ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 40);
-      ln_warp_rows_to_umma_tile(z, M, mt * 128 + warp * 32, ptx::smem_u32(sA + buf * kLnGemmABytes), warp * 32, lane, rm);
-      ptx::fence_proxy_async();
-      ptx::mbar_arrive(&a_full[buf]);
-    }
-  } else if (warp == 4) {
-    // ===================== weight TMA producer: for every m tile, N/256 chunks x 2 K blocks of [256 x 64]
-    int stage = 0; uint32_t phase = 0;
-    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
-      for (int c = 0; c < num_c; ++c) {
-        for (int kb = 0; kb < 2; ++kb) {
-          ptx::mbar_wait(&b_empty[stage], phase ^ 1, 41);
-          if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(&b_full[stage], kLnGemmBBytes);
-            ptx::tma_load_2d(sB + stage * kLnGemmBBytes, &tm_b, &b_full[stage], kb * 64, c * 256);
-          }
-          __syncwarp();
-          if (++stage == ST) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 5) {
-    // ===================== MMA issuer
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 256, 0, 0);
-    const uint64_t dA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024, ptx::kSwz128);
-    const uint64_t dB0 = ptx::make_smem_desc(ptx::smem_u32(sB), 16, 1024, ptx::kSwz128);
-    int stage = 0; uint32_t phase = 0;
-    int it = 0, acc_it = 0;
-    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
-      const int buf = it & 1;
-      ptx::mbar_wait(&a_full[buf], (it >> 1) & 1, 42);
-      for (int c = 0; c < num_c; ++c, ++acc_it) {
-        const int as = acc_it & 1;
-        ptx::mbar_wait(&t_empty[as], ((acc_it >> 1) & 1) ^ 1, 43);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * 256;
-        for (int kb = 0; kb < 2; ++kb) {
-          ptx::mbar_wait(&b_full[stage], phase, 44);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint64_t da = dA0 + (uint64_t)(buf * (kLnGemmABytes >> 4) + kb * ((128 * 128) >> 4));
-            const uint64_t db = dB0 + (uint64_t)stage * (kLnGemmBBytes >> 4);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-            ptx::umma_commit(&b_empty[stage]);
-            if (kb == 1) {
-              ptx::umma_commit(&t_full[as]);
-              if (c == num_c - 1) ptx::umma_commit(&a_empty[buf]);
-            }
-          }
-          __syncwarp();
-          if (++stage == ST) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp >= 8) {
-    // ===================== epilogue: TMEM -> +bias (ReLU) -> bf16 -> smem stage -> coalesced global stores
-    const int q = warp & 3, hf = (warp - 8) >> 2;
-    const uint32_t stage_warp = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 32 * kLnGemmStagePitch);
-    const uint32_t stage_row = stage_warp + (uint32_t)(lane * kLnGemmStagePitch);
-    const int sub = lane >> 3, l8 = lane & 7;  // copy-out: 4 rows per warp store, 8 lanes x 16 B per row
-    const int seq_T = seq_axis == 0 ? seq_d : seq_n, seq_H = N / 96;  // EPI 2: sequence length, heads (N = 3 * H * 32)
-    int acc_it = 0;
-    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
-      for (int c = 0; c < num_c; ++c, ++acc_it) {
-        const int as = acc_it & 1;
-        ptx::mbar_wait(&t_full[as], (acc_it >> 1) & 1, 45);
-        ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + as * 256 + hf * 128 + ((uint32_t)(q * 32) << 16);
-        const int col0 = c * 256 + hf * 128;
-#pragma unroll 1
-        for (int pc = 0; pc < 2; ++pc) {  // two pieces of 64 columns
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            float4 bb[8];  // bias of these 32 columns, requested before the TMEM load so the latencies overlap
-#pragma unroll
-            for (int e = 0; e < 8; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bias + col0 + pc * 64 + cc * 32) + e);
-            uint32_t v[32];
-            ptx::tmem_ld32(taddr + pc * 64 + cc * 32, v);
-            ptx::tmem_wait_ld();
-            if (pc == 1 && cc == 1) {  // accumulator fully read by this warp: hand it back to the MMA warp
-              ptx::tc_fence_before();
-              ptx::mbar_arrive(&t_empty[as]);
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float f[8];
-              f[0] = __uint_as_float(v[e * 8 + 0]) + bb[e * 2].x;     f[1] = __uint_as_float(v[e * 8 + 1]) + bb[e * 2].y;
-              f[2] = __uint_as_float(v[e * 8 + 2]) + bb[e * 2].z;     f[3] = __uint_as_float(v[e * 8 + 3]) + bb[e * 2].w;
-              f[4] = __uint_as_float(v[e * 8 + 4]) + bb[e * 2 + 1].x; f[5] = __uint_as_float(v[e * 8 + 5]) + bb[e * 2 + 1].y;
-              f[6] = __uint_as_float(v[e * 8 + 6]) + bb[e * 2 + 1].z; f[7] = __uint_as_float(v[e * 8 + 7]) + bb[e * 2 + 1].w;
-              if (EPI == 1) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], 0.f);
-              }
-              uint4 pk;
-              pk.x = ptx::pack_bf16(f[0], f[1]); pk.y = ptx::pack_bf16(f[2], f[3]);
-              pk.z = ptx::pack_bf16(f[4], f[5]); pk.w = ptx::pack_bf16(f[6], f[7]);
-              ptx::st_shared_v4(stage_row + (uint32_t)(cc * 64 + e * 16), pk);
-            }
-          }
-          __syncwarp();  // the 32 staged rows are written and read by this warp only
-          if (EPI == 2) {
-            // 64 staged columns = heads (hd0, hd0 + 1) of q, k or v.  A warp store covers 8 consecutive positions of
-            // one head = 512 contiguous bytes (lane = chunk * 8 + row: conflict-free reads of the padded stage).
-            const int colp = col0 + pc * 64, w = colp >> 8, hd0 = (colp & 255) >> 5;
-            const int r8 = lane & 7, c4 = lane >> 3;
-#pragma unroll
-            for (int rr = 0; rr < 32; rr += 8) {
-              const int row = rr + r8;
-              const int grow = mt * 128 + q * 32 + row;
-              const unsigned sq = (unsigned)grow / (unsigned)seq_T, pos = (unsigned)grow - sq * (unsigned)seq_T;
-              __nv_bfloat16* dst = out + ((((size_t)sq * 3 + w) * seq_H + hd0) * seq_T + pos) * 32 + ((c4 ^ ((pos >> 1) & 3)) << 3);
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                uint4 pk;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w)
-                             : "r"(stage_warp + (uint32_t)(row * kLnGemmStagePitch + hh * 64 + c4 * 16)));
-                if (grow < M) *reinterpret_cast<uint4*>(dst + (size_t)hh * seq_T * 32) = pk;
-              }
-            }
-          } else {
-#pragma unroll
-          for (int rr = 0; rr < 32; rr += 4) {
-            const int row = rr + sub;
-            const int grow = mt * 128 + q * 32 + row;
-            uint4 pk;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w)
-                         : "r"(stage_warp + (uint32_t)(row * kLnGemmStagePitch + l8 * 16)));
-            if (grow < M) *reinterpret_cast<uint4*>(out + (size_t)grow * ldo + col0 + pc * 64 + l8 * 8) = pk;
-          }
-          }
-          __syncwarp();
-        }
-      }
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 6) ptx::tmem_dealloc(tmem_base, 512);
-}
 
 // ------------------------------------------------------------------------------------------
 // CTA-pair version of ln_gemm_tc_kernel (cluster of 2, tcgen05 cta_group::2): the pair works on 256 rows, each CTA
@@ -984,7 +557,9 @@ template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLnGemmThreads, 1)
 ln_gemm2_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorMap tm_b,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int M, int N,
-                  int seq_n, int seq_d, int seq_axis) {
+                  int seq_n, int seq_d, int seq_axis, const int* __restrict__ run_if) {
+  // run_if: when not null the kernel returns at once unless *run_if != 0 (the guarded fallback behind dattn_tc_kernel)
+  if (run_if != nullptr && *run_if == 0) return;
   const RowMap rm{seq_n, seq_d, EPI == 2 ? seq_axis : 0};
   constexpr int ST = kLnGemmBStages;
   extern __shared__ uint8_t smem_raw[];
@@ -1187,228 +762,6 @@ constexpr int kFfnThreads = 512;
 constexpr int kFfnWBytes = 128 * 128 * 2;  // 32 KB: one [128 x 128] bf16 weight chunk = two 128B-swizzled K blocks
 constexpr int kFfnSmemBytes = 2 * kLnGemmABytes + 2 * 2 * kFfnWBytes + 8 * 4096 + 1024 + 256;  // + 8 x 4 KB epilogue stages
 
-__global__ void __launch_bounds__(kFfnThreads, 1)
-ffn_tc_kernel(float* __restrict__ z, const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
-              const float* __restrict__ b1, const float* __restrict__ b2, int M, int F) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                        // [2][32K] xhat
-  uint8_t* sW = sA + 2 * kLnGemmABytes;      // [2 stages][W1c 32K | W2c 32K]
-  uint8_t* sStage = sW + 4 * kFfnWBytes;     // [8 epilogue warps][4 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 8 * 4096);
-  uint64_t* a_full = bars;          // [2] 128 LN threads
-  uint64_t* a_empty = bars + 2;     // [2]
-  uint64_t* w1_full = bars + 4;     // [2]
-  uint64_t* w1_empty = bars + 6;    // [2]
-  uint64_t* w2_full = bars + 8;     // [2]
-  uint64_t* w2_empty = bars + 10;   // [2]
-  uint64_t* d1_full = bars + 12;    // [1]
-  uint64_t* d1_empty = bars + 13;   // [1] 256 epilogue threads
-  uint64_t* h_full = bars + 14;     // [2] 256 epilogue threads
-  uint64_t* h_empty = bars + 16;    // [2]
-  uint64_t* d2_full = bars + 18;    // [2]
-  uint64_t* d2_empty = bars + 20;   // [2] 256 epilogue threads
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
-
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int num_m = (M + 127) / 128, num_c = F / 128;
-  long long* trace = (blockIdx.x == 0 && (warp == 5 || warp == 8 || warp == 0) && lane == 0) ? g_attn_trace : nullptr;
-
-  if (warp == 4 && lane == 0) { ptx::prefetch_tmap(&tm_w1); ptx::prefetch_tmap(&tm_w2); }
-  if (warp == 5 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&a_full[i], 128); ptx::mbar_init(&a_empty[i], 1);
-      ptx::mbar_init(&w1_full[i], 1); ptx::mbar_init(&w1_empty[i], 1);
-      ptx::mbar_init(&w2_full[i], 1); ptx::mbar_init(&w2_empty[i], 1);
-      ptx::mbar_init(&h_full[i], 256); ptx::mbar_init(&h_empty[i], 1);
-      ptx::mbar_init(&d2_full[i], 1); ptx::mbar_init(&d2_empty[i], 256);
-    }
-    ptx::mbar_init(d1_full, 1); ptx::mbar_init(d1_empty, 256);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 6) {
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_D1 = tmem_base;        // 128
-  const uint32_t tmem_H = tmem_base + 128;   // 2 x 64
-  const uint32_t tmem_D2 = tmem_base + 256;  // 2 x 128 (by tile parity)
-
-  if (warp < 4) {
-    // ===================== LN producers (same as ln_gemm_tc_kernel)
-    int it = 0;
-    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
-      const int buf = it & 1;
-      AVB_TRACE(0, it, 0);
-      prefetch_rows_l2(z, M, (mt + (int)gridDim.x) * 128 + warp * 32, lane);
-      ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1, 50);
-      AVB_TRACE(0, it, 1);
-      ln_warp_rows_to_umma_tile(z, M, mt * 128 + warp * 32, ptx::smem_u32(sA + buf * kLnGemmABytes), warp * 32, lane);
-      ptx::fence_proxy_async();
-      ptx::mbar_arrive(&a_full[buf]);
-      AVB_TRACE(0, it, 2);
-    }
-  } else if (warp == 4) {
-    // ===================== weight TMA producer: per chunk W1c = W1t[128c.., 0..127], W2c = W2t[0..127, 128c..]
-    int g = 0;
-    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
-      for (int c = 0; c < num_c; ++c, ++g) {
-        const int st = g & 1;
-        const uint32_t ph = (uint32_t)((g >> 1) & 1) ^ 1;
-        uint8_t* w1 = sW + st * 2 * kFfnWBytes;
-        uint8_t* w2 = w1 + kFfnWBytes;
-        ptx::mbar_wait(&w1_empty[st], ph, 51);
-        if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(&w1_full[st], kFfnWBytes);
-          ptx::tma_load_2d(w1, &tm_w1, &w1_full[st], 0, c * 128);
-          ptx::tma_load_2d(w1 + 128 * 128, &tm_w1, &w1_full[st], 64, c * 128);
-        }
-        __syncwarp();
-        ptx::mbar_wait(&w2_empty[st], ph, 52);
-        if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(&w2_full[st], kFfnWBytes);
-          ptx::tma_load_2d(w2, &tm_w2, &w2_full[st], c * 128, 0);
-          ptx::tma_load_2d(w2 + 128 * 128, &tm_w2, &w2_full[st], c * 128 + 64, 0);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == 5) {
-    // ===================== MMA issuer: G1(g+1) is issued before G2(g) so the tensor core overlaps the E1 epilogue
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 128, 0, 0);
-    const uint64_t dA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024, ptx::kSwz128);
-    const uint64_t dW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024, ptx::kSwz128);
-    const int my_tiles = blockIdx.x < num_m ? (num_m - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int total = my_tiles * num_c;
-    auto issue_G1 = [&](int g) {
-      const int tile_it = g / num_c, c = g % num_c, buf = tile_it & 1, st = g & 1;
-      if (c == 0) ptx::mbar_wait(&a_full[buf], (uint32_t)((tile_it >> 1) & 1), 53);
-      ptx::mbar_wait(&w1_full[st], (uint32_t)((g >> 1) & 1), 54);
-      ptx::mbar_wait(d1_empty, (uint32_t)(g & 1) ^ 1, 55);  // E1 of the previous chunk has read D1
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint64_t da = dA0 + (uint64_t)(buf * (kLnGemmABytes >> 4));
-        const uint64_t dw = dW0 + (uint64_t)(st * ((2 * kFfnWBytes) >> 4));
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {  // K block (kk >> 2) is 16 KB further, 32 bytes per K=16 slice inside it
-          const uint64_t off = (uint64_t)((kk >> 2) * ((128 * 128) >> 4) + (kk & 3) * 2);
-          ptx::umma_bf16(tmem_D1, da + off, dw + off, idesc, kk != 0);
-        }
-        ptx::umma_commit(&w1_empty[st]);
-        ptx::umma_commit(d1_full);
-        if (c == num_c - 1) ptx::umma_commit(&a_empty[buf]);
-      }
-      __syncwarp();
-    };
-    if (total > 0) issue_G1(0);
-    for (int g = 0; g < total; ++g) {
-      AVB_TRACE(1, g, 0);
-      if (g + 1 < total) issue_G1(g + 1);
-      AVB_TRACE(1, g, 1);
-      const int tile_it = g / num_c, c = g % num_c, st = g & 1, hs = g & 1;
-      ptx::mbar_wait(&w2_full[st], (uint32_t)((g >> 1) & 1), 56);
-      AVB_TRACE(1, g, 2);
-      ptx::mbar_wait(&h_full[hs], (uint32_t)((g >> 1) & 1), 57);
-      AVB_TRACE(1, g, 3);
-      if (c == 0 && tile_it >= 2) ptx::mbar_wait(&d2_empty[tile_it & 1], (uint32_t)(((tile_it >> 1) - 1) & 1), 58);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint64_t dw = dW0 + (uint64_t)(st * ((2 * kFfnWBytes) >> 4) + (kFfnWBytes >> 4));
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t off = (uint64_t)((kk >> 2) * ((128 * 128) >> 4) + (kk & 3) * 2);
-          ptx::umma_bf16_ts(tmem_D2 + (tile_it & 1) * 128, tmem_H + hs * 64 + kk * 8, dw + off, idesc, (c | kk) != 0);
-        }
-        ptx::umma_commit(&w2_empty[st]);
-        ptx::umma_commit(&h_empty[hs]);
-        if (c == num_c - 1) ptx::umma_commit(&d2_full[tile_it & 1]);
-      }
-      __syncwarp();
-      AVB_TRACE(1, g, 4);
-    }
-  } else if (warp >= 8) {
-    // ===================== epilogue warps: (TMEM lane quarter q) x (64-column half)
-    const int q = warp & 3, half = (warp - 8) >> 2;
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t stage = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 4096);
-    // E2 of a tile (z += D2 + b2) is deferred until after the first E1 of the NEXT tile: D2 is double-buffered by tile
-    // parity, so the wait for the tile's last G2 MMAs and the z round trip overlap the next tile's MMAs.
-    auto E2 = [&](int t_it, int t_mt) {
-      ptx::mbar_wait(&d2_full[t_it & 1], (uint32_t)((t_it >> 1) & 1), 61);
-      ptx::tc_fence_after();
-      const int row0 = t_mt * 128 + q * 32;
-      const int rows_valid = M - row0 < 32 ? M - row0 : 32;  // may be <= 0 on the last tile
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tmem_D2 + (t_it & 1) * 128 + half * 64 + cc * 32 + lane_off, v);
-        ptx::tmem_wait_ld();
-        if (cc == 1) {
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&d2_empty[t_it & 1]);
-        }
-        residual_add_block_32x32(v, b2 + half * 64 + cc * 32, stage, z + (size_t)row0 * 128 + half * 64 + cc * 32, 128,
-                                 rows_valid, lane);
-      }
-    };
-    int g = 0, tile_it = 0, prev_mt = -1;
-    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++tile_it) {
-      for (int c = 0; c < num_c; ++c, ++g) {
-        // ---- E1: D1 -> +b1 -> ReLU -> bf16 pairs -> H
-        const int hs = g & 1;
-        const float* bp = b1 + c * 128 + half * 64;
-        float4 bb[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bp) + e);
-        AVB_TRACE(2, g, 0);
-        ptx::mbar_wait(d1_full, (uint32_t)(g & 1), 59);
-        AVB_TRACE(2, g, 1);
-        ptx::tc_fence_after();
-        uint32_t pk[32];
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t v[32];
-          ptx::tmem_ld32(tmem_D1 + half * 64 + cc * 32 + lane_off, v);
-          ptx::tmem_wait_ld();
-          if (cc == 1) {  // D1 fully read by this thread: the next chunk's G1 may overwrite it
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(d1_empty);
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float4 b4 = bb[cc * 8 + e];
-            const float f0 = fmaxf(__uint_as_float(v[e * 4 + 0]) + b4.x, 0.f), f1 = fmaxf(__uint_as_float(v[e * 4 + 1]) + b4.y, 0.f);
-            const float f2 = fmaxf(__uint_as_float(v[e * 4 + 2]) + b4.z, 0.f), f3 = fmaxf(__uint_as_float(v[e * 4 + 3]) + b4.w, 0.f);
-            pk[cc * 16 + e * 2 + 0] = ptx::pack_bf16(f0, f1);
-            pk[cc * 16 + e * 2 + 1] = ptx::pack_bf16(f2, f3);
-          }
-        }
-        AVB_TRACE(2, g, 2);
-        ptx::mbar_wait(&h_empty[hs], (uint32_t)((g >> 1) & 1) ^ 1, 60);  // G2 of two chunks ago has consumed H[hs]
-        AVB_TRACE(2, g, 3);
-        ptx::tc_fence_after();
-        ptx::tmem_st32(tmem_H + hs * 64 + half * 32 + lane_off, pk);
-        ptx::tmem_wait_st();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&h_full[hs]);
-        AVB_TRACE(2, g, 4);
-        if (c == 0 && prev_mt >= 0) {
-          E2(tile_it - 1, prev_mt);
-          AVB_TRACE(2, g, 6);
-        }
-      }
-      prev_mt = mt;
-    }
-    if (prev_mt >= 0) E2(tile_it - 1, prev_mt);
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 6) ptx::tmem_dealloc(tmem_base, 512);
-}
 
 // ------------------------------------------------------------------------------------------
 // CTA-pair version of ffn_tc_kernel (cluster of 2, tcgen05 cta_group::2).  Each CTA keeps its own 128-token tile,

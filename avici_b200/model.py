@@ -54,7 +54,7 @@ class Engine:
         _lib.check(self.lib, None, rc)
         self.handle = h
         self._ws = None
-        self.device = _torch().device("cuda", _torch().cuda.current_device())
+        self.device = _torch().device("cuda", _torch().cuda.current_device())  # avb_create binds the current device
 
     def __del__(self):
         try:
@@ -103,15 +103,17 @@ class Engine:
             self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def forward(self, x, interv=None, standardize=_lib.AVB_STANDARDIZE_DEFAULT, chunk_size=None, out=None):
-        """x, interv: float32 CUDA tensors [B,n,d] -> probs float32 CUDA tensor [B,d,d] (async on the
-        current torch stream)."""
+    def forward(self, x, interv=None, standardize=_lib.AVB_STANDARDIZE_DEFAULT, chunk_size=None, out=None,
+                log_probs=False):
+        """x, interv: float32 CUDA tensors [B,n,d] on this engine's device -> probs (or log-probs) float32 CUDA
+        tensor [B,d,d] (async on the current torch stream)."""
         torch = _torch()
         assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 3, "x must be a float32 CUDA tensor [B,n,d]"
+        assert x.device == self.device, f"this engine lives on {self.device}, got a tensor on {x.device}"
         x = x.contiguous()
         B, n, d = x.shape
         if interv is not None:
-            assert interv.shape == x.shape
+            assert interv.shape == x.shape and interv.device == x.device
             interv = interv.to(dtype=torch.float32).contiguous()
         cs = int(chunk_size) if chunk_size else 0
         need = self.lib.avb_workspace_bytes(self.handle, B, n, d, cs)
@@ -120,10 +122,11 @@ class Engine:
         ws = self.workspace(need)
         if out is None:
             out = torch.empty((B, d, d), dtype=torch.float32, device=x.device)
+        assert out.device == self.device
         stream = torch.cuda.current_stream(x.device).cuda_stream
-        self._check(self.lib.avb_forward(self.handle, x.data_ptr(), interv.data_ptr() if interv is not None else None,
-                                         B, n, d, int(standardize), cs, out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                         C.c_void_p(stream)))
+        fn = self.lib.avb_forward_logprobs if log_probs else self.lib.avb_forward
+        self._check(fn(self.handle, x.data_ptr(), interv.data_ptr() if interv is not None else None,
+                       B, n, d, int(standardize), cs, out.data_ptr(), ws.data_ptr(), ws.numel(), C.c_void_p(stream)))
         return out
 
     def forward_host(self, x, interv=None, standardize=_lib.AVB_STANDARDIZE_DEFAULT, chunk_size=None, out=None):
@@ -156,41 +159,66 @@ class InferenceModel:
         self.model_class = model_class
         self.model_kwargs = resolve_model_kwargs(dict(model_kwargs or {}))
         self.compute_dtype = compute_dtype
-        self._engine = None
-        self._params_id = None
+        self._engines = {}  # device index -> (Engine, fingerprint of the params it holds, the params object)
 
-    def engine(self, params):
-        if self._engine is None:
-            self._engine = Engine(self.model_kwargs, mask_diag=self.mask_diag, compute_dtype=self.compute_dtype)
-        if self._params_id != id(params):
-            self._engine.load_params(params)
-            self._params_id = id(params)
-            self._params_ref = params  # keep alive so the id stays unique
-        return self._engine
+    @staticmethod
+    def _fingerprint(params):
+        """Cheap identity of a parameter dict: the object, plus per leaf its buffer address, shape and three values.
+        The packed device copy is a SNAPSHOT taken at first use; replacing the dict, a leaf, or (for all practical
+        purposes) editing a leaf in place changes the fingerprint and triggers a re-upload.  `reload()` forces one."""
+        fp = [id(params)]
+        for mod, leaves in params.items():
+            for name, arr in leaves.items():
+                a = onp.asarray(arr)
+                flat = a.reshape(-1)
+                fp.append((mod, name, a.__array_interface__["data"][0], a.shape,
+                           float(flat[0]), float(flat[flat.size // 2]), float(flat[-1])) if flat.size else (mod, name))
+        return hash(tuple(fp))
+
+    def engine(self, params, device=None):
+        """The C-ABI handle holding `params` on `device` (default: the current CUDA device); one per device."""
+        torch = _torch()
+        idx = torch.cuda.current_device() if device is None else torch.device(device).index
+        idx = torch.cuda.current_device() if idx is None else idx
+        fp = self._fingerprint(params)
+        ent = self._engines.get(idx)
+        if ent is None or ent[1] != fp:
+            with torch.cuda.device(idx):
+                eng = ent[0] if ent is not None else Engine(self.model_kwargs, mask_diag=self.mask_diag,
+                                                            compute_dtype=self.compute_dtype)
+                eng.load_params(params)
+            self._engines[idx] = (eng, fp, params)  # the params reference keeps id(params) unique
+        return self._engines[idx][0]
+
+    def reload(self):
+        """Drop every cached device copy of the weights (next call re-uploads)."""
+        self._engines = {}
+
+    def _infer(self, params, x, experimental_chunk_size, log_probs):
+        torch = _torch()
+        is_np = isinstance(x, onp.ndarray)
+        xt = torch.as_tensor(x, dtype=torch.float32)
+        xt = xt.cuda() if not xt.is_cuda else xt
+        lead = xt.shape[:-3]
+        n, d = xt.shape[-3], xt.shape[-2]
+        xt = xt.reshape(-1, n, d, 2)
+        eng = self.engine(params, xt.device)
+        with torch.cuda.device(xt.device):
+            p = eng.forward(xt[..., 0].contiguous(), xt[..., 1].contiguous(), standardize=_lib.AVB_STANDARDIZE_NONE,
+                            chunk_size=experimental_chunk_size, log_probs=log_probs)
+        p = p.reshape(*lead, d, d)
+        return p.cpu().numpy() if is_np else p
 
     def infer_edge_probs(self, params, x, experimental_chunk_size=None):
         """x: [..., n, d, 2] (already standardized, channel 1 = intervention mask) -> [..., d, d]
         (model.py:225-240)."""
-        torch = _torch()
-        is_np = isinstance(x, onp.ndarray)
-        xt = torch.as_tensor(x, dtype=torch.float32).cuda()
-        lead = xt.shape[:-3]
-        n, d = xt.shape[-3], xt.shape[-2]
-        xt = xt.reshape(-1, n, d, 2)
-        eng = self.engine(params)
-        p = eng.forward(xt[..., 0].contiguous(), xt[..., 1].contiguous(), standardize=_lib.AVB_STANDARDIZE_NONE,
-                        chunk_size=experimental_chunk_size)
-        p = p.reshape(*lead, d, d)
-        return p.cpu().numpy() if is_np else p
+        return self._infer(params, x, experimental_chunk_size, False)
 
     def infer_edge_logprobs(self, params, rng, x, is_training=False, experimental_chunk_size=None):
-        """log of `infer_edge_probs` (diagonal = -inf when mask_diag), model.py:203-222."""
+        """`log_sigmoid(logits)` computed on the device from the logits themselves, diagonal = -inf when mask_diag
+        (model.py:203-222); not log(p), which loses precision once p underflows."""
         assert not is_training, "the B200 path implements inference only"
-        p = self.infer_edge_probs(params, x, experimental_chunk_size=experimental_chunk_size)
-        if isinstance(p, onp.ndarray):
-            with onp.errstate(divide="ignore"):
-                return onp.log(p)
-        return p.log()
+        return self._infer(params, x, experimental_chunk_size, True)
 
     def sample_graphs(self, n_samples, params, rng, x, experimental_chunk_size=None):
         """Bernoulli(p) graph samples [..., n_samples, d, d] with zero diagonal (model.py:175-200).
@@ -219,12 +247,17 @@ class AVICIModel:
     def engine(self):
         return self._model.engine(self.params)
 
+    def engine_on(self, device):
+        return self._model.engine(self.params, device)
+
     def __call_main__(self, x, interv=None, experimental_chunk_size=None):
         """pretrain.py:53-67 on device tensors [n,d] (or a batch [B,n,d])."""
         single = x.dim() == 2
         xb = x.unsqueeze(0) if single else x
         ib = None if interv is None else (interv.unsqueeze(0) if single else interv)
-        out = self.engine.forward(xb, ib, standardize=self._standardizer, chunk_size=experimental_chunk_size)
+        with _torch().cuda.device(x.device):
+            out = self.engine_on(x.device).forward(xb, ib, standardize=self._standardizer,
+                                                   chunk_size=experimental_chunk_size)
         return out[0] if single else out
 
     def __call__(self, x, interv=None, return_probs=True, devices=None, shard_if_possible=True,
@@ -280,6 +313,11 @@ class AVICIModel:
             if shard_if_possible and world > 1:
                 assert not x.shape[0] % world, ("observations `n` must be divisible by `device_count` if sharding "
                                                 "is enabled. ")
+                assert not x.shape[1] % world, ("variables `d` must be divisible by `device_count` for the axial "
+                                                "(n-shard <-> d-shard) sharding of this implementation. ")
+                assert not experimental_chunk_size or experimental_chunk_size >= x.shape[0], (
+                    "`experimental_chunk_size` is not supported together with axial sharding; pass "
+                    "`shard_if_possible=False` to run the chunked forward on one device. ")
                 out = sharded.forward_axial(self, xt, it)
             else:
                 out = self.__call_main__(xt, it, experimental_chunk_size=experimental_chunk_size)

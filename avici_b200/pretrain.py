@@ -33,7 +33,7 @@ ModelState = namedtuple("ModelState", ["step", "rng", "opt_state", "params", "du
 
 
 class _Opaque:
-    """Placeholder for classes we do not need (optax optimizer states, jax arrays wrappers)."""
+    """Placeholder for classes we do not need (optax optimizer states, jax array wrappers, pytree defs)."""
 
     def __init__(self, *args, **kwargs):
         self.args, self.kwargs = args, kwargs
@@ -42,18 +42,68 @@ class _Opaque:
         self.state = state
 
 
-class _CheckpointUnpickler(pickle.Unpickler):
-    """Resolves `avici.backbone.ModelState` (and the legacy `amortibs.*` alias, utils/load.py:3-4)
-    to a local namedtuple, lets numpy through, and stubs everything else."""
+# the only builtins / collections a checkpoint needs; `builtins.eval`, `exec`, `getattr`, `__import__` ... stay out
+_SAFE_BUILTINS = {"dict", "list", "tuple", "set", "frozenset", "slice", "complex", "int", "float", "bool", "str",
+                  "bytes", "bytearray", "object", "range"}
+_SAFE_COLLECTIONS = {"OrderedDict", "defaultdict", "deque"}
 
-    _SAFE_PREFIXES = ("numpy", "collections", "builtins")
+
+class _CheckpointUnpickler(pickle.Unpickler):
+    """Restricted unpickler: resolves `avici.backbone.ModelState` (and the legacy `amortibs.*` alias,
+    utils/load.py:3-4) to a local namedtuple, lets numpy and an explicit list of container builtins through, and
+    turns every other class (haiku's FlatMapping / FlatComponents, optax states, jax pytree defs) into an inert
+    `_Opaque` stub that only records its constructor arguments; `_plain_params` then rebuilds the parameter dict."""
 
     def find_class(self, module, name):
         if name == "ModelState":  # avici.backbone / legacy amortibs.backbone / our own writer
             return ModelState
-        if module.split(".")[0] in self._SAFE_PREFIXES:
+        root = module.split(".")[0]
+        if root == "numpy":
+            return super().find_class(module, name)
+        if module == "builtins" and name in _SAFE_BUILTINS:
+            return super().find_class(module, name)
+        if module == "collections" and name in _SAFE_COLLECTIONS:
             return super().find_class(module, name)
         return type(name, (_Opaque,), {"__module__": module})
+
+
+def _plain_params(obj, neural_net_kwargs=None):
+    """`state.params` as a plain `{module: {leaf: ndarray}}` dict.
+
+    haiku >= 0.0.10 pickles params as nested dicts.  Older versions (the published checkpoints date from 2022,
+    requirements.txt:12 `dm-haiku>=0.0.8`) wrap every level in `haiku._src.data_structures.FlatMapping`, which pickles
+    either as `FlatMapping(dict)` or as `FlatMapping(FlatComponents(leaves, structure))` with `structure` a jax pytree
+    definition.  The first form is unwrapped recursively; for the second the leaves (jax flattens dicts in sorted key
+    order) are matched by position and shape against the sorted parameter names of the configured architecture."""
+    if isinstance(obj, dict) or hasattr(obj, "items") and not isinstance(obj, _Opaque):
+        return {k: _plain_params(v, neural_net_kwargs) for k, v in obj.items()}
+    if isinstance(obj, _Opaque):
+        args = getattr(obj, "args", ())
+        state = getattr(obj, "state", None)
+        cand = args[0] if len(args) >= 1 else state
+        if isinstance(cand, dict) or (hasattr(cand, "items") and not isinstance(cand, _Opaque)):
+            return _plain_params(cand, neural_net_kwargs)
+        comp = cand if isinstance(cand, _Opaque) else None  # FlatComponents(leaves, structure)
+        leaves = None
+        if comp is not None and len(getattr(comp, "args", ())) >= 1:
+            leaves = comp.args[0]
+        elif isinstance(cand, (tuple, list)) and len(cand) == 2 and isinstance(cand[0], (tuple, list)):
+            leaves = cand[0]
+        if leaves is not None:
+            from .params import param_shapes
+            names = sorted((m, l, shp) for m, ls in param_shapes(neural_net_kwargs).items() for l, shp in ls.items())
+            if len(names) != len(leaves):
+                raise ValueError(f"checkpoint holds {len(leaves)} parameter leaves, the architecture in kwargs.json has "
+                                 f"{len(names)}")
+            out = {}
+            for (m, l, shp), arr in zip(names, leaves):
+                arr = onp.asarray(arr)
+                if tuple(arr.shape) != tuple(shp):
+                    raise ValueError(f"checkpoint leaf for {m}/{l} has shape {arr.shape}, expected {shp}")
+                out.setdefault(m, {})[l] = arr
+            return out
+        raise ValueError(f"cannot recover parameters from pickled object of class {type(obj).__name__}")
+    return onp.asarray(obj)
 
 
 def load_checkpoint(folder):
@@ -159,6 +209,7 @@ def load_pretrained(download=None, force_download=False, checkpoint_dir=None, ca
     inference_model = InferenceModel(**inference_model_kwargs, model_class=BaseModel,
                                      model_kwargs=neural_net_kwargs, compute_dtype=compute_dtype)
     params = state.params if hasattr(state, "params") else state["params"]
+    params = _plain_params(params, neural_net_kwargs)  # unwraps haiku < 0.0.10 FlatMapping containers
     return AVICIModel(params=params, model=inference_model, expects_counts=expects_counts)
 
 

@@ -10,6 +10,8 @@
  * Every entry point below replaces one piece of that seam and cites it.  Plain pointers and sizes
  * only; no torch types.  All `*_dev` pointers are CUDA device pointers on the current device, all
  * work is enqueued on `stream` (a cudaStream_t passed as void*) and is asynchronous unless stated.
+ * A handle belongs to the device that was current in avb_create; entry points taking a handle switch to
+ * that device for the duration of the call (pointers and stream must belong to it).
  * The library never falls back to a CPU path: without a CUDA device every compute call returns
  * AVB_ERR_CUDA.
  */
@@ -94,8 +96,15 @@ int avb_forward(avb_handle h, const float* x_dev, const float* interv_dev, int32
                 int32_t d, int32_t standardize, int32_t chunk_size, float* probs_dev,
                 void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* infer_edge_logprobs (model.py:203-222) on the same inputs: log_sigmoid(logits) in fp32, diagonal = -inf when
+ * mask_diag.  Unlike log(avb_forward's p) it keeps its relative precision where p underflows. */
+int avb_forward_logprobs(avb_handle h, const float* x_dev, const float* interv_dev, int32_t B, int32_t n,
+                         int32_t d, int32_t standardize, int32_t chunk_size, float* logprobs_dev,
+                         void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Same call with HOST buffers (what the Python wrapper's numpy path uses): copies x/interv to
- * the device, runs avb_forward on an internal workspace and copies probs back.  Synchronous. */
+ * the device, runs avb_forward on an internal workspace and the handle's own stream, and copies probs back.
+ * Synchronous; calls on the same handle are serialised. */
 int avb_forward_host(avb_handle h, const float* x_host, const float* interv_host, int32_t B,
                      int32_t n, int32_t d, int32_t standardize, int32_t chunk_size,
                      float* probs_host);
@@ -130,6 +139,10 @@ int avb_pool(avb_handle h, const float* z_dev, int32_t B, int32_t n, int32_t d, 
 int avb_head(avb_handle h, const float* pooled_dev, int32_t B, int32_t d, float* probs_dev,
              void* scratch_dev, size_t scratch_bytes, void* stream);
 
+/* Same head, log-probabilities: log_sigmoid(logits), diagonal = -inf (model.py:218-220). */
+int avb_head_logprobs(avb_handle h, const float* pooled_dev, int32_t B, int32_t d, float* logprobs_dev,
+                      void* scratch_dev, size_t scratch_bytes, void* stream);
+
 /* ---- graph metrics on the device: replaces the per-dataset numpy calls of the eval loop
  * avici/train.py:125-151 -> avici/metrics.py:5-24 (shd), :27-32 (n_edges), :35-51 (is_acyclic / is_cyclic),
  * :54-87 (classification_metrics: precision / recall / f1 follow from tp, fp, fn).
@@ -163,30 +176,21 @@ int64_t avb_launch_count(avb_handle h);
 /* Optional per-kernel-category timing with CUDA events recorded on the launching stream (bench.py's
  * `roofline`).  avb_profile_read synchronises the device, adds the elapsed times of all scopes
  * recorded since the last read to running totals and copies totals (ms) and scope counts out. */
-#define AVB_PROF_PROLOGUE 0  /* standardize + embed            */
-#define AVB_PROF_LN 1        /* LayerNorm -> bf16 (bf16 mode)  */
-#define AVB_PROF_QKV 2       /* Q/K/V projections              */
-#define AVB_PROF_ATTN_D 3    /* attention over d               */
-#define AVB_PROF_ATTN_N 4    /* attention over n               */
-#define AVB_PROF_OUT 5       /* output projection + residual   */
-#define AVB_PROF_FFN1 6      /* FFN up-projection + ReLU       */
-#define AVB_PROF_FFN2 7      /* FFN down-projection + residual */
-#define AVB_PROF_POOL_HEAD 8 /* final LN + max-pool + head     */
-#define AVB_PROF_CATEGORIES 9
+#define AVB_PROF_PROLOGUE 0  /* standardize + embed                                               */
+#define AVB_PROF_QKV 1       /* LayerNorm + Q/K/V projections (unfused blocks)                     */
+#define AVB_PROF_ATTN_D 2    /* attention over d (unfused blocks: d > 128, fp32 mode)              */
+#define AVB_PROF_ATTN_N 3    /* attention over n                                                   */
+#define AVB_PROF_OUT 4       /* output projection (unfused blocks)                                 */
+#define AVB_PROF_FFN 5       /* FFN sub-layer (LayerNorm, up-projection, ReLU, down-projection)    */
+#define AVB_PROF_POOL_HEAD 6 /* final LN + max-pool + head                                         */
+#define AVB_PROF_DATTN 7     /* fused LayerNorm + QKV + attention over d + out-projection (d<=128) */
+#define AVB_PROF_CATEGORIES 8
 int avb_profile_enable(avb_handle h, int32_t on);
 int avb_profile_read(avb_handle h, double* ms_out /*[AVB_PROF_CATEGORIES]*/,
                      int64_t* count_out /*[AVB_PROF_CATEGORIES]*/, int32_t reset);
 
 /* ---- unit-test hooks for the tensor-core kernels (bf16 handles only) ---- */
-/* C[M,N] = A[M,K] @ Wt[N,K]^T + bias, bf16 in, fp32 accumulate in TMEM.
- * epilogue 0: out bf16 [M,N]; 1: relu, out bf16; 2: out fp32 [M,N] += (residual add in place). */
-int avb_test_gemm_bf16(const void* a_bf16_dev, const void* wt_bf16_dev, const float* bias_dev,
-                       void* out_dev, int32_t M, int32_t N, int32_t K, int32_t epilogue,
-                       void* stream);
-/* out[M,N] bf16 = act(LayerNorm(z[M,128], no affine) @ Wt[N,128]^T + bias), N % 256 == 0, act = ReLU if relu. */
-int avb_test_ln_gemm_bf16(const float* z_dev, const void* wt_bf16_dev, const float* bias_dev, void* out_bf16_dev,
-                          int32_t M, int32_t N, int32_t relu, void* stream);
-/* z[M,128] fp32 += relu(LayerNorm(z, no affine) @ W1t[F,128]^T + b1) @ W2t[128,F]^T + b2, in place (F % 128 == 0). */
+/* z[M,128] fp32 += relu(LayerNorm(z, no affine) @ W1t[F,128]^T + b1) @ W2t[128,F]^T + b2, in place (F % 256 == 0). */
 int avb_test_ffn_bf16(float* z_dev, const void* w1t_bf16_dev, const void* w2t_bf16_dev, const float* b1_dev,
                       const float* b2_dev, int32_t M, int32_t F, void* stream);
 /* Axial attention on packed qkv[B,n,d,3*H*32] bf16 (q pre-scaled by log2e/sqrt(32)):
@@ -200,11 +204,11 @@ int avb_test_attention_bf16(const void* qkv_bf16_dev, void* out_bf16_dev, int32_
 int avb_test_qkv_layout_bf16(const float* z_dev, const void* wt_bf16_dev, const float* bias_dev,
                              void* out_tokmajor_bf16_dev, int32_t B, int32_t n, int32_t d, int32_t H,
                              int32_t axis, void* stream);
-/* The out-projection as the block runs it (outproj_tc_kernel): z[B*n*d,128] fp32 += attn @ Wot[128,256]^T + bias in
- * place, with attn given token-major [B,n,d,256] bf16 and packed by the hook into the kernel's A-operand layout
- * (sequence-major rows of `axis`). */
+/* The out-projection as the block runs it (outproj_tc_kernel): delta[B*n*d,128] bf16 (token order) = attn @
+ * Wot[128,256]^T + bias, with attn given token-major [B,n,d,256] bf16 and packed by the hook into the kernel's
+ * A-operand layout (sequence-major rows of `axis`). */
 int avb_test_outproj_bf16(const void* attn_tokmajor_bf16_dev, const void* wot_bf16_dev, const float* bias_dev,
-                          float* z_dev, int32_t B, int32_t n, int32_t d, int32_t axis, void* stream);
+                          void* delta_bf16_dev, int32_t B, int32_t n, int32_t d, int32_t axis, void* stream);
 
 /* Debug: device buffer of 3*4096 int64 that block 0 of the attention kernel fills with clock64() stamps of
  * its producer / MMA / softmax roles (NULL switches tracing off). */

@@ -219,7 +219,8 @@ def _cpm_standardizer(x):
 
 def _cpm_shift_scale(x, shift, scale):
     """_jax_cpm_shift_scale (data_jax.py:20-29)."""
-    x = (x - np.where(np.isnan(shift), 0.0, shift)) / np.where(np.isnan(scale), 1.0, scale)
+    with np.errstate(divide="ignore", invalid="ignore"):  # global std == 0: 0/0 -> NaN -> 0 below, as in the reference
+        x = (x - np.where(np.isnan(shift), 0.0, shift)) / np.where(np.isnan(scale), 1.0, scale)
     if x.size != 0:
         x = np.where(np.isnan(x), 0.0, x)
     return x

@@ -60,12 +60,18 @@ def block(z, P, i, cfg):
 
 def forward_probs(P, x, interv, cfg, mask_diag=True):
     """`__call_main__` with the default standardizer on x[..., n, d] (torch CPU tensors) -> p[..., d, d]."""
-    nb = 2 * cfg["layers"]
     mean = x.mean(-2, keepdim=True)
     std = x.std(-2, keepdim=True, unbiased=False)
     xs = (x - mean) / torch.where(std == 0.0, torch.ones_like(std), std)
     iv = torch.zeros_like(xs) if interv is None else interv.to(xs.dtype)
-    z = _linear(torch.stack([xs, iv], dim=-1), P["BaseModel/linear"])
+    return forward_probs_standardized(P, torch.stack([xs, iv], dim=-1), cfg, mask_diag=mask_diag)
+
+
+def forward_cosines(P, x2, cfg):
+    """BaseModel.__call__ (model.py:93-135) on an already standardized x2[..., n, d, 2] up to the cosine
+    similarities u.v^T [..., d, d] (before temperature and bias)."""
+    nb = 2 * cfg["layers"]
+    z = _linear(x2, P["BaseModel/linear"])
     for i in range(nb):
         z = block(z, P, i, cfg).transpose(-3, -2)
     z = _ln(z, P[f"BaseModel/layer_norm{_sfx(4 * nb)}"]).amax(dim=-3)
@@ -73,10 +79,20 @@ def forward_probs(P, x, interv, cfg, mask_diag=True):
     v = _linear(_ln(z, P[f"BaseModel/layer_norm{_sfx(4 * nb + 2)}"]), P[f"BaseModel/linear{_sfx(2 * nb + 2)}"])
     u = u / torch.linalg.norm(u, dim=-1, keepdim=True)
     v = v / torch.linalg.norm(v, dim=-1, keepdim=True)
-    logits = torch.einsum("...id,...jd->...ij", u, v) * torch.exp(P["BaseModel"]["learned_temp"].squeeze()) \
-        + P["BaseModel"]["final_matrix_bias"].squeeze()
+    return torch.einsum("...id,...jd->...ij", u, v)
+
+
+def probs_from_cosines(cos, temp, bias, mask_diag=True):
+    """model.py:136-141 (temperature, bias) + 218-220, 239 (exp(log_sigmoid), diagonal -> 0)."""
+    logits = cos * torch.exp(torch.as_tensor(temp, dtype=cos.dtype)) + torch.as_tensor(bias, dtype=cos.dtype)
     p = torch.exp(torch.nn.functional.logsigmoid(logits))
     if mask_diag:
         d = p.shape[-1]
         p = p * (1.0 - torch.eye(d, dtype=p.dtype))
     return p
+
+
+def forward_probs_standardized(P, x2, cfg, mask_diag=True):
+    cos = forward_cosines(P, x2, cfg)
+    return probs_from_cosines(cos, P["BaseModel"]["learned_temp"].squeeze(), P["BaseModel"]["final_matrix_bias"].squeeze(),
+                              mask_diag=mask_diag)

@@ -12,5 +12,5 @@ for v in exp base exp base; do
   timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); k=d['kernel_ms_per_step']
-print('$v', round(d['value'],1), 'out', k['out'], 'ffn', k['ffn1'], 'qkv', k['qkv'], 'attn_n', k['attn_n'], d['clocks']['sm_mhz'])"
+print('$v', round(d['value'],1), 'out', k['out'], 'ffn', k['ffn'], 'qkv', k['qkv'], 'attn_n', k['attn_n'], d['clocks']['sm_mhz'])"
 done

@@ -81,6 +81,80 @@ def test_checkpoint_roundtrip_and_legacy_alias(tmp_path):
     assert model._model.model_kwargs["layers"] == 1 and "some_deprecated_key" not in model._model.model_kwargs
 
 
+class _FakeFlatMapping:
+    """stands in for haiku._src.data_structures.FlatMapping (dm-haiku < 0.0.10): a Mapping that is NOT a dict and
+    pickles as FlatMapping(<payload>)"""
+    def __init__(self, payload):
+        self._payload = payload
+
+    def __reduce__(self):
+        return (type(self), (self._payload,))
+
+
+class _FakeFlatComponents:
+    """stands in for haiku's FlatComponents(leaves, structure) NamedTuple; `structure` is an opaque pytree def"""
+    def __init__(self, leaves, structure):
+        self.leaves, self.structure = leaves, structure
+
+    def __reduce__(self):
+        return (type(self), (self.leaves, self.structure))
+
+
+class _FakePyTreeDef:
+    def __reduce__(self):
+        return (type(self), ())
+
+
+@pytest.mark.parametrize("form", ["dict", "components"])
+def test_old_haiku_flatmapping_checkpoint(tmp_path, form):
+    """A checkpoint whose params are haiku FlatMapping containers (published models, dm-haiku 0.0.8/0.0.9) loads: the
+    restricted unpickler stubs the classes and `_plain_params` rebuilds the dict, for both pickled forms."""
+    import sys, types
+    kw = dict(layers=1, dim=128, key_size=32, num_heads=8, widening_factor=4)
+    params = init_params(kw, seed=5, perturb=True)
+    hk = types.ModuleType("haiku"); src = types.ModuleType("haiku._src"); ds = types.ModuleType("haiku._src.data_structures")
+    jl = types.ModuleType("jaxlib_fake")
+    for cls, name, mod in ((_FakeFlatMapping, "FlatMapping", ds), (_FakeFlatComponents, "FlatComponents", ds),
+                           (_FakePyTreeDef, "PyTreeDef", jl)):
+        cls.__qualname__ = cls.__name__ = name
+        cls.__module__ = mod.__name__
+        setattr(mod, name, cls)
+    mods = {"haiku": hk, "haiku._src": src, "haiku._src.data_structures": ds, "jaxlib_fake": jl}
+    sys.modules.update(mods)
+    try:
+        if form == "dict":  # FlatMapping(dict) at both levels
+            wrapped = _FakeFlatMapping({m: _FakeFlatMapping(dict(l)) for m, l in params.items()})
+        else:               # FlatMapping(FlatComponents(leaves in sorted key order, treedef))
+            leaves = [params[m][l] for m in sorted(params) for l in sorted(params[m])]
+            wrapped = _FakeFlatMapping(_FakeFlatComponents(tuple(leaves), _FakePyTreeDef()))
+        blob = pickle.dumps(ModelState(3, None, None, wrapped, None, None, None))
+    finally:
+        for k in mods:
+            sys.modules.pop(k)
+    (tmp_path / "old").mkdir()
+    (tmp_path / "old" / "checkpoint_0000003.pkl").write_bytes(blob)
+    (tmp_path / "old" / "kwargs.json").write_text(json.dumps({"neural_net_kwargs": kw, "inference_model_kwargs": {}}))
+    model = avici_b200.load_pretrained(checkpoint_dir=str(tmp_path / "old"), expects_counts=False, verbose=False)
+    assert isinstance(model.params, dict) and set(model.params) == set(params)
+    for m, leaves in params.items():
+        assert isinstance(model.params[m], dict)
+        for l, arr in leaves.items():
+            assert np.array_equal(model.params[m][l], arr), (m, l)
+    assert [n for n, _ in flatten_params(model.params)].count("BaseModel/linear/w") == 1
+
+
+def test_unpickler_refuses_dangerous_builtins(tmp_path):
+    """The allow-list is explicit: a pickle that names builtins.eval / os.system gets an inert stub, not the callable."""
+    class Evil:
+        def __reduce__(self):
+            return (eval, ("__import__('os').getpid()",))
+    (tmp_path / "evil").mkdir()
+    (tmp_path / "evil" / "checkpoint_0000001.pkl").write_bytes(pickle.dumps(ModelState(1, None, Evil(), {}, None, None, None)))
+    (tmp_path / "evil" / "kwargs.json").write_text(json.dumps({"neural_net_kwargs": {}, "inference_model_kwargs": {}}))
+    state, _ = load_checkpoint(tmp_path / "evil")
+    assert type(state.opt_state).__name__ == "eval" and not isinstance(state.opt_state, int)  # stub instance, never called
+
+
 def test_load_pretrained_argument_errors(tmp_path):
     with pytest.raises(AssertionError):
         avici_b200.load_pretrained()

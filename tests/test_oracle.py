@@ -192,3 +192,25 @@ def test_metrics_oracle_shd_properties():
     # a reversed edge counts once (metrics.py:8-9)
     a = np.zeros((4, 4), np.int32); a[0, 1] = 1
     assert MO.shd(a, a.T) == 1
+
+
+def _standardize_cases():
+    path = os.path.join(os.path.dirname(__file__), "golden", "standardize", "standardize_cases.npz")
+    blob = np.load(path)
+    return [(str(k), blob[f"{k}__x"], blob[f"{k}__y"], bool(blob[f"{k}__counts"])) for k in blob["names"]]
+
+
+def test_standardizer_oracles_match_reference_outputs():
+    """Rows a3 / a4 PINNED: the oracle's standardizers against outputs of the reference's own numpy twins
+    (avici/utils/data.py:10-29,66-78, generated by tests/golden/standardize/make_standardize_golden.py), including
+    constant / all-zero columns, all-zero rows (library size 0), an all-zero dataset and std == 0."""
+    cases = _standardize_cases()
+    assert len(cases) >= 40
+    for name, x, want, counts in cases:
+        x2 = np.stack([x, np.ones_like(x)], -1)  # channel 1 (here all ones) must come back untouched
+        got = (O.standardize_count_simple if counts else O.standardize_default_simple)(x2)
+        assert got.dtype == x.dtype and np.array_equal(got[..., 1], x2[..., 1]), name
+        assert np.isfinite(got).all(), name
+        tol = 1e-12 if x.dtype == np.float64 else 2e-6
+        err = np.abs(got[..., 0] - want).max() if want.size else 0.0
+        assert err <= tol * max(1.0, float(np.abs(want).max())), f"{name}: {err}"
