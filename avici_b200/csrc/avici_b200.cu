@@ -23,6 +23,7 @@
 
 #include "kernels_f32.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_dattn.cuh"
 #include "kernels_metrics.cuh"
 
 namespace {
@@ -38,6 +39,8 @@ struct Block {
   // bf16 tensor-core copies: K-major [N,K], LayerNorm affine and softmax scale folded in
   const bf16 *wqkv_t, *wo_t, *w1_t, *w2_t;
   const float *bqkv_f, *b1_f;
+  // per-head operand images of dattn_tc_kernel: Wqkv_h as 2 K blocks of [96 x 64] (128B swizzle), Wo_h as [128 x 32] (64B swizzle)
+  const uint8_t *wd_qkv, *wd_o;
   CUtensorMap tm_wqkv_h, tm_wo, tm_w1q, tm_w2q;  // wqkv: [128 x 64] boxes (CTA-pair QKV), wo: [128 x 64], w1 / w2: [64 x 64] (CTA-pair FFN)
 };
 
@@ -61,6 +64,7 @@ struct avb_model_s {
   cudaStream_t host_stream = nullptr;
   std::mutex host_mu;
   long long launches = 0;
+  int dattn_mode = 1;  // d-axis blocks with d <= 128: 1 = fully fused kernel, 2 = fused up to the attention output, 0 = unfused
   // optional per-kernel-category CUDA-event timing (avb_profile_*)
   bool prof = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -312,6 +316,34 @@ int launch_attention_tc(avb_handle h, const void* qkv, void* out, int B, int n, 
   return AVB_OK;
 }
 
+// Fused d-axis attention sub-layer (dattn_tc_kernel): one CTA per sequence of T = d <= 128 tokens.
+// fuse_out: delta rows (bf16, token order) come out of the kernel; otherwise the attention output in the
+// out-projection's A-operand layout.  `guard` must have been cleared by the caller.
+int launch_dattn_tc(avb_handle h, const float* z, const Block& W, void* out, int S, int T, bool fuse_out, cudaStream_t st,
+                    int num_sms, long long* launches, int* guard) {
+  static PerDeviceOnce once;
+  cudaError_t e = once.run([] {
+    cudaError_t r = cudaFuncSetAttribute(avb::dattn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         avb::DaCfg<true>::kSmemBytes);
+    if (r == cudaSuccess)
+      r = cudaFuncSetAttribute(avb::dattn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::DaCfg<false>::kSmemBytes);
+    return r;
+  });
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(dattn_tc): %s", cudaGetErrorString(e));
+  if (T < 1 || T > 128 || S < 1) return fail(h, AVB_ERR_INVALID, "dattn_tc: sequence length %d not in 1..128", T);
+  const int grid = std::min(S, num_sms);
+  if (fuse_out)
+    avb::dattn_tc_kernel<true><<<grid, avb::kDaThreads, avb::DaCfg<true>::kSmemBytes, st>>>(
+        z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo, reinterpret_cast<bf16*>(out), S, T, guard);
+  else
+    avb::dattn_tc_kernel<false><<<grid, avb::kDaThreads, avb::DaCfg<false>::kSmemBytes, st>>>(
+        z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo, reinterpret_cast<bf16*>(out), S, T, guard);
+  if (launches) ++*launches;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "dattn_tc launch: %s", cudaGetErrorString(e));
+  return AVB_OK;
+}
+
 template <int EPI, bool LN>
 void launch_sgemm(const float* A, int lda, const float* W, int ldw, const float* bias, const float* g,
                   const float* b, const float* R, int ldr, float* C, int ldc, size_t M, int N, int K,
@@ -433,6 +465,7 @@ int avb_create(avb_handle* out, const avb_config* cfg) {
   h->cfg = *cfg;
   h->device = dev;
   h->num_sms = prop.multiProcessorCount;
+  if (const char* m = ab_env("AVB_DATTN_MODE")) h->dattn_mode = m[0] == '0' ? 0 : (m[0] == '2' ? 2 : 1);
   e = cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return fail(nullptr, AVB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   *out = h;
@@ -517,7 +550,7 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
   };
   struct BlockOff {
     size_t ln_g[4], ln_b[4], wq, bq, wk, bk, wv, bv, wo, bo, w1, b1, w2, b2, bqkv_f, b1_f;
-    size_t wqkv_t, wo_t, w1_t, w2_t;
+    size_t wqkv_t, wo_t, w1_t, w2_t, wd_qkv, wd_o;
   };
   std::vector<BlockOff> offs(nb);
   const std::string R = "BaseModel/";
@@ -581,6 +614,31 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
       o.w2_t = push_b16((size_t)k * F);
       for (int col = 0; col < k; ++col)
         for (int r = 0; r < F; ++r) b16[o.w2_t + (size_t)col * F + r] = __float2bfloat16(w2[(size_t)r * k + col]);
+      // dattn_tc_kernel operand images (byte-exact shared-memory layouts, fetched with 1-D bulk copies)
+      if (c.num_heads == avb::kDaHeads) {
+        const size_t img_qkv = (size_t)avb::kDaHeads * 2 * avb::kDaWkbBytes / 2, img_o = (size_t)avb::kDaHeads * avb::kDaWoHeadBytes / 2;
+        o.wd_qkv = push_b16(img_qkv);
+        o.wd_o = push_b16(img_o);
+        for (int hh = 0; hh < avb::kDaHeads; ++hh) {
+          for (int kb = 0; kb < 2; ++kb)
+            for (int r = 0; r < 96; ++r) {  // row r = (q|k|v, channel jj of the head)
+              const int w = r >> 5, jj = r & 31;
+              const bf16* src = &b16[o.wqkv_t + ((size_t)w * HD + hh * 32 + jj) * k + kb * 64];
+              for (int ch = 0; ch < 8; ++ch) {  // 16-byte chunk ch -> slot ch ^ (r & 7) of the 128-byte row
+                const size_t dst = o.wd_qkv + ((size_t)(hh * 2 + kb) * avb::kDaWkbBytes + (size_t)(r >> 3) * 1024 + (r & 7) * 128 +
+                                               ((ch ^ (r & 7)) << 4)) / 2;
+                for (int e = 0; e < 8; ++e) b16[dst + e] = src[ch * 8 + e];
+              }
+            }
+          for (int r = 0; r < 128; ++r) {  // row r = output channel; 32 head channels = 64 bytes, chunk ch -> ch ^ ((r >> 1) & 3)
+            const bf16* src = &b16[o.wo_t + (size_t)r * HD + hh * 32];
+            for (int ch = 0; ch < 4; ++ch) {
+              const size_t dst = o.wd_o + ((size_t)hh * avb::kDaWoHeadBytes + (size_t)r * 64 + ((ch ^ ((r >> 1) & 3)) << 4)) / 2;
+              for (int e = 0; e < 8; ++e) b16[dst + e] = src[ch * 8 + e];
+            }
+          }
+        }
+      }
     }
   }
   const size_t lnf_g = push_f32(get(R + "layer_norm" + sfx(4 * nb) + "/scale", k), k);
@@ -619,6 +677,7 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
     B.bqkv_f = df + o.bqkv_f; B.b1_f = df + o.b1_f;
     if (c.compute_dtype == AVB_DTYPE_BF16) {
       B.wqkv_t = db + o.wqkv_t; B.wo_t = db + o.wo_t; B.w1_t = db + o.w1_t; B.w2_t = db + o.w2_t;
+      B.wd_qkv = reinterpret_cast<const uint8_t*>(db + o.wd_qkv); B.wd_o = reinterpret_cast<const uint8_t*>(db + o.wd_o);
       bool ok = make_tmap_2d(&B.tm_wqkv_h, B.wqkv_t, 3 * HD, k, 128) && make_tmap_2d(&B.tm_wo, B.wo_t, k, HD, 128) &&
                 make_tmap_2d(&B.tm_w1q, B.w1_t, F, k, 64) && make_tmap_2d(&B.tm_w2q, B.w2_t, k, F, 64);
       if (!ok) return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for block %d weights", i);
@@ -703,6 +762,22 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
     int* guard = reinterpret_cast<int*>(w8 + L.guard_off);
     // attention half: LN -> QKV -> attention -> out-projection, leaving the sub-layer's update as bf16 `delta` rows in
     // the qkv buffer (dead once the attention has run); the FFN's LayerNorm warps add it to z.
+    const long long S_d = (long long)B * n;
+    if (axis == AVB_AXIS_D && d <= 128 && H == avb::kDaHeads && h->dattn_mode != 0) {
+      // a whole sequence fits one tile: the sub-layer is ONE kernel, qkv and the attention output never reach HBM.
+      // The guarded exact fallback (unfused kernels, each returning at once while the guard is down) recomputes delta
+      // if a score left the fast softmax's range.
+      const bool fuse_out = h->dattn_mode == 1;
+      { ProfScope ps(h, AVB_PROF_DATTN, st);
+        if (cudaMemsetAsync(guard, 0, sizeof(int), st) != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention guard reset failed");
+        if ((rc = launch_dattn_tc(h, z, W, fuse_out ? (void*)qkv : (void*)attn, (int)S_d, d, fuse_out, st, h->num_sms, &h->launches, guard)))
+          return rc;
+        if ((rc = launch_ln_gemm2_tc(h, z, W.tm_wqkv_h, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, st, h->num_sms, &h->launches, n, d, axis, guard)))
+          return rc;
+        if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches, guard, 3))) return rc;
+        if ((rc = launch_outproj_tc(h, attn, W.tm_wo, W.bo, qkv, M, n, d, axis, st, h->num_sms, &h->launches,
+                                    fuse_out ? guard : nullptr))) return rc; }
+    } else {
     { ProfScope ps(h, AVB_PROF_QKV, st);  // LayerNorm fused into the projection's prologue;
       // rows in sequence-major order of `axis`, output in the attention kernel's operand layout
       if ((rc = launch_ln_gemm2_tc(h, z, W.tm_wqkv_h, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, st, h->num_sms, &h->launches,
@@ -711,6 +786,7 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
       if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches, guard))) return rc; }
     { ProfScope ps(h, AVB_PROF_OUT, st);
       if ((rc = launch_outproj_tc(h, attn, W.tm_wo, W.bo, qkv, M, n, d, axis, st, h->num_sms, &h->launches))) return rc; }
+    }
     // FFN half: z += delta; LN -> Linear + ReLU -> Linear + residual, one kernel
     { ProfScope ps(h, AVB_PROF_FFN, st);
       if ((rc = launch_ffn2_tc(h, z, W.tm_w1q, W.tm_w2q, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches, qkv, n, d, axis)))
@@ -1049,6 +1125,49 @@ int avb_threshold_metrics(const float* probs, const int32_t* g_true, int32_t B, 
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "avb_threshold_metrics: launch failed: %s", cudaGetErrorString(e));
   return AVB_OK;
+}
+
+int avb_test_set_dattn_mode(avb_handle h, int32_t mode) {
+  if (!h || mode < 0 || mode > 2) return fail(h, AVB_ERR_INVALID, "avb_test_set_dattn_mode: mode must be 0, 1 or 2");
+  h->dattn_mode = mode;
+  return AVB_OK;
+}
+
+int avb_test_dattn_bf16(avb_handle h, int32_t bi, const float* z, int32_t B, int32_t n, int32_t d, int32_t fuse_out,
+                        void* delta, int32_t* guard_host, void* stream) {
+  if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_test_dattn_bf16: weights not loaded");
+  if (h->cfg.compute_dtype != AVB_DTYPE_BF16 || h->cfg.num_heads != avb::kDaHeads)
+    return fail(h, AVB_ERR_INVALID, "avb_test_dattn_bf16: bf16 handle with 8 heads required");
+  if (!shape_ok(h, B, n, d) || d > 128 || !z || !delta || bi < 0 || bi >= (int)h->blocks.size())
+    return fail(h, AVB_ERR_INVALID, "avb_test_dattn_bf16: bad argument (d <= 128)");
+  DeviceGuard dg(h->device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const Block& W = h->blocks[bi];
+  const size_t ntok = (size_t)B * n * d;
+  const int HD = h->cfg.num_heads * h->cfg.key_size;
+  uint8_t* scratch = reinterpret_cast<uint8_t*>(test_scratch(((ntok + 127) / 128) * 128 * HD * sizeof(bf16) + 1024));
+  if (!scratch) return fail(h, AVB_ERR_CUDA, "cudaMalloc(test scratch) failed");
+  int* guard = reinterpret_cast<int*>(scratch);
+  bf16* attn = reinterpret_cast<bf16*>(scratch + 1024);
+  AVB_CUDA(h, cudaMemsetAsync(guard, 0, sizeof(int), st));
+  int rc;
+  if ((rc = launch_dattn_tc(h, z, W, fuse_out ? delta : (void*)attn, B * n, d, fuse_out != 0, st, h->num_sms, nullptr, guard))) return rc;
+  if (!fuse_out && (rc = launch_outproj_tc(h, attn, W.tm_wo, W.bo, delta, (int)ntok, n, d, 0, st, h->num_sms, nullptr))) return rc;
+  if (guard_host) {
+    AVB_CUDA(h, cudaMemcpyAsync(guard_host, guard, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AVB_CUDA(h, cudaStreamSynchronize(st));
+  }
+  return AVB_OK;
+}
+
+int avb_debug_set_dattn_dump(void* dump_dev) {
+#ifdef AVB_DATTN_DEBUG
+  float* p = reinterpret_cast<float*>(dump_dev);
+  return cudaMemcpyToSymbol(avb::g_dattn_dbg, &p, sizeof p) == cudaSuccess ? AVB_OK : AVB_ERR_CUDA;
+#else
+  (void)dump_dev;
+  return fail(nullptr, AVB_ERR_INVALID, "avb_debug_set_dattn_dump: not a -DAVB_DATTN_DEBUG build");
+#endif
 }
 
 int avb_debug_set_trace(void* trace_dev) {

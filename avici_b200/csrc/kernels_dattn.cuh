@@ -1,0 +1,469 @@
+// Fused attention sub-layer for blocks that attend over the variable axis d (even blocks, model.py:56-65) when a
+// whole sequence fits one 128-row tile (T = d <= 128):
+//
+//     delta[tokens of (b, i)] = MHA(LN_q(z), LN_k(z), LN_v(z)) . Wo + bo        (bf16 rows, added to z by the FFN kernel)
+//
+// One CTA owns a whole sequence (b, i): its T tokens are T consecutive 512-byte rows of z.  Unfused, this sub-layer
+// writes and re-reads qkv (1536 B/token each way) and the attention output (512 B/token) through HBM - three
+// launches that each sit at 70-84 % of the HBM peak (profiles/r1g-r1j).  Here neither exists in HBM: per token the
+// kernel reads 512 B of z and writes 256 B of delta.
+//
+// A sequence is processed head by head (a "unit" u = sequence * 8 + head):
+//   LN      : 4 warps normalise the T fp32 rows into a bf16 [128 x 128] A tile (128B-swizzled, double-buffered by
+//             sequence; rows >= T are zero)
+//   G_u     : [Q_h | K_h | V_h] = xhat . Wqkv_h^T          M=128, N=96, K=128  -> TMEM (fp32)
+//   conv_u  : + bias -> bf16 -> Q / K / V tiles in shared memory (the 64B-swizzled images the attention MMAs read)
+//   S_u     : S = Q K^T                                    M=128, N=kc, K=32   -> TMEM          (kc = T rounded up to 16)
+//   softmax : P = exp2(S) without a running maximum, bf16 pairs -> TMEM (same scheme and guard as attention_tc_kernel)
+//   PV_u    : O = P V, L = P 1                             M=128, N=32|16, K=kc -> TMEM
+//   Oepi_u  : O / L -> bf16 -> shared memory A tile [128 x 32]
+//   OP_u    : DELTA += O_h . Wo_h^T                        M=128, N=128, K=32  -> TMEM, accumulated over the 8 heads
+//   Depi    : DELTA + bo -> bf16 -> 256-byte rows of delta (token order)
+// kFuseOut = false stops after Oepi and writes the attention output in outproj_tc_kernel's A-operand layout instead
+// (the out-projection then runs as its own launch); kept as the staging step of this kernel and as its A/B reference.
+//
+// Weights: the per-head operand images are packed once at load time (avb_load_weights): Wqkv_h as two K blocks of
+// [96 rows x 64] bf16 in the 128B-swizzle image (12 KB each), Wo_h as [128 rows x 32] in the 64B-swizzle image
+// (8 KB).  Wo (64 KB) stays resident in shared memory; the Wqkv K blocks stream from L2 through a ring of 1-D bulk
+// copies (192 KB per sequence; the L2 -> SM path, not HBM, carries them).
+//
+// TMEM (512 columns): SBUF0 | SBUF1 (128 each: the QKV accumulator of a unit, then its S tile) | P 64 | O 32 | L 16 |
+// 16 spare | DELTA 128.  Software pipeline of the single MMA-issuing thread, iteration u:
+//     PV_{u-1}, S_{u+1}, G_{u+2}, OP_{u-1}
+// so that the tensor core computes the next units' projections and scores while the 8 softmax warps (the MUFU-bound
+// stage) work on unit u.
+//   warp 0: weight producer   warp 1: MMA issuer   warp 2: TMEM alloc   warps 4-7: LayerNorm
+//   warps 8-11: conv / Oepi / Depi (TMEM lane quarter = warp & 3)   warps 12-19: softmax (lane quarter x column half)
+#pragma once
+#include "kernels_tc.cuh"
+
+namespace avb {
+
+constexpr int kDaThreads = 640;
+constexpr int kDaXBytes = 128 * 128 * 2;    // xhat A tile: two 128B-swizzled K blocks of [128 x 64]
+constexpr int kDaWkbBytes = 96 * 128;       // one K block [96 rows x 64] of a head's Wqkv image
+constexpr int kDaWoHeadBytes = 128 * 64;    // one head's [128 rows x 32] slice of Wo
+constexpr int kDaTileBytes = 128 * 32 * 2;  // Q / K / V / O tile
+constexpr int kDaHeads = 8;
+constexpr int kDaVBufs = 3;
+
+template <bool kFuseOut>
+struct DaCfg {
+  static constexpr int kWStages = kFuseOut ? 3 : 6;
+  static constexpr int kWoBytes = kFuseOut ? kDaHeads * kDaWoHeadBytes : 0;
+  static constexpr int kOBufs = kFuseOut ? 2 : 0;
+  static constexpr int kDataBytes =
+      2 * kDaXBytes + kWStages * kDaWkbBytes + kWoBytes + (2 + kDaVBufs + kOBufs) * kDaTileBytes;
+  static constexpr int kSmemBytes = kDataBytes + 1024 /*barriers, TMEM slot, ones tile*/ + 1024 /*alignment slack*/;
+};
+static_assert(DaCfg<true>::kSmemBytes <= 232448, "dattn_tc_kernel: shared memory over the sm_100 limit");
+
+// Bounded (trapping) mbarrier waits in the softmax warps as well: a protocol bug must fail the launch, never hang the
+// GPU box.  0 selects the lean hot-loop waits once a build has been validated on hardware.
+#ifndef AVB_DATTN_BOUNDED_WAITS
+#define AVB_DATTN_BOUNDED_WAITS 1
+#endif
+#if AVB_DATTN_BOUNDED_WAITS
+#define AVB_DA_WAIT(bar_ptr, parity, tag) ptx::mbar_wait((bar_ptr), (parity), (tag))
+#else
+#define AVB_DA_WAIT(bar_ptr, parity, tag) ptx::mbar_wait_s(ptx::smem_u32(bar_ptr), (parity))
+#endif
+
+#ifdef AVB_DATTN_DEBUG
+// Debug builds only: CTA 0 dumps the intermediates of its first sequence (see scripts/debug_dattn.py)
+//   [0, 8*128*96)            Q|K|V rows after bias, as float, per head
+//   + 8*128*128              raw scores read by the softmax warps, per head
+//   + 8*128*32               O / L per head
+//   + 128*128                DELTA + bo
+__device__ float* g_dattn_dbg = nullptr;
+#endif
+
+template <bool kFuseOut>
+__global__ void __launch_bounds__(kDaThreads, 1)
+dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_img, const uint8_t* __restrict__ wo_img,
+                const float* __restrict__ bqkv, const float* __restrict__ bo, __nv_bfloat16* __restrict__ out, int S, int T,
+                int* __restrict__ guard) {
+  using Cfg = DaCfg<kFuseOut>;
+  constexpr int NS = Cfg::kWStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sX = smem;                               // [2][32 KB]
+  uint8_t* sW = sX + 2 * kDaXBytes;                 // [NS][12 KB]
+  uint8_t* sWo = sW + NS * kDaWkbBytes;             // [8][8 KB] (kFuseOut)
+  uint8_t* sQ = sWo + Cfg::kWoBytes;                // 8 KB
+  uint8_t* sK = sQ + kDaTileBytes;                  // 8 KB
+  uint8_t* sV = sK + kDaTileBytes;                  // [3][8 KB]
+  uint8_t* sO = sV + kDaVBufs * kDaTileBytes;       // [2][8 KB] (kFuseOut)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kDataBytes);
+  uint64_t* x_full = bars;                 // [2] 128 LN threads
+  uint64_t* x_empty = bars + 2;            // [2] commit
+  uint64_t* w_full = bars + 4;             // [NS] tx
+  uint64_t* w_empty = w_full + NS;         // [NS] commit
+  uint64_t* g_full = w_empty + NS;         // [2] commit: QKV accumulator of unit u in SBUF[u & 1]
+  uint64_t* qkv_ready = g_full + 2;        // [2] 128 conv threads
+  uint64_t* s_full = qkv_ready + 2;        // [2] commit
+  uint64_t* s_free = s_full + 2;           // [2] 256 softmax threads
+  uint64_t* o_ready = s_free + 2;          // [2] 128 conv threads: O read (and its bf16 tile written)
+  uint64_t* p_full = o_ready + 2;          // 256 softmax threads
+  uint64_t* pv_done = p_full + 1;          // commit
+  uint64_t* d_full = pv_done + 1;          // commit
+  uint64_t* d_free = d_full + 1;           // 128 conv threads
+  uint64_t* wo_full = d_free + 1;          // tx
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wo_full + 1);
+  uint32_t* s_ones = reinterpret_cast<uint32_t*>(smem + Cfg::kDataBytes + 512);  // 512 B of bf16 1.0
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int nseq = (int)blockIdx.x < S ? (S - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int U = nseq * kDaHeads;
+  const int kc = (T + 15) & ~15;  // key columns the MMAs touch
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&x_full[i], 128); ptx::mbar_init(&x_empty[i], 1);
+      ptx::mbar_init(&g_full[i], 1);   ptx::mbar_init(&qkv_ready[i], 128);
+      ptx::mbar_init(&s_full[i], 1);   ptx::mbar_init(&s_free[i], 256);
+      ptx::mbar_init(&o_ready[i], 128);
+    }
+    for (int i = 0; i < NS; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+    ptx::mbar_init(p_full, 256); ptx::mbar_init(pv_done, 1);
+    ptx::mbar_init(d_full, 1);   ptx::mbar_init(d_free, 128);
+    ptx::mbar_init(wo_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  if (threadIdx.x >= 128 && threadIdx.x < 256) s_ones[threadIdx.x - 128] = 0x3F803F80u;
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tP = tmem_base + 256, tO = tmem_base + 320, tL = tmem_base + 352, tD = tmem_base + 384;
+
+  // Register budget per warpgroup (the pool holds what the CTA was launched with, 640 x 96 = 128 x (64 + 104 + 88) +
+  // 256 x 112).  Each setmaxnreg sits at the top of its own role branch: ptxas sizes the register allocation of a
+  // region by the setmaxnreg that dominates it.
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  if (warp == 0) {
+    // ======================= weight producer: Wo once, then the Wqkv K blocks of every unit (head = unit & 7)
+    if (kFuseOut && nseq > 0) {
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(wo_full, kDaHeads * kDaWoHeadBytes);
+        for (int hh = 0; hh < kDaHeads; ++hh)
+          ptx::bulk_load_hint(sWo + hh * kDaWoHeadBytes, wo_img + hh * kDaWoHeadBytes, kDaWoHeadBytes, wo_full, ptx::kL2EvictLast);
+      }
+      __syncwarp();
+    }
+    for (int kbi = 0; kbi < 2 * U; ++kbi) {
+      const int st = kbi % NS;
+      ptx::mbar_wait(&w_empty[st], (uint32_t)((kbi / NS) & 1) ^ 1, 80, 100u);
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(&w_full[st], kDaWkbBytes);
+        ptx::bulk_load_hint(sW + st * kDaWkbBytes, wqkv_img + (size_t)((kbi >> 1) & 7) * (2 * kDaWkbBytes) + (kbi & 1) * kDaWkbBytes,
+                            kDaWkbBytes, &w_full[st], ptx::kL2EvictLast);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer
+    if (U > 0) {
+      constexpr uint32_t idesc_g = ptx::make_idesc_bf16(128, 96, 0, 0);
+      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, 32, 0, 1);  // B = V is MN-major
+      constexpr uint32_t idesc_l = ptx::make_idesc_bf16(128, 16, 0, 0);
+      constexpr uint32_t idesc_op = ptx::make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_s = ptx::make_idesc_bf16(128, kc, 0, 0);
+      const int ksteps = kc >> 4;
+      const uint64_t dX0 = ptx::make_smem_desc(ptx::smem_u32(sX), 16, 1024, ptx::kSwz128);
+      const uint64_t dW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024, ptx::kSwz128);
+      const uint64_t dQ = ptx::make_smem_desc(ptx::smem_u32(sQ), 16, 512, ptx::kSwz64);
+      const uint64_t dK = ptx::make_smem_desc(ptx::smem_u32(sK), 16, 512, ptx::kSwz64);
+      const uint64_t dV0 = ptx::make_smem_desc(ptx::smem_u32(sV), 16, 512, ptx::kSwz64);
+      const uint64_t dO0 = ptx::make_smem_desc(ptx::smem_u32(sO), 16, 512, ptx::kSwz64);
+      const uint64_t dWo0 = ptx::make_smem_desc(ptx::smem_u32(sWo), 16, 512, ptx::kSwz64);
+      const uint64_t d_ones = ptx::make_smem_desc(ptx::smem_u32(s_ones), 128, 256, ptx::kSwzNone);
+
+      auto issue_G = [&](int u) {  // QKV projection of unit u into SBUF[u & 1]
+        const int si = u >> 3, h = u & 7, buf = si & 1;
+        if (h == 0) ptx::mbar_wait(&x_full[buf], (uint32_t)((si >> 1) & 1), 81, 40u);
+        if (u >= 2) ptx::mbar_wait(&s_free[u & 1], (uint32_t)(((u >> 1) - 1) & 1), 82, 40u);  // softmax of unit u-2 has read S
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(u & 1) * 128u;
+        for (int kb = 0; kb < 2; ++kb) {
+          const int kbi = 2 * u + kb, st = kbi % NS;
+          ptx::mbar_wait(&w_full[st], (uint32_t)((kbi / NS) & 1), 83, 40u);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint64_t da = dX0 + (uint64_t)(buf * (kDaXBytes >> 4) + kb * ((128 * 128) >> 4));
+            const uint64_t db = dW0 + (uint64_t)(st * (kDaWkbBytes >> 4));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_g, (kb | k) != 0);
+            ptx::umma_commit(&w_empty[st]);
+            if (kb == 1) {
+              ptx::umma_commit(&g_full[u & 1]);
+              if (h == 7) ptx::umma_commit(&x_empty[buf]);
+            }
+          }
+          __syncwarp();
+        }
+      };
+      auto issue_S = [&](int u) {  // scores of unit u into SBUF[u & 1] (over the QKV accumulator conv_u has consumed)
+        ptx::mbar_wait(&qkv_ready[u & 1], (uint32_t)((u >> 1) & 1), 84, 40u);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(u & 1) * 128u;
+          ptx::umma_bf16(d_tmem, dQ, dK, idesc_s, 0);
+          ptx::umma_bf16(d_tmem, dQ + 2, dK + 2, idesc_s, 1);
+          ptx::umma_commit(&s_full[u & 1]);
+        }
+        __syncwarp();
+      };
+      auto issue_PV = [&](int u) {
+        ptx::mbar_wait(p_full, (uint32_t)(u & 1), 85, 40u);
+        if (u >= 1) ptx::mbar_wait(&o_ready[(u - 1) & 1], (uint32_t)(((u - 1) >> 1) & 1), 86, 40u);  // O of unit u-1 has been read
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t dv = dV0 + (uint64_t)((u % kDaVBufs) * (kDaTileBytes >> 4));
+          for (int k = 0; k < ksteps; ++k) {
+            ptx::umma_bf16_ts(tO, tP + k * 8, dv + (uint64_t)(k * 64), idesc_pv, k != 0);
+            ptx::umma_bf16_ts(tL, tP + k * 8, d_ones, idesc_l, k != 0);
+          }
+          ptx::umma_commit(pv_done);
+        }
+        __syncwarp();
+      };
+      auto issue_OP = [&](int u) {  // DELTA (+)= O_h . Wo_h^T
+        const int si = u >> 3, h = u & 7;
+        ptx::mbar_wait(&o_ready[u & 1], (uint32_t)((u >> 1) & 1), 87, 40u);
+        if (h == 0 && si >= 1) ptx::mbar_wait(d_free, (uint32_t)((si - 1) & 1), 88, 40u);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t da = dO0 + (uint64_t)((u & 1) * (kDaTileBytes >> 4));
+          const uint64_t db = dWo0 + (uint64_t)(h * (kDaWoHeadBytes >> 4));
+          ptx::umma_bf16(tD, da, db, idesc_op, h != 0);
+          ptx::umma_bf16(tD, da + 2, db + 2, idesc_op, 1);
+          if (h == 7) ptx::umma_commit(d_full);
+        }
+        __syncwarp();
+      };
+
+      if (kFuseOut) ptx::mbar_wait(wo_full, 0, 89, 40u);
+      issue_G(0);
+      issue_S(0);  // before G_1: conv_1 may only overwrite the Q / K tiles once S_0 has been issued
+      if (U > 1) issue_G(1);
+      for (int u = 0; u < U; ++u) {
+        if (u >= 1) issue_PV(u - 1);
+        if (u + 1 < U) issue_S(u + 1);
+        if (u + 2 < U) issue_G(u + 2);
+        if (kFuseOut && u >= 1) issue_OP(u - 1);
+      }
+      issue_PV(U - 1);
+      if (kFuseOut) issue_OP(U - 1);
+    }
+  }
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ======================= LayerNorm warps: rows 32w .. 32w+31 of the sequence, rows >= T are zero
+    const int w = warp - 4;
+    for (int si = 0; si < nseq; ++si) {
+      const int s = (int)blockIdx.x + si * (int)gridDim.x, buf = si & 1;
+      const float* zs = z + (size_t)s * T * 128;
+      if (si + 2 < nseq) prefetch_rows_l2(z + (size_t)(s + 2 * (int)gridDim.x) * T * 128, T, w * 32, lane);
+      ptx::mbar_wait(&x_empty[buf], (uint32_t)((si >> 1) & 1) ^ 1, 90);
+      ln_warp_rows_to_umma_tile(zs, T, w * 32, ptx::smem_u32(sX + buf * kDaXBytes), w * 32, lane);
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&x_full[buf]);
+    }
+  } else if (warp < 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    // ======================= conv / Oepi / Depi warps: thread = row r of the tile = TMEM lane
+    const int q = warp & 3, r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t row_off = (uint32_t)(r * 64), swz = (uint32_t)((r >> 1) & 3);
+    const uint32_t aQ = ptx::smem_u32(sQ), aK = ptx::smem_u32(sK), aV = ptx::smem_u32(sV), aO = ptx::smem_u32(sO);
+
+    auto conv = [&](int u) {  // QKV accumulator -> + bias -> bf16 -> Q / K / V tiles
+      const int h = u & 7;
+      ptx::mbar_wait(&g_full[u & 1], (uint32_t)((u >> 1) & 1), 91);
+      ptx::tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(u & 1) * 128u + lane_off;
+#pragma unroll
+      for (int w = 0; w < 3; ++w) {
+        float4 bb[8];
+        const float* bp = bqkv + w * 256 + h * 32;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bp) + e);
+        uint32_t v[32];
+        ptx::tmem_ld32(tacc + w * 32, v);
+        ptx::tmem_wait_ld();
+        const uint32_t tile = w == 0 ? aQ : (w == 1 ? aK : aV + (uint32_t)((u % kDaVBufs) * kDaTileBytes));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float f[8];
+          f[0] = __uint_as_float(v[e * 8 + 0]) + bb[e * 2].x;     f[1] = __uint_as_float(v[e * 8 + 1]) + bb[e * 2].y;
+          f[2] = __uint_as_float(v[e * 8 + 2]) + bb[e * 2].z;     f[3] = __uint_as_float(v[e * 8 + 3]) + bb[e * 2].w;
+          f[4] = __uint_as_float(v[e * 8 + 4]) + bb[e * 2 + 1].x; f[5] = __uint_as_float(v[e * 8 + 5]) + bb[e * 2 + 1].y;
+          f[6] = __uint_as_float(v[e * 8 + 6]) + bb[e * 2 + 1].z; f[7] = __uint_as_float(v[e * 8 + 7]) + bb[e * 2 + 1].w;
+#ifdef AVB_DATTN_DEBUG
+          if (g_dattn_dbg && blockIdx.x == 0 && u < 8)
+            for (int t = 0; t < 8; ++t) g_dattn_dbg[((size_t)u * 128 + r) * 96 + w * 32 + e * 8 + t] = f[t];
+#endif
+          uint4 pk;
+          pk.x = ptx::pack_bf16(f[0], f[1]); pk.y = ptx::pack_bf16(f[2], f[3]);
+          pk.z = ptx::pack_bf16(f[4], f[5]); pk.w = ptx::pack_bf16(f[6], f[7]);
+          ptx::st_shared_v4(tile + row_off + (((uint32_t)e ^ swz) << 4), pk);
+        }
+      }
+      ptx::fence_proxy_async();  // tile writes (generic proxy) -> visible to the tensor core (async proxy)
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&qkv_ready[u & 1]);
+    };
+    auto oepi = [&](int u) {  // O / L -> bf16 -> A tile of the out-projection (or the attention output in HBM)
+      const int h = u & 7;
+      ptx::mbar_wait(pv_done, (uint32_t)(u & 1), 92);
+      ptx::tc_fence_after();
+      uint32_t o[32];
+      ptx::tmem_ld32(tO + lane_off, o);
+      const float lsum = __uint_as_float(ptx::tmem_ld1(tL + lane_off));
+      ptx::tmem_wait_ld();
+      if (r < T && !(lsum < 1.2676506e30f && lsum > 7.8886091e-31f)) *guard = 1;  // outside (2^-100, 2^100), inf or NaN
+      const float inv = 1.0f / lsum;
+      uint4 pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        pk[e].x = ptx::pack_bf16(__uint_as_float(o[e * 8 + 0]) * inv, __uint_as_float(o[e * 8 + 1]) * inv);
+        pk[e].y = ptx::pack_bf16(__uint_as_float(o[e * 8 + 2]) * inv, __uint_as_float(o[e * 8 + 3]) * inv);
+        pk[e].z = ptx::pack_bf16(__uint_as_float(o[e * 8 + 4]) * inv, __uint_as_float(o[e * 8 + 5]) * inv);
+        pk[e].w = ptx::pack_bf16(__uint_as_float(o[e * 8 + 6]) * inv, __uint_as_float(o[e * 8 + 7]) * inv);
+      }
+#ifdef AVB_DATTN_DEBUG
+      if (g_dattn_dbg && blockIdx.x == 0 && u < 8)
+        for (int t = 0; t < 32; ++t) g_dattn_dbg[(size_t)8 * 128 * 96 + 8 * 128 * 128 + ((size_t)u * 128 + r) * 32 + t] = __uint_as_float(o[t]) * inv;
+#endif
+      if constexpr (kFuseOut) {
+        const uint32_t tile = aO + (uint32_t)((u & 1) * kDaTileBytes);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ptx::st_shared_v4(tile + row_off + (((uint32_t)e ^ swz) << 4), pk[e]);
+        ptx::fence_proxy_async();
+      } else {
+        if (r < T) {  // outproj_tc_kernel's A-operand layout: [m >> 7][head][m & 127][32 ch], chunks at c ^ ((m >> 1) & 3)
+          const int s = (int)blockIdx.x + (u >> 3) * (int)gridDim.x;
+          const unsigned m = (unsigned)s * (unsigned)T + (unsigned)r;
+          __nv_bfloat16* orow = out + (((size_t)(m >> 7) * kDaHeads + h) * 128 + (m & 127)) * 32;
+          const unsigned mswz = (m >> 1) & 3;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) *reinterpret_cast<uint4*>(orow + (((unsigned)e ^ mswz) << 3)) = pk[e];
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&o_ready[u & 1]);
+    };
+    auto depi = [&](int si) {  // DELTA + bo -> bf16 -> the sequence's 256-byte delta rows (token order)
+      ptx::mbar_wait(d_full, (uint32_t)(si & 1), 93);
+      ptx::tc_fence_after();
+      const int s = (int)blockIdx.x + si * (int)gridDim.x;
+      __nv_bfloat16* drow = out + ((size_t)s * T + r) * 128;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        float4 bb[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bo + cc * 32) + e);
+        uint32_t v[32];
+        ptx::tmem_ld32(tD + cc * 32 + lane_off, v);
+        ptx::tmem_wait_ld();
+        if (cc == 3) {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(d_free);  // accumulator read: the next sequence's first OP may overwrite it
+        }
+#ifdef AVB_DATTN_DEBUG
+        if (g_dattn_dbg && blockIdx.x == 0 && si == 0)
+          for (int t = 0; t < 32; ++t)
+            g_dattn_dbg[(size_t)8 * 128 * 96 + 8 * 128 * 128 + 8 * 128 * 32 + (size_t)r * 128 + cc * 32 + t] =
+                __uint_as_float(v[t]) + reinterpret_cast<const float*>(bb)[t];
+#endif
+        if (r < T) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint4 pk;
+            pk.x = ptx::pack_bf16(__uint_as_float(v[e * 8 + 0]) + bb[e * 2].x, __uint_as_float(v[e * 8 + 1]) + bb[e * 2].y);
+            pk.y = ptx::pack_bf16(__uint_as_float(v[e * 8 + 2]) + bb[e * 2].z, __uint_as_float(v[e * 8 + 3]) + bb[e * 2].w);
+            pk.z = ptx::pack_bf16(__uint_as_float(v[e * 8 + 4]) + bb[e * 2 + 1].x, __uint_as_float(v[e * 8 + 5]) + bb[e * 2 + 1].y);
+            pk.w = ptx::pack_bf16(__uint_as_float(v[e * 8 + 6]) + bb[e * 2 + 1].z, __uint_as_float(v[e * 8 + 7]) + bb[e * 2 + 1].w);
+            *reinterpret_cast<uint4*>(drow + cc * 32 + e * 8) = pk;
+          }
+        }
+      }
+    };
+
+    if (U > 0) {
+      conv(0);
+      if (U > 1) conv(1);
+      for (int u = 0; u < U; ++u) {
+        if (u >= 1) oepi(u - 1);
+        if (u + 2 < U) conv(u + 2);
+        if (kFuseOut && u >= 1 && ((u - 1) & 7) == 7) depi((u - 1) >> 3);
+      }
+      oepi(U - 1);
+      if (kFuseOut) depi((U - 1) >> 3);
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // ======================= softmax warps: warp (q, half) owns TMEM lanes 32q.. and key columns [64 half, 64 half + 64)
+    const int q = warp & 3, half = (warp - 12) >> 2;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t a_pfull = ptx::smem_u32(p_full);
+    const uint32_t tPw = tP + half * 32 + lane_off;
+    const int nv = T - half * 64;  // valid key columns in this warp's half (may be <= 0)
+    float pmax = -INFINITY;
+    for (int u = 0; u < U; ++u) {
+      AVB_DA_WAIT(&s_full[u & 1], (uint32_t)((u >> 1) & 1), 94);
+      ptx::tc_fence_after();
+      const uint32_t tS = tmem_base + (uint32_t)(u & 1) * 128u + half * 64 + lane_off;
+      uint32_t sa[32], sb[32];
+      ptx::tmem_ld32(tS, sa);
+      ptx::tmem_ld32(tS + 32, sb);
+      ptx::tmem_wait_ld();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive_s(ptx::smem_u32(&s_free[u & 1]));  // the only read of S: the buffer may take the next-but-one unit's projection
+      if (nv < 64) {  // keys beyond the sequence end: score -inf, probability 0
+        if (nv < 32) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (e >= nv) sa[e] = 0xff800000u;
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (32 + e >= nv) sb[e] = 0xff800000u;
+      }
+#ifdef AVB_DATTN_DEBUG
+      if (g_dattn_dbg && blockIdx.x == 0 && u < 8) {
+        const int r = q * 32 + lane;
+        for (int t = 0; t < 32; ++t) {
+          g_dattn_dbg[(size_t)8 * 128 * 96 + ((size_t)u * 128 + r) * 128 + half * 64 + t] = __uint_as_float(sa[t]);
+          g_dattn_dbg[(size_t)8 * 128 * 96 + ((size_t)u * 128 + r) * 128 + half * 64 + 32 + t] = __uint_as_float(sb[t]);
+        }
+      }
+#endif
+      uint32_t pk[32];
+      exp_chunk32(sa, pk, pmax);
+      exp_chunk32(sb, pk + 16, pmax);
+      if (u >= 1) {  // P is free once the PV / L MMAs of the previous unit have finished
+        AVB_DA_WAIT(pv_done, (uint32_t)((u - 1) & 1), 95);
+        ptx::tc_fence_after();
+      }
+      ptx::tmem_st32(tPw, pk);
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive_s(a_pfull);
+    }
+    if (pmax > kAttnOverflowGuard) *guard = 1;  // a polynomial lane left the safe exponent range
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace avb

@@ -1150,6 +1150,16 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
       for (int c = 0; c < num_c; ++c, ++g) {
         // ---- E1: D1 -> +b1 -> ReLU -> bf16 pairs -> H
         const int hs = g & 1;
+#if AVB_FFN_DECOUPLE
+        // E2 of the previous tile goes FIRST when this tile's first D1 is not there yet (the issuer is waiting for the
+        // LayerNorm warps, which in turn wait for the D2 buffer E2 releases)
+        bool e2_early = false;
+        if (c == 0 && prev_mt >= 0 && !ptx::mbar_test_warp(&d1_full[g & 1], (uint32_t)((g >> 1) & 1))) {
+          e2_g = g;
+          E2(tile_it - 1, prev_mt);
+          e2_early = true;
+        }
+#endif
 #if AVB_FFN_E1_X64
         // A/B build: the warp's 64 D1 columns in ONE tcgen05.ld (one TMEM round trip instead of two serial ones); the
         // bias then comes from L1 (b1 is 2 KB and hot) instead of 64 preloaded registers
@@ -1178,16 +1188,6 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
 #pragma unroll
         for (int e = 0; e < 16; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bp) + e);
         AVB_TRACE(2, g, 0);
-#if AVB_FFN_DECOUPLE
-        // E2 of the previous tile goes FIRST when this tile's first D1 is not there yet (the issuer is waiting for the
-        // LayerNorm warps, which in turn wait for the D2 buffer E2 releases)
-        bool e2_early = false;
-        if (c == 0 && prev_mt >= 0 && !ptx::mbar_test_warp(&d1_full[g & 1], (uint32_t)((g >> 1) & 1))) {
-          e2_g = g;
-          E2(tile_it - 1, prev_mt);
-          e2_early = true;
-        }
-#endif
         ptx::mbar_wait(&d1_full[g & 1], (uint32_t)((g >> 1) & 1), 59);
         AVB_TRACE(2, g, 1);
         ptx::tc_fence_after();

@@ -104,8 +104,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_forward_timing(n_datasets, threads=None):
-    """Time the torch-CPU restated reference forward on `n_datasets` datasets of the bench workload."""
+def cpu_forward_timing(n_datasets, threads=None, x=None, return_probs=False):
+    """Time the torch-CPU restated reference forward on `n_datasets` datasets of the bench workload (or on the given
+    datasets x[B,n,d]); with return_probs also hand back the oracle's edge probabilities (the bench line's parity check)."""
     import torch
     from avici_b200.params import init_params
     from oracle import avici_oracle as O
@@ -117,12 +118,15 @@ def cpu_forward_timing(n_datasets, threads=None):
         avail = os.cpu_count() or 1
     torch.set_num_threads(threads or avail)
     P = OT.to_torch(init_params(MODEL_KW, seed=0, perturb=True))
-    x = torch.as_tensor(make_batch(n_datasets, 1000))
+    x = torch.as_tensor(make_batch(n_datasets, 1000) if x is None else x[:n_datasets])
+    probs = []
     with torch.no_grad():
         t0 = time.perf_counter()
         for b in range(n_datasets):
-            OT.forward_probs(P, x[b], None, O.DEFAULT_CFG)
+            probs.append(OT.forward_probs(P, x[b], None, O.DEFAULT_CFG))
         dt = time.perf_counter() - t0
+    if return_probs:
+        return n_datasets / dt, dt, torch.get_num_threads(), torch.stack(probs).numpy()
     return n_datasets / dt, dt, torch.get_num_threads()
 
 
@@ -243,7 +247,20 @@ def run_ours(args):
         ms_attn, cnt_attn = prof["attn_n"]
         achieved = attn_flops / (ms_attn / max(cnt_attn, 1) * 1e-3) / 1e12 if ms_attn > 0 else 0.0
         breakdown = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
-        cpu_val, cpu_dt, cores = cpu_forward_timing(1) if not args.no_cpu_baseline else (None, None, None)
+        # CPU leg: the oracle restatement on dataset 0 of this very batch, same weights -> timing AND parity of the benched
+        # configuration (fp32 torch-CPU oracle; its own distance to the fp64 oracle is < 2e-5, tests/test_oracle.py)
+        parity = None
+        if not args.no_cpu_baseline:
+            cpu_val, cpu_dt, cores, p_cpu = cpu_forward_timing(1, x=x_host, return_probs=True)
+            tol = 1e-2 if args.dtype == "bf16" else 1e-4
+            err = float(np.abs(p_pin.numpy()[0].astype(np.float64) - p_cpu[0]).max())
+            margin = np.abs(p_cpu[0] - 0.5) <= tol
+            parity = {"max_abs_dp": err, "tol": tol, "ok": bool(err <= tol),
+                      "graph_equal_outside_margin": bool(np.array_equal((p_pin.numpy()[0] > 0.5)[~margin], (p_cpu[0] > 0.5)[~margin])),
+                      "what": "GPU probs (host-buffer call) vs the fp32 torch-CPU oracle on dataset 0 of the benched batch, "
+                              "same random-init weights (reference head init: temp 2, bias -3)"}
+        else:
+            cpu_val, cpu_dt, cores = None, None, None
         line = {
             "metric": "datasets/sec fwd @ n=1000,d=100", "value": value, "unit": "datasets/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
@@ -258,6 +275,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "datasets/s", "h2d_bytes_per_step": int(x_host.nbytes),
                     "d2h_bytes_per_step": int(B * N_VARS * N_VARS * 4), "steps": e2e_steps},
             "gpu_launches": launches,
+            "parity": parity,
             "clocks": clocks,
             "roofline": {"kernel": "attention_tc_kernel (attend over n)", "bound": "tensor", "achieved": achieved,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],

@@ -210,6 +210,21 @@ int avb_test_qkv_layout_bf16(const float* z_dev, const void* wt_bf16_dev, const 
 int avb_test_outproj_bf16(const void* attn_tokmajor_bf16_dev, const void* wot_bf16_dev, const float* bias_dev,
                           void* delta_bf16_dev, int32_t B, int32_t n, int32_t d, int32_t axis, void* stream);
 
+/* The fused d-axis attention sub-layer as the block runs it (dattn_tc_kernel, blocks that attend over d <= 128):
+ * delta[B*n*d,128] bf16 (token order) = MHA(LN_q(z), LN_k(z), LN_v(z)) . Wo + bo of block `block_idx` of the loaded
+ * weights, z[B*n*d,128] fp32.  fuse_out 0 runs the kernel up to the attention output and the out-projection as its
+ * own launch.  *guard_host (may be NULL) receives the fast softmax's range guard (0 = in range); reading it
+ * synchronises the stream. */
+int avb_test_dattn_bf16(avb_handle h, int32_t block_idx, const float* z_dev, int32_t B, int32_t n, int32_t d,
+                        int32_t fuse_out, void* delta_bf16_dev, int32_t* guard_host, void* stream);
+/* Which kernels run the attention half of a block that attends over d <= 128 (bf16 mode): 1 (default) the fully
+ * fused dattn_tc_kernel, 2 the same kernel up to the attention output + the separate out-projection, 0 the unfused
+ * QKV / attention / out-projection launches (what every other block uses).  A/B and test knob. */
+int avb_test_set_dattn_mode(avb_handle h, int32_t mode);
+/* Debug builds (-DAVB_DATTN_DEBUG) only: device buffer of 278528 floats that CTA 0 of dattn_tc_kernel fills with the
+ * intermediates of its first sequence (NULL switches the dump off); AVB_ERR_INVALID in production builds. */
+int avb_debug_set_dattn_dump(void* dump_dev);
+
 /* Debug: device buffer of 3*4096 int64 that block 0 of the attention kernel fills with clock64() stamps of
  * its producer / MMA / softmax roles (NULL switches tracing off). */
 int avb_debug_set_trace(void* trace_dev);

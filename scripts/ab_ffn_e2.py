@@ -1,6 +1,6 @@
-"""One-process A/B of two builds of the FFN pair kernel through the avb_test_ffn_bf16 hook: the default library against
-an experimental one (path in argv[1]).  Both must produce bit-identical z (same arithmetic, different store path);
-prints the time of each."""
+"""One-process A/B of builds of the FFN pair kernel through the avb_test_ffn_bf16 hook: the default library against
+experimental ones (paths in argv[1:]).  All must produce bit-identical z (same arithmetic, different schedule / store
+path); prints the time of each."""
 import ctypes as C
 import sys
 
@@ -9,10 +9,13 @@ import torch
 sys.path.insert(0, ".")
 from avici_b200 import _lib
 
-libs = {"default": _lib.load(), "experimental": C.CDLL(sys.argv[1])}
+libs = {"default": _lib.load()}
 res, args = _lib.SIGNATURES["avb_test_ffn_bf16"]
-libs["experimental"].avb_test_ffn_bf16.restype = res
-libs["experimental"].avb_test_ffn_bf16.argtypes = args
+for path in sys.argv[1:]:
+    lib = C.CDLL(path)
+    lib.avb_test_ffn_bf16.restype = res
+    lib.avb_test_ffn_bf16.argtypes = args
+    libs[path.split("/")[-1]] = lib
 M, F = 1600077, 512
 g = torch.Generator(device="cuda").manual_seed(0)
 z0 = torch.randn(M, 128, device="cuda", generator=g)
@@ -22,19 +25,21 @@ b1 = torch.randn(F, device="cuda", generator=g)
 b2 = torch.randn(128, device="cuda", generator=g)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 outs = {}
-for name, lib in libs.items():
-    times = []
-    for rep in range(4):
-        z = z0.clone()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        rc = lib.avb_test_ffn_bf16(z.data_ptr(), w1t.data_ptr(), w2t.data_ptr(), b1.data_ptr(), b2.data_ptr(), M, F, st)
-        e1.record()
-        torch.cuda.synchronize()
-        assert rc == 0, rc
-        times.append(e0.elapsed_time(e1))
-    outs[name] = z
-    print(f"{name}: {min(times[1:]):.3f} ms (runs {[round(t, 3) for t in times]})")
-same = torch.equal(outs["default"], outs["experimental"])
-print("bit-identical:", same, " max|diff|", float((outs["default"] - outs["experimental"]).abs().max()),
-      " finite:", bool(torch.isfinite(outs["experimental"]).all()))
+for rnd in range(2):  # two rounds over all libraries: clocks drift, the second round is the one to read
+    for name, lib in libs.items():
+        times = []
+        for rep in range(4):
+            z = z0.clone()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = lib.avb_test_ffn_bf16(z.data_ptr(), w1t.data_ptr(), w2t.data_ptr(), b1.data_ptr(), b2.data_ptr(), M, F, st)
+            e1.record()
+            torch.cuda.synchronize()
+            assert rc == 0, rc
+            times.append(e0.elapsed_time(e1))
+        outs[name] = z
+        print(f"round {rnd} {name}: {min(times[1:]):.3f} ms (runs {[round(t, 3) for t in times]})", flush=True)
+for name in libs:
+    same = torch.equal(outs["default"], outs[name])
+    print(name, "bit-identical:", same, " max|diff|", float((outs["default"] - outs[name]).abs().max()),
+          " finite:", bool(torch.isfinite(outs[name]).all()))
