@@ -166,7 +166,8 @@ def test_load_pretrained_argument_errors(tmp_path):
         avici_b200.load_pretrained(download="scm-v0", cache_path=str(tmp_path), verbose=False)
 
 
-@pytest.mark.parametrize("domain", ["lin-gauss", "rff-gauss", "gene-ecoli"])
+@pytest.mark.parametrize("domain", ["lin-gauss", "lin-gauss-heterosked", "lin-laplace-cauchy", "rff-gauss",
+                                    "rff-gauss-heterosked", "rff-laplace-cauchy", "gene-ecoli"])
 def test_simulate_data_contract(domain):
     g, x, interv = avici_b200.simulate_data(d=15, n=40, n_interv=10, seed=0, domain=domain)
     assert g.shape == (15, 15) and g.dtype.kind == "i" and x.shape == (50, 15) and interv.shape == (50, 15)
@@ -178,6 +179,45 @@ def test_simulate_data_contract(domain):
         assert np.all(x >= 0) and np.allclose(np.mod(x, 1), 0) and (x == 0).mean() > 0.02
     _, x3, _ = avici_b200.simulate_data(d=15, n=40, seed=0, domain=domain)
     assert np.array_equal(x2, x3)
+
+
+def test_simulate_data_graph_families_and_yaml_path(tmp_path):
+    """Every graph prior of the example domains gives a DAG with the requested size; a YAML domain file in the
+    reference's DSL (`path=`, example.py:44-47) with option lists and a custom class from `module_paths` loads."""
+    from avici_b200 import synthetic as S
+    rng = np.random.default_rng(0)
+    for gm in (S.ErdosRenyi(2), S.ScaleFree(2, 1.5), S.ScaleFreeTranspose(2, 0.5), S.WattsStrogatz(2, 1, 0.3),
+               S.WattsStrogatz(3, 1, 0.3), S.SBM(2, 5, 0.1), S.GRG(0.1)):
+        for d in (2, 7, 30, 100):
+            g = gm(rng, d)
+            assert g.shape == (d, d) and set(np.unique(g)) <= {0, 1}
+            assert len(S._toporder(g)) == d
+    specs = S.load_data_config(S.EXAMPLE_DOMAINS["lin-laplace-cauchy"], force_kwargs=dict(n_observations_obs=5, n_observations_int=0))
+    assert len(specs) == 11 * 2 and all(sp["n_observations_obs"] == 5 for sp in specs)  # 11 graph options x {Cauchy, Laplace}
+    (tmp_path / "mymod.py").write_text(
+        "import numpy as np\n"
+        "class Chain:\n"
+        "    def __init__(self, flip=False):\n        self.flip = flip\n"
+        "    def __call__(self, rng, n_vars):\n"
+        "        g = np.eye(n_vars, k=1, dtype=int)\n        return g.T.copy() if self.flip else g\n")
+    (tmp_path / "dom.yaml").write_text(
+        "---\ndata:\n  - n_observations_obs: null\n    n_observations_int: null\n"
+        "    graph:\n      - __class__: Chain\n        flip: [ false ]\n"
+        "    mechanism:\n      - __class__: LinearAdditive\n"
+        "        param:\n          - __class__: SignedUniform\n            low: 1.0\n            high: 2.0\n"
+        "        bias:\n          - __class__: Uniform\n            low: -1.0\n            high: 1.0\n"
+        "        noise:\n          - __class__: Gaussian\n          - __class__: Laplace\n"
+        "        noise_scale:\n          - __class__: Uniform\n            low: 0.5\n            high: 1.0\n"
+        "        n_interv_vars: -1\n        interv_dist:\n          - __class__: SignedUniform\n            low: 1.0\n            high: 5.0\n")
+    g, x, iv = avici_b200.simulate_data(d=6, n=20, n_interv=12, seed=3, path=str(tmp_path / "dom.yaml"),
+                                        module_paths=str(tmp_path / "mymod.py"))
+    assert np.array_equal(g, np.eye(6, k=1, dtype=int)) and x.shape == (32, 6) and iv.sum() == 12
+    with pytest.raises(SyntaxError):
+        avici_b200.simulate_data(d=6, n=20, seed=3, path=str(tmp_path / "dom.yaml"))  # Chain is not registered
+    with pytest.raises(KeyError):
+        avici_b200.simulate_data(d=6, n=20, seed=3, domain="no-such-domain")
+    with pytest.raises(KeyError):
+        avici_b200.simulate_data(d=6, n=20, seed=3)
 
 
 def test_wrapper_validation_matches_reference_asserts():
