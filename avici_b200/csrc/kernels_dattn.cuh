@@ -28,12 +28,17 @@
 // copies (192 KB per sequence; the L2 -> SM path, not HBM, carries them).
 //
 // TMEM (512 columns): SBUF0 | SBUF1 (128 each: the QKV accumulator of a unit, then its S tile) | P 64 | O 32 | L 16 |
-// 16 spare | DELTA 128.  Software pipeline of the single MMA-issuing thread, iteration u:
-//     PV_{u-1}, S_{u+1}, G_{u+2}, OP_{u-1}
-// so that the tensor core computes the next units' projections and scores while the 8 softmax warps (the MUFU-bound
-// stage) work on unit u.
-//   warp 0: weight producer   warp 1: MMA issuer   warp 2: TMEM alloc   warps 4-7: LayerNorm
-//   warps 8-11: conv / Oepi / Depi (TMEM lane quarter = warp & 3)   warps 12-19: softmax (lane quarter x column half)
+// 16 spare | DELTA 128.  Software pipeline, while the 8 softmax warps (the MUFU-bound stage) work on unit u:
+//     attention issuer:  PV_{u-1}, S_{u+1}          projection issuer:  G_{u+2}, OP_{u-1}
+// Two issuing warps because each MMA group waits on a different producer (softmax, conv, LayerNorm + weight ring,
+// Oepi): one thread blocking on them in turn serialised everything (r2b trace: 3550 clocks per unit).  What the
+// tensor pipe's in-order execution used to guarantee between the two groups is now explicit: conv_u waits for
+// S_{u-1} before it overwrites the single-buffered Q / K tiles, Oepi_u waits for OP_{u-2} before it reuses an O tile.
+// Measured cost of an M = 128, K = 16 tcgen05.mma on B200 (scripts/microbench_mma.cu): ~42 + N/2 clocks with A in
+// shared memory, ~10 + N/2 with A in TMEM - per unit G 8 x 89, S 2 x 97, PV 7 x 26, L 7 x 18, OP 2 x 105 = 1420 clocks.
+//   warp 0: weight producer   warp 1: attention MMA issuer   warp 2: TMEM alloc   warp 3: projection MMA issuer
+//   warps 4-7: LayerNorm      warps 8-11: conv / Oepi / Depi (TMEM lane quarter = warp & 3)
+//   warps 12-19: softmax (lane quarter x column half)
 #pragma once
 #include "kernels_tc.cuh"
 
@@ -54,7 +59,8 @@ struct DaCfg {
   static constexpr int kOBufs = kFuseOut ? 2 : 0;
   static constexpr int kDataBytes =
       2 * kDaXBytes + kWStages * kDaWkbBytes + kWoBytes + (2 + kDaVBufs + kOBufs) * kDaTileBytes;
-  static constexpr int kSmemBytes = kDataBytes + 1024 /*barriers, TMEM slot, ones tile*/ + 1024 /*alignment slack*/;
+  static constexpr int kBiasBytes = (3 * kDaHeads * 32 + 128) * 4;  // bqkv | bo as fp32, read as shared-memory broadcasts
+  static constexpr int kSmemBytes = kDataBytes + 1024 /*barriers, TMEM slot, ones tile*/ + kBiasBytes + 1024 /*alignment slack*/;
 };
 static_assert(DaCfg<true>::kSmemBytes <= 232448, "dattn_tc_kernel: shared memory over the sm_100 limit");
 
@@ -109,13 +115,19 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
   uint64_t* d_full = pv_done + 1;          // commit
   uint64_t* d_free = d_full + 1;           // 128 conv threads
   uint64_t* wo_full = d_free + 1;          // tx
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wo_full + 1);
+  uint64_t* op_done = wo_full + 1;         // [2] commit: OP of a unit has read its O tile (kFuseOut)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(op_done + 2);
   uint32_t* s_ones = reinterpret_cast<uint32_t*>(smem + Cfg::kDataBytes + 512);  // 512 B of bf16 1.0
+  // Biases live in shared memory: a __ldg from the epilogue warps queues in the L1 pipeline behind the LayerNorm warps'
+  // row loads (L2 latency each), which ncu showed as ~500 clocks of long-scoreboard stall per 32-column chunk.
+  float* s_bias = reinterpret_cast<float*>(smem + Cfg::kDataBytes + 1024);       // [768] bqkv | [128] bo
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int nseq = (int)blockIdx.x < S ? (S - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int U = nseq * kDaHeads;
   const int kc = (T + 15) & ~15;  // key columns the MMAs touch
+  // trace builds (-DAVB_TRACE_ENABLE, scripts/trace_dattn.py): CTA 0 stamps clock64() per role and unit
+  long long* trace = (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 3 || warp == 4 || warp == 8 || warp == 12)) ? g_attn_trace : nullptr;
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -128,6 +140,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     ptx::mbar_init(p_full, 256); ptx::mbar_init(pv_done, 1);
     ptx::mbar_init(d_full, 1);   ptx::mbar_init(d_free, 128);
     ptx::mbar_init(wo_full, 1);
+    ptx::mbar_init(&op_done[0], 1); ptx::mbar_init(&op_done[1], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -135,6 +148,8 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     ptx::tmem_relinquish();
   }
   if (threadIdx.x >= 128 && threadIdx.x < 256) s_ones[threadIdx.x - 128] = 0x3F803F80u;
+  for (int i = threadIdx.x; i < 3 * kDaHeads * 32 + 128; i += kDaThreads)
+    s_bias[i] = i < 3 * kDaHeads * 32 ? bqkv[i] : bo[i - 3 * kDaHeads * 32];
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();
@@ -159,7 +174,9 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     }
     for (int kbi = 0; kbi < 2 * U; ++kbi) {
       const int st = kbi % NS;
+      AVB_TRACE(0, kbi, 0);
       ptx::mbar_wait(&w_empty[st], (uint32_t)((kbi / NS) & 1) ^ 1, 80, 100u);
+      AVB_TRACE(0, kbi, 1);
       if (ptx::elect_one()) {
         ptx::mbar_expect_tx(&w_full[st], kDaWkbBytes);
         ptx::bulk_load_hint(sW + st * kDaWkbBytes, wqkv_img + (size_t)((kbi >> 1) & 7) * (2 * kDaWkbBytes) + (kbi & 1) * kDaWkbBytes,
@@ -168,27 +185,75 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       __syncwarp();
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer
+    // ======================= attention MMA issuer: scores S_u = Q K^T, then O = P V and L = P 1
+    // (The projection MMAs G / OP have their own issuing warp: a single issuer blocked on one of its four barrier
+    //  kinds held back the other three - trace r2b: 3550 clocks per unit with the tensor pipe idle most of the time.)
     if (U > 0) {
-      constexpr uint32_t idesc_g = ptx::make_idesc_bf16(128, 96, 0, 0);
       constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, 32, 0, 1);  // B = V is MN-major
       constexpr uint32_t idesc_l = ptx::make_idesc_bf16(128, 16, 0, 0);
-      constexpr uint32_t idesc_op = ptx::make_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_s = ptx::make_idesc_bf16(128, kc, 0, 0);
       const int ksteps = kc >> 4;
-      const uint64_t dX0 = ptx::make_smem_desc(ptx::smem_u32(sX), 16, 1024, ptx::kSwz128);
-      const uint64_t dW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024, ptx::kSwz128);
       const uint64_t dQ = ptx::make_smem_desc(ptx::smem_u32(sQ), 16, 512, ptx::kSwz64);
       const uint64_t dK = ptx::make_smem_desc(ptx::smem_u32(sK), 16, 512, ptx::kSwz64);
       const uint64_t dV0 = ptx::make_smem_desc(ptx::smem_u32(sV), 16, 512, ptx::kSwz64);
+      const uint64_t d_ones = ptx::make_smem_desc(ptx::smem_u32(s_ones), 128, 256, ptx::kSwzNone);
+      auto issue_S = [&](int u) {  // scores of unit u into SBUF[u & 1] (over the QKV accumulator conv_u has consumed)
+        ptx::mbar_wait(&qkv_ready[u & 1], (uint32_t)((u >> 1) & 1), 84, 40u);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(u & 1) * 128u;
+          ptx::umma_bf16(d_tmem, dQ, dK, idesc_s, 0);
+          ptx::umma_bf16(d_tmem, dQ + 2, dK + 2, idesc_s, 1);
+          ptx::umma_commit(&s_full[u & 1]);
+        }
+        __syncwarp();
+      };
+      auto issue_PV = [&](int u) {
+        ptx::mbar_wait(p_full, (uint32_t)(u & 1), 85, 40u);
+        if (u >= 1) ptx::mbar_wait(&o_ready[(u - 1) & 1], (uint32_t)(((u - 1) >> 1) & 1), 86, 40u);  // O of unit u-1 has been read
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t dv = dV0 + (uint64_t)((u % kDaVBufs) * (kDaTileBytes >> 4));
+          if (ksteps == 7) {  // T in 97..112 (d = 100): fully unrolled
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+              ptx::umma_bf16_ts(tO, tP + k * 8, dv + (uint64_t)(k * 64), idesc_pv, k != 0);
+              ptx::umma_bf16_ts(tL, tP + k * 8, d_ones, idesc_l, k != 0);
+            }
+          } else {
+            for (int k = 0; k < ksteps; ++k) {
+              ptx::umma_bf16_ts(tO, tP + k * 8, dv + (uint64_t)(k * 64), idesc_pv, k != 0);
+              ptx::umma_bf16_ts(tL, tP + k * 8, d_ones, idesc_l, k != 0);
+            }
+          }
+          ptx::umma_commit(pv_done);
+        }
+        __syncwarp();
+      };
+      issue_S(0);
+      for (int u = 0; u < U; ++u) {
+        AVB_TRACE(1, u, 0);
+        if (u >= 1) issue_PV(u - 1);
+        AVB_TRACE(1, u, 1);
+        if (u + 1 < U) issue_S(u + 1);
+        AVB_TRACE(1, u, 2);
+      }
+      issue_PV(U - 1);
+    }
+  } else if (warp == 3) {
+    // ======================= projection MMA issuer: G_u = xhat Wqkv_h^T two units ahead, DELTA += O_h Wo_h^T one behind
+    if (U > 0) {
+      constexpr uint32_t idesc_g = ptx::make_idesc_bf16(128, 96, 0, 0);
+      constexpr uint32_t idesc_op = ptx::make_idesc_bf16(128, 128, 0, 0);
+      const uint64_t dX0 = ptx::make_smem_desc(ptx::smem_u32(sX), 16, 1024, ptx::kSwz128);
+      const uint64_t dW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024, ptx::kSwz128);
       const uint64_t dO0 = ptx::make_smem_desc(ptx::smem_u32(sO), 16, 512, ptx::kSwz64);
       const uint64_t dWo0 = ptx::make_smem_desc(ptx::smem_u32(sWo), 16, 512, ptx::kSwz64);
-      const uint64_t d_ones = ptx::make_smem_desc(ptx::smem_u32(s_ones), 128, 256, ptx::kSwzNone);
-
       auto issue_G = [&](int u) {  // QKV projection of unit u into SBUF[u & 1]
         const int si = u >> 3, h = u & 7, buf = si & 1;
         if (h == 0) ptx::mbar_wait(&x_full[buf], (uint32_t)((si >> 1) & 1), 81, 40u);
         if (u >= 2) ptx::mbar_wait(&s_free[u & 1], (uint32_t)(((u >> 1) - 1) & 1), 82, 40u);  // softmax of unit u-2 has read S
+        AVB_TRACE(5, (u >= 2 ? u - 2 : 499), 5);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(u & 1) * 128u;
         for (int kb = 0; kb < 2; ++kb) {
@@ -210,31 +275,6 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
           __syncwarp();
         }
       };
-      auto issue_S = [&](int u) {  // scores of unit u into SBUF[u & 1] (over the QKV accumulator conv_u has consumed)
-        ptx::mbar_wait(&qkv_ready[u & 1], (uint32_t)((u >> 1) & 1), 84, 40u);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(u & 1) * 128u;
-          ptx::umma_bf16(d_tmem, dQ, dK, idesc_s, 0);
-          ptx::umma_bf16(d_tmem, dQ + 2, dK + 2, idesc_s, 1);
-          ptx::umma_commit(&s_full[u & 1]);
-        }
-        __syncwarp();
-      };
-      auto issue_PV = [&](int u) {
-        ptx::mbar_wait(p_full, (uint32_t)(u & 1), 85, 40u);
-        if (u >= 1) ptx::mbar_wait(&o_ready[(u - 1) & 1], (uint32_t)(((u - 1) >> 1) & 1), 86, 40u);  // O of unit u-1 has been read
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint64_t dv = dV0 + (uint64_t)((u % kDaVBufs) * (kDaTileBytes >> 4));
-          for (int k = 0; k < ksteps; ++k) {
-            ptx::umma_bf16_ts(tO, tP + k * 8, dv + (uint64_t)(k * 64), idesc_pv, k != 0);
-            ptx::umma_bf16_ts(tL, tP + k * 8, d_ones, idesc_l, k != 0);
-          }
-          ptx::umma_commit(pv_done);
-        }
-        __syncwarp();
-      };
       auto issue_OP = [&](int u) {  // DELTA (+)= O_h . Wo_h^T
         const int si = u >> 3, h = u & 7;
         ptx::mbar_wait(&o_ready[u & 1], (uint32_t)((u >> 1) & 1), 87, 40u);
@@ -245,22 +285,21 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
           const uint64_t db = dWo0 + (uint64_t)(h * (kDaWoHeadBytes >> 4));
           ptx::umma_bf16(tD, da, db, idesc_op, h != 0);
           ptx::umma_bf16(tD, da + 2, db + 2, idesc_op, 1);
+          ptx::umma_commit(&op_done[u & 1]);  // the O tile of unit u may be overwritten (oepi of unit u + 2)
           if (h == 7) ptx::umma_commit(d_full);
         }
         __syncwarp();
       };
-
       if (kFuseOut) ptx::mbar_wait(wo_full, 0, 89, 40u);
       issue_G(0);
-      issue_S(0);  // before G_1: conv_1 may only overwrite the Q / K tiles once S_0 has been issued
       if (U > 1) issue_G(1);
       for (int u = 0; u < U; ++u) {
-        if (u >= 1) issue_PV(u - 1);
-        if (u + 1 < U) issue_S(u + 1);
+        AVB_TRACE(5, u, 0);
         if (u + 2 < U) issue_G(u + 2);
+        AVB_TRACE(5, u, 1);
         if (kFuseOut && u >= 1) issue_OP(u - 1);
+        AVB_TRACE(5, u, 2);
       }
-      issue_PV(U - 1);
       if (kFuseOut) issue_OP(U - 1);
     }
   }
@@ -272,10 +311,13 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       const int s = (int)blockIdx.x + si * (int)gridDim.x, buf = si & 1;
       const float* zs = z + (size_t)s * T * 128;
       if (si + 2 < nseq) prefetch_rows_l2(z + (size_t)(s + 2 * (int)gridDim.x) * T * 128, T, w * 32, lane);
+      AVB_TRACE(4, si, 0);
       ptx::mbar_wait(&x_empty[buf], (uint32_t)((si >> 1) & 1) ^ 1, 90);
+      AVB_TRACE(4, si, 1);
       ln_warp_rows_to_umma_tile(zs, T, w * 32, ptx::smem_u32(sX + buf * kDaXBytes), w * 32, lane);
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&x_full[buf]);
+      AVB_TRACE(4, si, 2);
     }
   } else if (warp < 12) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
@@ -288,16 +330,19 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     auto conv = [&](int u) {  // QKV accumulator -> + bias -> bf16 -> Q / K / V tiles
       const int h = u & 7;
       ptx::mbar_wait(&g_full[u & 1], (uint32_t)((u >> 1) & 1), 91);
+      // the Q / K tiles are single-buffered: S of the previous unit (issued by another warp than G) must have read them
+      if (u >= 1) ptx::mbar_wait(&s_full[(u - 1) & 1], (uint32_t)(((u - 1) >> 1) & 1), 96);
+      AVB_TRACE(2, (u >= 2 ? u - 2 : 499), 2);
       ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(u & 1) * 128u + lane_off;
 #pragma unroll
       for (int w = 0; w < 3; ++w) {
-        float4 bb[8];
-        const float* bp = bqkv + w * 256 + h * 32;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bp) + e);
         uint32_t v[32];
         ptx::tmem_ld32(tacc + w * 32, v);
+        float4 bb[8];
+        const float4* bp = reinterpret_cast<const float4*>(s_bias + w * 256 + h * 32);  // shared-memory broadcast
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bb[e] = bp[e];
         ptx::tmem_wait_ld();
         const uint32_t tile = w == 0 ? aQ : (w == 1 ? aK : aV + (uint32_t)((u % kDaVBufs) * kDaTileBytes));
 #pragma unroll
@@ -324,6 +369,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     auto oepi = [&](int u) {  // O / L -> bf16 -> A tile of the out-projection (or the attention output in HBM)
       const int h = u & 7;
       ptx::mbar_wait(pv_done, (uint32_t)(u & 1), 92);
+      AVB_TRACE(2, u + 1, 5);
       ptx::tc_fence_after();
       uint32_t o[32];
       ptx::tmem_ld32(tO + lane_off, o);
@@ -344,6 +390,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         for (int t = 0; t < 32; ++t) g_dattn_dbg[(size_t)8 * 128 * 96 + 8 * 128 * 128 + ((size_t)u * 128 + r) * 32 + t] = __uint_as_float(o[t]) * inv;
 #endif
       if constexpr (kFuseOut) {
+        if (u >= 2) ptx::mbar_wait(&op_done[u & 1], (uint32_t)(((u >> 1) - 1) & 1), 97);  // OP of unit u-2 has read this O tile
         const uint32_t tile = aO + (uint32_t)((u & 1) * kDaTileBytes);
 #pragma unroll
         for (int e = 0; e < 4; ++e) ptx::st_shared_v4(tile + row_off + (((uint32_t)e ^ swz) << 4), pk[e]);
@@ -368,11 +415,11 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       __nv_bfloat16* drow = out + ((size_t)s * T + r) * 128;
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
-        float4 bb[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bo + cc * 32) + e);
         uint32_t v[32];
         ptx::tmem_ld32(tD + cc * 32 + lane_off, v);
+        float4 bb[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bb[e] = reinterpret_cast<const float4*>(s_bias + 3 * kDaHeads * 32 + cc * 32)[e];
         ptx::tmem_wait_ld();
         if (cc == 3) {
           ptx::tc_fence_before();
@@ -402,9 +449,13 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       conv(0);
       if (U > 1) conv(1);
       for (int u = 0; u < U; ++u) {
+        AVB_TRACE(2, u, 0);
         if (u >= 1) oepi(u - 1);
+        AVB_TRACE(2, u, 1);
         if (u + 2 < U) conv(u + 2);
+        AVB_TRACE(2, u, 3);
         if (kFuseOut && u >= 1 && ((u - 1) & 7) == 7) depi((u - 1) >> 3);
+        AVB_TRACE(2, u, 4);
       }
       oepi(U - 1);
       if (kFuseOut) depi((U - 1) >> 3);
@@ -419,7 +470,9 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     const int nv = T - half * 64;  // valid key columns in this warp's half (may be <= 0)
     float pmax = -INFINITY;
     for (int u = 0; u < U; ++u) {
+      AVB_TRACE(3, u, 0);
       AVB_DA_WAIT(&s_full[u & 1], (uint32_t)((u >> 1) & 1), 94);
+      AVB_TRACE(3, u, 1);
       ptx::tc_fence_after();
       const uint32_t tS = tmem_base + (uint32_t)(u & 1) * 128u + half * 64 + lane_off;
       uint32_t sa[32], sb[32];
@@ -428,6 +481,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       ptx::tmem_wait_ld();
       ptx::tc_fence_before();
       ptx::mbar_arrive_s(ptx::smem_u32(&s_free[u & 1]));  // the only read of S: the buffer may take the next-but-one unit's projection
+      AVB_TRACE(3, u, 2);
       if (nv < 64) {  // keys beyond the sequence end: score -inf, probability 0
         if (nv < 32) {
 #pragma unroll
@@ -450,14 +504,17 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       uint32_t pk[32];
       exp_chunk32(sa, pk, pmax);
       exp_chunk32(sb, pk + 16, pmax);
+      AVB_TRACE(3, u, 3);
       if (u >= 1) {  // P is free once the PV / L MMAs of the previous unit have finished
         AVB_DA_WAIT(pv_done, (uint32_t)((u - 1) & 1), 95);
         ptx::tc_fence_after();
       }
+      AVB_TRACE(3, u, 4);
       ptx::tmem_st32(tPw, pk);
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
       ptx::mbar_arrive_s(a_pfull);
+      AVB_TRACE(3, u, 5);
     }
     if (pmax > kAttnOverflowGuard) *guard = 1;  // a polynomial lane left the safe exponent range
   }

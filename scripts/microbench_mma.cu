@@ -23,11 +23,17 @@ __global__ void mma_bench(int N, int naccum, int iters, int a_mode, long long* c
     const uint64_t da = ptx::make_smem_desc(ptx::smem_u32(smem), 16, 1024, ptx::kSwz128);
     const uint64_t db = ptx::make_smem_desc(ptx::smem_u32(smem) + 32768, 16, 1024, ptx::kSwz128);
     long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) {
-      const uint32_t d = tmem + (uint32_t)(i & (naccum - 1)) * 64;
-      const uint64_t a = da + (uint64_t)((i & 3) * 2);
-      if (ptx::elect_one()) ptx::umma_bf16(d, a, db + (uint64_t)((i & 3) * 2), idesc, 1);
+    if (ptx::elect_one()) {  // back-to-back issue from one thread, as the kernels do: 8 MMAs per loop trip, fully unrolled
+      for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t d = tmem + (uint32_t)(j & (naccum - 1)) * 64;
+          if (a_mode == 0) ptx::umma_bf16(d, da + (uint64_t)((j & 3) * 2), db + (uint64_t)((j & 3) * 2), idesc, 1);
+          else ptx::umma_bf16_ts(d, tmem + 448 + (uint32_t)((j & 3) * 8), db + (uint64_t)((j & 3) * 2), idesc, 1);  // A from TMEM
+        }
+      }
     }
+    __syncwarp();
     if (ptx::elect_one()) ptx::umma_commit(&bar);
     ptx::mbar_wait(&bar, 0);
     if ((threadIdx.x & 31) == 0) cycles[blockIdx.x] = clock64() - t0;
@@ -41,14 +47,16 @@ int main() {
   long long h[148];
   cudaFuncSetAttribute(mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
   const int iters = 4096;
+  for (int a_mode : {0, 1})
   for (int naccum : {1, 2, 4})
-    for (int N : {16, 32, 48, 64, 128, 256}) {
+    for (int N : {16, 32, 48, 64, 96, 128, 256}) {
       if (naccum * 64 < N && naccum > 1 && N > 64) continue;
-      mma_bench<<<148, 64, 65536>>>(N, naccum, iters, 0, cyc);
+      if (a_mode == 1 && N > 64 && naccum > 1) continue;
+      mma_bench<<<148, 64, 65536>>>(N, naccum, iters, a_mode, cyc);
       cudaError_t e = cudaDeviceSynchronize();
       cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
-      printf("M=128 N=%3d K=16, %d accumulator(s): %.1f cycles/MMA (ideal N/2 = %d) (%s)\n", N, naccum, (double)h[0] / iters, N / 2,
-             cudaGetErrorString(e));
+      printf("%s M=128 N=%3d K=16, %d accumulator(s): %.1f cycles/MMA (ideal N/2 = %d) (%s)\n", a_mode ? "A=tmem" : "A=smem", N, naccum,
+             (double)h[0] / iters, N / 2, cudaGetErrorString(e));
     }
   return 0;
 }

@@ -1,0 +1,67 @@
+"""Timeline of dattn_tc_kernel's roles (CTA 0) from in-kernel clock64 stamps; needs a -DAVB_TRACE_ENABLE build
+(AVB_LIB=<that build>).  Prints per-role event offsets for a window of units and the mean unit period."""
+import ctypes as C
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+import avici_b200
+
+B, n, d = 1, int(sys.argv[1]) if len(sys.argv) > 1 else 16000, int(sys.argv[2]) if len(sys.argv) > 2 else 100
+fuse_out = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+model = avici_b200.random_init_model(dict(layers=1), seed=3, perturb=True, compute_dtype="bf16")
+eng = model.engine
+lib = eng.lib
+g = torch.Generator(device="cuda").manual_seed(1)
+z = torch.randn(B, n, d, 128, device="cuda", generator=g)
+delta = torch.zeros(B * n * d, 128, device="cuda", dtype=torch.bfloat16)
+guard = C.c_int32(-1)
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+trace = torch.zeros(6 * 4096, dtype=torch.int64, device="cuda")
+for rep in range(3):
+    if rep == 2:
+        lib.avb_debug_set_trace(C.c_void_p(trace.data_ptr()))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = lib.avb_test_dattn_bf16(eng.handle, 0, z.data_ptr(), B, n, d, fuse_out, delta.data_ptr(), None, st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"dattn S={B * n} T={d} fuse_out={fuse_out}: rc {rc} {ms:.3f} ms = {ms * 1e3 / (B * n) * 148:.2f} us per sequence per SM")
+lib.avb_debug_set_trace(None)
+t = trace.cpu().numpy().reshape(6, 512, 8)
+if t.max() == 0:
+    print("no stamps: not a -DAVB_TRACE_ENABLE build")
+    sys.exit(0)
+t0 = t[t > 0].min()
+names = {0: ["top", "w_empty"], 1: ["top", "PV(u-1)", "S(u+1)"], 5: ["top", "G(u+2)", "OP(u-1)", "-", "-", "G:s_free"],
+         2: ["top", "oepi(u-1)", "conv:g_full", "conv(u+2)", "depi", "oepi:pv_done"],
+         3: ["top", "s_full", "ld+free", "exp", "pv_done", "st+p_full"], 4: ["top", "x_empty", "ln_done"]}
+lo = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+for role, rn in ((1, "attn issuer"), (5, "proj issuer"), (2, "conv"), (3, "softmax"), (4, "layernorm"), (0, "producer")):
+    print(f"== {rn}: {names[role]}")
+    rng = range(lo // 8, lo // 8 + 4) if role == 4 else (range(2 * lo, 2 * lo + 16) if role == 0 else range(lo, lo + 12))
+    for step in rng:
+        row = t[role, step, :len(names[role])].astype(np.int64)
+        if row.max() == 0:
+            continue
+        rel = np.where(row > 0, row - t0, -1)
+        print(f" step {step:3d} ", rel.tolist(), " next_in", int(t[role, step + 1, 0] - row[0]))
+for role, rn in ((1, "attn issuer"), (3, "softmax")):
+    tops = t[role, 16:400, 0].astype(np.int64)
+    tops = tops[tops > 0]
+    if len(tops) > 1:
+        print(f"{rn}: mean unit period {(tops[-1] - tops[0]) / (len(tops) - 1):.0f} clocks over {len(tops)} units")
+sm = t[3, 16:400]
+ok = (sm[:, 0] > 0) & (sm[:, 5] > 0)
+for a, b, nm in ((0, 1, "wait s_full"), (1, 2, "tmem ld"), (2, 3, "exps"), (3, 4, "wait pv_done"), (4, 5, "tmem st")):
+    print(f"softmax {nm}: mean {(sm[ok, b] - sm[ok, a]).mean():.0f} clocks")
+cv = t[2, 16:400].astype(np.int64)
+ok = (cv[:, 0] > 0) & (cv[:, 4] > 0) & (cv[:, 2] > 0)
+print(f"conv warps: oepi {(cv[ok, 1] - cv[ok, 0]).mean():.0f}, wait g_full {(cv[ok, 2] - cv[ok, 1]).mean():.0f}, conv {(cv[ok, 3] - cv[ok, 2]).mean():.0f}, depi {(cv[ok, 4] - cv[ok, 3]).mean():.0f} clocks per unit")
+for role, nm, cols in ((1, "attn issuer", ((0, 1, "PV"), (1, 2, "S"))), (5, "proj issuer", ((0, 1, "G"), (1, 2, "OP")))):
+    m = t[role, 16:400].astype(np.int64)
+    ok = (m[:, 0] > 0) & (m[:, 2] > 0)
+    print(nm, ", ".join(f"{n} {(m[ok, b] - m[ok, a]).mean():.0f}" for a, b, n in cols))
