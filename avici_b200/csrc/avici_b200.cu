@@ -39,6 +39,7 @@ struct Block {
   // bf16 tensor-core copies: K-major [N,K], LayerNorm affine and softmax scale folded in
   const bf16 *wqkv_t, *wo_t, *w1_t, *w2_t;
   const float *bqkv_f, *b1_f;
+  const float *bo_d;  // dattn_tc_kernel: bo + bv' Wo (the value bias passes through the softmax average unchanged)
   // per-head operand images of dattn_tc_kernel: Wqkv_h as 2 K blocks of [96 x 64] (128B swizzle), Wo_h as [128 x 32] (64B swizzle)
   const uint8_t *wd_qkv, *wd_o;
   CUtensorMap tm_wqkv_h, tm_wo, tm_w1q, tm_w2q;  // wqkv: [128 x 64] boxes (CTA-pair QKV), wo: [128 x 64], w1 / w2: [64 x 64] (CTA-pair FFN)
@@ -334,10 +335,10 @@ int launch_dattn_tc(avb_handle h, const float* z, const Block& W, void* out, int
   const int grid = std::min(S, num_sms);
   if (fuse_out)
     avb::dattn_tc_kernel<true><<<grid, avb::kDaThreads, avb::DaCfg<true>::kSmemBytes, st>>>(
-        z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo, reinterpret_cast<bf16*>(out), S, T, guard);
+        z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo_d, reinterpret_cast<bf16*>(out), S, T, guard);
   else
     avb::dattn_tc_kernel<false><<<grid, avb::kDaThreads, avb::DaCfg<false>::kSmemBytes, st>>>(
-        z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo, reinterpret_cast<bf16*>(out), S, T, guard);
+        z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo_d, reinterpret_cast<bf16*>(out), S, T, guard);
   if (launches) ++*launches;
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "dattn_tc launch: %s", cudaGetErrorString(e));
@@ -549,7 +550,7 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
     return off;
   };
   struct BlockOff {
-    size_t ln_g[4], ln_b[4], wq, bq, wk, bk, wv, bv, wo, bo, w1, b1, w2, b2, bqkv_f, b1_f;
+    size_t ln_g[4], ln_b[4], wq, bq, wk, bk, wv, bv, wo, bo, w1, b1, w2, b2, bqkv_f, b1_f, bo_d;
     size_t wqkv_t, wo_t, w1_t, w2_t, wd_qkv, wd_o;
   };
   std::vector<BlockOff> offs(nb);
@@ -582,6 +583,7 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
     o.w2 = push_f32(w2, (size_t)F * k);  o.b2 = push_f32(b2, k);
     o.bqkv_f = push_f32(nullptr, 3 * HD);
     o.b1_f = push_f32(nullptr, F);
+    o.bo_d = push_f32(nullptr, k);
     if (!missing.empty()) continue;
     if (c.compute_dtype == AVB_DTYPE_BF16) {
       // LN(x) @ W + b = xhat @ (diag(gamma) W) + (beta @ W + b); q additionally carries log2e/sqrt(key)
@@ -600,8 +602,15 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
         }
       }
       o.wo_t = push_b16((size_t)k * HD);
-      for (int col = 0; col < k; ++col)
-        for (int r = 0; r < HD; ++r) b16[o.wo_t + (size_t)col * HD + r] = __float2bfloat16(wo[(size_t)r * k + col]);
+      for (int col = 0; col < k; ++col) {
+        double acc = bo[col];
+        for (int r = 0; r < HD; ++r) {
+          const bf16 wb = __float2bfloat16(wo[(size_t)r * k + col]);
+          b16[o.wo_t + (size_t)col * HD + r] = wb;
+          acc += (double)f32[o.bqkv_f + (size_t)2 * HD + r] * (double)__bfloat162float(wb);
+        }
+        f32[o.bo_d + col] = (float)acc;
+      }
       o.w1_t = push_b16((size_t)F * k);
       for (int col = 0; col < F; ++col) {
         double acc = b1[col];
@@ -674,7 +683,7 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
     for (int t = 0; t < 4; ++t) { B.ln_g[t] = df + o.ln_g[t]; B.ln_b[t] = df + o.ln_b[t]; }
     B.wq = df + o.wq; B.bq = df + o.bq; B.wk = df + o.wk; B.bk = df + o.bk; B.wv = df + o.wv; B.bv = df + o.bv;
     B.wo = df + o.wo; B.bo = df + o.bo; B.w1 = df + o.w1; B.b1 = df + o.b1; B.w2 = df + o.w2; B.b2 = df + o.b2;
-    B.bqkv_f = df + o.bqkv_f; B.b1_f = df + o.b1_f;
+    B.bqkv_f = df + o.bqkv_f; B.b1_f = df + o.b1_f; B.bo_d = df + o.bo_d;
     if (c.compute_dtype == AVB_DTYPE_BF16) {
       B.wqkv_t = db + o.wqkv_t; B.wo_t = db + o.wo_t; B.w1_t = db + o.w1_t; B.w2_t = db + o.w2_t;
       B.wd_qkv = reinterpret_cast<const uint8_t*>(db + o.wd_qkv); B.wd_o = reinterpret_cast<const uint8_t*>(db + o.wd_o);

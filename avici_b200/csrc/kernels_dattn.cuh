@@ -54,12 +54,12 @@ constexpr int kDaVBufs = 3;
 
 template <bool kFuseOut>
 struct DaCfg {
-  static constexpr int kWStages = kFuseOut ? 3 : 6;
+  static constexpr int kWStages = kFuseOut ? 4 : 6;
   static constexpr int kWoBytes = kFuseOut ? kDaHeads * kDaWoHeadBytes : 0;
-  static constexpr int kOBufs = kFuseOut ? 2 : 0;
+  static constexpr int kOBufs = 0;  // the bf16 O tile of the fused out-projection lives in TMEM (A operand of OP)
   static constexpr int kDataBytes =
       2 * kDaXBytes + kWStages * kDaWkbBytes + kWoBytes + (2 + kDaVBufs + kOBufs) * kDaTileBytes;
-  static constexpr int kBiasBytes = (3 * kDaHeads * 32 + 128) * 4;  // bqkv | bo as fp32, read as shared-memory broadcasts
+  static constexpr int kBiasBytes = (kDaHeads * 32 + 256) * 4;  // bq | bo' (or bv when the out-projection is not fused) as fp32
   static constexpr int kSmemBytes = kDataBytes + 1024 /*barriers, TMEM slot, ones tile*/ + kBiasBytes + 1024 /*alignment slack*/;
 };
 static_assert(DaCfg<true>::kSmemBytes <= 232448, "dattn_tc_kernel: shared memory over the sm_100 limit");
@@ -99,7 +99,6 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
   uint8_t* sQ = sWo + Cfg::kWoBytes;                // 8 KB
   uint8_t* sK = sQ + kDaTileBytes;                  // 8 KB
   uint8_t* sV = sK + kDaTileBytes;                  // [3][8 KB]
-  uint8_t* sO = sV + kDaVBufs * kDaTileBytes;       // [2][8 KB] (kFuseOut)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kDataBytes);
   uint64_t* x_full = bars;                 // [2] 128 LN threads
   uint64_t* x_empty = bars + 2;            // [2] commit
@@ -115,12 +114,14 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
   uint64_t* d_full = pv_done + 1;          // commit
   uint64_t* d_free = d_full + 1;           // 128 conv threads
   uint64_t* wo_full = d_free + 1;          // tx
-  uint64_t* op_done = wo_full + 1;         // [2] commit: OP of a unit has read its O tile (kFuseOut)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(op_done + 2);
+  uint64_t* op_done = wo_full + 1;         // commit: OP of a unit has read the bf16 O tile in TMEM (kFuseOut)
+  uint64_t* v_free = op_done + 1;          // [kDaVBufs] commit: PV of a unit has read its V tile
+  uint64_t* o_free = v_free + kDaVBufs;    // [2] 128 epilogue threads: the O / L accumulators are in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
   uint32_t* s_ones = reinterpret_cast<uint32_t*>(smem + Cfg::kDataBytes + 512);  // 512 B of bf16 1.0
   // Biases live in shared memory: a __ldg from the epilogue warps queues in the L1 pipeline behind the LayerNorm warps'
   // row loads (L2 latency each), which ncu showed as ~500 clocks of long-scoreboard stall per 32-column chunk.
-  float* s_bias = reinterpret_cast<float*>(smem + Cfg::kDataBytes + 1024);       // [768] bqkv | [128] bo
+  float* s_bias = reinterpret_cast<float*>(smem + Cfg::kDataBytes + 1024);       // [256] bq | [128] bo' = bo + bv Wo
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int nseq = (int)blockIdx.x < S ? (S - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -140,7 +141,9 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     ptx::mbar_init(p_full, 256); ptx::mbar_init(pv_done, 1);
     ptx::mbar_init(d_full, 1);   ptx::mbar_init(d_free, 128);
     ptx::mbar_init(wo_full, 1);
-    ptx::mbar_init(&op_done[0], 1); ptx::mbar_init(&op_done[1], 1);
+    ptx::mbar_init(op_done, 1);
+    for (int i = 0; i < kDaVBufs; ++i) ptx::mbar_init(&v_free[i], 1);
+    ptx::mbar_init(&o_free[0], 128); ptx::mbar_init(&o_free[1], 128);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -148,17 +151,17 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     ptx::tmem_relinquish();
   }
   if (threadIdx.x >= 128 && threadIdx.x < 256) s_ones[threadIdx.x - 128] = 0x3F803F80u;
-  for (int i = threadIdx.x; i < 3 * kDaHeads * 32 + 128; i += kDaThreads)
-    s_bias[i] = i < 3 * kDaHeads * 32 ? bqkv[i] : bo[i - 3 * kDaHeads * 32];
+  for (int i = threadIdx.x; i < kDaHeads * 32 + (kFuseOut ? 128 : 256); i += kDaThreads)
+    s_bias[i] = i < kDaHeads * 32 ? bqkv[i] : (kFuseOut ? bo[i - kDaHeads * 32] : bqkv[i + kDaHeads * 32]);  // bv = bqkv + 512
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tP = tmem_base + 256, tO = tmem_base + 320, tL = tmem_base + 352, tD = tmem_base + 384;
+  const uint32_t tP = tmem_base + 256, tO = tmem_base + 320, tL = tmem_base + 352, tOb = tmem_base + 368, tD = tmem_base + 384;
 
-  // Register budget per warpgroup (the pool holds what the CTA was launched with, 640 x 96 = 128 x (64 + 104 + 88) +
-  // 256 x 112).  Each setmaxnreg sits at the top of its own role branch: ptxas sizes the register allocation of a
+  // Register budget per warpgroup (the pool holds what the CTA was launched with, 640 x 96 = 128 x (64 + 120 + 88) +
+  // 256 x 104).  Each setmaxnreg sits at the top of its own role branch: ptxas sizes the register allocation of a
   // region by the setmaxnreg that dominates it.
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -210,23 +213,17 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       };
       auto issue_PV = [&](int u) {
         ptx::mbar_wait(p_full, (uint32_t)(u & 1), 85, 40u);
-        if (u >= 1) ptx::mbar_wait(&o_ready[(u - 1) & 1], (uint32_t)(((u - 1) >> 1) & 1), 86, 40u);  // O of unit u-1 has been read
+        if (u >= 1) ptx::mbar_wait(&o_free[(u - 1) & 1], (uint32_t)(((u - 1) >> 1) & 1), 86, 40u);  // O of unit u-1 has been read
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint64_t dv = dV0 + (uint64_t)((u % kDaVBufs) * (kDaTileBytes >> 4));
-          if (ksteps == 7) {  // T in 97..112 (d = 100): fully unrolled
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-              ptx::umma_bf16_ts(tO, tP + k * 8, dv + (uint64_t)(k * 64), idesc_pv, k != 0);
-              ptx::umma_bf16_ts(tL, tP + k * 8, d_ones, idesc_l, k != 0);
-            }
-          } else {
-            for (int k = 0; k < ksteps; ++k) {
-              ptx::umma_bf16_ts(tO, tP + k * 8, dv + (uint64_t)(k * 64), idesc_pv, k != 0);
-              ptx::umma_bf16_ts(tL, tP + k * 8, d_ones, idesc_l, k != 0);
-            }
+#pragma unroll 1  // compact code: the kernel's five roles share the instruction caches
+          for (int k = 0; k < ksteps; ++k) {
+            ptx::umma_bf16_ts(tO, tP + k * 8, dv + (uint64_t)(k * 64), idesc_pv, k != 0);
+            ptx::umma_bf16_ts(tL, tP + k * 8, d_ones, idesc_l, k != 0);
           }
           ptx::umma_commit(pv_done);
+          ptx::umma_commit(&v_free[u % kDaVBufs]);
         }
         __syncwarp();
       };
@@ -247,7 +244,6 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       constexpr uint32_t idesc_op = ptx::make_idesc_bf16(128, 128, 0, 0);
       const uint64_t dX0 = ptx::make_smem_desc(ptx::smem_u32(sX), 16, 1024, ptx::kSwz128);
       const uint64_t dW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024, ptx::kSwz128);
-      const uint64_t dO0 = ptx::make_smem_desc(ptx::smem_u32(sO), 16, 512, ptx::kSwz64);
       const uint64_t dWo0 = ptx::make_smem_desc(ptx::smem_u32(sWo), 16, 512, ptx::kSwz64);
       auto issue_G = [&](int u) {  // QKV projection of unit u into SBUF[u & 1]
         const int si = u >> 3, h = u & 7, buf = si & 1;
@@ -281,11 +277,10 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         if (h == 0 && si >= 1) ptx::mbar_wait(d_free, (uint32_t)((si - 1) & 1), 88, 40u);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          const uint64_t da = dO0 + (uint64_t)((u & 1) * (kDaTileBytes >> 4));
           const uint64_t db = dWo0 + (uint64_t)(h * (kDaWoHeadBytes >> 4));
-          ptx::umma_bf16(tD, da, db, idesc_op, h != 0);
-          ptx::umma_bf16(tD, da + 2, db + 2, idesc_op, 1);
-          ptx::umma_commit(&op_done[u & 1]);  // the O tile of unit u may be overwritten (oepi of unit u + 2)
+          ptx::umma_bf16_ts(tD, tOb, db, idesc_op, h != 0);  // A = the bf16 O tile in TMEM: 8 columns per K = 16 slice
+          ptx::umma_bf16_ts(tD, tOb + 8, db + 2, idesc_op, 1);
+          ptx::umma_commit(op_done);  // the O tile may be overwritten (Oepi of the next unit)
           if (h == 7) ptx::umma_commit(d_full);
         }
         __syncwarp();
@@ -304,79 +299,28 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     }
   }
   } else if (warp < 8) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    // ======================= LayerNorm warps: rows 32w .. 32w+31 of the sequence, rows >= T are zero
-    const int w = warp - 4;
-    for (int si = 0; si < nseq; ++si) {
-      const int s = (int)blockIdx.x + si * (int)gridDim.x, buf = si & 1;
-      const float* zs = z + (size_t)s * T * 128;
-      if (si + 2 < nseq) prefetch_rows_l2(z + (size_t)(s + 2 * (int)gridDim.x) * T * 128, T, w * 32, lane);
-      AVB_TRACE(4, si, 0);
-      ptx::mbar_wait(&x_empty[buf], (uint32_t)((si >> 1) & 1) ^ 1, 90);
-      AVB_TRACE(4, si, 1);
-      ln_warp_rows_to_umma_tile(zs, T, w * 32, ptx::smem_u32(sX + buf * kDaXBytes), w * 32, lane);
-      ptx::fence_proxy_async();
-      ptx::mbar_arrive(&x_full[buf]);
-      AVB_TRACE(4, si, 2);
-    }
-  } else if (warp < 12) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-    // ======================= conv / Oepi / Depi warps: thread = row r of the tile = TMEM lane
-    const int q = warp & 3, r = q * 32 + lane;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    // ======================= epilogue warps (Oepi + Depi): thread = row r of the tile = TMEM lane
+    const int w = warp - 4, q = w, r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t row_off = (uint32_t)(r * 64), swz = (uint32_t)((r >> 1) & 3);
-    const uint32_t aQ = ptx::smem_u32(sQ), aK = ptx::smem_u32(sK), aV = ptx::smem_u32(sV), aO = ptx::smem_u32(sO);
-
-    auto conv = [&](int u) {  // QKV accumulator -> + bias -> bf16 -> Q / K / V tiles
-      const int h = u & 7;
-      ptx::mbar_wait(&g_full[u & 1], (uint32_t)((u >> 1) & 1), 91);
-      // the Q / K tiles are single-buffered: S of the previous unit (issued by another warp than G) must have read them
-      if (u >= 1) ptx::mbar_wait(&s_full[(u - 1) & 1], (uint32_t)(((u - 1) >> 1) & 1), 96);
-      AVB_TRACE(2, (u >= 2 ? u - 2 : 499), 2);
-      ptx::tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(u & 1) * 128u + lane_off;
-#pragma unroll
-      for (int w = 0; w < 3; ++w) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tacc + w * 32, v);
-        float4 bb[8];
-        const float4* bp = reinterpret_cast<const float4*>(s_bias + w * 256 + h * 32);  // shared-memory broadcast
-#pragma unroll
-        for (int e = 0; e < 8; ++e) bb[e] = bp[e];
-        ptx::tmem_wait_ld();
-        const uint32_t tile = w == 0 ? aQ : (w == 1 ? aK : aV + (uint32_t)((u % kDaVBufs) * kDaTileBytes));
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float f[8];
-          f[0] = __uint_as_float(v[e * 8 + 0]) + bb[e * 2].x;     f[1] = __uint_as_float(v[e * 8 + 1]) + bb[e * 2].y;
-          f[2] = __uint_as_float(v[e * 8 + 2]) + bb[e * 2].z;     f[3] = __uint_as_float(v[e * 8 + 3]) + bb[e * 2].w;
-          f[4] = __uint_as_float(v[e * 8 + 4]) + bb[e * 2 + 1].x; f[5] = __uint_as_float(v[e * 8 + 5]) + bb[e * 2 + 1].y;
-          f[6] = __uint_as_float(v[e * 8 + 6]) + bb[e * 2 + 1].z; f[7] = __uint_as_float(v[e * 8 + 7]) + bb[e * 2 + 1].w;
-#ifdef AVB_DATTN_DEBUG
-          if (g_dattn_dbg && blockIdx.x == 0 && u < 8)
-            for (int t = 0; t < 8; ++t) g_dattn_dbg[((size_t)u * 128 + r) * 96 + w * 32 + e * 8 + t] = f[t];
-#endif
-          uint4 pk;
-          pk.x = ptx::pack_bf16(f[0], f[1]); pk.y = ptx::pack_bf16(f[2], f[3]);
-          pk.z = ptx::pack_bf16(f[4], f[5]); pk.w = ptx::pack_bf16(f[6], f[7]);
-          ptx::st_shared_v4(tile + row_off + (((uint32_t)e ^ swz) << 4), pk);
-        }
-      }
-      ptx::fence_proxy_async();  // tile writes (generic proxy) -> visible to the tensor core (async proxy)
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&qkv_ready[u & 1]);
-    };
     auto oepi = [&](int u) {  // O / L -> bf16 -> A tile of the out-projection (or the attention output in HBM)
       const int h = u & 7;
       ptx::mbar_wait(pv_done, (uint32_t)(u & 1), 92);
-      AVB_TRACE(2, u + 1, 5);
+      AVB_TRACE(4, u, 3);
+      AVB_TRACE(7, u, 0);
       ptx::tc_fence_after();
       uint32_t o[32];
       ptx::tmem_ld32(tO + lane_off, o);
       const float lsum = __uint_as_float(ptx::tmem_ld1(tL + lane_off));
       ptx::tmem_wait_ld();
+      // the accumulators are in registers: PV of the next unit may start (the O-accumulator hand-back is the unit
+      // pipeline's critical cycle - r2c trace - so it does not wait for the arithmetic below)
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&o_free[u & 1]);
+      AVB_TRACE(7, u, 1);
       if (r < T && !(lsum < 1.2676506e30f && lsum > 7.8886091e-31f)) *guard = 1;  // outside (2^-100, 2^100), inf or NaN
-      const float inv = 1.0f / lsum;
+      float inv;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(lsum));  // 1 ulp: far below the bf16 rounding of O
       uint4 pk[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -390,12 +334,29 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         for (int t = 0; t < 32; ++t) g_dattn_dbg[(size_t)8 * 128 * 96 + 8 * 128 * 128 + ((size_t)u * 128 + r) * 32 + t] = __uint_as_float(o[t]) * inv;
 #endif
       if constexpr (kFuseOut) {
-        if (u >= 2) ptx::mbar_wait(&op_done[u & 1], (uint32_t)(((u >> 1) - 1) & 1), 97);  // OP of unit u-2 has read this O tile
-        const uint32_t tile = aO + (uint32_t)((u & 1) * kDaTileBytes);
+        // straight back into TMEM as the A operand of OP: no shared-memory round trip, and no async-proxy fence
+        // (MEMBAR.ALL.CTA: it would drain this thread's LayerNorm loads in flight)
+        AVB_TRACE(7, u, 2);
+        if (u >= 1) ptx::mbar_wait(op_done, (uint32_t)((u - 1) & 1), 97);  // OP of unit u-1 has read the tile
+        AVB_TRACE(7, u, 3);
+        ptx::tc_fence_after();
+        uint32_t ob[16];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) ptx::st_shared_v4(tile + row_off + (((uint32_t)e ^ swz) << 4), pk[e]);
-        ptx::fence_proxy_async();
+        for (int e = 0; e < 4; ++e) { ob[e * 4 + 0] = pk[e].x; ob[e * 4 + 1] = pk[e].y; ob[e * 4 + 2] = pk[e].z; ob[e * 4 + 3] = pk[e].w; }
+        ptx::tmem_st16(tOb + lane_off, ob);
+        ptx::tmem_wait_st();
+        AVB_TRACE(7, u, 4);
       } else {
+        // (the separate out-projection launch uses the plain bo, so the value bias is added here)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4 b0 = reinterpret_cast<const float4*>(s_bias + kDaHeads * 32 + h * 32)[e * 2];
+          const float4 b1 = reinterpret_cast<const float4*>(s_bias + kDaHeads * 32 + h * 32)[e * 2 + 1];
+          pk[e].x = ptx::pack_bf16(__uint_as_float(o[e * 8 + 0]) * inv + b0.x, __uint_as_float(o[e * 8 + 1]) * inv + b0.y);
+          pk[e].y = ptx::pack_bf16(__uint_as_float(o[e * 8 + 2]) * inv + b0.z, __uint_as_float(o[e * 8 + 3]) * inv + b0.w);
+          pk[e].z = ptx::pack_bf16(__uint_as_float(o[e * 8 + 4]) * inv + b1.x, __uint_as_float(o[e * 8 + 5]) * inv + b1.y);
+          pk[e].w = ptx::pack_bf16(__uint_as_float(o[e * 8 + 6]) * inv + b1.z, __uint_as_float(o[e * 8 + 7]) * inv + b1.w);
+        }
         if (r < T) {  // outproj_tc_kernel's A-operand layout: [m >> 7][head][m & 127][32 ch], chunks at c ^ ((m >> 1) & 3)
           const int s = (int)blockIdx.x + (u >> 3) * (int)gridDim.x;
           const unsigned m = (unsigned)s * (unsigned)T + (unsigned)r;
@@ -408,18 +369,24 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       ptx::tc_fence_before();
       ptx::mbar_arrive(&o_ready[u & 1]);
     };
-    auto depi = [&](int si) {  // DELTA + bo -> bf16 -> the sequence's 256-byte delta rows (token order)
+    auto depi = [&](int si) {  // DELTA + bo' -> bf16 -> the sequence's 256-byte delta rows (token order)
+      // One row per thread, 64 contiguous bytes per chunk, straight from registers.  (Transposing through a shared-
+      // memory stage for 128-byte store segments measured the same ~4K clocks per sequence - the warp is latency-
+      // bound, not store-bound - and there is no shared memory left for a stage that the LayerNorm warps do not also
+      // write.)  A compact loop: this code runs once per sequence and is cold in the instruction caches.
+      AVB_TRACE(6, si, 0);
       ptx::mbar_wait(d_full, (uint32_t)(si & 1), 93);
+      AVB_TRACE(6, si, 1);
       ptx::tc_fence_after();
       const int s = (int)blockIdx.x + si * (int)gridDim.x;
       __nv_bfloat16* drow = out + ((size_t)s * T + r) * 128;
-#pragma unroll
+#pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t v[32];
         ptx::tmem_ld32(tD + cc * 32 + lane_off, v);
         float4 bb[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) bb[e] = reinterpret_cast<const float4*>(s_bias + 3 * kDaHeads * 32 + cc * 32)[e];
+        for (int e = 0; e < 8; ++e) bb[e] = reinterpret_cast<const float4*>(s_bias + kDaHeads * 32 + cc * 32)[e];
         ptx::tmem_wait_ld();
         if (cc == 3) {
           ptx::tc_fence_before();
@@ -443,25 +410,162 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
           }
         }
       }
+      AVB_TRACE(6, si, 5);
     };
 
-    if (U > 0) {
-      conv(0);
-      if (U > 1) conv(1);
-      for (int u = 0; u < U; ++u) {
-        AVB_TRACE(2, u, 0);
-        if (u >= 1) oepi(u - 1);
-        AVB_TRACE(2, u, 1);
-        if (u + 2 < U) conv(u + 2);
-        AVB_TRACE(2, u, 3);
-        if (kFuseOut && u >= 1 && ((u - 1) & 7) == 7) depi((u - 1) >> 3);
-        AVB_TRACE(2, u, 4);
+    for (int si = 0; si < nseq; ++si) {
+      for (int h = 0; h < kDaHeads; ++h) {
+        const int u = si * kDaHeads + h;
+        AVB_TRACE(4, u, 0);
+        oepi(u);
+        AVB_TRACE(4, u, 2);
+        if (kFuseOut && h == kDaHeads - 1) depi(si);
+        AVB_TRACE(4, u, 5);
       }
-      oepi(U - 1);
-      if (kFuseOut) depi((U - 1) >> 3);
+    }
+  } else if (warp < 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    // ======================= conv + LayerNorm warps: thread = row r of the tile = TMEM lane for conv.
+    // The LayerNorm of the NEXT sequence is cut into four 8-row slices per warp, one per unit h = 0..3: its loads are
+    // issued behind conv_u's async-proxy fence (which would otherwise drain them) and are in flight while the warp
+    // waits for the next unit's projection; these warps run about two units ahead of the softmax and had ~1300 idle
+    // clocks per unit (r2c trace), the epilogue warps none.
+    const int q = warp & 3, r = q * 32 + lane, w = q;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t row_off = (uint32_t)(r * 64), swz = (uint32_t)((r >> 1) & 3);
+    const uint32_t aQ = ptx::smem_u32(sQ), aK = ptx::smem_u32(sK), aV = ptx::smem_u32(sV);
+    const int rs = lane >> 3, j8 = lane & 7;
+    float4 ln[2][4];
+    auto ln8_load = [&](const float* zs, int r0) {  // rows 32w + r0 .. + 7 of the sequence (zeros past its end)
+#pragma unroll
+      for (int uu = 0; uu < 2; ++uu) {
+        const int row = w * 32 + r0 + uu * 4 + rs;
+        const float4* zp = reinterpret_cast<const float4*>(zs + (size_t)row * 128) + j8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ln[uu][k] = row < T ? __ldcg(zp + k * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto ln8_finish = [&](uint32_t a_tile, int r0) {  // same arithmetic and layout as ln_warp_rows_to_umma_tile
+#pragma unroll
+      for (int uu = 0; uu < 2; ++uu) {
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sum += (ln[uu][k].x + ln[uu][k].y) + (ln[uu][k].z + ln[uu][k].w);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        const float mean = sum * (1.0f / 128.0f);
+        float sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ln[uu][k].x -= mean; ln[uu][k].y -= mean; ln[uu][k].z -= mean; ln[uu][k].w -= mean;
+          sq += (ln[uu][k].x * ln[uu][k].x + ln[uu][k].y * ln[uu][k].y) + (ln[uu][k].z * ln[uu][k].z + ln[uu][k].w * ln[uu][k].w);
+        }
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+        const float rstd = rsqrtf(sq * (1.0f / 128.0f) + kLnEps);
+        const int rr = w * 32 + r0 + uu * 4 + rs;
+        const uint32_t rbase = a_tile + (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128 + (j8 & 1) * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int chunk = (j8 + 8 * (k & 1)) >> 1;
+          const uint32_t addr = rbase + (uint32_t)((k >> 1) * (128 * 128) + ((chunk ^ (rr & 7)) << 4));
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ptx::pack_bf16(ln[uu][k].x * rstd, ln[uu][k].y * rstd)),
+                       "r"(ptx::pack_bf16(ln[uu][k].z * rstd, ln[uu][k].w * rstd))
+                       : "memory");
+        }
+      }
+    };
+    auto conv_wait = [&](int u) {
+      ptx::mbar_wait(&g_full[u & 1], (uint32_t)((u >> 1) & 1), 91);
+      // the Q / K tiles are single-buffered: S of the previous unit (issued by another warp than G) must have read them
+      if (u >= 1) ptx::mbar_wait(&s_full[(u - 1) & 1], (uint32_t)(((u - 1) >> 1) & 1), 96);
+      // ... and the V buffer (three of them) is last read by PV of unit u - 3
+      if (u >= kDaVBufs) ptx::mbar_wait(&v_free[u % kDaVBufs], (uint32_t)((u / kDaVBufs - 1) & 1), 98);
+      AVB_TRACE(2, u, 2);
+    };
+    auto conv = [&](int u) {  // QKV accumulator -> + bias -> bf16 -> Q / K / V tiles
+      const int h = u & 7;
+      ptx::tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(u & 1) * 128u + lane_off;
+#pragma unroll
+      for (int w = 0; w < 3; ++w) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tacc + w * 32, v);
+        // Only Q carries its bias here.  The key bias shifts every score of a query row by the same q . bk, which the
+        // softmax cancels exactly; the value bias passes through the convex combination unchanged (sum_j p_j = 1) and
+        // is folded into the out-projection bias at load time (bo + bv Wo, avb_load_weights) - 64 FADD and 16 shared
+        // loads less per row and unit on warps whose instruction count is what bounds the unit period.
+        float4 bb[8];
+        if (w == 0) {
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + h * 32);  // shared-memory broadcast
+#pragma unroll
+          for (int e = 0; e < 8; ++e) bb[e] = bp[e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) bb[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        ptx::tmem_wait_ld();
+        const uint32_t tile = w == 0 ? aQ : (w == 1 ? aK : aV + (uint32_t)((u % kDaVBufs) * kDaTileBytes));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float f[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(v[e * 8 + t]);
+          if (w == 0) {
+            f[0] += bb[e * 2].x;     f[1] += bb[e * 2].y;     f[2] += bb[e * 2].z;     f[3] += bb[e * 2].w;
+            f[4] += bb[e * 2 + 1].x; f[5] += bb[e * 2 + 1].y; f[6] += bb[e * 2 + 1].z; f[7] += bb[e * 2 + 1].w;
+          }
+#ifdef AVB_DATTN_DEBUG
+          if (g_dattn_dbg && blockIdx.x == 0 && u < 8)
+            for (int t = 0; t < 8; ++t) g_dattn_dbg[((size_t)u * 128 + r) * 96 + w * 32 + e * 8 + t] = f[t];
+#endif
+          uint4 pk;
+          pk.x = ptx::pack_bf16(f[0], f[1]); pk.y = ptx::pack_bf16(f[2], f[3]);
+          pk.z = ptx::pack_bf16(f[4], f[5]); pk.w = ptx::pack_bf16(f[6], f[7]);
+          ptx::st_shared_v4(tile + row_off + (((uint32_t)e ^ swz) << 4), pk);
+        }
+        AVB_TRACE(2, u, 4 + w);
+      }
+      ptx::fence_proxy_async();  // tile writes (generic proxy) -> visible to the tensor core (async proxy)
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&qkv_ready[u & 1]);
+    };
+
+    if (nseq > 0) {  // the first sequence's LayerNorm, slice by slice
+      const float* zs = z + (size_t)blockIdx.x * T * 128;
+      if (nseq > 1) prefetch_rows_l2(z + (size_t)((int)blockIdx.x + (int)gridDim.x) * T * 128, T, w * 32, lane);
+#pragma unroll 1
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        ln8_load(zs, r0);
+        ln8_finish(ptx::smem_u32(sX), r0);
+      }
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&x_full[0]);
+    }
+    bool pending = false;  // a LayerNorm slice whose loads are in flight
+    for (int u = 0; u < U; ++u) {
+      const int si = u >> 3, h = u & 7, nbuf = (si + 1) & 1;
+      AVB_TRACE(2, u, 0);
+      conv_wait(u);
+      if (pending) ln8_finish(ptx::smem_u32(sX + nbuf * kDaXBytes), (h - 1) * 8);  // slice h - 1, loaded behind conv_{u-1}
+      conv(u);  // ends with the async-proxy fence: it also covers the slice's shared-memory stores
+      if (pending && h == 4) ptx::mbar_arrive(&x_full[nbuf]);
+      pending = false;
+      AVB_TRACE(2, u, 3);
+      if (si + 1 < nseq && h < 4) {
+        const int s_next = (int)blockIdx.x + (si + 1) * (int)gridDim.x;
+        if (h == 0) {
+          if (si + 2 < nseq) prefetch_rows_l2(z + (size_t)(s_next + (int)gridDim.x) * T * 128, T, w * 32, lane);
+          ptx::mbar_wait(&x_empty[nbuf], (uint32_t)(((si + 1) >> 1) & 1) ^ 1, 90);
+        }
+        ln8_load(z + (size_t)s_next * T * 128, h * 8);
+        pending = true;
+      }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ======================= softmax warps: warp (q, half) owns TMEM lanes 32q.. and key columns [64 half, 64 half + 64)
     const int q = warp & 3, half = (warp - 12) >> 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;

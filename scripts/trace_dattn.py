@@ -19,7 +19,7 @@ z = torch.randn(B, n, d, 128, device="cuda", generator=g)
 delta = torch.zeros(B * n * d, 128, device="cuda", dtype=torch.bfloat16)
 guard = C.c_int32(-1)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-trace = torch.zeros(6 * 4096, dtype=torch.int64, device="cuda")
+trace = torch.zeros(8 * 4096, dtype=torch.int64, device="cuda")
 for rep in range(3):
     if rep == 2:
         lib.avb_debug_set_trace(C.c_void_p(trace.data_ptr()))
@@ -31,18 +31,18 @@ for rep in range(3):
     ms = e0.elapsed_time(e1)
     print(f"dattn S={B * n} T={d} fuse_out={fuse_out}: rc {rc} {ms:.3f} ms = {ms * 1e3 / (B * n) * 148:.2f} us per sequence per SM")
 lib.avb_debug_set_trace(None)
-t = trace.cpu().numpy().reshape(6, 512, 8)
+t = trace.cpu().numpy().reshape(8, 512, 8)
 if t.max() == 0:
     print("no stamps: not a -DAVB_TRACE_ENABLE build")
     sys.exit(0)
 t0 = t[t > 0].min()
 names = {0: ["top", "w_empty"], 1: ["top", "PV(u-1)", "S(u+1)"], 5: ["top", "G(u+2)", "OP(u-1)", "-", "-", "G:s_free"],
-         2: ["top", "oepi(u-1)", "conv:g_full", "conv(u+2)", "depi", "oepi:pv_done"],
-         3: ["top", "s_full", "ld+free", "exp", "pv_done", "st+p_full"], 4: ["top", "x_empty", "ln_done"]}
+         2: ["top", "-", "conv:waits", "conv(u)"],
+         3: ["top", "s_full", "ld+free", "exp", "pv_done", "st+p_full"], 4: ["top", "ln_loads", "oepi(u)", "oepi:pv_done", "ln_slice", "depi"]}
 lo = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 for role, rn in ((1, "attn issuer"), (5, "proj issuer"), (2, "conv"), (3, "softmax"), (4, "layernorm"), (0, "producer")):
     print(f"== {rn}: {names[role]}")
-    rng = range(lo // 8, lo // 8 + 4) if role == 4 else (range(2 * lo, 2 * lo + 16) if role == 0 else range(lo, lo + 12))
+    rng = range(2 * lo, 2 * lo + 16) if role == 0 else range(lo, lo + 12)
     for step in rng:
         row = t[role, step, :len(names[role])].astype(np.int64)
         if row.max() == 0:
@@ -59,9 +59,36 @@ ok = (sm[:, 0] > 0) & (sm[:, 5] > 0)
 for a, b, nm in ((0, 1, "wait s_full"), (1, 2, "tmem ld"), (2, 3, "exps"), (3, 4, "wait pv_done"), (4, 5, "tmem st")):
     print(f"softmax {nm}: mean {(sm[ok, b] - sm[ok, a]).mean():.0f} clocks")
 cv = t[2, 16:400].astype(np.int64)
-ok = (cv[:, 0] > 0) & (cv[:, 4] > 0) & (cv[:, 2] > 0)
-print(f"conv warps: oepi {(cv[ok, 1] - cv[ok, 0]).mean():.0f}, wait g_full {(cv[ok, 2] - cv[ok, 1]).mean():.0f}, conv {(cv[ok, 3] - cv[ok, 2]).mean():.0f}, depi {(cv[ok, 4] - cv[ok, 3]).mean():.0f} clocks per unit")
+ok = (cv[:, 0] > 0) & (cv[:, 3] > 0) & (cv[:, 2] > 0)
+print(f"conv warps: waits {(cv[ok, 2] - cv[ok, 0]).mean():.0f}, conv {(cv[ok, 3] - cv[ok, 2]).mean():.0f} clocks per unit")
+ln = t[4, 16:400].astype(np.int64)
+ok = (ln[:, 0] > 0) & (ln[:, 5] > 0) & (ln[:, 3] > 0) & (ln[:, 2] > 0)
+print(f"epilogue warps: wait pv_done {(ln[ok, 3] - ln[ok, 0]).mean():.0f}, oepi {(ln[ok, 2] - ln[ok, 3]).mean():.0f}, depi {(ln[ok, 5] - ln[ok, 2]).mean():.0f} clocks per unit")
 for role, nm, cols in ((1, "attn issuer", ((0, 1, "PV"), (1, 2, "S"))), (5, "proj issuer", ((0, 1, "G"), (1, 2, "OP")))):
     m = t[role, 16:400].astype(np.int64)
     ok = (m[:, 0] > 0) & (m[:, 2] > 0)
     print(nm, ", ".join(f"{n} {(m[ok, b] - m[ok, a]).mean():.0f}" for a, b, n in cols))
+oe = t[7, 16:400].astype(np.int64)
+ok = (oe[:, 0] > 0) & (oe[:, 4] > 0)
+print(f"oepi detail: tmem ld {(oe[ok, 1] - oe[ok, 0]).mean():.0f}, math {(oe[ok, 2] - oe[ok, 1]).mean():.0f}, wait op_done {(oe[ok, 3] - oe[ok, 2]).mean():.0f}, tmem st {(oe[ok, 4] - oe[ok, 3]).mean():.0f}")
+de = t[6, 2:48].astype(np.int64)
+ok = (de[:, 0] > 0) & (de[:, 5] > 0)
+print(f"depi detail: wait d_full {(de[ok, 1] - de[ok, 0]).mean():.0f}, body {(de[ok, 5] - de[ok, 1]).mean():.0f}")
+ok = (cv[:, 2] > 0) & (cv[:, 6] > 0)
+print(f"conv detail: Q chunk {(cv[ok, 4] - cv[ok, 2]).mean():.0f}, K chunk {(cv[ok, 5] - cv[ok, 4]).mean():.0f}, V chunk {(cv[ok, 6] - cv[ok, 5]).mean():.0f}, fence+arrive {(cv[ok, 3] - cv[ok, 6]).mean():.0f}")
+if len(sys.argv) > 5:
+    # merged timeline of the events that concern units u0..u0+2, in time order
+    u0 = int(sys.argv[5])
+    ev = []
+    for u in range(u0, u0 + 3):
+        add = lambda role, step, e, name: ev.append((int(t[role, step, e]), f"u{u} {name}")) if t[role, step, e] > 0 else None  # noqa: E731
+        add(5, u - 2, 5, "G: s_free seen"); add(5, u - 2, 1, "G issued")
+        add(2, u, 0, "conv top"); add(2, u, 2, "conv waits done (g_full, s_full(u-1), v_free)"); add(2, u, 3, "conv done -> qkv_ready")
+        add(1, u - 1, 2, "S issued"); add(3, u, 0, "softmax top"); add(3, u, 1, "softmax: s_full"); add(3, u, 2, "softmax: S loaded -> s_free")
+        add(3, u, 3, "softmax: exps done"); add(3, u, 4, "softmax: pv_done(u-1) seen"); add(3, u, 5, "softmax: P stored -> p_full")
+        add(1, u + 1, 0, "attn issuer top (before PV)"); add(1, u + 1, 1, "PV issued")
+        add(4, u, 0, "epi top"); add(4, u, 1, "epi: ln loads issued"); add(7, u, 0, "oepi: pv_done seen"); add(7, u, 1, "oepi: O loaded")
+        add(7, u, 3, "oepi: op_done(u-1) seen"); add(7, u, 4, "oepi: O stored -> o_ready"); add(4, u, 4, "epi: ln slice done")
+        add(5, u + 1, 1, "proj issuer: G(u+3) issued, now OP(u)"); add(5, u + 1, 2, "OP issued")
+    for tt, nm in sorted(ev):
+        print(f"{tt - t0:9d}  {nm}")
