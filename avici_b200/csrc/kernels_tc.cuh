@@ -1277,6 +1277,9 @@ constexpr int kAttnPolyEvery = 4;  // 1 of every kAttnPolyEvery exponent pairs i
 #ifndef AVB_ATTN_POLY_MASK  // which of the 16 pairs of a 32-score chunk take the polynomial (default: every 3rd, 5 of 16)
 #define AVB_ATTN_POLY_MASK 0
 #endif
+#ifndef AVB_ATTN_PIPE_LD  // 1: the softmax warps prefetch the next S tile behind the P store (A/B build, measured r2c:
+#define AVB_ATTN_PIPE_LD 0  // 15.4 vs 11.05 ms - S, P and the next S do not fit the 104 registers and the loop spills)
+#endif
 #ifndef AVB_ATTN_KV_POLICY  // L2 eviction priority of the K / V tile loads
 #define AVB_ATTN_KV_POLICY (nqt > 1 ? ptx::kL2EvictLast : ptx::kL2EvictFirst)
 #endif
@@ -1650,19 +1653,24 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       uint32_t gp = 0;  // parity of the current step (g & 1)
       float pmax = -INFINITY;
       ItemPos ip = first_item();
+      // -DAVB_ATTN_PIPE_LD=1 (A/B build, slower - see the macro): the S tile of the NEXT step is requested from TMEM right
+      // behind this step's P store, so that its load latency overlaps the store's completion and the p_full hand-off.
+      uint32_t sa[32], sb[32];
+      bool have_s = false;
       for (int item = 0; item < my_items; ++item, ++it) {
         const int s = ip.s, h = ip.h, qt = ip.qt;
         for (int j = 0; j < nqt; ++j, ++g, gp ^= 1u) {
           AVB_TRACE(trole, g, 0);
-          ptx::mbar_wait_s(a_sfull, gp);
-          AVB_TRACE(trole, g, 1);
-          ptx::tc_fence_after();
-          uint32_t sa[32], sb[32];
-          ptx::tmem_ld32(tS, sa);
-          ptx::tmem_ld32(tS + 32, sb);
-          ptx::tmem_wait_ld();
-          ptx::tc_fence_before();
-          ptx::mbar_arrive_s(a_sfree);  // the only read of S: the tensor core may start the next S right away
+          if (!have_s) {
+            ptx::mbar_wait_s(a_sfull, gp);
+            AVB_TRACE(trole, g, 1);
+            ptx::tc_fence_after();
+            ptx::tmem_ld32(tS, sa);
+            ptx::tmem_ld32(tS + 32, sb);
+            ptx::tmem_wait_ld();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive_s(a_sfree);  // the only read of S: the tensor core may start the next S right away
+          }
           AVB_TRACE(trole, g, 2);
           const int nv = T - j * 128 - half * 64;  // valid key columns in this warp's half (may be <= 0)
           if (nv < 64) {  // keys beyond the sequence end: score -inf, probability 0
@@ -1687,9 +1695,27 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
           if (j == 0 && pend) { epilogue(); pend = false; }
           AVB_TRACE(trole, g, 5);
           ptx::tmem_st32(tP, pk);
+#if AVB_ATTN_PIPE_LD
+          // non-blocking test (a phase may complete between two lanes' tests, so the warp takes lane 0's answer); if the
+          // tile is not there yet the next step fetches it the ordinary way
+          have_s = ((j + 1 < nqt) || (item + 1 < my_items)) && ptx::mbar_test_s(a_sfull, gp ^ 1u);
+          have_s = __shfl_sync(0xffffffffu, (int)have_s, 0) != 0;
+          if (have_s) {
+            ptx::tc_fence_after();
+            ptx::tmem_ld32(tS, sa);
+            ptx::tmem_ld32(tS + 32, sb);
+          }
+#endif
           ptx::tmem_wait_st();
           ptx::tc_fence_before();
           ptx::mbar_arrive_s(a_pfull);
+#if AVB_ATTN_PIPE_LD
+          if (have_s) {
+            ptx::tmem_wait_ld();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive_s(a_sfree);
+          }
+#endif
           AVB_TRACE(trole, g, 7);
         }
         pend = true;

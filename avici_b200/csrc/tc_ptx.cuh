@@ -106,6 +106,13 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity)
       : "memory");
 #endif
 }
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test_s(uint32_t bar_saddr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+               : "=r"(ok) : "r"(bar_saddr), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar_saddr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_saddr) : "memory");
 }
