@@ -17,7 +17,7 @@ AVB_OK, AVB_ERR_INVALID, AVB_ERR_CUDA, AVB_ERR_MISSING, AVB_ERR_WORKSPACE = 0, 1
 AVB_DTYPE_F32, AVB_DTYPE_BF16 = 0, 1
 AVB_STANDARDIZE_NONE, AVB_STANDARDIZE_DEFAULT, AVB_STANDARDIZE_COUNT = 0, 1, 2
 AVB_AXIS_D, AVB_AXIS_N = 0, 1
-PROF_CATEGORIES = ("prologue", "qkv", "attn_d", "attn_n", "out", "ffn", "pool_head", "dattn")
+PROF_CATEGORIES = ("prologue", "qkv", "attn_d", "attn_n", "out", "ffn", "pool_head", "dattn", "comm")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -54,6 +54,14 @@ SIGNATURES = {
     "avb_block_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "avb_block": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                             C.c_void_p, C.c_size_t, C.c_void_p]),
+    "avb_block_sharded": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                    C.c_size_t, C.c_void_p]),
+    "avb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "avb_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "avb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "avb_sharded_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "avb_forward_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                      C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "avb_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                            C.c_void_p]),
     "avb_head": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t,

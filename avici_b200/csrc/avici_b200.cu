@@ -8,6 +8,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -47,6 +48,54 @@ struct Block {
 
 }  // namespace
 
+// ------------------------------------------------------------------ NCCL (resolved at run time)
+// The library carries no link-time dependency on NCCL: the handful of entry points the axially sharded forward needs
+// are looked up in the libnccl.so.2 that is already loaded in the process (PyTorch bundles one) or, failing that,
+// in the system's.  The declarations below restate the stable public ABI of nccl.h (2.x).
+extern "C" {
+typedef struct ncclComm* avb_nccl_comm_t;
+typedef struct { char internal[128]; } avb_nccl_unique_id;
+}
+namespace {
+struct NcclApi {
+  int (*GetUniqueId)(avb_nccl_unique_id*) = nullptr;
+  int (*CommInitRank)(avb_nccl_comm_t*, int, avb_nccl_unique_id, int) = nullptr;
+  int (*CommDestroy)(avb_nccl_comm_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void*, size_t, int, int, avb_nccl_comm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, avb_nccl_comm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, avb_nccl_comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+constexpr int kNcclFloat32 = 7;  // ncclDataType_t::ncclFloat32
+
+const NcclApi& nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy PyTorch has loaded, if any
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { api.why = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : "?"); return; }
+    auto sym = [&](const char* name) { void* p = dlsym(lib, name); if (!p && api.why.empty()) api.why = std::string("missing NCCL symbol ") + name; return p; };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    api.ok = api.why.empty();
+  });
+  return api;
+}
+}  // namespace
+
 struct avb_model_s {
   avb_config cfg{};
   std::string err;
@@ -66,6 +115,8 @@ struct avb_model_s {
   std::mutex host_mu;
   long long launches = 0;
   int dattn_mode = 1;  // d-axis blocks with d <= 128: 1 = fully fused kernel, 2 = fused up to the attention output, 0 = unfused
+  avb_nccl_comm_t comm = nullptr;  // avb_comm_init: communicator of the axially sharded forward (one rank per handle)
+  int comm_rank = 0, comm_world = 1;
   // optional per-kernel-category CUDA-event timing (avb_profile_*)
   bool prof = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -209,7 +260,7 @@ inline const char* ab_env(const char* name) {
 // run_if: see ln_gemm2_tc_kernel.
 int launch_ln_gemm2_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, const float* bias, void* out, int ldo,
                        int M, int N, cudaStream_t st, int num_sms, long long* launches, int seq_n, int seq_d, int seq_axis,
-                       const int* run_if = nullptr) {
+                       const int* run_if = nullptr, int seq_dg = 0) {
   static PerDeviceOnce once;
   cudaError_t e = once.run([] {
     return cudaFuncSetAttribute(avb::ln_gemm2_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kLnGemmSmemBytes);
@@ -218,7 +269,7 @@ int launch_ln_gemm2_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, co
   const int num_pairs = ((M + 127) / 128 + 1) / 2;
   const int grid = 2 * std::min(num_pairs, num_sms / 2);
   avb::ln_gemm2_tc_kernel<2><<<grid, avb::kLnGemmThreads, avb::kLnGemmSmemBytes, st>>>(
-      z, tm_b, bias, reinterpret_cast<bf16*>(out), ldo, M, N, seq_n, seq_d, seq_axis, run_if);
+      z, tm_b, bias, reinterpret_cast<bf16*>(out), ldo, M, N, seq_n, seq_d, seq_axis, seq_dg, run_if);
   if (launches) ++*launches;
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ln_gemm2_tc launch: %s", cudaGetErrorString(e));
@@ -227,7 +278,8 @@ int launch_ln_gemm2_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, co
 
 // delta[token][128] (bf16) = attn . Wo^T + bo
 int launch_outproj_tc(avb_handle h, const void* attn, const CUtensorMap& tm_w, const float* bias, void* delta, int M,
-                      int n, int d, int axis, cudaStream_t st, int num_sms, long long* launches, const int* run_if = nullptr) {
+                      int n, int d, int axis, cudaStream_t st, int num_sms, long long* launches, const int* run_if = nullptr,
+                      int seq_dg = 0) {
   static PerDeviceOnce once;
   cudaError_t e = once.run([] {
     return cudaFuncSetAttribute(avb::outproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kOutProjSmemBytes);
@@ -235,7 +287,7 @@ int launch_outproj_tc(avb_handle h, const void* attn, const CUtensorMap& tm_w, c
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(outproj_tc): %s", cudaGetErrorString(e));
   const int grid = std::min((M + 127) / 128, num_sms);
   avb::outproj_tc_kernel<<<grid, avb::kOutProjThreads, avb::kOutProjSmemBytes, st>>>(
-      reinterpret_cast<const bf16*>(attn), tm_w, bias, reinterpret_cast<bf16*>(delta), M, n, d, axis, run_if);
+      reinterpret_cast<const bf16*>(attn), tm_w, bias, reinterpret_cast<bf16*>(delta), M, n, d, axis, seq_dg, run_if);
   if (launches) ++*launches;
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "outproj_tc launch: %s", cudaGetErrorString(e));
@@ -476,6 +528,7 @@ int avb_create(avb_handle* out, const avb_config* cfg) {
 void avb_destroy(avb_handle h) {
   if (!h) return;
   DeviceGuard dg(h->device);
+  if (h->comm) nccl_api().CommDestroy(h->comm);
   if (h->arena) cudaFree(h->arena);
   if (h->host_ws) cudaFree(h->host_ws);
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
@@ -747,12 +800,18 @@ size_t avb_block_workspace_bytes(avb_handle h, int32_t B, int32_t n, int32_t d) 
   return block_ws_layout(h->cfg, (size_t)B * n * d).total;
 }
 
-int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t d, int32_t axis, void* ws,
-              size_t ws_bytes, void* stream) {
+// dg > 0: the tokens of the (single-dataset, n-sharded) block are stored in d / dg column blocks (RowMap); axis d only.
+static int block_impl(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t d, int32_t axis, int32_t dg, void* ws,
+                      size_t ws_bytes, void* stream) {
   if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_block: weights not loaded");
   if (!shape_ok(h, B, n, d) || !z || (axis != 0 && axis != 1) || bi < 0 || bi >= (int)h->blocks.size())
     return fail(h, AVB_ERR_INVALID, "avb_block: bad argument");
-  DeviceGuard dg(h->device);
+  if (dg != 0 && (dg < 0 || axis != AVB_AXIS_D || B != 1 || d % dg != 0))
+    return fail(h, AVB_ERR_INVALID, "avb_block_sharded: column blocks need axis d, one dataset and dg | d (dg=%d, d=%d)", dg, d);
+#if !AVB_DELTA_TOKENS
+  if (dg != 0) return fail(h, AVB_ERR_INVALID, "avb_block_sharded: not available in -DAVB_DELTA_TOKENS=0 builds");
+#endif
+  DeviceGuard dev_guard(h->device);
   const avb_config& c = h->cfg;
   const size_t ntok = (size_t)B * n * d;
   if (ntok > (size_t)0x7fffff00) return fail(h, AVB_ERR_INVALID, "avb_block: too many tokens per call (%zu)", ntok);
@@ -772,7 +831,7 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
     // attention half: LN -> QKV -> attention -> out-projection, leaving the sub-layer's update as bf16 `delta` rows in
     // the qkv buffer (dead once the attention has run); the FFN's LayerNorm warps add it to z.
     const long long S_d = (long long)B * n;
-    if (axis == AVB_AXIS_D && d <= 128 && H == avb::kDaHeads && h->dattn_mode != 0) {
+    if (axis == AVB_AXIS_D && d <= 128 && H == avb::kDaHeads && h->dattn_mode != 0 && dg == 0) {
       // a whole sequence fits one tile: the sub-layer is ONE kernel, qkv and the attention output never reach HBM.
       // The guarded exact fallback (unfused kernels, each returning at once while the guard is down) recomputes delta
       // if a score left the fast softmax's range.
@@ -790,11 +849,12 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
     { ProfScope ps(h, AVB_PROF_QKV, st);  // LayerNorm fused into the projection's prologue;
       // rows in sequence-major order of `axis`, output in the attention kernel's operand layout
       if ((rc = launch_ln_gemm2_tc(h, z, W.tm_wqkv_h, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, st, h->num_sms, &h->launches,
-                                   n, d, axis))) return rc; }
+                                   n, d, axis, nullptr, dg))) return rc; }
     { ProfScope ps(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
       if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches, guard))) return rc; }
     { ProfScope ps(h, AVB_PROF_OUT, st);
-      if ((rc = launch_outproj_tc(h, attn, W.tm_wo, W.bo, qkv, M, n, d, axis, st, h->num_sms, &h->launches))) return rc; }
+      if ((rc = launch_outproj_tc(h, attn, W.tm_wo, W.bo, qkv, M, n, d, axis, st, h->num_sms, &h->launches, nullptr, dg)))
+        return rc; }
     }
     // FFN half: z += delta; LN -> Linear + ReLU -> Linear + residual, one kernel
     { ProfScope ps(h, AVB_PROF_FFN, st);
@@ -821,7 +881,8 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
       for (long long s0 = 0; s0 < S; s0 += 65535) {  // grid.z is limited to 65535
         const int sz = (int)std::min<long long>(65535, S - s0);
         avb::attention_f32_kernel<<<dim3((T + 127) / 128, H, sz), 128, 0, st>>>(
-            qkv, attn, T, H, s0, inner, outer_stride, inner_stride, tok_stride, 1.0f / sqrtf((float)c.key_size));
+            qkv, attn, T, H, s0, inner, outer_stride, inner_stride, tok_stride, 1.0f / sqrtf((float)c.key_size), dg,
+            (long long)n * dg);
         h->launches++;
       } }
     { cudaError_t e__ = cudaGetLastError();
@@ -836,6 +897,16 @@ int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t 
       AVB_LAUNCH_CHECK(h); }
   }
   return AVB_OK;
+}
+
+int avb_block(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, int32_t d, int32_t axis, void* ws,
+              size_t ws_bytes, void* stream) {
+  return block_impl(h, bi, z, B, n, d, axis, 0, ws, ws_bytes, stream);
+}
+
+int avb_block_sharded(avb_handle h, int32_t bi, float* z, int32_t rows, int32_t d, int32_t dg, void* ws, size_t ws_bytes,
+                      void* stream) {
+  return block_impl(h, bi, z, 1, rows, d, AVB_AXIS_D, dg, ws, ws_bytes, stream);
 }
 
 int avb_pool(avb_handle h, const float* z, int32_t B, int32_t n, int32_t d, float* pooled, int32_t accumulate,
@@ -996,6 +1067,151 @@ int avb_forward_host(avb_handle h, const float* x_host, const float* interv_host
   AVB_CUDA(h, cudaMemcpyAsync(probs_host, dp, pbytes, cudaMemcpyDeviceToHost, st));
   AVB_CUDA(h, cudaStreamSynchronize(st));
   return AVB_OK;
+}
+
+// ----------------------------------------------------------------------------------- axially sharded forward (config 4)
+namespace {
+struct ShardWs {
+  size_t xs_off, stat_off, xsb_off, ivb_off, za_off, zb_off, blk_off, pl_off, pooled_off, uv_off, total;
+};
+ShardWs shard_ws_layout(const avb_config& c, int n, int d, int world) {
+  ShardWs w{};
+  const size_t ng = (size_t)n / world, ntok = ng * d;
+  size_t off = 0;
+  w.xs_off = off; off = align_up(off + (size_t)n * d * 4, 1024);
+  w.stat_off = off; off = align_up(off + (size_t)(n + d + 8) * 8, 1024);
+  w.xsb_off = off; off = align_up(off + ntok * 4, 1024);
+  w.ivb_off = off; off = align_up(off + ntok * 4, 1024);
+  w.za_off = off; off = align_up(off + ntok * c.dim * 4, 1024);
+  w.zb_off = off; off = align_up(off + ntok * c.dim * 4, 1024);
+  w.blk_off = off; off += block_ws_layout(c, ntok).total;
+  w.pl_off = off; off = align_up(off + (size_t)(d / world) * c.dim * 4, 1024);
+  w.pooled_off = off; off = align_up(off + (size_t)d * c.dim * 4, 1024);
+  w.uv_off = off; off = align_up(off + (size_t)2 * d * c.out_dim * 4, 1024);
+  w.total = off;
+  return w;
+}
+
+// rows [r0, r0 + ng) of src[n, d] -> column-blocked [G][ng][dg] (RowMap with dg > 0)
+__global__ void shard_gather_kernel(const float* __restrict__ src, float* __restrict__ dst, int r0, int ng, int d, int dg) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)ng * d) return;
+  const size_t blk = (size_t)ng * dg;
+  const int q = (int)(idx / blk);
+  const size_t rem = idx - (size_t)q * blk;
+  const int i = (int)(rem / dg), jj = (int)(rem - (size_t)i * dg);
+  dst[idx] = src[(size_t)(r0 + i) * d + (size_t)q * dg + jj];
+}
+}  // namespace
+
+int avb_comm_unique_id(void* id_out) {
+  if (!id_out) return fail(nullptr, AVB_ERR_INVALID, "avb_comm_unique_id: null argument");
+  const NcclApi& nc = nccl_api();
+  if (!nc.ok) return fail(nullptr, AVB_ERR_CUDA, "NCCL unavailable: %s", nc.why.c_str());
+  avb_nccl_unique_id id;
+  const int rc = nc.GetUniqueId(&id);
+  if (rc != 0) return fail(nullptr, AVB_ERR_CUDA, "ncclGetUniqueId: %s", nc.GetErrorString(rc));
+  memcpy(id_out, &id, sizeof id);
+  return AVB_OK;
+}
+
+int avb_comm_init(avb_handle h, const void* id128, int32_t rank, int32_t world) {
+  if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return fail(h, AVB_ERR_INVALID, "avb_comm_init: bad argument");
+  const NcclApi& nc = nccl_api();
+  if (!nc.ok) return fail(h, AVB_ERR_CUDA, "NCCL unavailable: %s", nc.why.c_str());
+  DeviceGuard dg(h->device);
+  if (h->comm) { nc.CommDestroy(h->comm); h->comm = nullptr; }
+  avb_nccl_unique_id id;
+  memcpy(&id, id128, sizeof id);
+  const int rc = nc.CommInitRank(&h->comm, world, id, rank);
+  if (rc != 0) { h->comm = nullptr; return fail(h, AVB_ERR_CUDA, "ncclCommInitRank(rank %d of %d): %s", rank, world, nc.GetErrorString(rc)); }
+  h->comm_rank = rank; h->comm_world = world;
+  return AVB_OK;
+}
+
+int avb_comm_destroy(avb_handle h) {
+  if (!h) return AVB_ERR_INVALID;
+  if (h->comm) {
+    DeviceGuard dg(h->device);
+    nccl_api().CommDestroy(h->comm);
+    h->comm = nullptr; h->comm_rank = 0; h->comm_world = 1;
+  }
+  return AVB_OK;
+}
+
+size_t avb_sharded_workspace_bytes(avb_handle h, int32_t n, int32_t d, int32_t world) {
+  if (!shape_ok(h, 1, n, d) || world < 1 || n % world || d % world) return 0;
+  return shard_ws_layout(h->cfg, n, d, world).total;
+}
+
+int avb_forward_sharded(avb_handle h, const float* x, const float* interv, int32_t n, int32_t d, int32_t standardize,
+                        float* probs, void* ws, size_t ws_bytes, void* stream, void* comm, int32_t rank, int32_t world) {
+  if (!h || !h->loaded) return fail(h, AVB_ERR_INVALID, "avb_forward_sharded: weights not loaded");
+  if (!shape_ok(h, 1, n, d) || !x || !probs) return fail(h, AVB_ERR_INVALID, "avb_forward_sharded: bad argument");
+  avb_nccl_comm_t cm = comm ? reinterpret_cast<avb_nccl_comm_t>(comm) : h->comm;
+  if (!comm && h->comm) { rank = h->comm_rank; world = h->comm_world; }
+  if (world < 1 || rank < 0 || rank >= world) return fail(h, AVB_ERR_INVALID, "avb_forward_sharded: bad rank %d / world %d", rank, world);
+  if (n % world) return fail(h, AVB_ERR_INVALID, "observations `n` must be divisible by `device_count` if sharding is enabled. ");
+  if (d % world) return fail(h, AVB_ERR_INVALID, "variables `d` must be divisible by `device_count` for the axial (n-shard <-> d-shard) sharding. ");
+  if (world > 1 && !cm) return fail(h, AVB_ERR_INVALID, "avb_forward_sharded: no communicator (avb_comm_init)");
+  const NcclApi& nc = nccl_api();
+  if (world > 1 && !nc.ok) return fail(h, AVB_ERR_CUDA, "NCCL unavailable: %s", nc.why.c_str());
+  DeviceGuard dev_guard(h->device);
+  const avb_config& c = h->cfg;
+  const ShardWs L = shard_ws_layout(c, n, d, world);
+  if (!ws || ws_bytes < L.total) return fail(h, AVB_ERR_WORKSPACE, "avb_forward_sharded: workspace %zu < %zu", ws_bytes, L.total);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  const int ng = n / world, dg = d / world;
+  const size_t ntok = (size_t)ng * d, chunk = (size_t)ng * dg * c.dim;
+  float* xs = reinterpret_cast<float*>(w8 + L.xs_off);
+  float* xsb = reinterpret_cast<float*>(w8 + L.xsb_off);
+  float* ivb = reinterpret_cast<float*>(w8 + L.ivb_off);
+  float* zc = reinterpret_cast<float*>(w8 + L.za_off);   // current residual stream
+  float* zn = reinterpret_cast<float*>(w8 + L.zb_off);   // target of the next exchange
+  float* pooled_loc = reinterpret_cast<float*>(w8 + L.pl_off);
+  float* pooled = reinterpret_cast<float*>(w8 + L.pooled_off);
+  int rc;
+  // every rank standardizes the whole [n, d] matrix (the z-score needs all n rows of a column; 20 MB at n=5000, d=1000),
+  // then keeps its n/G rows in column-blocked order
+  if ((rc = avb_standardize(h, x, 1, n, d, standardize, xs, w8 + L.stat_off, (size_t)(n + d + 8) * 8, stream))) return rc;
+  { ProfScope ps(h, AVB_PROF_PROLOGUE, st);
+    const unsigned gb = (unsigned)((ntok + 255) / 256);
+    shard_gather_kernel<<<gb, 256, 0, st>>>(xs, xsb, rank * ng, ng, d, dg);
+    AVB_LAUNCH_CHECK(h);
+    if (interv) { shard_gather_kernel<<<gb, 256, 0, st>>>(interv, ivb, rank * ng, ng, d, dg); AVB_LAUNCH_CHECK(h); } }
+  if ((rc = avb_embed(h, xsb, interv ? ivb : nullptr, (int64_t)ntok, zc, stream))) return rc;
+  const int nb = (int)h->blocks.size();
+  const size_t bws = block_ws_layout(c, ntok).total;
+  for (int i = 0; i < nb; ++i) {
+    if ((i & 1) == 0) {  // attend over d on the n-shard [G][n/G][d/G] (column blocks)
+      if ((rc = block_impl(h, i, zc, 1, ng, d, AVB_AXIS_D, world > 1 ? dg : 0, w8 + L.blk_off, bws, stream))) return rc;
+    } else {             // attend over n on the d-shard [n][d/G]
+      if ((rc = block_impl(h, i, zc, 1, n, dg, AVB_AXIS_N, 0, w8 + L.blk_off, bws, stream))) return rc;
+    }
+    if (i + 1 < nb && world > 1) {
+      // n-shard <-> d-shard: both layouts are G chunks of [n/G][d/G][dim]; chunk p goes to rank p and the chunk received
+      // from rank p lands at position p - one grouped send/recv, no pack or unpack pass, fp32 (bit-identical to one GPU)
+      ProfScope ps(h, AVB_PROF_COMM, st);
+      int e = nc.GroupStart();
+      for (int p = 0; p < world && e == 0; ++p) {
+        e = nc.Send(zc + (size_t)p * chunk, chunk, kNcclFloat32, p, cm, st);
+        if (e == 0) e = nc.Recv(zn + (size_t)p * chunk, chunk, kNcclFloat32, p, cm, st);
+      }
+      const int e2 = nc.GroupEnd();
+      if (e == 0) e = e2;
+      if (e != 0) return fail(h, AVB_ERR_CUDA, "NCCL exchange after block %d: %s", i, nc.GetErrorString(e));
+      std::swap(zc, zn);
+    }
+  }
+  // the last block attends over n: z is d-sharded [n][d/G], so the final LayerNorm + max over n is local (model.py:86-89)
+  if ((rc = avb_pool(h, zc, 1, n, dg, world > 1 ? pooled_loc : pooled, 0, stream))) return rc;
+  if (world > 1) {
+    ProfScope ps(h, AVB_PROF_COMM, st);
+    const int e = nc.AllGather(pooled_loc, pooled, (size_t)dg * c.dim, kNcclFloat32, cm, st);
+    if (e != 0) return fail(h, AVB_ERR_CUDA, "ncclAllGather(pooled): %s", nc.GetErrorString(e));
+  }
+  return head_impl(h, pooled, 1, d, probs, w8 + L.uv_off, (size_t)2 * d * c.out_dim * 4, stream, 0);
 }
 
 // ----------------------------------------------------------------------------------- test hooks

@@ -398,17 +398,21 @@ __global__ void __launch_bounds__(256) sgemm_kernel(
 //   sequence s, position t  ->  token  (s / inner) * outer_stride + (s % inner) * inner_stride
 //                                       + t * tok_stride
 //   (axis d: inner = 1 -> token = s*d + t;   axis n: inner = d -> token = b*n*d + j + t*d)
+//   dg > 0 (column-blocked n-shard of avb_forward_sharded, axis d): token = (t / dg) * blk_stride + s * dg + t % dg
 // grid (ceil(T/128), H, S); 128 threads, one query per thread; keys streamed through smem in
 // tiles of 32 with an online softmax (tile-wise rescale).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) attention_f32_kernel(
     const float* __restrict__ qkv, float* __restrict__ out, int T, int H, long long s_off, long long inner,
-    long long outer_stride, long long inner_stride, long long tok_stride, float scale) {
+    long long outer_stride, long long inner_stride, long long tok_stride, float scale, int dg, long long blk_stride) {
   __shared__ float4 Ks[32][8];
   __shared__ float4 Vs[32][8];
   const int h = blockIdx.y;
   const long long s = s_off + blockIdx.z;
-  const long long base = (s / inner) * outer_stride + (s % inner) * inner_stride;
+  const long long base = dg > 0 ? s * dg : (s / inner) * outer_stride + (s % inner) * inner_stride;
+  auto tok_of = [&](int t) -> long long {
+    return dg > 0 ? base + (long long)(t / dg) * blk_stride + (t % dg) : base + (long long)t * tok_stride;
+  };
   const int ld = 3 * H * 32;
   const int tq = blockIdx.x * 128 + threadIdx.x;
   const bool valid = tq < T;
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(128) attention_f32_kernel(
 #pragma unroll
   for (int e = 0; e < 32; ++e) { q[e] = 0.f; o[e] = 0.f; }
   if (valid) {
-    const float4* qp = reinterpret_cast<const float4*>(qkv + (size_t)(base + (long long)tq * tok_stride) * ld + h * 32);
+    const float4* qp = reinterpret_cast<const float4*>(qkv + (size_t)tok_of(tq) * ld + h * 32);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float4 t = qp[e];
@@ -433,7 +437,7 @@ __global__ void __launch_bounds__(128) attention_f32_kernel(
       const int kr = idx >> 3, kc = idx & 7;
       float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
       if (k0 + kr < T) {
-        const float* rowp = qkv + (size_t)(base + (long long)(k0 + kr) * tok_stride) * ld + h * 32;
+        const float* rowp = qkv + (size_t)tok_of(k0 + kr) * ld + h * 32;
         kk = reinterpret_cast<const float4*>(rowp + H * 32)[kc];
         vv = reinterpret_cast<const float4*>(rowp + 2 * H * 32)[kc];
       }
@@ -477,7 +481,7 @@ __global__ void __launch_bounds__(128) attention_f32_kernel(
   }
   if (valid) {
     const float inv = 1.0f / l;
-    float4* op = reinterpret_cast<float4*>(out + (size_t)(base + (long long)tq * tok_stride) * (H * 32) + h * 32);
+    float4* op = reinterpret_cast<float4*>(out + (size_t)tok_of(tq) * (H * 32) + h * 32);
 #pragma unroll
     for (int e = 0; e < 8; ++e)
       op[e] = make_float4(o[e * 4 + 0] * inv, o[e * 4 + 1] * inv, o[e * 4 + 2] * inv, o[e * 4 + 3] * inv);

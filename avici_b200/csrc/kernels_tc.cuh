@@ -38,17 +38,32 @@ __device__ long long* g_attn_trace = nullptr;
 #ifndef AVB_DELTA_TOKENS
 #define AVB_DELTA_TOKENS 1
 #endif
+// Column-blocked storage (dg > 0, axis 0 only, one dataset): the n-shard of an axially sharded forward
+// (avb_forward_sharded) keeps its rows in G = d / dg column blocks, token = (q * n + i) * dg + jj for row i and column
+// j = q * dg + jj, so that block q is exactly the contiguous chunk the all-to-all sends to rank q - the exchange between
+// an n-sharded and a d-sharded block then needs no pack or unpack pass.  `n` is the number of rows of the shard.
 struct RowMap {
   int n, d, axis;
+  int dg = 0;
   __device__ __forceinline__ int token(int m) const {
-    if (axis == 0) return m;
+    if (axis == 0) {
+      if (dg == 0) return m;
+      const unsigned i = (unsigned)m / (unsigned)d, j = (unsigned)m - i * (unsigned)d;
+      const unsigned q = j / (unsigned)dg, jj = j - q * (unsigned)dg;
+      return (int)((q * (unsigned)n + i) * (unsigned)dg + jj);
+    }
     const unsigned nd = (unsigned)n * (unsigned)d, b = (unsigned)m / nd, rem = (unsigned)m - b * nd;
     const unsigned j = rem / (unsigned)n, i = rem - j * (unsigned)n;
     return (int)((b * (unsigned)n + i) * (unsigned)d + j);
   }
   // inverse: token index -> sequence-major row
   __device__ __forceinline__ int seq_row(int t) const {
-    if (axis == 0) return t;
+    if (axis == 0) {
+      if (dg == 0) return t;
+      const unsigned blk = (unsigned)n * (unsigned)dg, q = (unsigned)t / blk, rem = (unsigned)t - q * blk;
+      const unsigned i = rem / (unsigned)dg, jj = rem - i * (unsigned)dg;
+      return (int)(i * (unsigned)d + q * (unsigned)dg + jj);
+    }
     const unsigned nd = (unsigned)n * (unsigned)d, b = (unsigned)t / nd, rem = (unsigned)t - b * nd;
     const unsigned i = rem / (unsigned)d, jj = rem - i * (unsigned)d;
     return (int)((b * (unsigned)d + jj) * (unsigned)n + i);
@@ -58,7 +73,7 @@ struct RowMap {
   __device__ __forceinline__ void seq_rows(int t, int step, int M, int (&out)[COUNT]) const {
     if (axis == 0) {
 #pragma unroll
-      for (int k = 0; k < COUNT; ++k) out[k] = t + k * step < M ? t + k * step : -1;
+      for (int k = 0; k < COUNT; ++k) out[k] = t + k * step < M ? (dg == 0 ? t + k * step : seq_row(t + k * step)) : -1;
       return;
     }
     const unsigned nd = (unsigned)n * (unsigned)d;
@@ -80,8 +95,24 @@ struct RowMap {
   template <int COUNT>
   __device__ __forceinline__ void tokens(int m, int step, int M, int (&tok)[COUNT]) const {
     if (axis == 0) {
+      if (dg == 0) {
 #pragma unroll
-      for (int k = 0; k < COUNT; ++k) tok[k] = m + k * step < M ? m + k * step : -1;
+        for (int k = 0; k < COUNT; ++k) tok[k] = m + k * step < M ? m + k * step : -1;
+        return;
+      }
+      unsigned i = (unsigned)m / (unsigned)d;
+      const unsigned j = (unsigned)m - i * (unsigned)d;
+      unsigned q = j / (unsigned)dg, jj = j - q * (unsigned)dg;
+      const unsigned G = (unsigned)d / (unsigned)dg;
+#pragma unroll
+      for (int k = 0; k < COUNT; ++k) {
+        tok[k] = m + k * step < M ? (int)((q * (unsigned)n + i) * (unsigned)dg + jj) : -1;
+        jj += (unsigned)step;
+        while (jj >= (unsigned)dg) {
+          jj -= (unsigned)dg;
+          if (++q >= G) { q = 0; ++i; }
+        }
+      }
       return;
     }
     const unsigned nd = (unsigned)n * (unsigned)d;
@@ -205,9 +236,9 @@ constexpr int kOutProjSmemBytes = kOutProjKB * 128 * 128 + kOutProjStages * 128 
 __global__ void __launch_bounds__(kOutProjThreads, 1)
 outproj_tc_kernel(const __nv_bfloat16* __restrict__ attn, const __grid_constant__ CUtensorMap tm_w,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ delta, int M, int seq_n,
-                  int seq_d, int seq_axis, const int* __restrict__ run_if) {
+                  int seq_d, int seq_axis, int seq_dg, const int* __restrict__ run_if) {
   if (run_if != nullptr && *run_if == 0) return;
-  const RowMap rm{seq_n, seq_d, seq_axis};
+  const RowMap rm{seq_n, seq_d, seq_axis, seq_dg};
   constexpr int ST = kOutProjStages, KB = kOutProjKB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -557,10 +588,10 @@ template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLnGemmThreads, 1)
 ln_gemm2_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorMap tm_b,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int M, int N,
-                  int seq_n, int seq_d, int seq_axis, const int* __restrict__ run_if) {
+                  int seq_n, int seq_d, int seq_axis, int seq_dg, const int* __restrict__ run_if) {
   // run_if: when not null the kernel returns at once unless *run_if != 0 (the guarded fallback behind dattn_tc_kernel)
   if (run_if != nullptr && *run_if == 0) return;
-  const RowMap rm{seq_n, seq_d, EPI == 2 ? seq_axis : 0};
+  const RowMap rm{seq_n, seq_d, EPI == 2 ? seq_axis : 0, EPI == 2 ? seq_dg : 0};
   constexpr int ST = kLnGemmBStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);

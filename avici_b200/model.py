@@ -268,12 +268,14 @@ class AVICIModel:
             interv (optional): binary matrix of the same shape, `interv[i,j] == 1` iff node `j` was
                 intervened upon in observation `i`
             return_probs (optional): `False` thresholds the prediction at 0.5 (pretrain.py:149-150)
-            devices (optional): CUDA device (index / `torch.device` / list, first entry used) to run on.
-                `None` = current device.  Under an initialised `torch.distributed` NCCL group with
-                `shard_if_possible=True`, one large dataset is sharded axially over the ranks
-                (see `avici_b200.sharded`), which like the reference requires `n` (and here also `d`)
-                to be divisible by the device count.
-            shard_if_possible (optional): see `devices`.
+            devices (optional): "gpu" / "cuda", a CUDA device, or a list of them.  `None`: every visible GPU of this
+                process, like the reference's `jax.local_devices()` (under an initialised `torch.distributed`
+                group: this rank's GPU, with the ranks of the group playing the role of the devices).
+            shard_if_possible (optional): with several devices, shard ONE dataset axially over them
+                (`avici_b200.sharded`: n-shards for the blocks that attend over d, d-shards for those that attend
+                over n, an all-to-all in between; results are bit-identical to one GPU).  Like the reference it
+                requires `n` divisible by the device count; the number of devices actually used is the largest
+                G <= device_count that also divides `d`, and 1 for small or chunked datasets.  `False`: first device.
             experimental_chunk_size (optional): as in the reference (model.py:99-116).
         Returns:
             `[d, d]` matrix of predicted edge probabilities (or 0/1 ints)
@@ -298,28 +300,39 @@ class AVICIModel:
             if not onp.allclose(onp.mod(xm, 1), 0):
                 warnings.warn("Model expects count data but `x` contains non-integer values. ")
 
-        if isinstance(devices, (list, tuple)):
-            devices = devices[0] if len(devices) else None
-        if isinstance(devices, str):
-            devices = torch.device(devices if devices != "gpu" else "cuda")
-        dev = torch.device("cuda", torch.cuda.current_device()) if devices is None else torch.device(devices)
-        assert dev.type == "cuda", "avici_b200 runs on CUDA (sm_100a) devices only"
-
         from . import sharded
+        devs = self._resolve_devices(devices)
+        dev = devs[0]
         world = sharded.world_size()
+        n_obs, n_vars = x.shape
         with torch.cuda.device(dev):
-            xt = torch.as_tensor(x).to(device=dev, dtype=torch.float32)
-            it = None if interv is None else torch.as_tensor(interv).to(device=dev, dtype=torch.float32)
-            if shard_if_possible and world > 1:
-                assert not x.shape[0] % world, ("observations `n` must be divisible by `device_count` if sharding "
-                                                "is enabled. ")
-                assert not x.shape[1] % world, ("variables `d` must be divisible by `device_count` for the axial "
-                                                "(n-shard <-> d-shard) sharding of this implementation. ")
-                assert not experimental_chunk_size or experimental_chunk_size >= x.shape[0], (
+            if shard_if_possible and world > 1 and devices is None:
+                # one process per GPU (torchrun): shard over the ranks of the default group
+                assert not n_obs % world, ("observations `n` must be divisible by `device_count` if sharding "
+                                           "is enabled. ")
+                assert not n_vars % world, ("variables `d` must be divisible by `device_count` for the axial "
+                                            "(n-shard <-> d-shard) sharding of this implementation. ")
+                assert not experimental_chunk_size or experimental_chunk_size >= n_obs, (
                     "`experimental_chunk_size` is not supported together with axial sharding; pass "
                     "`shard_if_possible=False` to run the chunked forward on one device. ")
+                xt = torch.as_tensor(x).to(device=dev, dtype=torch.float32)
+                it = None if interv is None else torch.as_tensor(interv).to(device=dev, dtype=torch.float32)
                 out = sharded.forward_axial(self, xt, it)
+            elif shard_if_possible and len(devs) > 1:
+                # one process, several GPUs - the reference's own mode (pretrain.py:124-143)
+                assert not n_obs % len(devs), ("observations `n` must be divisible by `device_count` if sharding "
+                                               "is enabled. ")
+                G = self._shard_count(n_obs, n_vars, len(devs), experimental_chunk_size)
+                xt = torch.as_tensor(x).to(dtype=torch.float32)
+                it = None if interv is None else torch.as_tensor(interv).to(dtype=torch.float32)
+                if G > 1:
+                    out = sharded.forward_axial_devices(self, xt, it, devs[:G])
+                else:
+                    out = self.__call_main__(xt.to(dev), None if it is None else it.to(dev),
+                                             experimental_chunk_size=experimental_chunk_size)
             else:
+                xt = torch.as_tensor(x).to(device=dev, dtype=torch.float32)
+                it = None if interv is None else torch.as_tensor(interv).to(device=dev, dtype=torch.float32)
                 out = self.__call_main__(xt, it, experimental_chunk_size=experimental_chunk_size)
             if not return_probs:
                 out = (out > 0.5).to(torch.int64)
@@ -329,13 +342,59 @@ class AVICIModel:
                     out = out.astype(int)
         return out
 
-    def infer_batch(self, x, interv=None, return_probs=True, experimental_chunk_size=None):
-        """Batched forward `[B,n,d] -> [B,d,d]` (the reference's batched call site is train.py:61)."""
+    # datasets smaller than this many cells are not worth an exchange per block: they run on the first device
+    SHARD_MIN_CELLS = 1 << 17
+
+    @staticmethod
+    def _resolve_devices(devices):
+        """`devices` of the reference's `__call__` -> list of CUDA devices.  None / "gpu" / "cuda": every visible GPU in a
+        plain process, the current device under an initialised `torch.distributed` group (one process per GPU)."""
+        torch = _torch()
+        from . import sharded
+        if devices is None or (isinstance(devices, str) and devices in ("gpu", "cuda")):
+            if sharded.world_size() > 1:
+                return [torch.device("cuda", torch.cuda.current_device())]
+            cur = torch.cuda.current_device()
+            idx = [cur] + [i for i in range(torch.cuda.device_count()) if i != cur]
+            return [torch.device("cuda", i) for i in idx]
+        if not isinstance(devices, (list, tuple)):
+            devices = [devices]
+        out = []
+        for dv in devices:
+            dv = torch.device("cuda", dv) if isinstance(dv, int) else torch.device(dv)
+            assert dv.type == "cuda", "avici_b200 runs on CUDA (sm_100a) devices only"
+            out.append(torch.device("cuda", torch.cuda.current_device() if dv.index is None else dv.index))
+        assert out, "`devices` must not be empty"
+        return out
+
+    @classmethod
+    def _shard_count(cls, n, d, device_count, chunk_size=None):
+        """Number of devices one dataset is sharded over: the largest G <= device_count with G | n and G | d (the
+        axial scheme re-shards between the n and the d axis, so both must divide; the reference shards n only).
+        1 for small datasets and for the chunked forward."""
+        if (chunk_size and 0 < chunk_size < n) or n * d < cls.SHARD_MIN_CELLS:
+            return 1
+        for G in range(device_count, 0, -1):
+            if n % G == 0 and d % G == 0:
+                return G
+        return 1
+
+    def infer_batch(self, x, interv=None, return_probs=True, experimental_chunk_size=None, devices=None):
+        """Batched forward `[B,n,d] -> [B,d,d]` (the reference's batched call site is train.py:61).
+        `devices`: a list of CUDA devices spreads the independent datasets over them (one host thread and one
+        handle per device, no collective); default: the current device."""
         torch = _torch()
         is_np = isinstance(x, onp.ndarray)
         assert x.ndim == 3, "`x` must be a 3D array of shape [B, n, d]."
         if interv is not None:
             assert x.shape == interv.shape, "`x` and `interv` must have the same shape when provided."
+        if devices is not None and len(self._resolve_devices(devices)) > 1:
+            from . import sharded
+            xt = torch.as_tensor(x)
+            out = sharded.infer_batch_devices(self, xt, None if interv is None else torch.as_tensor(interv),
+                                              self._resolve_devices(devices), chunk_size=experimental_chunk_size)
+            out = out if return_probs else (out > 0.5).to(torch.int64)
+            return out.cpu().numpy() if is_np else out
         if is_np:
             out = self.engine.forward_host(x, interv, standardize=self._standardizer,
                                            chunk_size=experimental_chunk_size)

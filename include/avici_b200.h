@@ -129,6 +129,12 @@ size_t avb_block_workspace_bytes(avb_handle h, int32_t B, int32_t n, int32_t d);
 int avb_block(avb_handle h, int32_t block_idx, float* z_dev, int32_t B, int32_t n, int32_t d,
               int32_t axis, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* The same `_block`, attending over d, on the n-shard of ONE axially sharded dataset whose `rows` x d tokens are stored
+ * in d / dg column blocks: token (i, j) at ((j / dg) * rows + i) * dg + j % dg.  Column block q is the contiguous chunk the
+ * all-to-all of avb_forward_sharded sends to rank q, so re-sharding needs no pack / unpack pass.  dg = 0: plain layout. */
+int avb_block_sharded(avb_handle h, int32_t block_idx, float* z_dev, int32_t rows, int32_t d, int32_t dg,
+                      void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Final LayerNorm + max over n (model.py:86-89): pooled_dev[B,d,dim].  When `accumulate` != 0
  * the result is max-combined into pooled_dev (chunk path model.py:116, n-sharded ranks). */
 int avb_pool(avb_handle h, const float* z_dev, int32_t B, int32_t n, int32_t d, float* pooled_dev,
@@ -142,6 +148,27 @@ int avb_head(avb_handle h, const float* pooled_dev, int32_t B, int32_t d, float*
 /* Same head, log-probabilities: log_sigmoid(logits), diagonal = -inf (model.py:218-220). */
 int avb_head_logprobs(avb_handle h, const float* pooled_dev, int32_t B, int32_t d, float* logprobs_dev,
                       void* scratch_dev, size_t scratch_bytes, void* stream);
+
+/* ---- one large dataset sharded axially over the GPUs of a node (BASELINE config 4; replaces the reference's
+ * `shard_if_possible` path, avici/pretrain.py:124-143, which shards n only and leaves the collectives to XLA/GSPMD).
+ * One handle and one rank per GPU.  Blocks that attend over d run on the rank's n-shard [n/G, d] (column-blocked, see
+ * avb_block_sharded), blocks that attend over n on its d-shard [n, d/G]; between consecutive blocks the fp32 residual
+ * stream is re-sharded with ONE grouped ncclSend/ncclRecv all-to-all (chunk p -> rank p), in place of the layout, so the
+ * result is bit-identical to the single-GPU forward.  The final LayerNorm + max over n is local to the d-shard; the pooled
+ * [d/G, dim] rows are all-gathered and every rank computes the head.  Requires G | n and G | d.
+ *   avb_comm_unique_id : rank 0 creates the 128-byte NCCL unique id (broadcast it to the other ranks by any means)
+ *   avb_comm_init      : every rank, collectively: ncclCommInitRank on the handle's device; the handle owns the comm
+ *   avb_forward_sharded: x_dev / interv_dev are the FULL [n, d] matrices on every rank (20 MB at n=5000, d=1000),
+ *                        probs_dev[d, d] is produced on every rank.  `comm`: an ncclComm_t of the caller's, or NULL for
+ *                        the handle's own (then rank / world are the handle's).  NCCL is resolved with dlopen at the first
+ *                        call (the libnccl.so.2 already loaded in the process, e.g. PyTorch's); world = 1 needs none. */
+int avb_comm_unique_id(void* id_out /*128 bytes*/);
+int avb_comm_init(avb_handle h, const void* id /*128 bytes*/, int32_t rank, int32_t world);
+int avb_comm_destroy(avb_handle h);
+size_t avb_sharded_workspace_bytes(avb_handle h, int32_t n, int32_t d, int32_t world);
+int avb_forward_sharded(avb_handle h, const float* x_dev, const float* interv_dev, int32_t n, int32_t d,
+                        int32_t standardize, float* probs_dev, void* workspace_dev, size_t workspace_bytes, void* stream,
+                        void* comm /*ncclComm_t or NULL*/, int32_t rank, int32_t world);
 
 /* ---- graph metrics on the device: replaces the per-dataset numpy calls of the eval loop
  * avici/train.py:125-151 -> avici/metrics.py:5-24 (shd), :27-32 (n_edges), :35-51 (is_acyclic / is_cyclic),
@@ -184,7 +211,8 @@ int64_t avb_launch_count(avb_handle h);
 #define AVB_PROF_FFN 5       /* FFN sub-layer (LayerNorm, up-projection, ReLU, down-projection)    */
 #define AVB_PROF_POOL_HEAD 6 /* final LN + max-pool + head                                         */
 #define AVB_PROF_DATTN 7     /* fused LayerNorm + QKV + attention over d + out-projection (d<=128) */
-#define AVB_PROF_CATEGORIES 8
+#define AVB_PROF_COMM 8      /* axially sharded forward: all-to-all exchanges + the pooled all-gather  */
+#define AVB_PROF_CATEGORIES 9
 int avb_profile_enable(avb_handle h, int32_t on);
 int avb_profile_read(avb_handle h, double* ms_out /*[AVB_PROF_CATEGORIES]*/,
                      int64_t* count_out /*[AVB_PROF_CATEGORIES]*/, int32_t reset);

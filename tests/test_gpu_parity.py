@@ -398,7 +398,8 @@ def test_config5_stated_size_vs_oracle(dtype):
 def test_config4_twin_axial_shards_vs_oracle(dtype):
     """BASELINE config 4's twin (n=640, d=256; the full n=5000, d=1000 is hours of oracle time): the axially sharded
     schedule - d-axis blocks on row shards, n-axis blocks on column shards, 4 shards processed in turn through the
-    stage-level C-ABI, exactly what each rank of `sharded.forward_axial` runs - against the ORACLE."""
+    stage-level C-ABI in the layouts each rank of `avb_forward_sharded` uses (column-blocked n-shards) - against the
+    ORACLE."""
     x, interv, cos, counts, seed = _full_case("c4twin_n640_d256")
     G = 4
     for head, tols in ((REF_INIT, TOL), (STRESS, TOL_STRESS)):
@@ -415,12 +416,13 @@ def test_config4_twin_axial_shards_vs_oracle(dtype):
         eng._check(lib.avb_embed(h, xs.data_ptr(), None, n * d, z.data_ptr(), st))
         ws = torch.empty(int(max(lib.avb_block_workspace_bytes(h, 1, n // G, d), lib.avb_block_workspace_bytes(h, 1, n, d // G))),
                          dtype=torch.uint8, device="cuda")
+        from avici_b200 import sharded
         for i in range(16):
-            if i % 2 == 0:
-                shards = [z[r * n // G:(r + 1) * n // G].contiguous() for r in range(G)]
+            if i % 2 == 0:  # the n-shard in column blocks [G][n/G][d/G][k], as avb_forward_sharded keeps it
+                shards = [sharded.to_column_blocks(z[r * n // G:(r + 1) * n // G], G) for r in range(G)]
                 for s_ in shards:
-                    eng._check(lib.avb_block(h, i, s_.data_ptr(), 1, n // G, d, 0, ws.data_ptr(), ws.numel(), st))
-                z = torch.cat(shards, 0)
+                    eng._check(lib.avb_block_sharded(h, i, s_.data_ptr(), n // G, d, d // G, ws.data_ptr(), ws.numel(), st))
+                z = torch.cat([sharded.from_column_blocks(s_) for s_ in shards], 0)
             else:
                 shards = [z[:, r * d // G:(r + 1) * d // G].contiguous() for r in range(G)]
                 for s_ in shards:
@@ -501,6 +503,71 @@ def test_stage_api_matches_forward_and_axial_layouts():
     eng._check(lib.avb_head(h, pooled.data_ptr(), 1, d, probs.data_ptr(), hs.data_ptr(), hs.numel(), st))
     torch.cuda.synchronize()
     assert (probs - full).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_block_sharded_column_blocks_bit_identical(dtype):
+    """avb_block_sharded on a column-blocked n-shard == avb_block on the same rows in plain order, bit for bit (the
+    layout only changes where a token lives).  The plain run is pinned to the unfused kernels, which is what the sharded
+    block uses for every d (the fused d <= 128 kernel rounds at different points)."""
+    from avici_b200 import sharded
+    model = avici_b200.random_init_model(dict(layers=1, **STRESS), seed=2, perturb=True, compute_dtype=dtype)
+    eng = model.engine
+    lib, h = eng.lib, eng.handle
+    eng._check(lib.avb_test_set_dattn_mode(h, 0))
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for rows, d, G in ((37, 144, 4), (16, 40, 2), (5, 1000, 8)):
+        z0 = torch.randn(rows, d, 128, device="cuda", generator=g) * 1.5
+        ws = torch.empty(int(lib.avb_block_workspace_bytes(h, 1, rows, d)), dtype=torch.uint8, device="cuda")
+        plain = z0.clone()
+        eng._check(lib.avb_block(h, 0, plain.data_ptr(), 1, rows, d, 0, ws.data_ptr(), ws.numel(), st))
+        blk = sharded.to_column_blocks(z0, G)
+        eng._check(lib.avb_block_sharded(h, 0, blk.data_ptr(), rows, d, d // G, ws.data_ptr(), ws.numel(), st))
+        torch.cuda.synchronize()
+        assert torch.equal(sharded.from_column_blocks(blk), plain), (rows, d, G)
+    with pytest.raises(AssertionError, match="column blocks"):
+        eng._check(lib.avb_block_sharded(h, 0, z0.data_ptr(), 5, 1000, 7, ws.data_ptr(), ws.numel(), st))
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_forward_sharded_world1_equals_forward(dtype):
+    """avb_forward_sharded with one rank (no communicator needed) is avb_forward."""
+    model = avici_b200.random_init_model(dict(layers=2, **STRESS), seed=5, perturb=True, compute_dtype=dtype)
+    eng = model.engine
+    lib, h = eng.lib, eng.handle
+    g, x, iv = avici_b200.simulate_data(d=24, n=96, n_interv=32, seed=9, domain="lin-gauss")
+    n, d = x.shape  # 128 rows: 96 observational + 32 interventional
+    xt, it = torch.as_tensor(x, dtype=torch.float32).cuda(), torch.as_tensor(iv, dtype=torch.float32).cuda()
+    full = model(x=xt, interv=it.clone())
+    ws = torch.empty(int(lib.avb_sharded_workspace_bytes(h, n, d, 1)), dtype=torch.uint8, device="cuda")
+    probs = torch.empty(d, d, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    eng._check(lib.avb_forward_sharded(h, xt.data_ptr(), it.data_ptr(), n, d, 1, probs.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       st, None, 0, 1))
+    torch.cuda.synchronize()
+    assert torch.equal(probs, full)
+    assert lib.avb_sharded_workspace_bytes(h, n, d, 5) == 0  # 5 does not divide n
+    with pytest.raises(AssertionError, match="divisible"):
+        eng._check(lib.avb_forward_sharded(h, xt.data_ptr(), None, n, d, 1, probs.data_ptr(), ws.data_ptr(), ws.numel(), st,
+                                           None, 0, 5))
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_axial_sharding_over_two_gpus(dtype):
+    """One process, two GPUs (the reference's `devices=` + `shard_if_possible=True`): the axially sharded forward with
+    its NCCL exchanges is bit-identical to the single-GPU forward; `infer_batch(devices=...)` spreads a batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    model = avici_b200.random_init_model(dict(layers=3, **STRESS), seed=6, perturb=True, compute_dtype=dtype)
+    model.SHARD_MIN_CELLS = 0
+    g, x, iv = avici_b200.simulate_data(d=136, n=320, n_interv=64, seed=3, domain="lin-gauss")
+    x = x.astype(np.float32); iv = iv.astype(np.float32)
+    one = model(x=x, interv=iv.copy(), devices=[0])
+    two = model(x=x, interv=iv.copy(), devices=[0, 1])
+    assert np.array_equal(one, two)
+    xb = np.stack([x[:200, :50], x[100:300, 50:100], x[120:320, 86:136]])
+    assert np.array_equal(model.infer_batch(xb, devices=[0, 1]), model.infer_batch(xb))
 
 
 def test_edge_shapes_and_errors():
