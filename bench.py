@@ -16,6 +16,8 @@ One JSON line on rank 0:
   roofline   dominant kernel (n-axis attention) algorithmic FLOP/s against the measured bf16 peak,
              from CUDA events on the launching stream over a second pass of the same K steps
   cpu_baseline  the torch-CPU restatement of the reference forward (oracle/) on a bounded sample
+  axial      (WORLD_SIZE > 1 only, after the timed region) BASELINE config 4: one n=5000, d=1000 dataset sharded axially
+             over all ranks vs the same forward on one GPU: ms, speed-up, NCCL share, max|dp| (bit-identical = 0)
 
 The reference itself (JAX + Haiku) cannot be installed offline, so `--impl reference` times
 the oracle restatement on the host cores — the tier's meaning of the reference arm.
@@ -167,6 +169,59 @@ def ncu_traffic(key):
         return None
 
 
+AXIAL_N, AXIAL_D = 5000, 1000  # BASELINE config 4: one large dataset, axially sharded over the ranks
+
+
+def axial_leg(model, world, rank, dist, timed, barrier):
+    """BASELINE config 4 (runs behind the main timed region when WORLD_SIZE > 1): ONE rff-gauss dataset n=5000, d=1000
+    through `avb_forward_sharded` on all ranks (n-shards <-> d-shards, an NCCL all-to-all of the fp32 residual stream
+    between consecutive blocks) against the same forward on rank 0's GPU alone: ms, speed-up, comm share, max|dp|."""
+    import torch
+    from avici_b200 import _lib, sharded
+    n, d = AXIAL_N, AXIAL_D
+    if n % world or d % world:
+        return {"skipped": f"n={n}, d={d} not divisible by {world} ranks"}
+    x = torch.empty((n, d), dtype=torch.float32, device="cuda")
+    if rank == 0:  # ~12 s of numpy on one rank; the others receive the matrix
+        from avici_b200.synthetic import simulate_data
+        x.copy_(torch.as_tensor(simulate_data(d, n, seed=4, domain="rff-gauss")[1].astype(np.float32)))
+    dist.broadcast(x, src=0)
+    eng = model.engine
+    f = lambda: sharded.forward_axial(model, x)  # noqa: E731
+    p_sh = f()  # creates the communicator, sizes the workspace
+    steps = 3
+    ms_sh = timed(f, steps) / steps
+    eng.profile(True)
+    eng.profile_read(reset=True)
+    timed(f, 1)
+    prof = eng.profile_read(reset=True)
+    eng.profile(False)
+    comm_ms = torch.tensor([prof["comm"][0]], device="cuda")
+    dist.all_reduce(comm_ms, op=dist.ReduceOp.MAX)
+    out = None
+    if rank == 0:  # the same dataset on one GPU (the other ranks wait at the barrier)
+        g = lambda: eng.forward(x[None], None, standardize=_lib.AVB_STANDARDIZE_DEFAULT)  # noqa: E731
+        p_1 = g()[0]
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_1 = e0.elapsed_time(e1)
+        F = flops_per_dataset(n, d)
+        out = {"workload": f"rff-gauss n={n} d={d}, one dataset, 16 blocks, bf16, sharded axially over {world} GPUs "
+                           "(n-shard <-> d-shard, fp32 all-to-all between blocks)",
+               "ms_sharded": ms_sh, "ms_single_gpu": ms_1, "speedup": ms_1 / ms_sh, "n_gpus": world,
+               "comm_ms_per_forward": float(comm_ms.item()), "comm_share": float(comm_ms.item()) / ms_sh,
+               "exchange_bytes_per_gpu_per_forward": int(15 * (world - 1) / world * n * d * 128 * 4 / world),
+               "tflops_sharded": F / (ms_sh * 1e-3) / 1e12, "tflops_single_gpu": F / (ms_1 * 1e-3) / 1e12,
+               "max_abs_dp_vs_single_gpu": float((p_sh - p_1).abs().max().item()),
+               "steps": steps, "timing": "CUDA events, max over ranks"}
+    barrier()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -239,6 +294,16 @@ def run_ours(args):
     prof = eng.profile_read(reset=True)
     eng.profile(False)
 
+    axial = None
+    if world > 1 and not args.no_axial:
+        del x_dev, out  # the axial leg needs the memory of rank 0 for the single-GPU run of the same dataset
+        eng._ws = None
+        torch.cuda.empty_cache()
+        try:
+            axial = axial_leg(model, world, rank, dist, timed, barrier)
+        except Exception as e:  # the headline line must still be printed
+            axial = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if rank == 0:
         peaks = measured_peaks()
         F = flops_per_dataset(N_OBS, N_VARS)
@@ -291,6 +356,7 @@ def run_ours(args):
                                       if ms_attn > 0 else 0.0,
                                       "mufu_peak_Texp_s": 16 * 148 * 1.965e9 / 1e12}},
             "kernel_ms_per_step": breakdown, "profiled_ms_per_step": ms_prof / args.steps,
+            "axial": axial,
             "cpu_baseline": None if cpu_val is None else {
                 "value": cpu_val, "unit": "datasets/s", "cores": cores, "kind": "port",
                 "sample": f"1 dataset of the bench workload (n={N_OBS}, d={N_VARS}), torch-CPU fp32 restatement, {cpu_dt:.1f} s"},
@@ -309,6 +375,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-axial", action="store_true", help="skip the config-4 leg that runs when WORLD_SIZE > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
