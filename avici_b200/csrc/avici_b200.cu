@@ -260,7 +260,7 @@ inline const char* ab_env(const char* name) {
 // run_if: see ln_gemm2_tc_kernel.
 int launch_ln_gemm2_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, const float* bias, void* out, int ldo,
                        int M, int N, cudaStream_t st, int num_sms, long long* launches, int seq_n, int seq_d, int seq_axis,
-                       const int* run_if = nullptr, int seq_dg = 0) {
+                       const int* run_if = nullptr, int seq_dg = 0, float* norms = nullptr) {
   static PerDeviceOnce once;
   cudaError_t e = once.run([] {
     return cudaFuncSetAttribute(avb::ln_gemm2_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kLnGemmSmemBytes);
@@ -269,7 +269,7 @@ int launch_ln_gemm2_tc(avb_handle h, const float* z, const CUtensorMap& tm_b, co
   const int num_pairs = ((M + 127) / 128 + 1) / 2;
   const int grid = 2 * std::min(num_pairs, num_sms / 2);
   avb::ln_gemm2_tc_kernel<2><<<grid, avb::kLnGemmThreads, avb::kLnGemmSmemBytes, st>>>(
-      z, tm_b, bias, reinterpret_cast<bf16*>(out), ldo, M, N, seq_n, seq_d, seq_axis, seq_dg, run_if);
+      z, tm_b, bias, reinterpret_cast<bf16*>(out), ldo, M, N, seq_n, seq_d, seq_axis, seq_dg, run_if, norms);
   if (launches) ++*launches;
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ln_gemm2_tc launch: %s", cudaGetErrorString(e));
@@ -335,7 +335,8 @@ int launch_ffn2_tc(avb_handle h, float* z, const CUtensorMap& tm_w1q, const CUte
 // mode 0: fast + guarded exact (reset_guard: clear the guard first); 1: the exact kernel alone, unconditionally;
 // 3: the exact kernel alone, only if the guard is already up (fallback behind dattn_tc_kernel).
 int launch_attention_tc(avb_handle h, const void* qkv, void* out, int B, int n, int d, int H, int axis,
-                        cudaStream_t st, int num_sms, long long* launches, int* guard, int mode = 0) {
+                        cudaStream_t st, int num_sms, long long* launches, int* guard, int mode = 0,
+                        const float* norms = nullptr) {
   static PerDeviceOnce once;
   cudaError_t e = once.run([] {
     cudaError_t r = cudaFuncSetAttribute(avb::attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kAttnSmemBytes);
@@ -356,12 +357,12 @@ int launch_attention_tc(avb_handle h, const void* qkv, void* out, int B, int n, 
   if (mode == 0 || mode == 2) {
     if (cudaMemsetAsync(guard, 0, sizeof(int), st) != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention guard reset failed");
     avb::attention_tc_kernel<true><<<grid, avb::kAttnThreads, avb::kAttnSmemBytes, st>>>(
-        reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis, guard);
+        reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis, guard, norms);
     if (launches) ++*launches;
   }
   if (mode != 2) {
     avb::attention_tc_kernel<false><<<grid, avb::kAttnThreads, avb::kAttnSmemBytes, st>>>(
-        reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis, mode == 1 ? nullptr : guard);
+        reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis, mode == 1 ? nullptr : guard, nullptr);
     if (launches) ++*launches;
   }
   e = cudaGetLastError();
@@ -846,12 +847,14 @@ static int block_impl(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, 
         if ((rc = launch_outproj_tc(h, attn, W.tm_wo, W.bo, qkv, M, n, d, axis, st, h->num_sms, &h->launches,
                                     fuse_out ? guard : nullptr))) return rc; }
     } else {
+    float* norms = reinterpret_cast<float*>(guard) + 1;  // {max |q_h|^2, max |k_h|^2} of this block's projection
     { ProfScope ps(h, AVB_PROF_QKV, st);  // LayerNorm fused into the projection's prologue;
       // rows in sequence-major order of `axis`, output in the attention kernel's operand layout
+      if (cudaMemsetAsync(norms, 0, 2 * sizeof(float), st) != cudaSuccess) return fail(h, AVB_ERR_CUDA, "score-bound reset failed");
       if ((rc = launch_ln_gemm2_tc(h, z, W.tm_wqkv_h, W.bqkv_f, qkv, 3 * HD, M, 3 * HD, st, h->num_sms, &h->launches,
-                                   n, d, axis, nullptr, dg))) return rc; }
+                                   n, d, axis, nullptr, dg, norms))) return rc; }
     { ProfScope ps(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
-      if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches, guard))) return rc; }
+      if ((rc = launch_attention_tc(h, qkv, attn, B, n, d, H, axis, st, h->num_sms, &h->launches, guard, 0, norms))) return rc; }
     { ProfScope ps(h, AVB_PROF_OUT, st);
       if ((rc = launch_outproj_tc(h, attn, W.tm_wo, W.bo, qkv, M, n, d, axis, st, h->num_sms, &h->launches, nullptr, dg)))
         return rc; }
@@ -1407,10 +1410,11 @@ int avb_test_attention_bf16(const void* qkv, void* out, int32_t B, int32_t n, in
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "no CUDA device");
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  static int* guard = nullptr;  // test entry point: one process-wide guard word and repack buffer
+  static int* guard = nullptr;  // test entry point: one process-wide guard word (+ score bound) and repack buffer
   static void* packed = nullptr;
   static size_t packed_bytes = 0;
-  if (!guard && cudaMalloc(&guard, sizeof(int)) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "cudaMalloc(guard) failed");
+  if (!guard && cudaMalloc(&guard, 4 * sizeof(int)) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "cudaMalloc(guard) failed");
+  float* norms = reinterpret_cast<float*>(guard) + 1;
   const size_t need = ((size_t)B * n * d * 3 + (((size_t)B * n * d + 127) / 128) * 128) * H * 32 * sizeof(bf16);
   if (packed_bytes < need) {
     if (packed) cudaFree(packed);
@@ -1420,13 +1424,24 @@ int avb_test_attention_bf16(const void* qkv, void* out, int32_t B, int32_t n, in
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static const bool prepacked = ab_env("AVB_ATTN_PREPACKED") != nullptr;  // profiling scripts: time the attention alone
-  if (prepacked) return launch_attention_tc(nullptr, qkv, out, B, n, d, H, axis, st, sms, nullptr, guard);
+  if (prepacked) {  // the score bound the QKV projection would have recorded (profiling runs: once per process, so that
+    static bool have_norms = false;  // the timed launches are the attention kernel alone)
+    if (!have_norms) {
+      if (cudaMemsetAsync(norms, 0, 2 * sizeof(float), st) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "memset failed");
+      avb::qk_norms_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const bf16*>(qkv), (size_t)B * n * d * H, H, axis == 0 ? d : n, norms);
+      cudaStreamSynchronize(st);
+      have_norms = true;
+    }
+    return launch_attention_tc(nullptr, qkv, out, B, n, d, H, axis, st, sms, nullptr, guard, 0, norms);
+  }
   // token-major test tensors <-> the kernels' operand layouts; `out` must hold whole 128-row tiles in the packed form,
   // so the packed output lives behind the packed input in the scratch buffer
   bf16* pin = reinterpret_cast<bf16*>(packed);
   bf16* pout = pin + (size_t)B * n * d * 3 * H * 32;
   avb::repack_qkv_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const bf16*>(qkv), pin, B, n, d, H, axis);
-  const int rc = launch_attention_tc(nullptr, pin, pout, B, n, d, H, axis, st, sms, nullptr, guard);
+  if (cudaMemsetAsync(norms, 0, 2 * sizeof(float), st) != cudaSuccess) return fail(nullptr, AVB_ERR_CUDA, "memset failed");
+  avb::qk_norms_kernel<<<sms * 8, 256, 0, st>>>(pin, (size_t)B * n * d * H, H, axis == 0 ? d : n, norms);
+  const int rc = launch_attention_tc(nullptr, pin, pout, B, n, d, H, axis, st, sms, nullptr, guard, 0, norms);
   if (rc != AVB_OK) return rc;
   avb::unpack_attn_kernel<<<sms * 8, 256, 0, st>>>(pout, reinterpret_cast<bf16*>(out), B, n, d, H, axis);
   return cudaGetLastError() == cudaSuccess ? AVB_OK : fail(nullptr, AVB_ERR_CUDA, "unpack_attn launch failed");

@@ -588,8 +588,10 @@ template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLnGemmThreads, 1)
 ln_gemm2_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensorMap tm_b,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int M, int N,
-                  int seq_n, int seq_d, int seq_axis, int seq_dg, const int* __restrict__ run_if) {
+                  int seq_n, int seq_d, int seq_axis, int seq_dg, const int* __restrict__ run_if, float* __restrict__ norms) {
   // run_if: when not null the kernel returns at once unless *run_if != 0 (the guarded fallback behind dattn_tc_kernel)
+  // norms (may be null, zeroed by the caller): {max |q_h|^2, max |k_h|^2} over the (row, head) vectors this launch writes,
+  //   the score bound that lets the attention kernel drop the range clamps of its polynomial exp2 lanes
   if (run_if != nullptr && *run_if == 0) return;
   const RowMap rm{seq_n, seq_d, EPI == 2 ? seq_axis : 0, EPI == 2 ? seq_dg : 0};
   constexpr int ST = kLnGemmBStages;
@@ -705,6 +707,7 @@ ln_gemm2_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensor
     const int seq_T = seq_axis == 0 ? seq_d : seq_n, seq_H = N / 96;  // sequence length, heads (N = 3 * H * 32)
     int acc_it = 0;
     uint32_t piece = 0;  // stage buffer parity
+    float nrm_q = 0.f, nrm_k = 0.f;
     for (int pr = pair0, mt = 2 * pair0 + (int)rank; pr < num_pairs; pr += pair_stride, mt += 2 * pair_stride) {
       const int grow0 = mt * 128 + q * 32;                    // first row (sequence-major index) of this warp
       const int rows_valid = M - grow0 < 32 ? M - grow0 : 32;  // may be <= 0
@@ -735,6 +738,7 @@ ln_gemm2_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensor
               ptx::tc_fence_before();
               ptx::mbar_arrive_cluster(&t_empty[as], 0);
             }
+            float ss0 = 0.f, ss1 = 0.f;  // |row . head|^2 of these 32 channels (q and k chunks only)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float f[8];
@@ -742,10 +746,17 @@ ln_gemm2_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensor
               f[2] = __uint_as_float(v[e * 8 + 2]) + bb[e * 2].z;     f[3] = __uint_as_float(v[e * 8 + 3]) + bb[e * 2].w;
               f[4] = __uint_as_float(v[e * 8 + 4]) + bb[e * 2 + 1].x; f[5] = __uint_as_float(v[e * 8 + 5]) + bb[e * 2 + 1].y;
               f[6] = __uint_as_float(v[e * 8 + 6]) + bb[e * 2 + 1].z; f[7] = __uint_as_float(v[e * 8 + 7]) + bb[e * 2 + 1].w;
+              if (c < 2) {  // columns [0, 512): q and k (N = 768, 256-column chunks)
+#pragma unroll
+                for (int t = 0; t < 8; t += 2) { ss0 = fmaf(f[t], f[t], ss0); ss1 = fmaf(f[t + 1], f[t + 1], ss1); }
+              }
               uint4 pk;
               pk.x = ptx::pack_bf16(f[0], f[1]); pk.y = ptx::pack_bf16(f[2], f[3]);
               pk.z = ptx::pack_bf16(f[4], f[5]); pk.w = ptx::pack_bf16(f[6], f[7]);
               ptx::st_shared_v4(stage + (uint32_t)(cc * 2048 + lane * 64 + (((uint32_t)e ^ my_swz) << 4)), pk);
+            }
+            if (c < 2 && lane < rows_valid) {
+              if (c == 0) nrm_q = fmaxf(nrm_q, ss0 + ss1); else nrm_k = fmaxf(nrm_k, ss0 + ss1);
             }
           }
           ptx::fence_proxy_async();  // staging writes (generic proxy) -> visible to the bulk copy engine
@@ -769,6 +780,17 @@ ln_gemm2_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensor
     }
     if (lane == 0) ptx::bulk_wait_all();
     __syncwarp();
+    if (norms != nullptr) {  // one atomic per warp and operand (non-negative floats order like their bit patterns)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        nrm_q = fmaxf(nrm_q, __shfl_xor_sync(0xffffffffu, nrm_q, o));
+        nrm_k = fmaxf(nrm_k, __shfl_xor_sync(0xffffffffu, nrm_k, o));
+      }
+      if (lane == 0) {
+        atomicMax(reinterpret_cast<int*>(norms), __float_as_int(nrm_q));
+        atomicMax(reinterpret_cast<int*>(norms) + 1, __float_as_int(nrm_k));
+      }
+    }
   }
   ptx::tc_fence_before();
   ptx::cluster_sync_all();  // the peer's shared memory and barriers stay valid until both CTAs are done
@@ -1367,7 +1389,14 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 // poly_exp2, evaluated on packed pairs), the others through MUFU.  pmax accumulates the maximum of the raw scores on
 // the polynomial lanes: MUFU saturates to +inf when a score is out of range (the epilogue sees it in the row sum) but
 // the polynomial's exponent arithmetic wraps, so those lanes are range-checked by the caller.
+// kClamp = false: the caller guarantees |s| <= 100 for every score of the launch (the QKV projection records the largest
+// |q_h|^2 and |k_h|^2 it writes: |s| <= |q||k|), so the polynomial lanes need neither the lower clamp nor the running
+// maximum - 9 instead of 12 issue slots per pair, which is what lets a larger share of the exponentials leave the MUFU.
 constexpr int kAttnFastPolyEvery = AVB_ATTN_POLY_EVERY;
+#ifndef AVB_ATTN_POLY_MASK_NC  // polynomial pairs of the unclamped variant: 7 of 16.  Measured (r2d, n-axis launch, B = 64, ms):
+#define AVB_ATTN_POLY_MASK_NC 0x52A5  // clamped 5/16 11.05 | unclamped 5/16 10.61, 6/16 10.15-10.18 (three patterns),
+#endif                                // 7/16 {0,2,5,7,9,12,14} 9.98, 7/16 {1,3,5,8,10,12,15} 10.33-10.41, 8/16 ~10.5
+template <bool kClamp = true>
 __device__ __forceinline__ void exp_chunk32(const uint32_t (&s)[32], uint32_t* pk, float& pmax) {
   const uint64_t magic2 = pack2(12582912.0f, 12582912.0f), nmagic2 = pack2(-12582912.0f, -12582912.0f);
   const uint64_t c3 = pack2(0.055171650f, 0.055171650f), c2 = pack2(0.24261113f, 0.24261113f);
@@ -1376,9 +1405,10 @@ __device__ __forceinline__ void exp_chunk32(const uint32_t (&s)[32], uint32_t* p
 #pragma unroll
   for (int e = 0; e < 16; ++e) {
     const float a = __uint_as_float(s[2 * e]), b = __uint_as_float(s[2 * e + 1]);
-    if (AVB_ATTN_POLY_MASK ? ((AVB_ATTN_POLY_MASK >> e) & 1) : ((e % kAttnFastPolyEvery) == kAttnFastPolyEvery - 1)) {
-      pmax = max3(pmax, a, b);
-      const uint64_t x2 = pack2(fmaxf(a, -126.0f), fmaxf(b, -126.0f));
+    constexpr unsigned kMask = kClamp ? (unsigned)(AVB_ATTN_POLY_MASK) : (unsigned)(AVB_ATTN_POLY_MASK_NC);
+    if (kMask ? ((kMask >> e) & 1) : ((e % kAttnFastPolyEvery) == kAttnFastPolyEvery - 1)) {
+      if (kClamp) pmax = max3(pmax, a, b);
+      const uint64_t x2 = kClamp ? pack2(fmaxf(a, -126.0f), fmaxf(b, -126.0f)) : pack2(a, b);
       const uint64_t t2 = add2(x2, magic2);           // integer part lands in the low mantissa bits
       const uint64_t f2 = fma2(add2(t2, nmagic2), neg1, x2);  // f = x - round(x), in [-0.5, 0.5]
       uint64_t p2 = fma2(f2, c3, c2);
@@ -1403,7 +1433,9 @@ __device__ __forceinline__ void exp_chunk32(const uint32_t (&s)[32], uint32_t* p
 template <bool kFast>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int n, int d, int H,
-                    int axis, int* __restrict__ guard) {
+                    int axis, int* __restrict__ guard, const float* __restrict__ norms) {
+  // norms (fast variant, may be null): {max |q_h|^2, max |k_h|^2} over every (row, head) of this launch, recorded by the
+  // QKV projection that wrote qkv.  |score| <= |q||k| <= 100 licenses the unclamped polynomial lanes (exp_chunk32).
   // guard: one int per launch pair.  The fast variant (stale row maximum, see the softmax section) raises it when a
   // score tile exceeds the running maximum by more than kAttnOverflowGuard; the exact variant, launched right after
   // it on the same stream, returns immediately unless the guard is up and otherwise recomputes the whole launch.
@@ -1683,6 +1715,7 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       const uint32_t a_pfull = ptx::smem_u32(p_full), a_pvdone = ptx::smem_u32(pv_done);
       uint32_t gp = 0;  // parity of the current step (g & 1)
       float pmax = -INFINITY;
+      const bool bounded = norms != nullptr && norms[0] * norms[1] <= 1.0e4f;  // false also for NaN
       ItemPos ip = first_item();
       // -DAVB_ATTN_PIPE_LD=1 (A/B build, slower - see the macro): the S tile of the NEXT step is requested from TMEM right
       // behind this step's P store, so that its load latency overlaps the store's completion and the p_full hand-off.
@@ -1704,20 +1737,25 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
           }
           AVB_TRACE(trole, g, 2);
           const int nv = T - j * 128 - half * 64;  // valid key columns in this warp's half (may be <= 0)
-          if (nv < 64) {  // keys beyond the sequence end: score -inf, probability 0
-            if (nv < 32) {
-#pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if (e >= nv) sa[e] = 0xff800000u;
-            }
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (32 + e >= nv) sb[e] = 0xff800000u;
-          }
           // ---- P = exp2(S) -> packed bf16 pairs
           uint32_t pk[32];
-          exp_chunk32(sa, pk, pmax);
-          exp_chunk32(sb, pk + 16, pmax);
+          if (nv < 64 || !bounded) {  // ragged tile (masked keys are -inf) or no score bound: clamped polynomial lanes
+            if (nv < 64) {  // keys beyond the sequence end: score -inf, probability 0
+              if (nv < 32) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                  if (e >= nv) sa[e] = 0xff800000u;
+              }
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (32 + e >= nv) sb[e] = 0xff800000u;
+            }
+            exp_chunk32<true>(sa, pk, pmax);
+            exp_chunk32<true>(sb, pk + 16, pmax);
+          } else {
+            exp_chunk32<false>(sa, pk, pmax);
+            exp_chunk32<false>(sb, pk + 16, pmax);
+          }
           AVB_TRACE(trole, g, 4);
           if (g >= 1) {  // P is free and O complete once the PV / L MMAs of the previous step have finished
             ptx::mbar_wait_s(a_pvdone, gp ^ 1u);
@@ -1895,6 +1933,42 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// Test helper: the score bound {max |q_h|^2, max |k_h|^2} of a qkv buffer in the attention operand layout
+// [seq][q,k,v][head][pos][32 ch] (what ln_gemm2_tc_kernel records in the product path); rows = S * T * H (pos, head) rows
+// per operand.  The chunk swizzle permutes within a 64-byte row, which a sum of squares does not see.
+__global__ void qk_norms_kernel(const __nv_bfloat16* __restrict__ qkv, size_t rows, int H, int T, float* __restrict__ norms) {
+  float mq = 0.f, mk = 0.f;
+  const size_t per_seq = (size_t)H * T;  // (head, pos) rows of one operand of one sequence
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t sq = i / per_seq, rem = i - sq * per_seq;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const uint4* p = reinterpret_cast<const uint4*>(qkv + ((sq * 3 + w) * per_seq + rem) * 32);
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 v = p[c];
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float lo = __uint_as_float(u[t] << 16), hi = __uint_as_float(u[t] & 0xffff0000u);
+          ss = fmaf(lo, lo, fmaf(hi, hi, ss));
+        }
+      }
+      if (w == 0) mq = fmaxf(mq, ss); else mk = fmaxf(mk, ss);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mq = fmaxf(mq, __shfl_xor_sync(0xffffffffu, mq, o));
+    mk = fmaxf(mk, __shfl_xor_sync(0xffffffffu, mk, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(reinterpret_cast<int*>(norms), __float_as_int(mq));
+    atomicMax(reinterpret_cast<int*>(norms) + 1, __float_as_int(mk));
+  }
 }
 
 // Test helper: token-major qkv[tok][3*H*32] -> the attention operand layout of ln_gemm_tc_kernel<2> (one thread per
