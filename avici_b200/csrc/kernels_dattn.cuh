@@ -66,6 +66,9 @@ static_assert(DaCfg<true>::kSmemBytes <= 232448, "dattn_tc_kernel: shared memory
 
 // Bounded (trapping) mbarrier waits in the softmax warps as well: a protocol bug must fail the launch, never hang the
 // GPU box.  0 selects the lean hot-loop waits once a build has been validated on hardware.
+#ifndef AVB_DATTN_G_GROUP  // projection MMAs issued per pacing group (1, 2 or 4 = unpaced).  Measured (r2d): 4.20 / 4.62 /
+#define AVB_DATTN_G_GROUP 4  // 5.49 ms for 4 / 2 / 1 - the projection's own latency (s_free -> G -> conv -> S) is as critical
+#endif                       // as the PV MMAs it delays, so pacing it loses more than it frees
 #ifndef AVB_DATTN_BOUNDED_WAITS
 #define AVB_DATTN_BOUNDED_WAITS 1
 #endif
@@ -117,7 +120,8 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
   uint64_t* op_done = wo_full + 1;         // commit: OP of a unit has read the bf16 O tile in TMEM (kFuseOut)
   uint64_t* v_free = op_done + 1;          // [kDaVBufs] commit: PV of a unit has read its V tile
   uint64_t* o_free = v_free + kDaVBufs;    // [2] 128 epilogue threads: the O / L accumulators are in registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* g_pace = o_free + 2;           // commit: a group of projection MMAs has completed (issue pacing)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_pace + 1);
   uint32_t* s_ones = reinterpret_cast<uint32_t*>(smem + Cfg::kDataBytes + 512);  // 512 B of bf16 1.0
   // Biases live in shared memory: a __ldg from the epilogue warps queues in the L1 pipeline behind the LayerNorm warps'
   // row loads (L2 latency each), which ncu showed as ~500 clocks of long-scoreboard stall per 32-column chunk.
@@ -144,6 +148,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     ptx::mbar_init(op_done, 1);
     for (int i = 0; i < kDaVBufs; ++i) ptx::mbar_init(&v_free[i], 1);
     ptx::mbar_init(&o_free[0], 128); ptx::mbar_init(&o_free[1], 128);
+    ptx::mbar_init(g_pace, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -245,6 +250,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       const uint64_t dX0 = ptx::make_smem_desc(ptx::smem_u32(sX), 16, 1024, ptx::kSwz128);
       const uint64_t dW0 = ptx::make_smem_desc(ptx::smem_u32(sW), 16, 1024, ptx::kSwz128);
       const uint64_t dWo0 = ptx::make_smem_desc(ptx::smem_u32(sWo), 16, 512, ptx::kSwz64);
+      uint32_t pace_phase = 0;
       auto issue_G = [&](int u) {  // QKV projection of unit u into SBUF[u & 1]
         const int si = u >> 3, h = u & 7, buf = si & 1;
         if (h == 0) ptx::mbar_wait(&x_full[buf], (uint32_t)((si >> 1) & 1), 81, 40u);
@@ -256,19 +262,30 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
           const int kbi = 2 * u + kb, st = kbi % NS;
           ptx::mbar_wait(&w_full[st], (uint32_t)((kbi / NS) & 1), 83, 40u);
           ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint64_t da = dX0 + (uint64_t)(buf * (kDaXBytes >> 4) + kb * ((128 * 128) >> 4));
-            const uint64_t db = dW0 + (uint64_t)(st * (kDaWkbBytes >> 4));
+          // The tensor pipe executes in issue order and a blocked issue holds the issuing thread: eight projection MMAs
+          // queued back to back (712 clocks, needed two units from now) held up the PV MMAs of the attention issuer
+          // (needed now) - r2d trace: PV issue 1450 clocks.  The projection is paced in groups of AVB_DATTN_G_GROUP MMAs,
+          // each waited for, so the attention MMAs slip in between.
+          const uint64_t da = dX0 + (uint64_t)(buf * (kDaXBytes >> 4) + kb * ((128 * 128) >> 4));
+          const uint64_t db = dW0 + (uint64_t)(st * (kDaWkbBytes >> 4));
+#pragma unroll 1
+          for (int k0 = 0; k0 < 4; k0 += AVB_DATTN_G_GROUP) {
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_g, (kb | k) != 0);
-            ptx::umma_commit(&w_empty[st]);
-            if (kb == 1) {
-              ptx::umma_commit(&g_full[u & 1]);
-              if (h == 7) ptx::umma_commit(&x_empty[buf]);
+              for (int k = k0; k < k0 + AVB_DATTN_G_GROUP; ++k)
+                ptx::umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_g, (kb | k) != 0);
+              if (AVB_DATTN_G_GROUP < 4) ptx::umma_commit(g_pace);
+              if (k0 + AVB_DATTN_G_GROUP == 4) {
+                ptx::umma_commit(&w_empty[st]);
+                if (kb == 1) {
+                  ptx::umma_commit(&g_full[u & 1]);
+                  if (h == 7) ptx::umma_commit(&x_empty[buf]);
+                }
+              }
             }
+            __syncwarp();
+            if (AVB_DATTN_G_GROUP < 4) { ptx::mbar_wait(g_pace, pace_phase, 99, 20u); pace_phase ^= 1u; }
           }
-          __syncwarp();
         }
       };
       auto issue_OP = [&](int u) {  // DELTA (+)= O_h . Wo_h^T
@@ -549,11 +566,16 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       const int si = u >> 3, h = u & 7, nbuf = (si + 1) & 1;
       AVB_TRACE(2, u, 0);
       conv_wait(u);
-      if (pending) ln8_finish(ptx::smem_u32(sX + nbuf * kDaXBytes), (h - 1) * 8);  // slice h - 1, loaded behind conv_{u-1}
-      conv(u);  // ends with the async-proxy fence: it also covers the slice's shared-memory stores
-      if (pending && h == 4) ptx::mbar_arrive(&x_full[nbuf]);
-      pending = false;
+      conv(u);  // first: qkv_ready -> S_u -> softmax_u is the unit pipeline's critical chain (r2c trace)
       AVB_TRACE(2, u, 3);
+      if (pending) {  // slice h - 1, loaded behind conv_{u-1}: its loads have landed by now
+        ln8_finish(ptx::smem_u32(sX + nbuf * kDaXBytes), (h - 1) * 8);
+        if (h == 4) {
+          ptx::fence_proxy_async();
+          ptx::mbar_arrive(&x_full[nbuf]);
+        }
+      }
+      pending = false;
       if (si + 1 < nseq && h < 4) {
         const int s_next = (int)blockIdx.x + (si + 1) * (int)gridDim.x;
         if (h == 0) {
