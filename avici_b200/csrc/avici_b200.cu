@@ -25,6 +25,7 @@
 #include "kernels_f32.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_dattn.cuh"
+#include "kernels_split.cuh"
 #include "kernels_metrics.cuh"
 
 namespace {
@@ -41,6 +42,10 @@ struct Block {
   const bf16 *wqkv_t, *wo_t, *w1_t, *w2_t;
   const float *bqkv_f, *b1_f;
   const float *bo_d;  // dattn_tc_kernel: bo + bv' Wo (the value bias passes through the softmax average unchanged)
+  // fp32 mode, split-precision tensor-core GEMMs (kernels_split.cuh): hi / lo bf16 halves of the K-major weights with the
+  // LayerNorm affine folded in (no softmax scale: the fp32 attention kernel applies it), their [128 x 64] tensor maps
+  CUtensorMap tm_s_qkv[2], tm_s_o[2], tm_s_1[2], tm_s_2[2];
+  const float *zero_k;
   // per-head operand images of dattn_tc_kernel: Wqkv_h as 2 K blocks of [96 x 64] (128B swizzle), Wo_h as [128 x 32] (64B swizzle)
   const uint8_t *wd_qkv, *wd_o;
   CUtensorMap tm_wqkv_h, tm_wo, tm_w1q, tm_w2q;  // wqkv: [128 x 64] boxes (CTA-pair QKV), wo: [128 x 64], w1 / w2: [64 x 64] (CTA-pair FFN)
@@ -115,6 +120,7 @@ struct avb_model_s {
   std::mutex host_mu;
   long long launches = 0;
   int dattn_mode = 1;  // d-axis blocks with d <= 128: 1 = fully fused kernel, 2 = fused up to the attention output, 0 = unfused
+  int f32_tc = 1;  // fp32 mode: projections and FFN as split-precision tensor-core GEMMs (0: SIMT sgemm_kernel)
   avb_nccl_comm_t comm = nullptr;  // avb_comm_init: communicator of the axially sharded forward (one rank per handle)
   int comm_rank = 0, comm_world = 1;
   // optional per-kernel-category CUDA-event timing (avb_profile_*)
@@ -398,6 +404,26 @@ int launch_dattn_tc(avb_handle h, const float* z, const Block& W, void* out, int
   return AVB_OK;
 }
 
+// C = epi(A' W + bias) with fp32 operands split into bf16 pairs (kernels_split.cuh); K = 64 * KB columns of A starting at A,
+// weight columns [k_off, k_off + K) of the pre-split W^T behind tm[0] (hi) / tm[1] (lo).
+template <int KB, bool LN, int EPI>
+int launch_gemm_split(avb_handle h, const float* A, int lda, const CUtensorMap* tm, int k_off, const float* bias, const float* R,
+                      int ldr, float* C, int ldc, int M, int N, cudaStream_t st) {
+  static PerDeviceOnce once;
+  cudaError_t e = once.run([] {
+    return cudaFuncSetAttribute(avb::gemm_split_tc_kernel<KB, LN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                avb::SplitCfg<KB>::kSmemBytes);
+  });
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(gemm_split_tc): %s", cudaGetErrorString(e));
+  const int grid = std::min((M + 127) / 128, h->num_sms);
+  avb::gemm_split_tc_kernel<KB, LN, EPI><<<grid, avb::kSplitThreads, avb::SplitCfg<KB>::kSmemBytes, st>>>(
+      A, lda, tm[0], tm[1], k_off, bias, R, ldr, C, ldc, M, N);
+  h->launches++;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "gemm_split_tc launch: %s", cudaGetErrorString(e));
+  return AVB_OK;
+}
+
 template <int EPI, bool LN>
 void launch_sgemm(const float* A, int lda, const float* W, int ldw, const float* bias, const float* g,
                   const float* b, const float* R, int ldr, float* C, int ldc, size_t M, int N, int K,
@@ -604,7 +630,8 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
     return off;
   };
   struct BlockOff {
-    size_t ln_g[4], ln_b[4], wq, bq, wk, bk, wv, bv, wo, bo, w1, b1, w2, b2, bqkv_f, b1_f, bo_d;
+    size_t ln_g[4], ln_b[4], wq, bq, wk, bk, wv, bv, wo, bo, w1, b1, w2, b2, bqkv_f, b1_f, bo_d, zero_k;
+    size_t s_qkv[2], s_o[2], s_1[2], s_2[2];
     size_t wqkv_t, wo_t, w1_t, w2_t, wd_qkv, wd_o;
   };
   std::vector<BlockOff> offs(nb);
@@ -638,7 +665,43 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
     o.bqkv_f = push_f32(nullptr, 3 * HD);
     o.b1_f = push_f32(nullptr, F);
     o.bo_d = push_f32(nullptr, k);
+    o.zero_k = push_f32(nullptr, k);
     if (!missing.empty()) continue;
+    if (c.compute_dtype == AVB_DTYPE_F32) {
+      // split-precision operands of gemm_split_tc_kernel: W' = diag(gamma) W in fp64 -> fp32 -> (hi, lo) bf16, K-major [N, K]
+      auto split_store = [&](size_t hi_off, size_t lo_off, size_t idx, double w) {
+        const float wf = (float)w;
+        const bf16 hi = __float2bfloat16(wf);
+        b16[hi_off + idx] = hi;
+        b16[lo_off + idx] = __float2bfloat16(wf - __bfloat162float(hi));
+      };
+      for (int p = 0; p < 2; ++p) {
+        o.s_qkv[p] = push_b16((size_t)3 * HD * k); o.s_o[p] = push_b16((size_t)k * HD);
+        o.s_1[p] = push_b16((size_t)F * k);        o.s_2[p] = push_b16((size_t)k * F);
+      }
+      const float* ws[3] = {wq, wk, wv}; const float* bs[3] = {bq, bk, bv};
+      for (int t = 0; t < 3; ++t)
+        for (int col = 0; col < HD; ++col) {
+          double acc = bs[t][col];
+          for (int r = 0; r < k; ++r) {
+            acc += (double)b[t][r] * ws[t][(size_t)r * HD + col];
+            split_store(o.s_qkv[0], o.s_qkv[1], ((size_t)t * HD + col) * k + r, (double)g[t][r] * ws[t][(size_t)r * HD + col]);
+          }
+          f32[o.bqkv_f + (size_t)t * HD + col] = (float)acc;
+        }
+      for (int col = 0; col < k; ++col)
+        for (int r = 0; r < HD; ++r) split_store(o.s_o[0], o.s_o[1], (size_t)col * HD + r, wo[(size_t)r * k + col]);
+      for (int col = 0; col < F; ++col) {
+        double acc = b1[col];
+        for (int r = 0; r < k; ++r) {
+          acc += (double)b[3][r] * w1[(size_t)r * F + col];
+          split_store(o.s_1[0], o.s_1[1], (size_t)col * k + r, (double)g[3][r] * w1[(size_t)r * F + col]);
+        }
+        f32[o.b1_f + col] = (float)acc;
+      }
+      for (int col = 0; col < k; ++col)
+        for (int r = 0; r < F; ++r) split_store(o.s_2[0], o.s_2[1], (size_t)col * F + r, w2[(size_t)r * k + col]);
+    }
     if (c.compute_dtype == AVB_DTYPE_BF16) {
       // LN(x) @ W + b = xhat @ (diag(gamma) W) + (beta @ W + b); q additionally carries log2e/sqrt(key)
       o.wqkv_t = push_b16((size_t)3 * HD * k);
@@ -737,7 +800,14 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
     for (int t = 0; t < 4; ++t) { B.ln_g[t] = df + o.ln_g[t]; B.ln_b[t] = df + o.ln_b[t]; }
     B.wq = df + o.wq; B.bq = df + o.bq; B.wk = df + o.wk; B.bk = df + o.bk; B.wv = df + o.wv; B.bv = df + o.bv;
     B.wo = df + o.wo; B.bo = df + o.bo; B.w1 = df + o.w1; B.b1 = df + o.b1; B.w2 = df + o.w2; B.b2 = df + o.b2;
-    B.bqkv_f = df + o.bqkv_f; B.b1_f = df + o.b1_f; B.bo_d = df + o.bo_d;
+    B.bqkv_f = df + o.bqkv_f; B.b1_f = df + o.b1_f; B.bo_d = df + o.bo_d; B.zero_k = df + o.zero_k;
+    if (c.compute_dtype == AVB_DTYPE_F32) {
+      bool ok = true;
+      for (int p = 0; p < 2; ++p)
+        ok = ok && make_tmap_2d(&B.tm_s_qkv[p], db + o.s_qkv[p], 3 * HD, k, 128) && make_tmap_2d(&B.tm_s_o[p], db + o.s_o[p], k, HD, 128) &&
+             make_tmap_2d(&B.tm_s_1[p], db + o.s_1[p], F, k, 128) && make_tmap_2d(&B.tm_s_2[p], db + o.s_2[p], k, F, 128);
+      if (!ok) return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for block %d split weights", i);
+    }
     if (c.compute_dtype == AVB_DTYPE_BF16) {
       B.wqkv_t = db + o.wqkv_t; B.wo_t = db + o.wo_t; B.w1_t = db + o.w1_t; B.w2_t = db + o.w2_t;
       B.wd_qkv = reinterpret_cast<const uint8_t*>(db + o.wd_qkv); B.wd_o = reinterpret_cast<const uint8_t*>(db + o.wd_o);
@@ -867,6 +937,13 @@ static int block_impl(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, 
     float* qkv = reinterpret_cast<float*>(w8 + L.big_off);
     float* hid = qkv;
     float* attn = reinterpret_cast<float*>(w8 + L.attn_off);
+    // projections and FFN on the tensor cores as split-precision products (kernels_split.cuh) when the shape fits
+    const bool tc = h->f32_tc && k == 128 && HD == 256 && F % 256 == 0 && ntok <= (size_t)0x7fffff00;
+    int rc;
+    if (tc) {
+      ProfScope ps(h, AVB_PROF_QKV, st);
+      if ((rc = launch_gemm_split<2, true, avb::kSplitEpiBias>(h, z, k, W.tm_s_qkv, 0, W.bqkv_f, nullptr, 0, qkv, 3 * HD, M, 3 * HD, st))) return rc;
+    } else
     { ProfScope ps(h, AVB_PROF_QKV, st);
       launch_sgemm<0, true>(z, k, W.wq, HD, W.bq, W.ln_g[0], W.ln_b[0], nullptr, 0, qkv, 3 * HD, ntok, HD, k, st);
       AVB_LAUNCH_CHECK(h);
@@ -890,6 +967,15 @@ static int block_impl(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, 
       } }
     { cudaError_t e__ = cudaGetLastError();
       if (e__ != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention_f32 launch failed: %s", cudaGetErrorString(e__)); }
+    if (tc) {
+      { ProfScope ps(h, AVB_PROF_OUT, st);
+        if ((rc = launch_gemm_split<4, false, avb::kSplitEpiResidual>(h, attn, HD, W.tm_s_o, 0, W.bo, z, k, z, k, M, k, st))) return rc; }
+      { ProfScope ps(h, AVB_PROF_FFN, st);
+        if ((rc = launch_gemm_split<2, true, avb::kSplitEpiRelu>(h, z, k, W.tm_s_1, 0, W.b1_f, nullptr, 0, hid, F, M, F, st))) return rc;
+        for (int k0 = 0; k0 < F; k0 += 256)  // K = 256 per launch; the later passes accumulate through the residual epilogue
+          if ((rc = launch_gemm_split<4, false, avb::kSplitEpiResidual>(h, hid + k0, F, W.tm_s_2, k0, k0 == 0 ? W.b2 : W.zero_k, z, k, z,
+                                                                       k, M, k, st))) return rc; }
+    } else {
     { ProfScope ps(h, AVB_PROF_OUT, st);
       launch_sgemm<2, false>(attn, HD, W.wo, k, W.bo, nullptr, nullptr, z, k, z, k, ntok, k, HD, st);
       AVB_LAUNCH_CHECK(h); }
@@ -898,6 +984,7 @@ static int block_impl(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, 
       AVB_LAUNCH_CHECK(h);
       launch_sgemm<2, false>(hid, F, W.w2, k, W.b2, nullptr, nullptr, z, k, z, k, ntok, k, F, st);
       AVB_LAUNCH_CHECK(h); }
+    }
   }
   return AVB_OK;
 }
@@ -1358,6 +1445,12 @@ int avb_threshold_metrics(const float* probs, const int32_t* g_true, int32_t B, 
 int avb_test_set_dattn_mode(avb_handle h, int32_t mode) {
   if (!h || mode < 0 || mode > 2) return fail(h, AVB_ERR_INVALID, "avb_test_set_dattn_mode: mode must be 0, 1 or 2");
   h->dattn_mode = mode;
+  return AVB_OK;
+}
+
+int avb_test_set_f32_tc(avb_handle h, int32_t on) {
+  if (!h) return AVB_ERR_INVALID;
+  h->f32_tc = on != 0;
   return AVB_OK;
 }
 

@@ -570,6 +570,27 @@ def test_axial_sharding_over_two_gpus(dtype):
     assert np.array_equal(model.infer_batch(xb, devices=[0, 1]), model.infer_batch(xb))
 
 
+def test_f32_split_tensor_core_gemms_vs_simt_and_oracle():
+    """fp32 mode: the split-precision (bf16 x 3) tensor-core projections / FFN against the SIMT fp32 GEMMs of the same
+    handle and against the fp64 oracle, ragged token counts included (tiles of 128 rows)."""
+    kw = dict(layers=3, **STRESS)
+    model = avici_b200.random_init_model(kw, seed=11, perturb=True, compute_dtype="fp32")
+    eng = model.engine
+    for n, d, seed in ((150, 37, 0), (257, 64, 1), (64, 130, 2)):
+        g, x, iv = avici_b200.simulate_data(d=d, n=n, n_interv=n // 4, seed=seed, domain="lin-gauss")
+        x = x.astype(np.float32); iv = iv.astype(np.float32)
+        ref = oracle_probs(model.params, x.astype(np.float64), iv, 3)
+        eng._check(eng.lib.avb_test_set_f32_tc(eng.handle, 1))
+        p_tc = model(x=x, interv=iv.copy())
+        eng._check(eng.lib.avb_test_set_f32_tc(eng.handle, 0))
+        p_simt = model(x=x, interv=iv.copy())
+        eng._check(eng.lib.avb_test_set_f32_tc(eng.handle, 1))
+        e_tc, e_simt = float(np.abs(p_tc - ref).max()), float(np.abs(p_simt - ref).max())
+        print(f"fp32 n={n + n // 4} d={d}: split tensor-core max|dp| = {e_tc:.2e}, SIMT {e_simt:.2e}")
+        check_parity(p_tc, ref, TOL_STRESS["fp32"])
+        check_parity(p_simt, ref, TOL_STRESS["fp32"])
+
+
 def test_edge_shapes_and_errors():
     kw = dict(layers=1, **STRESS)
     for dtype in ("fp32", "bf16"):
