@@ -408,7 +408,7 @@ int launch_dattn_tc(avb_handle h, const float* z, const Block& W, void* out, int
 // weight columns [k_off, k_off + K) of the pre-split W^T behind tm[0] (hi) / tm[1] (lo).
 template <int KB, bool LN, int EPI>
 int launch_gemm_split(avb_handle h, const float* A, int lda, const CUtensorMap* tm, int k_off, const float* bias, const float* R,
-                      int ldr, float* C, int ldc, int M, int N, cudaStream_t st) {
+                      int ldr, float* C, int ldc, int M, int N, cudaStream_t st, avb::SplitSeq sq = avb::SplitSeq{0, 0, 0, 0, 0}) {
   static PerDeviceOnce once;
   cudaError_t e = once.run([] {
     return cudaFuncSetAttribute(avb::gemm_split_tc_kernel<KB, LN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -417,10 +417,30 @@ int launch_gemm_split(avb_handle h, const float* A, int lda, const CUtensorMap* 
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(gemm_split_tc): %s", cudaGetErrorString(e));
   const int grid = std::min((M + 127) / 128, h->num_sms);
   avb::gemm_split_tc_kernel<KB, LN, EPI><<<grid, avb::kSplitThreads, avb::SplitCfg<KB>::kSmemBytes, st>>>(
-      A, lda, tm[0], tm[1], k_off, bias, R, ldr, C, ldc, M, N);
+      A, lda, tm[0], tm[1], k_off, bias, R, ldr, C, ldc, M, N, sq);
   h->launches++;
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "gemm_split_tc launch: %s", cudaGetErrorString(e));
+  return AVB_OK;
+}
+
+// fp32-mode attention on the tensor cores (attention_split_tc_kernel): operands from the split QKV projection
+int launch_attention_split(avb_handle h, const void* qkvs, float* attn, int B, int n, int d, int H, int axis, int dg, cudaStream_t st) {
+  static PerDeviceOnce once;
+  cudaError_t e = once.run([] {
+    return cudaFuncSetAttribute(avb::attention_split_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kSplitAttnSmemBytes);
+  });
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(attention_split_tc): %s", cudaGetErrorString(e));
+  const int T = axis == 0 ? d : n;
+  const long long S = axis == 0 ? (long long)B * n : (long long)B * d;
+  const long long items = S * H * ((T + 127) / 128);
+  if (items >= (1LL << 31)) return fail(h, AVB_ERR_INVALID, "attention: too many (sequence, head, tile) items in one call (%lld)", items);
+  const int grid = (int)std::min<long long>(items, 2LL * h->num_sms);
+  avb::attention_split_tc_kernel<<<grid, avb::kSplitAttnThreads, avb::kSplitAttnSmemBytes, st>>>(
+      reinterpret_cast<const bf16*>(qkvs), attn, B, n, d, H, axis, dg);
+  h->launches++;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention_split_tc launch: %s", cudaGetErrorString(e));
   return AVB_OK;
 }
 
@@ -680,15 +700,17 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
         o.s_1[p] = push_b16((size_t)F * k);        o.s_2[p] = push_b16((size_t)k * F);
       }
       const float* ws[3] = {wq, wk, wv}; const float* bs[3] = {bq, bk, bv};
-      for (int t = 0; t < 3; ++t)
+      for (int t = 0; t < 3; ++t) {
+        const double sc = t == 0 ? qscale : 1.0;  // q carries log2e / sqrt(key): the split attention kernel uses exp2
         for (int col = 0; col < HD; ++col) {
           double acc = bs[t][col];
           for (int r = 0; r < k; ++r) {
             acc += (double)b[t][r] * ws[t][(size_t)r * HD + col];
-            split_store(o.s_qkv[0], o.s_qkv[1], ((size_t)t * HD + col) * k + r, (double)g[t][r] * ws[t][(size_t)r * HD + col]);
+            split_store(o.s_qkv[0], o.s_qkv[1], ((size_t)t * HD + col) * k + r, (double)g[t][r] * ws[t][(size_t)r * HD + col] * sc);
           }
-          f32[o.bqkv_f + (size_t)t * HD + col] = (float)acc;
+          f32[o.bqkv_f + (size_t)t * HD + col] = (float)(acc * sc);
         }
+      }
       for (int col = 0; col < k; ++col)
         for (int r = 0; r < HD; ++r) split_store(o.s_o[0], o.s_o[1], (size_t)col * HD + r, wo[(size_t)r * k + col]);
       for (int col = 0; col < F; ++col) {
@@ -942,7 +964,8 @@ static int block_impl(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, 
     int rc;
     if (tc) {
       ProfScope ps(h, AVB_PROF_QKV, st);
-      if ((rc = launch_gemm_split<2, true, avb::kSplitEpiBias>(h, z, k, W.tm_s_qkv, 0, W.bqkv_f, nullptr, 0, qkv, 3 * HD, M, 3 * HD, st))) return rc;
+      if ((rc = launch_gemm_split<2, true, avb::kSplitEpiQkvOperands>(h, z, k, W.tm_s_qkv, 0, W.bqkv_f, nullptr, 0, qkv, 3 * HD, M, 3 * HD,
+                                                                       st, avb::SplitSeq{n, d, axis, dg, H}))) return rc;
     } else
     { ProfScope ps(h, AVB_PROF_QKV, st);
       launch_sgemm<0, true>(z, k, W.wq, HD, W.bq, W.ln_g[0], W.ln_b[0], nullptr, 0, qkv, 3 * HD, ntok, HD, k, st);
@@ -957,6 +980,10 @@ static int block_impl(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, 
     const long long outer_stride = axis == 0 ? d : (long long)n * d;
     const long long inner_stride = axis == 0 ? 0 : 1;
     const long long tok_stride = axis == 0 ? 1 : d;
+    if (tc) {
+      ProfScope ps(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
+      if ((rc = launch_attention_split(h, qkv, attn, B, n, d, H, axis, dg, st))) return rc;
+    } else
     { ProfScope ps(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
       for (long long s0 = 0; s0 < S; s0 += 65535) {  // grid.z is limited to 65535
         const int sz = (int)std::min<long long>(65535, S - s0);

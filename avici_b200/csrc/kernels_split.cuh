@@ -34,7 +34,11 @@ struct SplitCfg {
   static constexpr int kSmemBytes = kABytes + kBBytes + 1024 + 256;
 };
 
-enum { kSplitEpiBias = 0, kSplitEpiRelu = 1, kSplitEpiResidual = 2 };
+enum { kSplitEpiBias = 0, kSplitEpiRelu = 1, kSplitEpiResidual = 2, kSplitEpiQkvOperands = 3 };
+
+// kSplitEpiQkvOperands: the QKV projection writes hi / lo bf16 halves straight into the operand layout of
+// attention_split_tc_kernel (below) instead of fp32 rows; the row order of the attended axis comes from RowMap.
+struct SplitSeq { int n, d, axis, dg, H; };
 
 // 32 fp32 rows of width 64*KB (row pitch lda floats) -> hi / lo bf16 K-major tiles; eight lanes share a row (128-byte
 // coalesced segments), optional LayerNorm without affine (exact two-pass statistics in fp32, K = 128 only).
@@ -95,7 +99,7 @@ template <int KB, bool kLn, int EPI>
 __global__ void __launch_bounds__(kSplitThreads, 1)
 gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant__ CUtensorMap tm_hi,
                      const __grid_constant__ CUtensorMap tm_lo, int k_off, const float* __restrict__ bias,
-                     const float* R, int ldr, float* C, int ldc, int M, int N) {
+                     const float* R, int ldr, float* C, int ldc, int M, int N, SplitSeq sq) {
   using Cfg = SplitCfg<KB>;
   constexpr int ST = kSplitBStages;
   extern __shared__ uint8_t smem_raw[];
@@ -197,8 +201,15 @@ gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant
     const int q = warp & 3;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     int acc_it = 0;
+    const RowMap rm{sq.n, sq.d, sq.axis, sq.dg};
+    const int seq_T = sq.axis == 0 ? sq.d : sq.n;
     for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
       const int row = mt * 128 + q * 32 + lane;
+      [[maybe_unused]] unsigned seq = 0, pos = 0;
+      if (EPI == kSplitEpiQkvOperands && row < M) {  // GEMM rows are tokens: sequence and position under the attended axis
+        const unsigned m = (unsigned)rm.seq_row(row);
+        seq = m / (unsigned)seq_T; pos = m - seq * (unsigned)seq_T;
+      }
       for (int c = 0; c < num_c; ++c, ++acc_it) {
         const int as = acc_it & 1;
         ptx::mbar_wait(&t_full[as], (uint32_t)((acc_it >> 1) & 1), 65);
@@ -218,7 +229,35 @@ gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant
             ptx::tc_fence_before();
             ptx::mbar_arrive(&t_empty[as]);
           }
-          if (row < M) {
+          if (EPI == kSplitEpiQkvOperands) {
+            if (row < M) {  // 32 columns = one (operand w, head): 64 bytes of hi and of lo at [seq][w][part][head][pos]
+              const int w = col >> 8, hd = (col & 255) >> 5;
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(C) +
+                                   ((((size_t)seq * 3 + w) * 2 * sq.H + hd) * seq_T + pos) * 32;
+              const size_t part = (size_t)sq.H * seq_T * 32;
+              const unsigned swz = (pos >> 1) & 3;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col) + 2 * e);
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col) + 2 * e + 1);
+                float f[8];
+                f[0] = __uint_as_float(v[e * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[e * 8 + 1]) + b0.y;
+                f[2] = __uint_as_float(v[e * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[e * 8 + 3]) + b0.w;
+                f[4] = __uint_as_float(v[e * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[e * 8 + 5]) + b1.y;
+                f[6] = __uint_as_float(v[e * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[e * 8 + 7]) + b1.w;
+                uint4 hi, lo;
+                uint32_t* hp = &hi.x; uint32_t* lp = &lo.x;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const uint32_t h2 = ptx::pack_bf16(f[2 * t], f[2 * t + 1]);
+                  hp[t] = h2;
+                  lp[t] = ptx::pack_bf16(f[2 * t] - __uint_as_float(h2 << 16), f[2 * t + 1] - __uint_as_float(h2 & 0xffff0000u));
+                }
+                *reinterpret_cast<uint4*>(dst + (((unsigned)e ^ swz) << 3)) = hi;
+                *reinterpret_cast<uint4*>(dst + part + (((unsigned)e ^ swz) << 3)) = lo;
+              }
+            }
+          } else if (row < M) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col) + e);
@@ -237,6 +276,239 @@ gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace avb
+
+namespace avb {
+
+// ------------------------------------------------------------------------------------------
+// Split-precision axial attention for the fp32 mode (hk.MultiHeadAttention core, model.py:59-64), head dim 32.
+//   Operands come from the QKV projection (gemm_split_tc_kernel, kSplitEpiQkvOperands) as hi / lo bf16 halves in the
+//   tensor-core attention's operand layout, qkvs[seq][w = q,k,v][part = hi,lo][head][pos][32 ch] with the 16-byte chunks
+//   of a 64-byte row at chunk ^ ((pos >> 1) & 3); q carries log2e / sqrt(32).
+//     S = Q K^T  as  Qhi Khi + Qhi Klo + Qlo Khi                 (6 MMAs M 128, N <= 128, K 16, fp32 in TMEM)
+//     exact online softmax in fp32, one query row per thread: running maximum, p = exp2(s - m), row sum in fp32
+//     O += P V   as  Phi Vhi + Phi Vlo + Plo Vhi                 (A = P from TMEM, 3 MMAs N 32 per 16 keys)
+//   P (hi | lo, packed bf16 pairs) overwrites the S tile it came from, half by half - a thread owns its whole row - so a
+//   CTA needs 160 TMEM columns and 80 KB of shared memory and two CTAs share an SM: within a CTA the steps S -> softmax ->
+//   PV run strictly in sequence (the tensor pipe's in-order execution replaces most barriers), the second CTA fills the gaps.
+//   out: fp32 attn[token][H * 32] (token order, the A operand of the split-precision out-projection).
+//   warp 0: bulk-copy producer   warp 1: MMA issuer + TMEM alloc   warps 2-5: softmax / epilogue (TMEM lane quarter = warp & 3)
+// ------------------------------------------------------------------------------------------
+constexpr int kSplitAttnThreads = 192;
+constexpr int kSplitAttnStages = 2;
+constexpr int kSplitAttnTile = 128 * 32 * 2;  // 8 KB: one [128 x 32] bf16 tile
+constexpr int kSplitAttnSmemBytes = 2 * kSplitAttnTile + kSplitAttnStages * 4 * kSplitAttnTile + 1024 + 256;  // Q hi|lo, stages of K hi|lo|V hi|lo
+
+__global__ void __launch_bounds__(kSplitAttnThreads, 2)
+attention_split_tc_kernel(const __nv_bfloat16* __restrict__ qkvs, float* __restrict__ out, int B, int n, int d, int H, int axis,
+                          int dg) {
+  constexpr int NS = kSplitAttnStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                           // hi 8K | lo 8K
+  uint8_t* sKV = sQ + 2 * kSplitAttnTile;       // [NS][K hi | K lo | V hi | V lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NS * 4 * kSplitAttnTile);
+  uint64_t* q_full = bars;             // tx
+  uint64_t* q_empty = bars + 1;        // commit
+  uint64_t* kv_full = bars + 2;        // [NS] tx
+  uint64_t* kv_empty = kv_full + NS;   // [NS] commit
+  uint64_t* s_full = kv_empty + NS;    // commit
+  uint64_t* p_full = s_full + 1;       // 128 softmax threads
+  uint64_t* pv_done = p_full + 1;      // commit
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int T = axis == 0 ? d : n;
+  const int S = axis == 0 ? B * n : B * d;
+  const int nqt = (T + 127) / 128;
+  const int items = S * H * nqt;  // the host guarantees < 2^31
+  const size_t part_elems = (size_t)H * T * 32;  // one (sequence, operand, hi|lo) block
+
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(q_full, 1); ptx::mbar_init(q_empty, 1);
+    for (int i = 0; i < NS; ++i) { ptx::mbar_init(&kv_full[i], 1); ptx::mbar_init(&kv_empty[i], 1); }
+    ptx::mbar_init(s_full, 1); ptx::mbar_init(p_full, 128); ptx::mbar_init(pv_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  // ragged tiles copy only their valid rows: whatever else the tensor core reads in a slot must be finite
+  for (int i = threadIdx.x; i < (2 + NS * 4) * kSplitAttnTile / 16; i += kSplitAttnThreads)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  if (warp == 0) {
+    // ======================= producer
+    uint32_t g = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const int qt = item % nqt, pair = item / nqt, h = pair % H, s = pair / H;
+      const __nv_bfloat16* base = qkvs + (size_t)s * 6 * part_elems + (size_t)h * T * 32;  // (s, q, hi, h)
+      ptx::mbar_wait(q_empty, (uint32_t)(it & 1) ^ 1, 50, 100u);
+      if (ptx::elect_one()) {
+        const uint32_t bytes = (uint32_t)min(128, T - qt * 128) * 64u;
+        ptx::mbar_expect_tx(q_full, 2 * bytes);
+        ptx::bulk_load(sQ, base + (size_t)qt * 128 * 32, bytes, q_full);
+        ptx::bulk_load(sQ + kSplitAttnTile, base + part_elems + (size_t)qt * 128 * 32, bytes, q_full);
+      }
+      __syncwarp();
+      for (int j = 0; j < nqt; ++j, ++g) {
+        const int st = (int)(g % NS);
+        ptx::mbar_wait(&kv_empty[st], (uint32_t)((g / NS) & 1) ^ 1, 51, 100u);
+        if (ptx::elect_one()) {
+          uint8_t* sk = sKV + st * 4 * kSplitAttnTile;
+          const uint32_t bytes = (uint32_t)min(128, T - j * 128) * 64u;
+          ptx::mbar_expect_tx(&kv_full[st], 4 * bytes);
+#pragma unroll
+          for (int t = 0; t < 4; ++t)  // K hi, K lo, V hi, V lo: operand blocks 2..5 of the sequence
+            ptx::bulk_load_hint(sk + t * kSplitAttnTile, base + (size_t)(2 + t) * part_elems + (size_t)j * 128 * 32, bytes, &kv_full[st],
+                                ptx::kL2EvictLast);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer.  One thread issues every MMA, the tensor pipe executes them in order: S of a step
+    // is behind the PV of the previous one, so the P tile it overwrites has been consumed, and O is complete when S is.
+    constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, 32, 0, 1);  // B = V is MN-major
+    const uint64_t dQ = ptx::make_smem_desc(ptx::smem_u32(sQ), 16, 512, ptx::kSwz64);
+    const uint64_t dKV = ptx::make_smem_desc(ptx::smem_u32(sKV), 16, 512, ptx::kSwz64);
+    constexpr uint64_t kT = kSplitAttnTile >> 4;
+    uint32_t g = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      ptx::mbar_wait(q_full, (uint32_t)(it & 1), 52, 40u);
+      for (int j = 0; j < nqt; ++j, ++g) {
+        const int st = (int)(g % NS);
+        int kc = T - j * 128; kc = kc > 128 ? 128 : kc; kc = (kc + 15) & ~15;  // key columns the MMAs touch
+        const uint32_t idesc_s = ptx::make_idesc_bf16(128, kc, 0, 0);
+        ptx::mbar_wait(&kv_full[st], (uint32_t)((g / NS) & 1), 53, 40u);
+        ptx::tc_fence_after();
+        const uint64_t dk = dKV + (uint64_t)st * (4 * kT);
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            ptx::umma_bf16(tS, dQ + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k != 0);            // Qhi Khi
+            ptx::umma_bf16(tS, dQ + (uint64_t)(k * 2), dk + kT + (uint64_t)(k * 2), idesc_s, 1);             // Qhi Klo
+            ptx::umma_bf16(tS, dQ + kT + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, 1);             // Qlo Khi
+          }
+          ptx::umma_commit(s_full);
+          if (j == nqt - 1) ptx::umma_commit(q_empty);
+        }
+        __syncwarp();
+        ptx::mbar_wait(p_full, g & 1u, 54, 40u);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t dvh = dk + 2 * kT, dvl = dk + 3 * kT;
+          const int ksteps = kc >> 4;
+#pragma unroll 1
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t ph = tS + (uint32_t)((ks >> 2) * 64 + (ks & 3) * 8), pl = ph + 32;
+            ptx::umma_bf16_ts(tO, ph, dvh + (uint64_t)(ks * 64), idesc_pv, (j | ks) != 0);                   // Phi Vhi
+            ptx::umma_bf16_ts(tO, ph, dvl + (uint64_t)(ks * 64), idesc_pv, 1);                                // Phi Vlo
+            ptx::umma_bf16_ts(tO, pl, dvh + (uint64_t)(ks * 64), idesc_pv, 1);                                // Plo Vhi
+          }
+          ptx::umma_commit(&kv_empty[st]);
+          ptx::umma_commit(pv_done);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ======================= softmax / epilogue: thread = query row r of the tile = TMEM lane
+    const int q = warp & 3, r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const RowMap rm{n, d, axis, dg};
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int qt = item % nqt, pair = item / nqt, h = pair % H, s = pair / H;
+      float m = -INFINITY, l = 0.f;
+      for (int j = 0; j < nqt; ++j, ++g) {
+        ptx::mbar_wait(s_full, g & 1u, 55);
+        ptx::tc_fence_after();
+        const int nv = T - j * 128;  // valid key columns of this tile (>= 1)
+        // ---- pass 1: row maximum
+        float mx = m;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          if (c * 32 < nv) {
+            uint32_t sv[32];
+            ptx::tmem_ld32(tS + c * 32 + lane_off, sv);
+            ptx::tmem_wait_ld();
+            const int rem = nv - c * 32;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, e < rem ? __uint_as_float(sv[e]) : -INFINITY);
+          }
+        }
+        // ---- rescale O and the row sum (O is complete: S of this step was issued behind the previous PV)
+        if (j > 0 && __any_sync(0xffffffffu, mx > m)) {  // warp-uniform: tcgen05.ld / st are warp-collective
+          const float alpha = fast_exp2(m - mx);          // 1 for the rows whose maximum did not move
+          uint32_t o[32];
+          ptx::tmem_ld32(tO + lane_off, o);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+          ptx::tmem_st32(tO + lane_off, o);
+          l *= alpha;
+        }
+        m = mx;
+        // ---- pass 2: p = exp2(s - m), split into hi | lo bf16 pairs over the S columns they came from
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t ph[32], pl[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t sv[32];
+            ptx::tmem_ld32(tS + hf * 64 + c * 32 + lane_off, sv);
+            ptx::tmem_wait_ld();
+            const int rem = nv - hf * 64 - c * 32;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float p0 = 2 * e < rem ? fast_exp2(__uint_as_float(sv[2 * e]) - m) : 0.f;
+              const float p1 = 2 * e + 1 < rem ? fast_exp2(__uint_as_float(sv[2 * e + 1]) - m) : 0.f;
+              l += p0 + p1;
+              const uint32_t hi = ptx::pack_bf16(p0, p1);
+              ph[c * 16 + e] = hi;
+              pl[c * 16 + e] = ptx::pack_bf16(p0 - __uint_as_float(hi << 16), p1 - __uint_as_float(hi & 0xffff0000u));
+            }
+          }
+          ptx::tmem_st32(tS + hf * 64 + lane_off, ph);
+          ptx::tmem_st32(tS + hf * 64 + 32 + lane_off, pl);
+        }
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(p_full);
+      }
+      // ---- epilogue: O / l -> fp32 attn[token][h * 32 ..]
+      ptx::mbar_wait(pv_done, (g - 1) & 1u, 56);
+      ptx::tc_fence_after();
+      uint32_t o[32];
+      ptx::tmem_ld32(tO + lane_off, o);
+      ptx::tmem_wait_ld();
+      const int pos = qt * 128 + r;
+      if (pos < T) {
+        const float inv = 1.0f / l;
+        float4* op = reinterpret_cast<float4*>(out + (size_t)rm.token(s * T + pos) * (H * 32) + h * 32);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          op[e] = make_float4(__uint_as_float(o[e * 4 + 0]) * inv, __uint_as_float(o[e * 4 + 1]) * inv,
+                              __uint_as_float(o[e * 4 + 2]) * inv, __uint_as_float(o[e * 4 + 3]) * inv);
+      }
+      ptx::tc_fence_before();  // O has been read before this thread's next p_full arrival lets the first PV of the next item start
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
 }
 
 }  // namespace avb
