@@ -960,7 +960,7 @@ static int block_impl(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, 
     float* hid = qkv;
     float* attn = reinterpret_cast<float*>(w8 + L.attn_off);
     // projections and FFN on the tensor cores as split-precision products (kernels_split.cuh) when the shape fits
-    const bool tc = h->f32_tc && k == 128 && HD == 256 && F % 256 == 0 && ntok <= (size_t)0x7fffff00;
+    const bool tc = h->f32_tc && k == 128 && HD == 256 && F % 256 == 0 && F <= 768 && ntok <= (size_t)0x7fffff00;
     int rc;
     if (tc) {
       ProfScope ps(h, AVB_PROF_QKV, st);

@@ -367,8 +367,8 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         // (the separate out-projection launch uses the plain bo, so the value bias is added here)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float4 b0 = reinterpret_cast<const float4*>(s_bias + kDaHeads * 32 + h * 32)[e * 2];
-          const float4 b1 = reinterpret_cast<const float4*>(s_bias + kDaHeads * 32 + h * 32)[e * 2 + 1];
+          const float4 b0 = ptx::ld_shared_v4f(ptx::smem_u32(s_bias) + (uint32_t)((kDaHeads * 32 + h * 32 + e * 8) * 4));
+          const float4 b1 = ptx::ld_shared_v4f(ptx::smem_u32(s_bias) + (uint32_t)((kDaHeads * 32 + h * 32 + e * 8 + 4) * 4));
           pk[e].x = ptx::pack_bf16(__uint_as_float(o[e * 8 + 0]) * inv + b0.x, __uint_as_float(o[e * 8 + 1]) * inv + b0.y);
           pk[e].y = ptx::pack_bf16(__uint_as_float(o[e * 8 + 2]) * inv + b0.z, __uint_as_float(o[e * 8 + 3]) * inv + b0.w);
           pk[e].z = ptx::pack_bf16(__uint_as_float(o[e * 8 + 4]) * inv + b1.x, __uint_as_float(o[e * 8 + 5]) * inv + b1.y);
@@ -403,7 +403,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         ptx::tmem_ld32(tD + cc * 32 + lane_off, v);
         float4 bb[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) bb[e] = reinterpret_cast<const float4*>(s_bias + kDaHeads * 32 + cc * 32)[e];
+        for (int e = 0; e < 8; ++e) bb[e] = ptx::ld_shared_v4f(ptx::smem_u32(s_bias) + (uint32_t)((kDaHeads * 32 + cc * 32 + e * 4) * 4));
         ptx::tmem_wait_ld();
         if (cc == 3) {
           ptx::tc_fence_before();
@@ -516,9 +516,9 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         // loads less per row and unit on warps whose instruction count is what bounds the unit period.
         float4 bb[8];
         if (w == 0) {
-          const float4* bp = reinterpret_cast<const float4*>(s_bias + h * 32);  // shared-memory broadcast
+          const uint32_t bp = ptx::smem_u32(s_bias) + (uint32_t)(h * 32 * 4);  // shared-memory broadcast (explicit ld.shared)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) bb[e] = bp[e];
+          for (int e = 0; e < 8; ++e) bb[e] = ptx::ld_shared_v4f(bp + e * 16);
         } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) bb[e] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -12,11 +12,12 @@
 // kernel).  The LayerNorm affine and the softmax scale are folded into W / bias in fp64 at load time, like in the bf16
 // mode, so one normalised A tile serves the q, k and v projections.
 //
-// Per CTA and 128-row tile: four producer warps normalise / split the fp32 rows once into K/64 pairs of 128B-swizzled
-// [128 x 64] bf16 tiles (hi, lo), which stay resident for all N/128 column chunks; the weight tiles (hi, lo, [128 x 64]
-// each, pre-split at load time) stream through a TMA ring; 12 MMAs (M 128, N 128, K 16) per K block; accumulators
-// double-buffered in TMEM; four epilogue warps add the bias, apply ReLU or the residual and write full 128-byte fp32
-// segments, one row per thread.  K is 128 or 256 per launch (the 512-wide FFN down-projection runs as two launches, the
+// Per CTA and 128-row tile: four producer warps normalise / split the fp32 rows into A units (128 columns = two K blocks
+// of 128B-swizzled [128 x 64] bf16 tiles, hi and lo), double-buffered so the next tile (K = 128) or the next half tile
+// (K = 256) is split while the tensor core works, and kept for all N/128 column chunks; the weight tiles (hi, lo, [128 x
+// 64] each, pre-split at load time) stream through a TMA ring; 12 MMAs (M 128, N 128, K 16) per K block; accumulators
+// double-buffered in TMEM; four epilogue warps add the bias (from shared memory), apply ReLU or the residual and write
+// full 128-byte fp32 segments, one row per thread.  K is 128 or 256 per launch (the 512-wide FFN down-projection runs as two launches, the
 // second accumulating onto the first through the residual epilogue).
 //   warp 0: weight TMA   warp 1: MMA issuer   warp 2: TMEM alloc   warps 4-7: A producers   warps 8-11: epilogue
 #pragma once
@@ -27,11 +28,14 @@ namespace avb {
 constexpr int kSplitThreads = 384;
 constexpr int kSplitBStages = 2;
 constexpr int kSplitTile = 128 * 64 * 2;  // one [128 x 64] bf16 tile, 16 KB
+constexpr int kSplitUnit = 2 * 2 * kSplitTile;  // an A unit: two K blocks x (hi, lo) = 64 KB = 128 columns of 128 rows
 template <int KB>
 struct SplitCfg {
-  static constexpr int kABytes = KB * 2 * kSplitTile;             // resident A: (hi, lo) per K block
+  static constexpr int kABytes = 2 * kSplitUnit;                  // two A units: double-buffered by tile (KB 2) / half tile (KB 4)
   static constexpr int kBBytes = kSplitBStages * 2 * kSplitTile;  // weight ring: (hi, lo) per stage
-  static constexpr int kSmemBytes = kABytes + kBBytes + 1024 + 256;
+  static constexpr int kBiasBytes = 768 * 4;
+  static constexpr int kStageBytes = 4 * 4096;                    // per epilogue warp: [32 rows x 128 B] transposition stage
+  static constexpr int kSmemBytes = kABytes + kBBytes + kBiasBytes + kStageBytes + 1024 + 256;
 };
 
 enum { kSplitEpiBias = 0, kSplitEpiRelu = 1, kSplitEpiResidual = 2, kSplitEpiQkvOperands = 3 };
@@ -40,20 +44,29 @@ enum { kSplitEpiBias = 0, kSplitEpiRelu = 1, kSplitEpiResidual = 2, kSplitEpiQkv
 // attention_split_tc_kernel (below) instead of fp32 rows; the row order of the attended axis comes from RowMap.
 struct SplitSeq { int n, d, axis, dg, H; };
 
-// 32 fp32 rows of width 64*KB (row pitch lda floats) -> hi / lo bf16 K-major tiles; eight lanes share a row (128-byte
-// coalesced segments), optional LayerNorm without affine (exact two-pass statistics in fp32, K = 128 only).
-template <int KB, bool kLn>
-__device__ __forceinline__ void split_rows_to_tiles(const float* __restrict__ a, int lda, int M, int grow0, uint32_t a_tiles,
-                                                    int row0, int lane) {
-  constexpr int NK = 2 * KB;  // float4 per lane and row: columns 4 (j + 8 k)
+// 32 fp32 rows x 128 columns (row pitch lda floats) -> one A unit (two K blocks of hi / lo bf16 K-major tiles); eight
+// lanes share a row (128-byte coalesced segments), optional LayerNorm without affine over those 128 columns (exact
+// two-pass statistics in fp32).
+template <bool kLn>
+__device__ __forceinline__ void split_rows_to_unit(const float* __restrict__ a, int lda, int M, int grow0, uint32_t a_unit,
+                                                   int row0, int lane, const RowMap rm = RowMap{0, 0, 0}) {
+  constexpr int NK = 4;  // float4 per lane and row: columns 4 (j + 8 k)
   const int rs = lane >> 3, j = lane & 7;
-#pragma unroll 1
-  for (int r0 = 0; r0 < 32; r0 += 4) {
+  float4 nxt[NK];
+  auto load = [&](float4 (&dst)[NK], int r0) {
     const int grow = grow0 + r0 + rs;
-    float4 v[NK];
+    const int tok = grow < M ? rm.token(grow) : 0;  // the QKV projection walks its rows in sequence-major order
 #pragma unroll
     for (int k = 0; k < NK; ++k)
-      v[k] = grow < M ? __ldcg(reinterpret_cast<const float4*>(a + (size_t)grow * lda) + j + 8 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dst[k] = grow < M ? __ldcg(reinterpret_cast<const float4*>(a + (size_t)tok * lda) + j + 8 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  load(nxt, 0);
+#pragma unroll 1
+  for (int r0 = 0; r0 < 32; r0 += 4) {
+    float4 v[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) v[k] = nxt[k];
+    if (r0 + 4 < 32) load(nxt, r0 + 4);  // the next four rows are in flight while these are split
     if (kLn) {
       float sum = 0.f;
 #pragma unroll
@@ -61,7 +74,7 @@ __device__ __forceinline__ void split_rows_to_tiles(const float* __restrict__ a,
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       sum += __shfl_xor_sync(0xffffffffu, sum, 2);
       sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-      const float mean = sum * (1.0f / (64 * KB));
+      const float mean = sum * (1.0f / 128.0f);
       float sq = 0.f;
 #pragma unroll
       for (int k = 0; k < NK; ++k) {
@@ -71,12 +84,12 @@ __device__ __forceinline__ void split_rows_to_tiles(const float* __restrict__ a,
       sq += __shfl_xor_sync(0xffffffffu, sq, 1);
       sq += __shfl_xor_sync(0xffffffffu, sq, 2);
       sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-      const float rstd = rsqrtf(sq * (1.0f / (64 * KB)) + kLnEps);
+      const float rstd = rsqrtf(sq * (1.0f / 128.0f) + kLnEps);
 #pragma unroll
       for (int k = 0; k < NK; ++k) { v[k].x *= rstd; v[k].y *= rstd; v[k].z *= rstd; v[k].w *= rstd; }
     }
     const int r = row0 + r0 + rs;
-    const uint32_t rbase = a_tiles + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (j & 1) * 8);
+    const uint32_t rbase = a_unit + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (j & 1) * 8);
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
       // columns 4 (j + 8k) .. +3: K block k >> 1, 16-byte chunk (j + 8 (k & 1)) >> 1 of its 128-byte row
@@ -100,16 +113,19 @@ __global__ void __launch_bounds__(kSplitThreads, 1)
 gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant__ CUtensorMap tm_hi,
                      const __grid_constant__ CUtensorMap tm_lo, int k_off, const float* __restrict__ bias,
                      const float* R, int ldr, float* C, int ldc, int M, int N, SplitSeq sq) {
+  static_assert(!kLn || KB == 2, "the LayerNorm prologue normalises over one A unit (128 columns)");
   using Cfg = SplitCfg<KB>;
-  constexpr int ST = kSplitBStages;
+  constexpr int ST = kSplitBStages, UNITS = KB / 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                    // [KB][hi 16K | lo 16K]
+  uint8_t* sA = smem;                    // [2 units][2 K blocks][hi 16K | lo 16K]
   uint8_t* sB = sA + Cfg::kABytes;       // [ST][hi 16K | lo 16K]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + Cfg::kBBytes);
-  uint64_t* a_full = bars;               // 128 producer threads
-  uint64_t* a_empty = bars + 1;          // commit
-  uint64_t* b_full = bars + 2;           // [ST] tx
+  float* s_bias = reinterpret_cast<float*>(sB + Cfg::kBBytes);  // [N <= 768]: a __ldg would queue behind the producers' row loads
+  uint8_t* sStage = sB + Cfg::kBBytes + Cfg::kBiasBytes;        // [4 epilogue warps][4 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::kStageBytes);
+  uint64_t* a_full = bars;               // [2] 128 producer threads
+  uint64_t* a_empty = bars + 2;          // [2] commit
+  uint64_t* b_full = bars + 4;           // [ST] tx
   uint64_t* b_empty = b_full + ST;       // [ST] commit
   uint64_t* t_full = b_empty + ST;       // [2] commit
   uint64_t* t_empty = t_full + 2;        // [2] 128 epilogue threads
@@ -120,7 +136,7 @@ gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant
 
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tm_hi); ptx::prefetch_tmap(&tm_lo); }
   if (warp == 1 && lane == 0) {
-    ptx::mbar_init(a_full, 128); ptx::mbar_init(a_empty, 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_full[i], 128); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < ST; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 128); }
     ptx::fence_barrier_init();
@@ -129,6 +145,7 @@ gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant
     ptx::tmem_alloc(tmem_slot, 256);
     ptx::tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < N; i += kSplitThreads) s_bias[i] = bias[i];
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -150,65 +167,84 @@ gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant
           if (++stage == ST) { stage = 0; phase ^= 1; }
         }
   } else if (warp == 1) {
-    // ===================== MMA issuer
+    // ===================== MMA issuer.  An A unit (128 columns) is waited for in the first column chunk that uses it and
+    // released after the last one: with KB = 2 the tile's single unit alternates between the two buffers (the producers
+    // split the next tile meanwhile), with KB = 4 and one chunk the two halves of a tile do.
     constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 128, 0, 0);
     const uint64_t dA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024, ptx::kSwz128);
     const uint64_t dB0 = ptx::make_smem_desc(ptx::smem_u32(sB), 16, 1024, ptx::kSwz128);
-    constexpr uint64_t kLo = kSplitTile >> 4;
+    constexpr uint64_t kLo = kSplitTile >> 4, kUnit = kSplitUnit >> 4;
     int stage = 0; uint32_t phase = 0;
-    int it = 0, acc_it = 0;
-    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
-      ptx::mbar_wait(a_full, (uint32_t)(it & 1), 61, 40u);
+    int acc_it = 0;
+    uint32_t uc0 = 0;  // running unit count at the start of the tile
+    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, uc0 += UNITS) {
       for (int c = 0; c < num_c; ++c, ++acc_it) {
         const int as = acc_it & 1;
         ptx::mbar_wait(&t_empty[as], (uint32_t)((acc_it >> 1) & 1) ^ 1, 62, 40u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * 128u;
-        for (int kb = 0; kb < KB; ++kb) {
-          ptx::mbar_wait(&b_full[stage], phase, 63, 40u);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint64_t da = dA0 + (uint64_t)kb * (2 * kLo), db = dB0 + (uint64_t)stage * (2 * kLo);
+        for (int u = 0; u < UNITS; ++u) {
+          const uint32_t uc = uc0 + (uint32_t)u, ab = uc & 1u;
+          if (c == 0) ptx::mbar_wait(&a_full[ab], (uc >> 1) & 1u, 61, 40u);
+          for (int kb2 = 0; kb2 < 2; ++kb2) {
+            const int kb = u * 2 + kb2;
+            ptx::mbar_wait(&b_full[stage], phase, 63, 40u);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint64_t da = dA0 + (uint64_t)ab * kUnit + (uint64_t)kb2 * (2 * kLo), db = dB0 + (uint64_t)stage * (2 * kLo);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              ptx::umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);              // hi hi
-              ptx::umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + kLo + (uint64_t)(k * 2), idesc, 1);                     // hi lo
-              ptx::umma_bf16(d_tmem, da + kLo + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1);                     // lo hi
+              for (int k = 0; k < 4; ++k) {
+                ptx::umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);              // hi hi
+                ptx::umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + kLo + (uint64_t)(k * 2), idesc, 1);                     // hi lo
+                ptx::umma_bf16(d_tmem, da + kLo + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1);                     // lo hi
+              }
+              ptx::umma_commit(&b_empty[stage]);
+              if (kb2 == 1 && c == num_c - 1) ptx::umma_commit(&a_empty[ab]);
+              if (kb == KB - 1) ptx::umma_commit(&t_full[as]);
             }
-            ptx::umma_commit(&b_empty[stage]);
-            if (kb == KB - 1) {
-              ptx::umma_commit(&t_full[as]);
-              if (c == num_c - 1) ptx::umma_commit(a_empty);
-            }
+            __syncwarp();
+            if (++stage == ST) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == ST) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    // ===================== A producers: warp w splits rows 32w .. 32w+31 of each tile
+    // ===================== A producers: warp w splits rows 32w .. 32w+31 of each unit
     const int w = warp - 4;
-    int it = 0;
-    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++it) {
-      ptx::mbar_wait(a_empty, (uint32_t)(it & 1) ^ 1, 64);
-      split_rows_to_tiles<KB, kLn>(A, lda, M, mt * 128 + w * 32, ptx::smem_u32(sA), w * 32, lane);
-      ptx::fence_proxy_async();
-      ptx::mbar_arrive(a_full);
+    uint32_t uc = 0;
+    const RowMap prm = EPI == kSplitEpiQkvOperands ? RowMap{sq.n, sq.d, sq.axis, sq.dg} : RowMap{0, 0, 0};
+    for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
+      // L2 prefetch of this warp's 32 rows of the NEXT tile: a warp keeps only 2 KB of row loads in flight, far below
+      // HBM latency x bandwidth (measured without it: 42K clocks per tile, the whole kernel latency-bound on these loads)
+      {
+        const int nrow0 = (mt + (int)gridDim.x) * 128 + w * 32;
+#pragma unroll
+        for (int i = 0; i < 2 * KB; ++i) {
+          const int line = i * 32 + lane, row = nrow0 + line / (2 * KB), seg = line % (2 * KB);
+          if (row < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)prm.token(row) * lda + seg * 32));
+        }
+      }
+      for (int u = 0; u < UNITS; ++u, ++uc) {
+        const uint32_t ab = uc & 1u;
+        ptx::mbar_wait(&a_empty[ab], ((uc >> 1) & 1u) ^ 1u, 64);
+        split_rows_to_unit<kLn>(A + u * 128, lda, M, mt * 128 + w * 32, ptx::smem_u32(sA) + ab * kSplitUnit, w * 32, lane, prm);
+        ptx::fence_proxy_async();
+        ptx::mbar_arrive(&a_full[ab]);
+      }
     }
   } else if (warp >= 8) {
     // ===================== epilogue: one row per thread, 32 columns (one full 128-byte line) at a time
     const int q = warp & 3;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     int acc_it = 0;
+    const uint32_t a_bias = ptx::smem_u32(s_bias);
     const RowMap rm{sq.n, sq.d, sq.axis, sq.dg};
     const int seq_T = sq.axis == 0 ? sq.d : sq.n;
     for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x) {
       const int row = mt * 128 + q * 32 + lane;
       [[maybe_unused]] unsigned seq = 0, pos = 0;
-      if (EPI == kSplitEpiQkvOperands && row < M) {  // GEMM rows are tokens: sequence and position under the attended axis
-        const unsigned m = (unsigned)rm.seq_row(row);
-        seq = m / (unsigned)seq_T; pos = m - seq * (unsigned)seq_T;
+      if (EPI == kSplitEpiQkvOperands && row < M) {  // GEMM rows are in sequence-major order (the producers gather them)
+        seq = (unsigned)row / (unsigned)seq_T; pos = (unsigned)row - seq * (unsigned)seq_T;
       }
       for (int c = 0; c < num_c; ++c, ++acc_it) {
         const int as = acc_it & 1;
@@ -219,11 +255,6 @@ gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant
           const int col = c * 128 + cc * 32;
           uint32_t v[32];
           ptx::tmem_ld32(tmem_base + (uint32_t)as * 128u + cc * 32 + lane_off, v);
-          float4 rr[8];
-          if (EPI == kSplitEpiResidual && row < M) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) rr[e] = __ldcg(reinterpret_cast<const float4*>(R + (size_t)row * ldr + col) + e);
-          }
           ptx::tmem_wait_ld();
           if (cc == 3) {
             ptx::tc_fence_before();
@@ -238,8 +269,8 @@ gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant
               const unsigned swz = (pos >> 1) & 3;
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col) + 2 * e);
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col) + 2 * e + 1);
+                const float4 b0 = ptx::ld_shared_v4f(a_bias + (uint32_t)((col + 8 * e) * 4));
+                const float4 b1 = ptx::ld_shared_v4f(a_bias + (uint32_t)((col + 8 * e + 4) * 4));
                 float f[8];
                 f[0] = __uint_as_float(v[e * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[e * 8 + 1]) + b0.y;
                 f[2] = __uint_as_float(v[e * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[e * 8 + 3]) + b0.w;
@@ -257,17 +288,39 @@ gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant
                 *reinterpret_cast<uint4*>(dst + part + (((unsigned)e ^ swz) << 3)) = lo;
               }
             }
-          } else if (row < M) {
+          } else {
+            // A row-per-thread global access touches 32 different lines per warp instruction (bound by L1 wavefronts, ~11K
+            // clocks per 128 x 128 chunk measured): the [32 rows x 32 columns] block goes through a 4 KB XOR-swizzled stage
+            // owned by the warp, after which every instruction covers 4 rows x 128 contiguous bytes.
+            const uint32_t stage = ptx::smem_u32(sStage) + (uint32_t)((warp - 8) * 4096);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col) + e);
+            for (int e = 0; e < 8; ++e) {  // thread = row `lane`: 16-byte chunk e goes to slot e ^ (lane & 7)
+              const float4 b4 = ptx::ld_shared_v4f(a_bias + (uint32_t)((col + 4 * e) * 4));
               float4 o;
               o.x = __uint_as_float(v[e * 4 + 0]) + b4.x; o.y = __uint_as_float(v[e * 4 + 1]) + b4.y;
               o.z = __uint_as_float(v[e * 4 + 2]) + b4.z; o.w = __uint_as_float(v[e * 4 + 3]) + b4.w;
               if (EPI == kSplitEpiRelu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              if (EPI == kSplitEpiResidual) { o.x += rr[e].x; o.y += rr[e].y; o.z += rr[e].z; o.w += rr[e].w; }
-              reinterpret_cast<float4*>(C + (size_t)row * ldc + col)[e] = o;
+              ptx::st_shared_v4(stage + (uint32_t)(lane * 128 + ((e ^ (lane & 7)) << 4)),
+                                make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
             }
+            __syncwarp();
+            const int sub = lane >> 3, l8 = lane & 7, brow0 = mt * 128 + q * 32;
+            float4 rr2[8];
+            if (EPI == kSplitEpiResidual) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rw = brow0 + i * 4 + sub;
+                rr2[i] = rw < M ? __ldcg(reinterpret_cast<const float4*>(R + (size_t)rw * ldr + col) + l8) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rl = i * 4 + sub, rw = brow0 + rl;
+              float4 o = ptx::ld_shared_v4f(stage + (uint32_t)(rl * 128 + ((l8 ^ (rl & 7)) << 4)));
+              if (EPI == kSplitEpiResidual) { o.x += rr2[i].x; o.y += rr2[i].y; o.z += rr2[i].z; o.w += rr2[i].w; }
+              if (rw < M) reinterpret_cast<float4*>(C + (size_t)rw * ldc + col)[l8] = o;
+            }
+            __syncwarp();
           }
         }
       }

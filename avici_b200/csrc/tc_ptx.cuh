@@ -132,6 +132,13 @@ __device__ __forceinline__ float ld_shared_f32(uint32_t saddr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
   return v;
 }
+// explicit shared-space vector load: through a generic pointer the compiler emits LD.E (generic), which the ncu source page
+// showed as ~1000-clock long-scoreboard stalls in the epilogues that read their biases from shared memory
+__device__ __forceinline__ float4 ld_shared_v4f(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ void st_shared_f32(uint32_t saddr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
 }
