@@ -232,6 +232,8 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         }
         __syncwarp();
       };
+      // (Tried, r2e: non-blocking tests of both groups' barriers, whichever is ready first - 4.42 vs 4.00 ms: the polling warp
+      //  competes with the softmax warps of its SM sub-partition for issue slots.)
       issue_S(0);
       for (int u = 0; u < U; ++u) {
         AVB_TRACE(1, u, 0);
@@ -317,9 +319,56 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
   }
   } else if (warp < 8) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-    // ======================= epilogue warps (Oepi + Depi): thread = row r of the tile = TMEM lane
+    // ======================= LayerNorm + epilogue warps (Oepi, Depi): thread = row r of the tile = TMEM lane for the
+    // epilogues.  The LayerNorm of the NEXT sequence is cut into four 8-row slices per warp, one per unit h = 0..3, with
+    // the slice's loads in flight across that unit's Oepi (which has no async-proxy fence any more - a fence is
+    // MEMBAR.ALL.CTA and would drain them): a whole 32-row LayerNorm in one piece would hold up the O hand-back once per
+    // sequence.  These warps wait ~1200 clocks per unit for PV otherwise (r2d trace); the conv warps have no slack.
     const int w = warp - 4, q = w, r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int rs = lane >> 3, j8 = lane & 7;
+    float4 ln[2][4];
+    auto ln8_load = [&](const float* zs, int r0) {  // rows 32w + r0 .. + 7 of the sequence (zeros past its end)
+#pragma unroll
+      for (int uu = 0; uu < 2; ++uu) {
+        const int row = w * 32 + r0 + uu * 4 + rs;
+        const float4* zp = reinterpret_cast<const float4*>(zs + (size_t)row * 128) + j8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ln[uu][k] = row < T ? __ldcg(zp + k * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto ln8_finish = [&](uint32_t a_tile, int r0) {  // same arithmetic and layout as ln_warp_rows_to_umma_tile
+#pragma unroll
+      for (int uu = 0; uu < 2; ++uu) {
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sum += (ln[uu][k].x + ln[uu][k].y) + (ln[uu][k].z + ln[uu][k].w);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        const float mean = sum * (1.0f / 128.0f);
+        float sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ln[uu][k].x -= mean; ln[uu][k].y -= mean; ln[uu][k].z -= mean; ln[uu][k].w -= mean;
+          sq += (ln[uu][k].x * ln[uu][k].x + ln[uu][k].y * ln[uu][k].y) + (ln[uu][k].z * ln[uu][k].z + ln[uu][k].w * ln[uu][k].w);
+        }
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+        const float rstd = rsqrtf(sq * (1.0f / 128.0f) + kLnEps);
+        const int rr = w * 32 + r0 + uu * 4 + rs;
+        const uint32_t rbase = a_tile + (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128 + (j8 & 1) * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int chunk = (j8 + 8 * (k & 1)) >> 1;
+          const uint32_t addr = rbase + (uint32_t)((k >> 1) * (128 * 128) + ((chunk ^ (rr & 7)) << 4));
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ptx::pack_bf16(ln[uu][k].x * rstd, ln[uu][k].y * rstd)),
+                       "r"(ptx::pack_bf16(ln[uu][k].z * rstd, ln[uu][k].w * rstd))
+                       : "memory");
+        }
+      }
+    };
     auto oepi = [&](int u) {  // O / L -> bf16 -> A tile of the out-projection (or the attention output in HBM)
       const int h = u & 7;
       ptx::mbar_wait(pv_done, (uint32_t)(u & 1), 92);
@@ -430,70 +479,50 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       AVB_TRACE(6, si, 5);
     };
 
+    if (nseq > 0) {  // the first sequence's LayerNorm, slice by slice
+      const float* zs = z + (size_t)blockIdx.x * T * 128;
+      if (nseq > 1) prefetch_rows_l2(z + (size_t)((int)blockIdx.x + (int)gridDim.x) * T * 128, T, w * 32, lane);
+#pragma unroll 1
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        ln8_load(zs, r0);
+        ln8_finish(ptx::smem_u32(sX), r0);
+      }
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&x_full[0]);
+    }
     for (int si = 0; si < nseq; ++si) {
+      const int s_next = (int)blockIdx.x + (si + 1) * (int)gridDim.x, nbuf = (si + 1) & 1;
+      const bool has_next = si + 1 < nseq;
+      if (si + 2 < nseq) prefetch_rows_l2(z + (size_t)(s_next + (int)gridDim.x) * T * 128, T, w * 32, lane);
       for (int h = 0; h < kDaHeads; ++h) {
         const int u = si * kDaHeads + h;
+        const bool slice = has_next && h < 4;
         AVB_TRACE(4, u, 0);
+        if (slice) {
+          if (h == 0) ptx::mbar_wait(&x_empty[nbuf], (uint32_t)(((si + 1) >> 1) & 1) ^ 1, 90);
+          ln8_load(z + (size_t)s_next * T * 128, h * 8);
+        }
         oepi(u);
         AVB_TRACE(4, u, 2);
+        if (slice) {
+          ln8_finish(ptx::smem_u32(sX + nbuf * kDaXBytes), h * 8);
+          if (h == 3) {
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive(&x_full[nbuf]);
+          }
+        }
         if (kFuseOut && h == kDaHeads - 1) depi(si);
         AVB_TRACE(4, u, 5);
       }
     }
   } else if (warp < 12) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-    // ======================= conv + LayerNorm warps: thread = row r of the tile = TMEM lane for conv.
-    // The LayerNorm of the NEXT sequence is cut into four 8-row slices per warp, one per unit h = 0..3: its loads are
-    // issued behind conv_u's async-proxy fence (which would otherwise drain them) and are in flight while the warp
-    // waits for the next unit's projection; these warps run about two units ahead of the softmax and had ~1300 idle
-    // clocks per unit (r2c trace), the epilogue warps none.
-    const int q = warp & 3, r = q * 32 + lane, w = q;
+    // ======================= conv warps: thread = row r of the tile = TMEM lane.  Nothing else runs here: qkv_ready ->
+    // S_u -> softmax_u is the unit pipeline's critical chain.
+    const int q = warp & 3, r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t row_off = (uint32_t)(r * 64), swz = (uint32_t)((r >> 1) & 3);
     const uint32_t aQ = ptx::smem_u32(sQ), aK = ptx::smem_u32(sK), aV = ptx::smem_u32(sV);
-    const int rs = lane >> 3, j8 = lane & 7;
-    float4 ln[2][4];
-    auto ln8_load = [&](const float* zs, int r0) {  // rows 32w + r0 .. + 7 of the sequence (zeros past its end)
-#pragma unroll
-      for (int uu = 0; uu < 2; ++uu) {
-        const int row = w * 32 + r0 + uu * 4 + rs;
-        const float4* zp = reinterpret_cast<const float4*>(zs + (size_t)row * 128) + j8;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ln[uu][k] = row < T ? __ldcg(zp + k * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    auto ln8_finish = [&](uint32_t a_tile, int r0) {  // same arithmetic and layout as ln_warp_rows_to_umma_tile
-#pragma unroll
-      for (int uu = 0; uu < 2; ++uu) {
-        float sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) sum += (ln[uu][k].x + ln[uu][k].y) + (ln[uu][k].z + ln[uu][k].w);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-        const float mean = sum * (1.0f / 128.0f);
-        float sq = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          ln[uu][k].x -= mean; ln[uu][k].y -= mean; ln[uu][k].z -= mean; ln[uu][k].w -= mean;
-          sq += (ln[uu][k].x * ln[uu][k].x + ln[uu][k].y * ln[uu][k].y) + (ln[uu][k].z * ln[uu][k].z + ln[uu][k].w * ln[uu][k].w);
-        }
-        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-        const float rstd = rsqrtf(sq * (1.0f / 128.0f) + kLnEps);
-        const int rr = w * 32 + r0 + uu * 4 + rs;
-        const uint32_t rbase = a_tile + (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128 + (j8 & 1) * 8);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int chunk = (j8 + 8 * (k & 1)) >> 1;
-          const uint32_t addr = rbase + (uint32_t)((k >> 1) * (128 * 128) + ((chunk ^ (rr & 7)) << 4));
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ptx::pack_bf16(ln[uu][k].x * rstd, ln[uu][k].y * rstd)),
-                       "r"(ptx::pack_bf16(ln[uu][k].z * rstd, ln[uu][k].w * rstd))
-                       : "memory");
-        }
-      }
-    };
     auto conv_wait = [&](int u) {
       ptx::mbar_wait(&g_full[u & 1], (uint32_t)((u >> 1) & 1), 91);
       // the Q / K tiles are single-buffered: S of the previous unit (issued by another warp than G) must have read them
@@ -550,41 +579,11 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       ptx::mbar_arrive(&qkv_ready[u & 1]);
     };
 
-    if (nseq > 0) {  // the first sequence's LayerNorm, slice by slice
-      const float* zs = z + (size_t)blockIdx.x * T * 128;
-      if (nseq > 1) prefetch_rows_l2(z + (size_t)((int)blockIdx.x + (int)gridDim.x) * T * 128, T, w * 32, lane);
-#pragma unroll 1
-      for (int r0 = 0; r0 < 32; r0 += 8) {
-        ln8_load(zs, r0);
-        ln8_finish(ptx::smem_u32(sX), r0);
-      }
-      ptx::fence_proxy_async();
-      ptx::mbar_arrive(&x_full[0]);
-    }
-    bool pending = false;  // a LayerNorm slice whose loads are in flight
     for (int u = 0; u < U; ++u) {
-      const int si = u >> 3, h = u & 7, nbuf = (si + 1) & 1;
       AVB_TRACE(2, u, 0);
       conv_wait(u);
-      conv(u);  // first: qkv_ready -> S_u -> softmax_u is the unit pipeline's critical chain (r2c trace)
+      conv(u);
       AVB_TRACE(2, u, 3);
-      if (pending) {  // slice h - 1, loaded behind conv_{u-1}: its loads have landed by now
-        ln8_finish(ptx::smem_u32(sX + nbuf * kDaXBytes), (h - 1) * 8);
-        if (h == 4) {
-          ptx::fence_proxy_async();
-          ptx::mbar_arrive(&x_full[nbuf]);
-        }
-      }
-      pending = false;
-      if (si + 1 < nseq && h < 4) {
-        const int s_next = (int)blockIdx.x + (si + 1) * (int)gridDim.x;
-        if (h == 0) {
-          if (si + 2 < nseq) prefetch_rows_l2(z + (size_t)(s_next + (int)gridDim.x) * T * 128, T, w * 32, lane);
-          ptx::mbar_wait(&x_empty[nbuf], (uint32_t)(((si + 1) >> 1) & 1) ^ 1, 90);
-        }
-        ln8_load(z + (size_t)s_next * T * 128, h * 8);
-        pending = true;
-      }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
