@@ -45,6 +45,7 @@ struct Block {
   // fp32 mode, split-precision tensor-core GEMMs (kernels_split.cuh): hi / lo bf16 halves of the K-major weights with the
   // LayerNorm affine folded in (no softmax scale: the fp32 attention kernel applies it), their [128 x 64] tensor maps
   CUtensorMap tm_s_qkv[2], tm_s_o[2], tm_s_1[2], tm_s_2[2];
+  avb::FfnBias ffn_bias;  // host copy of b1' (LayerNorm-folded) and b2 for the resident FFN kernel's parameter (F = 512)
   const float *zero_k;
   // per-head operand images of dattn_tc_kernel: Wqkv_h as 2 K blocks of [96 x 64] (128B swizzle), Wo_h as [128 x 32] (64B swizzle)
   const uint8_t *wd_qkv, *wd_o;
@@ -304,7 +305,7 @@ int launch_outproj_tc(avb_handle h, const void* attn, const CUtensorMap& tm_w, c
 // serves the published width (F = 512, four resident chunks), the weight-ring variant every other multiple of 256.
 int launch_ffn2_tc(avb_handle h, float* z, const CUtensorMap& tm_w1q, const CUtensorMap& tm_w2q, const float* b1,
                    const float* b2, int M, int F, cudaStream_t st, int num_sms, long long* launches,
-                   const void* delta = nullptr, int n = 0, int d = 0, int axis = 0) {
+                   const void* delta = nullptr, int n = 0, int d = 0, int axis = 0, const avb::FfnBias* host_bias = nullptr) {
   static PerDeviceOnce once;
   cudaError_t e = once.run([] {
     cudaError_t r = cudaFuncSetAttribute(avb::ffn2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kFfnSmemBytes);
@@ -322,12 +323,20 @@ int launch_ffn2_tc(avb_handle h, float* z, const CUtensorMap& tm_w1q, const CUte
   const int grid = 2 * std::min(num_pairs, num_sms / 2);
   CUtensorMap tm_z;  // the residual stream of this call, for the final epilogue's tensor-map stores
   if (!make_tmap_2d_f32(&tm_z, z, (uint64_t)M, 128, 32)) return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for z");
+  static const avb::FfnBias zero_bias{};
+  avb::FfnBias fetched;
+  if (use_resident && !host_bias) {  // test hook: the biases live on the device only
+    if (cudaMemcpy(fetched.b1, b1, sizeof fetched.b1, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(fetched.b2, b2, sizeof fetched.b2, cudaMemcpyDeviceToHost) != cudaSuccess)
+      return fail(h, AVB_ERR_CUDA, "ffn2_tc: fetching the biases failed");
+    host_bias = &fetched;
+  }
   if (use_resident)
     avb::ffn2_tc_kernel<true><<<grid, avb::kFfnThreads, avb::kFfnSmemBytes, st>>>(z, reinterpret_cast<const bf16*>(delta), n, d, axis,
-                                                                                   tm_z, tm_w1q, tm_w2q, b1, b2, M, F);
+                                                                                   tm_z, tm_w1q, tm_w2q, b1, b2, M, F, *host_bias);
   else
     avb::ffn2_tc_kernel<false><<<grid, avb::kFfnThreads, avb::kFfnSmemBytes, st>>>(z, reinterpret_cast<const bf16*>(delta), n, d, axis,
-                                                                                    tm_z, tm_w1q, tm_w2q, b1, b2, M, F);
+                                                                                    tm_z, tm_w1q, tm_w2q, b1, b2, M, F, zero_bias);
   if (launches) ++*launches;
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "ffn2_tc launch: %s", cudaGetErrorString(e));
@@ -823,6 +832,10 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
     B.wq = df + o.wq; B.bq = df + o.bq; B.wk = df + o.wk; B.bk = df + o.bk; B.wv = df + o.wv; B.bv = df + o.bv;
     B.wo = df + o.wo; B.bo = df + o.bo; B.w1 = df + o.w1; B.b1 = df + o.b1; B.w2 = df + o.w2; B.b2 = df + o.b2;
     B.bqkv_f = df + o.bqkv_f; B.b1_f = df + o.b1_f; B.bo_d = df + o.bo_d; B.zero_k = df + o.zero_k;
+    if (c.compute_dtype == AVB_DTYPE_BF16 && F == 512) {
+      memcpy(B.ffn_bias.b1, f32.data() + o.b1_f, sizeof B.ffn_bias.b1);
+      memcpy(B.ffn_bias.b2, f32.data() + o.b2, sizeof B.ffn_bias.b2);
+    }
     if (c.compute_dtype == AVB_DTYPE_F32) {
       bool ok = true;
       for (int p = 0; p < 2; ++p)
@@ -953,7 +966,8 @@ static int block_impl(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, 
     }
     // FFN half: z += delta; LN -> Linear + ReLU -> Linear + residual, one kernel
     { ProfScope ps(h, AVB_PROF_FFN, st);
-      if ((rc = launch_ffn2_tc(h, z, W.tm_w1q, W.tm_w2q, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches, qkv, n, d, axis)))
+      if ((rc = launch_ffn2_tc(h, z, W.tm_w1q, W.tm_w2q, W.b1_f, W.b2, M, F, st, h->num_sms, &h->launches, qkv, n, d, axis,
+                               F == 512 ? &W.ffn_bias : nullptr)))
         return rc; }
   } else {
     float* qkv = reinterpret_cast<float*>(w8 + L.big_off);

@@ -851,12 +851,20 @@ constexpr int kFfnSmemBytes = 2 * kLnGemmABytes + 2 * 2 * kFfnWBytes + 8 * 4096 
 #ifndef AVB_FFN_E2_PLAIN
 #define AVB_FFN_E2_PLAIN 0  // 1: final epilogue leaves through plain coalesced stores instead of tensor-map stores (A/B build)
 #endif
+// The FFN biases of the resident-weight variant (F = 512) travel as a kernel parameter and are read from the constant
+// bank: a __ldg from the epilogue warps queues in the L1 pipeline behind the LayerNorm warps' streaming row loads (found
+// on the fused d-axis kernel, r2b: ~500 clocks of long-scoreboard stall per 32-column chunk), and there are 1.7 KB of
+// shared memory left in this kernel, less than b1.  Measured in the bench step: FFN 33.7 -> 30.6 ms (standalone, without
+// the delta rows and the other kernels' L2 traffic, no difference).  The same change in the QKV projection (HBM-bound)
+// made no difference and was not kept.
+struct FfnBias { float b1[512]; float b2[128]; };
 template <bool kResident>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFfnThreads, 1)
 ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, int seq_n, int seq_d, int seq_axis,
                const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_w1,
                const __grid_constant__ CUtensorMap tm_w2,
-              const float* __restrict__ b1, const float* __restrict__ b2, int M, int F) {
+              const float* __restrict__ b1, const float* __restrict__ b2, int M, int F,
+               const __grid_constant__ FfnBias cb) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                        // [2][32K] xhat
@@ -1163,7 +1171,8 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
         const float* bias = b2 + half * 64 + cc * 32;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {  // thread = row `lane`: 16-byte chunk c goes to slot c ^ (lane & 7)
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + c);
+          const float4 b4 = kResident ? *reinterpret_cast<const float4*>(&cb.b2[half * 64 + cc * 32 + c * 4])
+                                      : __ldg(reinterpret_cast<const float4*>(bias) + c);
           uint4 pk;
           pk.x = __float_as_uint(__uint_as_float(v[c * 4 + 0]) + b4.x);
           pk.y = __float_as_uint(__uint_as_float(v[c * 4 + 1]) + b4.y);
@@ -1239,7 +1248,8 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
         const float* bp = b1 + c * 128 + half * 64;
         float4 bb[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bp) + e);
+        for (int e = 0; e < 16; ++e)
+          bb[e] = kResident ? *reinterpret_cast<const float4*>(&cb.b1[c * 128 + half * 64 + e * 4]) : __ldg(reinterpret_cast<const float4*>(bp) + e);
         AVB_TRACE(2, g, 0);
         ptx::mbar_wait(&d1_full[g & 1], (uint32_t)((g >> 1) & 1), 59);
         AVB_TRACE(2, g, 1);
