@@ -131,6 +131,26 @@ struct RowMap {
   }
 };
 
+// Packed fp32 pairs (sm_100 add/fma.f32x2): two results per issued instruction.  The softmax warps are bound by
+// issue slots and the MUFU pipe together, so everything that is not an ex2 is done two elements at a time.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 // ------------------------------------------------------------------------------------------
 // Residual update of a [32 rows x 32 cols] fp32 block held row-per-thread in registers (the tcgen05.ld layout):
 //     zblk[r][c] += acc[r][c] + bias[c]
@@ -738,7 +758,7 @@ ln_gemm2_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensor
               ptx::tc_fence_before();
               ptx::mbar_arrive_cluster(&t_empty[as], 0);
             }
-            float ss0 = 0.f, ss1 = 0.f;  // |row . head|^2 of these 32 channels (q and k chunks only)
+            uint64_t ss2 = pack2(0.f, 0.f);  // |row . head|^2 of these 32 channels (q and k chunks only), two partial sums
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float f[8];
@@ -746,9 +766,12 @@ ln_gemm2_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensor
               f[2] = __uint_as_float(v[e * 8 + 2]) + bb[e * 2].z;     f[3] = __uint_as_float(v[e * 8 + 3]) + bb[e * 2].w;
               f[4] = __uint_as_float(v[e * 8 + 4]) + bb[e * 2 + 1].x; f[5] = __uint_as_float(v[e * 8 + 5]) + bb[e * 2 + 1].y;
               f[6] = __uint_as_float(v[e * 8 + 6]) + bb[e * 2 + 1].z; f[7] = __uint_as_float(v[e * 8 + 7]) + bb[e * 2 + 1].w;
-              if (c < 2) {  // columns [0, 512): q and k (N = 768, 256-column chunks)
+              if (c < 2) {  // columns [0, 512): q and k (N = 768, 256-column chunks); packed f32x2: half the issue slots
 #pragma unroll
-                for (int t = 0; t < 8; t += 2) { ss0 = fmaf(f[t], f[t], ss0); ss1 = fmaf(f[t + 1], f[t + 1], ss1); }
+                for (int t = 0; t < 8; t += 2) {
+                  const uint64_t f2 = pack2(f[t], f[t + 1]);
+                  ss2 = fma2(f2, f2, ss2);
+                }
               }
               uint4 pk;
               pk.x = ptx::pack_bf16(f[0], f[1]); pk.y = ptx::pack_bf16(f[2], f[3]);
@@ -756,6 +779,8 @@ ln_gemm2_tc_kernel(const float* __restrict__ z, const __grid_constant__ CUtensor
               ptx::st_shared_v4(stage + (uint32_t)(cc * 2048 + lane * 64 + (((uint32_t)e ^ my_swz) << 4)), pk);
             }
             if (c < 2 && lane < rows_valid) {
+              float ss0, ss1;
+              unpack2(ss2, ss0, ss1);
               if (c == 0) nrm_q = fmaxf(nrm_q, ss0 + ss1); else nrm_k = fmaxf(nrm_k, ss0 + ss1);
             }
           }
@@ -1368,26 +1393,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// Packed fp32 pairs (sm_100 add/fma.f32x2): two results per issued instruction.  The softmax warps are bound by
-// issue slots and the MUFU pipe together, so everything that is not an ex2 is done two elements at a time.
-__device__ __forceinline__ uint64_t pack2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
