@@ -367,17 +367,22 @@ int launch_attention_tc(avb_handle h, const void* qkv, void* out, int B, int n, 
   const long long S = axis == 0 ? (long long)B * n : (long long)B * d;
   const long long items = S * H * ((T + 127) / 128);
   if (items >= (1LL << 31)) return fail(h, AVB_ERR_INVALID, "attention: too many (sequence, head, tile) items in one call (%lld)", items);
-  // a stream owns whole (sequence, head) pairs and walks their query tiles itself
-  const int grid = (int)std::min<long long>((S * H + avb::kAttnStreams - 1) / avb::kAttnStreams, num_sms);
+  // a stream owns whole (sequence, head) pairs and walks their query tiles itself; with fewer than ~12 pairs per stream
+  // the pairs are cut into qsplit parts of query tiles (a divisor of their number) so that the last round fills up
+  const int nqt = (T + 127) / 128;
+  int qsplit = 1;
+  for (int cand = 2; cand <= nqt && S * H * qsplit < 12LL * avb::kAttnStreams * num_sms; ++cand)
+    if (nqt % cand == 0) qsplit = cand;
+  const int grid = (int)std::min<long long>((S * H * qsplit + avb::kAttnStreams - 1) / avb::kAttnStreams, num_sms);
   if (mode == 0 || mode == 2) {
     if (cudaMemsetAsync(guard, 0, sizeof(int), st) != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention guard reset failed");
     avb::attention_tc_kernel<true><<<grid, avb::kAttnThreads, avb::kAttnSmemBytes, st>>>(
-        reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis, guard, norms);
+        reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis, guard, norms, qsplit);
     if (launches) ++*launches;
   }
   if (mode != 2) {
     avb::attention_tc_kernel<false><<<grid, avb::kAttnThreads, avb::kAttnSmemBytes, st>>>(
-        reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis, mode == 1 ? nullptr : guard, nullptr);
+        reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, n, d, H, axis, mode == 1 ? nullptr : guard, nullptr, qsplit);
     if (launches) ++*launches;
   }
   e = cudaGetLastError();

@@ -1448,7 +1448,7 @@ __device__ __forceinline__ void exp_chunk32(const uint32_t (&s)[32], uint32_t* p
 template <bool kFast>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int B, int n, int d, int H,
-                    int axis, int* __restrict__ guard, const float* __restrict__ norms) {
+                    int axis, int* __restrict__ guard, const float* __restrict__ norms, int qsplit) {
   // norms (fast variant, may be null): {max |q_h|^2, max |k_h|^2} over every (row, head) of this launch, recorded by the
   // QKV projection that wrote qkv.  |score| <= |q||k| <= 100 licenses the unclamped polynomial lanes (exp_chunk32).
   // guard: one int per launch pair.  The fast variant (stale row maximum, see the softmax section) raises it when a
@@ -1523,21 +1523,25 @@ attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   // own passes instead of depending on how well eight different streams keep time (measured: 2.2x the algorithmic
   // DRAM reads with the query tiles spread over streams).  Coordinates are carried incrementally: a division by a
   // run-time value costs a long dependent MUFU.RCP / I2F chain on the softmax warps' critical path per item.
-  const int num_pairs = S * H;
+  // qsplit (a divisor of nqt, chosen by the host) cuts every pair's query tiles into qsplit contiguous parts that different
+  // streams own: with few pairs per stream (one large dataset sharded over 8 GPUs: 1000 pairs for 296 streams) whole pairs
+  // leave the last round 38 % full; the parts of a pair run at the same time and share its K / V through L2.
+  const int num_pairs = S * H * qsplit;                 // (sequence, head, part) triples
+  const int qn = nqt / qsplit;                          // query tiles per part
   const int pair0 = (int)blockIdx.x * kAttnStreams + sid;
   const int pair_stride = (int)gridDim.x * kAttnStreams;
-  const int my_items = pair0 < num_pairs ? ((num_pairs - pair0 + pair_stride - 1) / pair_stride) * nqt : 0;
-  struct ItemPos { int s, h, qt; };
-  const int step_h = pair_stride % H, step_s = pair_stride / H;
-  auto first_item = [&]() { ItemPos p; p.s = pair0 / H; p.h = pair0 % H; p.qt = 0; return p; };
-  auto advance = [&](ItemPos& p) {  // branch-free: next query tile, or first tile of the stream's next pair
+  const int my_items = pair0 < num_pairs ? ((num_pairs - pair0 + pair_stride - 1) / pair_stride) * qn : 0;
+  struct ItemPos { int s, h, qt, v, left; };
+  // coordinates of triple v: two divisions per (sequence, head, part) - amortised over qn * nqt softmax steps (per query
+  // tile they were ~1000 dependent cycles on the softmax warps' critical path)
+  auto locate = [&](ItemPos& p) {
+    const int pair = p.v / qsplit, part = p.v - pair * qsplit;
+    p.s = pair / H; p.h = pair - p.s * H; p.qt = part * qn; p.left = qn;
+  };
+  auto first_item = [&]() { ItemPos p; p.v = pair0; locate(p); return p; };
+  auto advance = [&](ItemPos& p) {  // next query tile of the part, or the first tile of the stream's next triple
     p.qt += 1;
-    const int c = p.qt >= nqt;
-    p.qt = c ? 0 : p.qt;
-    p.h += c ? step_h : 0;
-    const int c2 = p.h >= H;
-    p.h -= c2 ? H : 0;
-    p.s += (c ? step_s : 0) + c2;
+    if (--p.left == 0) { p.v += pair_stride; locate(p); }
   };
 
   // Register budget per role (warpgroup-wide, setmaxnreg): 640 threads leave 96 registers each, and the softmax loop
