@@ -422,7 +422,8 @@ int launch_dattn_tc(avb_handle h, const float* z, const Block& W, void* out, int
 // weight columns [k_off, k_off + K) of the pre-split W^T behind tm[0] (hi) / tm[1] (lo).
 template <int KB, bool LN, int EPI>
 int launch_gemm_split(avb_handle h, const float* A, int lda, const CUtensorMap* tm, int k_off, const float* bias, const float* R,
-                      int ldr, float* C, int ldc, int M, int N, cudaStream_t st, avb::SplitSeq sq = avb::SplitSeq{0, 0, 0, 0, 0}) {
+                      int ldr, float* C, int ldc, int M, int N, cudaStream_t st, avb::SplitSeq sq = avb::SplitSeq{0, 0, 0, 0, 0},
+                      float* norms = nullptr) {
   static PerDeviceOnce once;
   cudaError_t e = once.run([] {
     return cudaFuncSetAttribute(avb::gemm_split_tc_kernel<KB, LN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -431,7 +432,7 @@ int launch_gemm_split(avb_handle h, const float* A, int lda, const CUtensorMap* 
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(gemm_split_tc): %s", cudaGetErrorString(e));
   const int grid = std::min((M + 127) / 128, h->num_sms);
   avb::gemm_split_tc_kernel<KB, LN, EPI><<<grid, avb::kSplitThreads, avb::SplitCfg<KB>::kSmemBytes, st>>>(
-      A, lda, tm[0], tm[1], k_off, bias, R, ldr, C, ldc, M, N, sq);
+      A, lda, tm[0], tm[1], k_off, bias, R, ldr, C, ldc, M, N, sq, norms);
   h->launches++;
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "gemm_split_tc launch: %s", cudaGetErrorString(e));
@@ -439,7 +440,8 @@ int launch_gemm_split(avb_handle h, const float* A, int lda, const CUtensorMap* 
 }
 
 // fp32-mode attention on the tensor cores (attention_split_tc_kernel): operands from the split QKV projection
-int launch_attention_split(avb_handle h, const void* qkvs, float* attn, int B, int n, int d, int H, int axis, int dg, cudaStream_t st) {
+int launch_attention_split(avb_handle h, const void* qkvs, float* attn, int B, int n, int d, int H, int axis, int dg, cudaStream_t st,
+                           const float* norms) {
   static PerDeviceOnce once;
   cudaError_t e = once.run([] {
     return cudaFuncSetAttribute(avb::attention_split_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kSplitAttnSmemBytes);
@@ -451,7 +453,7 @@ int launch_attention_split(avb_handle h, const void* qkvs, float* attn, int B, i
   if (items >= (1LL << 31)) return fail(h, AVB_ERR_INVALID, "attention: too many (sequence, head, tile) items in one call (%lld)", items);
   const int grid = (int)std::min<long long>(items, 2LL * h->num_sms);
   avb::attention_split_tc_kernel<<<grid, avb::kSplitAttnThreads, avb::kSplitAttnSmemBytes, st>>>(
-      reinterpret_cast<const bf16*>(qkvs), attn, B, n, d, H, axis, dg);
+      reinterpret_cast<const bf16*>(qkvs), attn, B, n, d, H, axis, dg, norms);
   h->launches++;
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "attention_split_tc launch: %s", cudaGetErrorString(e));
@@ -484,6 +486,7 @@ BlockWs block_ws_layout(const avb_config& c, size_t ntok) {
   } else {
     w.big_off = off;  off = align_up(off + ntok * std::max(3 * HD, F) * 4, 1024);
     w.attn_off = off; off = align_up(off + ntok * HD * 4, 1024);
+    w.guard_off = off; off += 1024;  // score bound of the split-precision attention
   }
   w.total = off;
   return w;
@@ -981,10 +984,12 @@ static int block_impl(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, 
     // projections and FFN on the tensor cores as split-precision products (kernels_split.cuh) when the shape fits
     const bool tc = h->f32_tc && k == 128 && HD == 256 && F % 256 == 0 && F <= 768 && ntok <= (size_t)0x7fffff00;
     int rc;
+    float* snorms = reinterpret_cast<float*>(w8 + L.guard_off);  // {max |q_h|^2, max |k_h|^2} of this block's projection
     if (tc) {
       ProfScope ps(h, AVB_PROF_QKV, st);
+      if (cudaMemsetAsync(snorms, 0, 2 * sizeof(float), st) != cudaSuccess) return fail(h, AVB_ERR_CUDA, "score-bound reset failed");
       if ((rc = launch_gemm_split<2, true, avb::kSplitEpiQkvOperands>(h, z, k, W.tm_s_qkv, 0, W.bqkv_f, nullptr, 0, qkv, 3 * HD, M, 3 * HD,
-                                                                       st, avb::SplitSeq{n, d, axis, dg, H}))) return rc;
+                                                                       st, avb::SplitSeq{n, d, axis, dg, H}, snorms))) return rc;
     } else
     { ProfScope ps(h, AVB_PROF_QKV, st);
       launch_sgemm<0, true>(z, k, W.wq, HD, W.bq, W.ln_g[0], W.ln_b[0], nullptr, 0, qkv, 3 * HD, ntok, HD, k, st);
@@ -1001,7 +1006,7 @@ static int block_impl(avb_handle h, int32_t bi, float* z, int32_t B, int32_t n, 
     const long long tok_stride = axis == 0 ? 1 : d;
     if (tc) {
       ProfScope ps(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
-      if ((rc = launch_attention_split(h, qkv, attn, B, n, d, H, axis, dg, st))) return rc;
+      if ((rc = launch_attention_split(h, qkv, attn, B, n, d, H, axis, dg, st, snorms))) return rc;
     } else
     { ProfScope ps(h, axis == 0 ? AVB_PROF_ATTN_D : AVB_PROF_ATTN_N, st);
       for (long long s0 = 0; s0 < S; s0 += 65535) {  // grid.z is limited to 65535

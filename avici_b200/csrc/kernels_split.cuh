@@ -112,7 +112,9 @@ template <int KB, bool kLn, int EPI>
 __global__ void __launch_bounds__(kSplitThreads, 1)
 gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant__ CUtensorMap tm_hi,
                      const __grid_constant__ CUtensorMap tm_lo, int k_off, const float* __restrict__ bias,
-                     const float* R, int ldr, float* C, int ldc, int M, int N, SplitSeq sq) {
+                     const float* R, int ldr, float* C, int ldc, int M, int N, SplitSeq sq, float* __restrict__ norms) {
+  // norms (kSplitEpiQkvOperands, may be null, zeroed by the caller): {max |q_h|^2, max |k_h|^2} over the (row, head) vectors
+  // written - the score bound with which attention_split_tc_kernel skips its row-maximum pass (as in the bf16 mode)
   static_assert(!kLn || KB == 2, "the LayerNorm prologue normalises over one A unit (128 columns)");
   using Cfg = SplitCfg<KB>;
   constexpr int ST = kSplitBStages, UNITS = KB / 2;
@@ -237,6 +239,7 @@ gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant
     const int q = warp & 3;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     int acc_it = 0;
+    [[maybe_unused]] float nrm_q = 0.f, nrm_k = 0.f;
     const uint32_t a_bias = ptx::smem_u32(s_bias);
     const RowMap rm{sq.n, sq.d, sq.axis, sq.dg};
     const int seq_T = sq.axis == 0 ? sq.d : sq.n;
@@ -267,6 +270,7 @@ gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant
                                    ((((size_t)seq * 3 + w) * 2 * sq.H + hd) * seq_T + pos) * 32;
               const size_t part = (size_t)sq.H * seq_T * 32;
               const unsigned swz = (pos >> 1) & 3;
+              float ss = 0.f;
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float4 b0 = ptx::ld_shared_v4f(a_bias + (uint32_t)((col + 8 * e) * 4));
@@ -276,6 +280,10 @@ gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant
                 f[2] = __uint_as_float(v[e * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[e * 8 + 3]) + b0.w;
                 f[4] = __uint_as_float(v[e * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[e * 8 + 5]) + b1.y;
                 f[6] = __uint_as_float(v[e * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[e * 8 + 7]) + b1.w;
+                if (w < 2) {
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) ss = fmaf(f[t], f[t], ss);
+                }
                 uint4 hi, lo;
                 uint32_t* hp = &hi.x; uint32_t* lp = &lo.x;
 #pragma unroll
@@ -287,6 +295,7 @@ gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant
                 *reinterpret_cast<uint4*>(dst + (((unsigned)e ^ swz) << 3)) = hi;
                 *reinterpret_cast<uint4*>(dst + part + (((unsigned)e ^ swz) << 3)) = lo;
               }
+              if (w == 0) nrm_q = fmaxf(nrm_q, ss); else if (w == 1) nrm_k = fmaxf(nrm_k, ss);
             }
           } else {
             // A row-per-thread global access touches 32 different lines per warp instruction (bound by L1 wavefronts, ~11K
@@ -325,6 +334,17 @@ gemm_split_tc_kernel(const float* __restrict__ A, int lda, const __grid_constant
         }
       }
     }
+    if (EPI == kSplitEpiQkvOperands && norms != nullptr) {  // one atomic per warp and operand (non-negative floats order like ints)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        nrm_q = fmaxf(nrm_q, __shfl_xor_sync(0xffffffffu, nrm_q, o));
+        nrm_k = fmaxf(nrm_k, __shfl_xor_sync(0xffffffffu, nrm_k, o));
+      }
+      if (lane == 0) {
+        atomicMax(reinterpret_cast<int*>(norms), __float_as_int(nrm_q));
+        atomicMax(reinterpret_cast<int*>(norms) + 1, __float_as_int(nrm_k));
+      }
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -356,7 +376,10 @@ constexpr int kSplitAttnSmemBytes = 2 * kSplitAttnTile + kSplitAttnStages * 4 * 
 
 __global__ void __launch_bounds__(kSplitAttnThreads, 2)
 attention_split_tc_kernel(const __nv_bfloat16* __restrict__ qkvs, float* __restrict__ out, int B, int n, int d, int H, int axis,
-                          int dg) {
+                          int dg, const float* __restrict__ norms) {
+  // norms (may be null): {max |q_h|^2, max |k_h|^2} of the projection that wrote qkvs.  With |score| <= |q||k| <= 100 (log2
+  // units) exp2(s) needs no reference: fp32 (and the bf16 halves of P) carry an 8-bit exponent and O / l cancels the missing
+  // shift exactly - the row-maximum pass over S and the rescaling of O drop out.  Without the bound: exact online softmax.
   constexpr int NS = kSplitAttnStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -481,18 +504,19 @@ attention_split_tc_kernel(const __nv_bfloat16* __restrict__ qkvs, float* __restr
     const int q = warp & 3, r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const RowMap rm{n, d, axis, dg};
+    const bool bounded = norms != nullptr && norms[0] * norms[1] <= 1.0e4f;  // false also for NaN
     uint32_t g = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int qt = item % nqt, pair = item / nqt, h = pair % H, s = pair / H;
-      float m = -INFINITY, l = 0.f;
+      float m = bounded ? 0.f : -INFINITY, l = 0.f;
       for (int j = 0; j < nqt; ++j, ++g) {
         ptx::mbar_wait(s_full, g & 1u, 55);
         ptx::tc_fence_after();
         const int nv = T - j * 128;  // valid key columns of this tile (>= 1)
-        // ---- pass 1: row maximum
+        // ---- pass 1: row maximum (skipped under the score bound: m stays 0)
         float mx = m;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < (bounded ? 0 : 4); ++c) {
           if (c * 32 < nv) {
             uint32_t sv[32];
             ptx::tmem_ld32(tS + c * 32 + lane_off, sv);
@@ -503,7 +527,7 @@ attention_split_tc_kernel(const __nv_bfloat16* __restrict__ qkvs, float* __restr
           }
         }
         // ---- rescale O and the row sum (O is complete: S of this step was issued behind the previous PV)
-        if (j > 0 && __any_sync(0xffffffffu, mx > m)) {  // warp-uniform: tcgen05.ld / st are warp-collective
+        if (!bounded && j > 0 && __any_sync(0xffffffffu, mx > m)) {  // warp-uniform: tcgen05.ld / st are warp-collective
           const float alpha = fast_exp2(m - mx);          // 1 for the rows whose maximum did not move
           uint32_t o[32];
           ptx::tmem_ld32(tO + lane_off, o);

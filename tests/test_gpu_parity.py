@@ -589,6 +589,26 @@ def test_f32_split_tensor_core_gemms_vs_simt_and_oracle():
         print(f"fp32 n={n + n // 4} d={d}: split tensor-core max|dp| = {e_tc:.2e}, SIMT {e_simt:.2e}")
         check_parity(p_tc, ref, TOL_STRESS["fp32"])
         check_parity(p_simt, ref, TOL_STRESS["fp32"])
+    # scores far beyond the +-100 bound the fast path relies on: the projection's recorded norms must send the attention
+    # kernel down its exact online-softmax path (row maximum, rescaled accumulators)
+    params = {k: dict(v) for k, v in model.params.items()}
+    for i in range(6):
+        sfx = "" if i == 0 else f"_{i}"
+        for nm in ("query", "key"):
+            mod = f"BaseModel/multi_head_attention{sfx}/{nm}"
+            params[mod] = {"w": params[mod]["w"] * 3.5, "b": params[mod]["b"] * 3.5}
+    big = avici_b200.AVICIModel(params=params, model=model._model, expects_counts=False)
+    g, x, iv = avici_b200.simulate_data(d=37, n=150, n_interv=37, seed=0, domain="lin-gauss")
+    x = x.astype(np.float32); iv = iv.astype(np.float32)
+    ref = oracle_probs(params, x.astype(np.float64), iv, 3)
+    p_big = big(x=x, interv=iv.copy())
+    eng_big = big.engine
+    eng_big._check(eng_big.lib.avb_test_set_f32_tc(eng_big.handle, 0))
+    p_big_simt = big(x=x, interv=iv.copy())
+    e_tc, e_simt = float(np.abs(p_big - ref).max()), float(np.abs(p_big_simt - ref).max())
+    print(f"fp32 split, scores x12: max|dp| = {e_tc:.2e}, SIMT {e_simt:.2e}")
+    check_parity(p_big_simt, ref, 1e-4)
+    check_parity(p_big, ref, 5e-4)  # sharply peaked softmax: a score error of 1e-5 relative moves the weights more
 
 
 def test_edge_shapes_and_errors():

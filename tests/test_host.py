@@ -353,3 +353,32 @@ def test_eval_batch_composition_matches_the_reference_loop(monkeypatch):
     assert set(scalars) == set(want) and "f1_0_25" in scalars and "cyclic_0_5" in scalars
     for k in want:
         assert scalars[k] == pytest.approx(want[k], abs=1e-12), k
+
+
+def test_shard_count_policy():
+    """How many devices one dataset is sharded over (AVICIModel.__call__ with several devices): the largest G <= device_count
+    with G | n and G | d, one device for small or chunked datasets.  The reference shards n only and asserts G | n
+    (pretrain.py:129-131); the axial scheme also needs G | d."""
+    from avici_b200.model import AVICIModel
+    f = AVICIModel._shard_count
+    assert f(5000, 1000, 8) == 8 and f(5000, 1000, 4) == 4 and f(5000, 1000, 3) == 2
+    assert f(5000, 999, 8) == 1            # no common divisor with d
+    assert f(4096, 96, 8) == 8 and f(4096, 100, 8) == 4
+    assert f(1000, 100, 8) == 1            # below SHARD_MIN_CELLS: an exchange per block is not worth it
+    assert f(5000, 1000, 8, chunk_size=500) == 1 and f(5000, 1000, 8, chunk_size=5000) == 8
+
+
+def test_column_block_layout_roundtrip():
+    """The column-blocked n-shard of avb_forward_sharded: token (i, j) at ((j // dg) * rows + i) * dg + j % dg, and back."""
+    import torch
+    from avici_b200 import sharded
+    rows, d, G, k = 6, 12, 4, 3
+    z = torch.arange(rows * d * k, dtype=torch.float32).reshape(rows, d, k)
+    blk = sharded.to_column_blocks(z, G)
+    assert blk.shape == (G, rows, d // G, k)
+    dg = d // G
+    flat = blk.reshape(-1, k)
+    for i in (0, 3, 5):
+        for j in (0, 2, 3, 7, 11):
+            assert torch.equal(flat[((j // dg) * rows + i) * dg + j % dg], z[i, j])
+    assert torch.equal(sharded.from_column_blocks(blk), z)
