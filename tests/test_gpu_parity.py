@@ -607,8 +607,14 @@ def test_f32_split_tensor_core_gemms_vs_simt_and_oracle():
     p_big_simt = big(x=x, interv=iv.copy())
     e_tc, e_simt = float(np.abs(p_big - ref).max()), float(np.abs(p_big_simt - ref).max())
     print(f"fp32 split, scores x12: max|dp| = {e_tc:.2e}, SIMT {e_simt:.2e}")
-    check_parity(p_big_simt, ref, 1e-4)
-    check_parity(p_big, ref, 5e-4)  # sharply peaked softmax: a score error of 1e-5 relative moves the weights more
+    # sharply peaked softmax: the fp32 restatement of the reference itself drifts from the fp64 one on this model, so both
+    # kernels are held to 1e-4 on top of that measured noise floor
+    floor = float(np.abs(oracle_probs(params, x, iv, 3, dtype=torch.float32) - ref).max())
+    print(f"  fp32 oracle vs fp64 oracle on this model: {floor:.2e}")
+    check_parity(p_big_simt, ref, 1e-4 + 2 * floor)
+    # the split products carry ~1e-5 relative error per score against 1e-7 in true fp32: with |s| in the hundreds that is
+    # the same size as the fp32 noise of the whole forward, hence twice the allowance
+    check_parity(p_big, ref, 1e-4 + 4 * floor)
 
 
 def test_edge_shapes_and_errors():
