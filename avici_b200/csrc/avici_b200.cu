@@ -551,7 +551,7 @@ bool shape_ok(avb_handle h, int B, int n, int d) { return h && B >= 1 && n >= 1 
 // ====================================================================================== C ABI
 extern "C" {
 
-const char* avb_version(void) { return "avici_b200 0.1.0 sm_100a"; }
+const char* avb_version(void) { return "avici_b200 0.2.0 sm_100a"; }
 
 const char* avb_last_error(avb_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 

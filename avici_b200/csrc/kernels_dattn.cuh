@@ -69,6 +69,9 @@ static_assert(DaCfg<true>::kSmemBytes <= 232448, "dattn_tc_kernel: shared memory
 #ifndef AVB_DATTN_G_GROUP  // projection MMAs issued per pacing group (1, 2 or 4 = unpaced).  Measured (r2d): 4.20 / 4.62 /
 #define AVB_DATTN_G_GROUP 4  // 5.49 ms for 4 / 2 / 1 - the projection's own latency (s_free -> G -> conv -> S) is as critical
 #endif                       // as the PV MMAs it delays, so pacing it loses more than it frees
+#ifndef AVB_DATTN_WAIT_NS  // nanosleep between polls of the two long waits of the conv / epilogue warps (0 = tight polling)
+#define AVB_DATTN_WAIT_NS 0
+#endif
 #ifndef AVB_DATTN_BOUNDED_WAITS
 #define AVB_DATTN_BOUNDED_WAITS 1
 #endif
@@ -371,7 +374,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     };
     auto oepi = [&](int u) {  // O / L -> bf16 -> A tile of the out-projection (or the attention output in HBM)
       const int h = u & 7;
-      ptx::mbar_wait(pv_done, (uint32_t)(u & 1), 92);
+      ptx::mbar_wait(pv_done, (uint32_t)(u & 1), 92, AVB_DATTN_WAIT_NS);
       AVB_TRACE(4, u, 3);
       AVB_TRACE(7, u, 0);
       ptx::tc_fence_after();
@@ -524,7 +527,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     const uint32_t row_off = (uint32_t)(r * 64), swz = (uint32_t)((r >> 1) & 3);
     const uint32_t aQ = ptx::smem_u32(sQ), aK = ptx::smem_u32(sK), aV = ptx::smem_u32(sV);
     auto conv_wait = [&](int u) {
-      ptx::mbar_wait(&g_full[u & 1], (uint32_t)((u >> 1) & 1), 91);
+      ptx::mbar_wait(&g_full[u & 1], (uint32_t)((u >> 1) & 1), 91, AVB_DATTN_WAIT_NS);
       // the Q / K tiles are single-buffered: S of the previous unit (issued by another warp than G) must have read them
       if (u >= 1) ptx::mbar_wait(&s_full[(u - 1) & 1], (uint32_t)(((u - 1) >> 1) & 1), 96);
       // ... and the V buffer (three of them) is last read by PV of unit u - 3
