@@ -14,4 +14,4 @@ from .evaluate import eval_batch  # noqa: F401  (train.py:51-69,125-151 on the d
 
 __all__ = ["load_pretrained", "AVICIModel", "simulate_data", "InferenceModel", "BaseModel", "init_params",
            "param_count", "load_checkpoint", "save_checkpoint", "random_init_model"]
-__version__ = "0.1.0"
+__version__ = "0.2.0"

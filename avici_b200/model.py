@@ -163,16 +163,17 @@ class InferenceModel:
 
     @staticmethod
     def _fingerprint(params):
-        """Cheap identity of a parameter dict: the object, plus per leaf its buffer address, shape and three values.
+        """Cheap identity of a parameter dict: the object, plus per leaf its object identity, shape and three values.
         The packed device copy is a SNAPSHOT taken at first use; replacing the dict, a leaf, or (for all practical
         purposes) editing a leaf in place changes the fingerprint and triggers a re-upload.  `reload()` forces one."""
         fp = [id(params)]
+        add = fp.append
         for mod, leaves in params.items():
             for name, arr in leaves.items():
-                a = onp.asarray(arr)
-                flat = a.reshape(-1)
-                fp.append((mod, name, a.__array_interface__["data"][0], a.shape,
-                           float(flat[0]), float(flat[flat.size // 2]), float(flat[-1])) if flat.size else (mod, name))
+                a = arr if isinstance(arr, onp.ndarray) else onp.asarray(arr)
+                n = a.size
+                # (0.2 ms for the 334 leaves of the published architecture; it runs on every call)
+                add((mod, name, id(arr), a.shape, a.item(0), a.item(n >> 1), a.item(n - 1)) if n else (mod, name))
         return hash(tuple(fp))
 
     def engine(self, params, device=None):
