@@ -617,6 +617,23 @@ def test_f32_split_tensor_core_gemms_vs_simt_and_oracle():
     check_parity(p_big, ref, 1e-4 + 4 * floor)
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_forward_captures_as_a_cuda_graph(dtype):
+    """avb_forward only enqueues on the caller's stream: a CUDA graph of it replays bit-identically on refilled inputs."""
+    model = avici_b200.random_init_model(dict(layers=2, **STRESS), seed=8, perturb=True, compute_dtype=dtype)
+    eng = model.engine
+    data = [avici_b200.simulate_data(d=40, n=120, n_interv=40, seed=s, domain="lin-gauss") for s in range(2)]
+    xs = [torch.as_tensor(t[1], dtype=torch.float32).cuda()[None] for t in data]
+    ivs = [torch.as_tensor(t[2], dtype=torch.float32).cuda()[None] for t in data]
+    x, iv = xs[0].clone(), ivs[0].clone()
+    graph, out = eng.capture(x, iv)
+    for k in (1, 0):
+        x.copy_(xs[k]); iv.copy_(ivs[k])
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, eng.forward(xs[k], ivs[k]))
+
+
 def test_edge_shapes_and_errors():
     kw = dict(layers=1, **STRESS)
     for dtype in ("fp32", "bf16"):
