@@ -873,6 +873,9 @@ constexpr int kFfnSmemBytes = 2 * kLnGemmABytes + 2 * 2 * kFfnWBytes + 8 * 4096 
 #ifndef AVB_FFN_E1_X64
 #define AVB_FFN_E1_X64 0  // 1: E1 reads its 64 D1 columns with one tcgen05.ld.x64 (A/B build, not measured yet)
 #endif
+#ifndef AVB_FFN_E2_EARLY
+#define AVB_FFN_E2_EARLY 1  // 1: E2 reads both halves of D2 and releases the buffer before staging / storing them
+#endif
 #ifndef AVB_FFN_E2_PLAIN
 #define AVB_FFN_E2_PLAIN 0  // 1: final epilogue leaves through plain coalesced stores instead of tensor-map stores (A/B build)
 #endif
@@ -1179,8 +1182,22 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
       AVB_TRACE(2, e2_g, 5);
       ptx::tc_fence_after();
       const int row0 = t_mt * 128 + q * 32;
+#if AVB_FFN_E2_EARLY
+      // both 32-column halves leave TMEM first and the D2 buffer is handed back at once: the LayerNorm warps of the tile after
+      // next wait for exactly this (r2f trace: 3.6K of their 8.7K clocks per tile), not for the staging and stores below
+      uint32_t vv[2][32];
+      ptx::tmem_ld32(tmem_D2 + (t_it & 1) * 128 + half * 64 + lane_off, vv[0]);
+      ptx::tmem_ld32(tmem_D2 + (t_it & 1) * 128 + half * 64 + 32 + lane_off, vv[1]);
+      ptx::tmem_wait_ld();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&d2_empty[t_it & 1]);
+      AVB_TRACE(2, e2_g, 7);
+#endif
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
+#if AVB_FFN_E2_EARLY
+        uint32_t (&v)[32] = vv[cc];
+#else
         uint32_t v[32];
         ptx::tmem_ld32(tmem_D2 + (t_it & 1) * 128 + half * 64 + cc * 32 + lane_off, v);
         ptx::tmem_wait_ld();
@@ -1189,6 +1206,7 @@ ffn2_tc_kernel(float* __restrict__ z, const __nv_bfloat16* __restrict__ delta, i
           ptx::tc_fence_before();
           ptx::mbar_arrive(&d2_empty[t_it & 1]);
         }
+#endif
 #if !AVB_FFN_E2_PLAIN
         if (lane == 0) ptx::bulk_wait_read<0>();  // the previous block's store has read the stage
 #endif
