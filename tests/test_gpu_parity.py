@@ -634,6 +634,28 @@ def test_forward_captures_as_a_cuda_graph(dtype):
         assert torch.equal(out, eng.forward(xs[k], ivs[k]))
 
 
+def test_shape_sweep_bf16_vs_fp32_paths():
+    """Tile-boundary shapes through BOTH kernel families (bf16: fused d-axis kernel for d <= 128 / unfused above, two-stream
+    attention, CTA-pair QKV and FFN; fp32: split-precision GEMMs and attention): the two share no kernel, so agreement to
+    the bf16 tolerance on every shape cross-checks the layouts of each (ragged tiles, d = 112 / 113 / 127 / 128 / 129,
+    n around multiples of 128, batches)."""
+    kw = dict(layers=2, **REF_INIT)
+    m16 = avici_b200.random_init_model(kw, seed=21, perturb=True, compute_dtype="bf16")
+    m32 = avici_b200.random_init_model(kw, seed=21, perturb=True, compute_dtype="fp32")
+    rng = np.random.default_rng(5)
+    shapes = [(1, 127, 112), (1, 129, 113), (2, 256, 127), (1, 255, 128), (1, 257, 129), (3, 64, 16), (1, 1, 5), (2, 385, 33),
+              (1, 640, 130), (1, 100, 257), (4, 130, 100), (1, 1000, 7)]
+    for B, n, d in shapes:
+        x = rng.normal(size=(B, n, d)).astype(np.float32) * rng.uniform(0.5, 3.0, size=(1, 1, d)).astype(np.float32)
+        iv = (rng.random(size=(B, n, d)) < 0.1).astype(np.float32)
+        p16 = m16.infer_batch(x, iv)
+        p32 = m32.infer_batch(x, iv)
+        assert np.isfinite(p16).all() and np.isfinite(p32).all(), (B, n, d)
+        err = float(np.abs(p16 - p32).max())
+        assert err <= TOL["bf16"], f"shape {(B, n, d)}: bf16 vs fp32 path max|dp| = {err:.3e}"
+        assert np.all(np.diagonal(p16, axis1=1, axis2=2) == 0)
+
+
 def test_edge_shapes_and_errors():
     kw = dict(layers=1, **STRESS)
     for dtype in ("fp32", "bf16"):
