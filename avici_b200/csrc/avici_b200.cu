@@ -121,6 +121,7 @@ struct avb_model_s {
   std::mutex host_mu;
   long long launches = 0;
   int dattn_mode = 1;  // d-axis blocks with d <= 128: 1 = fully fused kernel, 2 = fused up to the attention output, 0 = unfused
+  int head_tc = 1;  // bf16 mode: edge-logit contraction of the head on the tensor cores (0: SIMT head_logits_kernel)
   int f32_tc = 1;  // fp32 mode: projections and FFN as split-precision tensor-core GEMMs (0: SIMT sgemm_kernel)
   avb_nccl_comm_t comm = nullptr;  // avb_comm_init: communicator of the axially sharded forward (one rank per handle)
   int comm_rank = 0, comm_world = 1;
@@ -1079,8 +1080,19 @@ static int head_impl(avb_handle h, const float* pooled, int32_t B, int32_t d, fl
   avb::head_uv_kernel<<<(unsigned)((size_t)B * d), 128, 0, st>>>(pooled, h->lnu_g, h->lnu_b, h->wu, h->bu, h->lnv_g,
                                                                h->lnv_b, h->wv, h->bv, c.out_dim, u, v);
   AVB_LAUNCH_CHECK(h);
-  avb::head_logits_kernel<<<dim3((d + 15) / 16, (d + 15) / 16, B), dim3(16, 16), 0, st>>>(
-      u, v, d, c.out_dim, h->temp, h->bias, c.mask_diag, log_probs, probs);
+  if (c.compute_dtype == AVB_DTYPE_BF16 && c.out_dim == 128 && h->head_tc) {
+    // the u . v^T contraction on the tensor cores (split-precision operands, kernels_split.cuh)
+    static PerDeviceOnce once;
+    cudaError_t e = once.run([] {
+      return cudaFuncSetAttribute(avb::head_logits_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::kHeadTcSmemBytes);
+    });
+    if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(head_logits_tc): %s", cudaGetErrorString(e));
+    avb::head_logits_tc_kernel<<<dim3((d + 127) / 128, (d + 127) / 128, B), avb::kHeadTcThreads, avb::kHeadTcSmemBytes, st>>>(
+        u, v, d, h->temp, h->bias, c.mask_diag, log_probs, probs);
+  } else {
+    avb::head_logits_kernel<<<dim3((d + 15) / 16, (d + 15) / 16, B), dim3(16, 16), 0, st>>>(
+        u, v, d, c.out_dim, h->temp, h->bias, c.mask_diag, log_probs, probs);
+  }
   AVB_LAUNCH_CHECK(h);
   return AVB_OK;
 }
@@ -1502,6 +1514,12 @@ int avb_test_set_dattn_mode(avb_handle h, int32_t mode) {
 int avb_test_set_f32_tc(avb_handle h, int32_t on) {
   if (!h) return AVB_ERR_INVALID;
   h->f32_tc = on != 0;
+  return AVB_OK;
+}
+
+int avb_test_set_head_tc(avb_handle h, int32_t on) {
+  if (!h) return AVB_ERR_INVALID;
+  h->head_tc = on != 0;
   return AVB_OK;
 }
 

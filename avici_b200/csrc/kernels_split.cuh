@@ -589,3 +589,94 @@ attention_split_tc_kernel(const __nv_bfloat16* __restrict__ qkvs, float* __restr
 }
 
 }  // namespace avb
+
+namespace avb {
+
+// ------------------------------------------------------------------------------------------
+// Edge-logit contraction of the head on the tensor cores (model.py:133-141, 218-239):
+//     p[b, i, j] = sigmoid( <u_i, v_j> * exp(temp) + bias ),   diag = 0      (u, v: L2-normalised rows from head_uv_kernel)
+//   One CTA per (dataset, 128 x 128 tile of the [d, d] matrix).  Both operands are [rows x 128] fp32 matrices that the
+//   producer warps split into hi / lo bf16 K-major tiles (the same A-unit image for both: u rows are the M side, v rows
+//   the N side), 24 MMAs (M 128, N 128, K 16: hi hi + hi lo + lo hi) into 128 TMEM columns, epilogue one row per thread.
+//   The cosines carry ~1e-5 relative error (split precision), far inside the bf16 mode's budget; the fp32 mode keeps the
+//   SIMT head.  d^2 * 256 FLOP per dataset - 2.6 MFLOP at d = 100, 256 MFLOP at d = 1000: this is about where the
+//   contraction runs, not about time (< 0.1 % of a forward either way).
+//   warps 0-3: u tile, then epilogue (TMEM lane quarter = warp)   warps 4-7: v tile (warp 4 also allocates TMEM, issues)
+// ------------------------------------------------------------------------------------------
+constexpr int kHeadTcThreads = 256;
+constexpr int kHeadTcSmemBytes = 2 * kSplitUnit + 1024 + 256;
+
+__global__ void __launch_bounds__(kHeadTcThreads, 1)
+head_logits_tc_kernel(const float* __restrict__ u, const float* __restrict__ v, int d, const float* __restrict__ temp,
+                      const float* __restrict__ bias, int mask_diag, int log_probs, float* __restrict__ probs) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                 // u tile: [2 K blocks][hi 16K | lo 16K]
+  uint8_t* sB = smem + kSplitUnit;    // v tile, same image
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + 2 * kSplitUnit);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int b = blockIdx.z, i0 = blockIdx.y * 128, j0 = blockIdx.x * 128;
+  const float* ub = u + (size_t)b * d * 128;
+  const float* vb = v + (size_t)b * d * 128;
+
+  if (warp == 4 && lane == 0) { ptx::mbar_init(done, 1); ptx::fence_barrier_init(); }
+  if (warp == 4) { ptx::tmem_alloc(tmem_slot, 128); ptx::tmem_relinquish(); }
+  if (warp < 4) split_rows_to_unit<false>(ub, 128, d, i0 + warp * 32, ptx::smem_u32(sA), warp * 32, lane);
+  else split_rows_to_unit<false>(vb, 128, d, j0 + (warp - 4) * 32, ptx::smem_u32(sB), (warp - 4) * 32, lane);
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 4) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 128, 0, 0);
+      const uint64_t dA0 = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 1024, ptx::kSwz128);
+      const uint64_t dB0 = ptx::make_smem_desc(ptx::smem_u32(sB), 16, 1024, ptx::kSwz128);
+      constexpr uint64_t kLo = kSplitTile >> 4;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = dA0 + (uint64_t)kb * (2 * kLo) + (uint64_t)(k * 2), db = dB0 + (uint64_t)kb * (2 * kLo) + (uint64_t)(k * 2);
+          ptx::umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+          ptx::umma_bf16(tmem_base, da, db + kLo, idesc, 1);
+          ptx::umma_bf16(tmem_base, da + kLo, db, idesc, 1);
+        }
+      ptx::umma_commit(done);
+    }
+    __syncwarp();
+  }
+  if (warp < 4) {
+    ptx::mbar_wait(done, 0, 66);
+    ptx::tc_fence_after();
+    const int i = i0 + warp * 32 + lane;
+    const float scale = expf(temp[0]), bs = bias[0];
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t acc[32];
+      ptx::tmem_ld32(tmem_base + cc * 32 + ((uint32_t)(warp * 32) << 16), acc);
+      ptx::tmem_wait_ld();
+      if (i < d) {
+        float* prow = probs + ((size_t)b * d + i) * d;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int j = j0 + cc * 32 + e;
+          if (j < d) {
+            const float l = __uint_as_float(acc[e]) * scale + bs;
+            const float logp = -(fmaxf(-l, 0.f) + log1pf(expf(-fabsf(l))));  // log_sigmoid(l)
+            float p = log_probs ? logp : expf(logp);
+            if (mask_diag && i == j) p = log_probs ? -INFINITY : 0.f;
+            prow[j] = p;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) ptx::tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace avb

@@ -248,6 +248,8 @@ int avb_test_dattn_bf16(avb_handle h, int32_t block_idx, const float* z_dev, int
 /* fp32 handles: 1 (default) = projections and FFN as split-precision (bf16 x 3, fp32 accumulate) tensor-core GEMMs,
  * 0 = the SIMT fp32 GEMM kernels (A/B reference of the parity mode). */
 int avb_test_set_f32_tc(avb_handle h, int32_t on);
+/* bf16 handles: 1 (default) = the head's u . v^T contraction on the tensor cores (head_logits_tc_kernel), 0 = SIMT. */
+int avb_test_set_head_tc(avb_handle h, int32_t on);
 /* Which kernels run the attention half of a block that attends over d <= 128 (bf16 mode): 1 (default) the fully
  * fused dattn_tc_kernel, 2 the same kernel up to the attention output + the separate out-projection, 0 the unfused
  * QKV / attention / out-projection launches (what every other block uses).  A/B and test knob. */

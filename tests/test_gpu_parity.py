@@ -656,6 +656,34 @@ def test_shape_sweep_bf16_vs_fp32_paths():
         assert np.all(np.diagonal(p16, axis1=1, axis2=2) == 0)
 
 
+def test_head_contraction_on_tensor_cores_matches_simt():
+    """bf16 handles run the head's u . v^T on the tensor cores (split-precision operands): against the SIMT head of the same
+    handle on identical pooled features, probabilities and log-probabilities, d below / at / above the 128 tile."""
+    model = avici_b200.random_init_model(dict(layers=1, **STRESS), seed=13, perturb=True, compute_dtype="bf16")
+    eng = model.engine
+    lib, h = eng.lib, eng.handle
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for B, d in ((3, 100), (1, 128), (2, 300), (1, 1)):
+        pooled = torch.randn(B, d, 128, device="cuda", generator=g)
+        hs = torch.empty(2 * B * d * 128 * 4, dtype=torch.uint8, device="cuda")
+        res = {}
+        for tc in (1, 0):
+            eng._check(lib.avb_test_set_head_tc(h, tc))
+            p = torch.full((B, d, d), float("nan"), device="cuda")
+            lp = torch.full((B, d, d), float("nan"), device="cuda")
+            eng._check(lib.avb_head(h, pooled.data_ptr(), B, d, p.data_ptr(), hs.data_ptr(), hs.numel(), st))
+            eng._check(lib.avb_head_logprobs(h, pooled.data_ptr(), B, d, lp.data_ptr(), hs.data_ptr(), hs.numel(), st))
+            torch.cuda.synchronize()
+            res[tc] = (p, lp)
+        eng._check(lib.avb_test_set_head_tc(h, 1))
+        assert (res[1][0] - res[0][0]).abs().max().item() <= 2e-4, (B, d)  # 20 x cos: 1e-5 of split precision
+        fin = torch.isfinite(res[0][1])
+        assert torch.equal(fin, torch.isfinite(res[1][1]))
+        assert (res[1][1][fin] - res[0][1][fin]).abs().max().item() <= 1e-3 if fin.any() else True
+        assert torch.all(torch.diagonal(res[1][0], dim1=1, dim2=2) == 0)
+
+
 def test_edge_shapes_and_errors():
     kw = dict(layers=1, **STRESS)
     for dtype in ("fp32", "bf16"):
