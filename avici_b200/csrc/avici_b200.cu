@@ -45,6 +45,7 @@ struct Block {
   // fp32 mode, split-precision tensor-core GEMMs (kernels_split.cuh): hi / lo bf16 halves of the K-major weights with the
   // LayerNorm affine folded in (no softmax scale: the fp32 attention kernel applies it), their [128 x 64] tensor maps
   CUtensorMap tm_s_qkv[2], tm_s_o[2], tm_s_1[2], tm_s_2[2];
+  avb::DaBias dattn_bias;  // host copy of bo_d for dattn_tc_kernel's parameter
   avb::FfnBias ffn_bias;  // host copy of b1' (LayerNorm-folded) and b2 for the resident FFN kernel's parameter (F = 512)
   const float *zero_k;
   // per-head operand images of dattn_tc_kernel: Wqkv_h as 2 K blocks of [96 x 64] (128B swizzle), Wo_h as [128 x 32] (64B swizzle)
@@ -407,12 +408,25 @@ int launch_dattn_tc(avb_handle h, const float* z, const Block& W, void* out, int
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(dattn_tc): %s", cudaGetErrorString(e));
   if (T < 1 || T > 128 || S < 1) return fail(h, AVB_ERR_INVALID, "dattn_tc: sequence length %d not in 1..128", T);
   const int grid = std::min(S, num_sms);
-  if (fuse_out)
+  CUtensorMap tm_delta;
+  memset(&tm_delta, 0, sizeof tm_delta);
+  if (fuse_out) {
+    // delta rows as {128 channels, T rows, S sequences} bf16, stored in [32 ch x 32 rows] boxes (64B swizzle): the row
+    // bound of the map clips what a warp's box holds past the end of its sequence
+    EncodeTiledFn fn = encode_tiled_fn();
+    cuuint64_t gdim[3] = {128, (cuuint64_t)T, (cuuint64_t)S};
+    cuuint64_t gstr[2] = {256, (cuuint64_t)T * 256};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (!fn || fn(&tm_delta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for the delta rows");
     avb::dattn_tc_kernel<true><<<grid, avb::kDaThreads, avb::DaCfg<true>::kSmemBytes, st>>>(
-        z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo_d, reinterpret_cast<bf16*>(out), S, T, guard);
-  else
+        z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo_d, reinterpret_cast<bf16*>(out), S, T, guard, tm_delta, W.dattn_bias);
+  } else {
     avb::dattn_tc_kernel<false><<<grid, avb::kDaThreads, avb::DaCfg<false>::kSmemBytes, st>>>(
-        z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo_d, reinterpret_cast<bf16*>(out), S, T, guard);
+        z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo_d, reinterpret_cast<bf16*>(out), S, T, guard, tm_delta, W.dattn_bias);
+  }
   if (launches) ++*launches;
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "dattn_tc launch: %s", cudaGetErrorString(e));
@@ -841,6 +855,7 @@ int avb_load_weights(avb_handle h, const avb_tensor_desc* tensors, int32_t count
     B.wq = df + o.wq; B.bq = df + o.bq; B.wk = df + o.wk; B.bk = df + o.bk; B.wv = df + o.wv; B.bv = df + o.bv;
     B.wo = df + o.wo; B.bo = df + o.bo; B.w1 = df + o.w1; B.b1 = df + o.b1; B.w2 = df + o.w2; B.b2 = df + o.b2;
     B.bqkv_f = df + o.bqkv_f; B.b1_f = df + o.b1_f; B.bo_d = df + o.bo_d; B.zero_k = df + o.zero_k;
+    if (k == 128) memcpy(B.dattn_bias.bo, f32.data() + o.bo_d, sizeof B.dattn_bias.bo);
     if (c.compute_dtype == AVB_DTYPE_BF16 && F == 512) {
       memcpy(B.ffn_bias.b1, f32.data() + o.b1_f, sizeof B.ffn_bias.b1);
       memcpy(B.ffn_bias.b2, f32.data() + o.b2, sizeof B.ffn_bias.b2);

@@ -52,6 +52,8 @@ constexpr int kDaTileBytes = 128 * 32 * 2;  // Q / K / V / O tile
 constexpr int kDaHeads = 8;
 constexpr int kDaVBufs = 3;
 
+struct DaBias { float bo[128]; };  // bo' = bo + bv Wo as a kernel parameter: Depi adds it straight from the constant bank
+
 template <bool kFuseOut>
 struct DaCfg {
   static constexpr int kWStages = kFuseOut ? 4 : 6;
@@ -59,8 +61,10 @@ struct DaCfg {
   static constexpr int kOBufs = 0;  // the bf16 O tile of the fused out-projection lives in TMEM (A operand of OP)
   static constexpr int kDataBytes =
       2 * kDaXBytes + kWStages * kDaWkbBytes + kWoBytes + (2 + kDaVBufs + kOBufs) * kDaTileBytes;
-  static constexpr int kBiasBytes = (kDaHeads * 32 + 256) * 4;  // bq | bo' (or bv when the out-projection is not fused) as fp32
-  static constexpr int kSmemBytes = kDataBytes + 1024 /*barriers, TMEM slot, ones tile*/ + kBiasBytes + 1024 /*alignment slack*/;
+  static constexpr int kBiasBytes = (kDaHeads * 32 + (kFuseOut ? 0 : 256)) * 4;  // bq (| bv when the out-projection is not fused) as fp32; bo' is a kernel parameter
+  static constexpr int kStageBytes = 0;  // Depi stages its boxes in the xhat tile of the sequence it finishes
+  // (no alignment slack: the dynamic shared memory window starts 1024-aligned - the kernel traps if it ever does not)
+  static constexpr int kSmemBytes = kDataBytes + 1024 /*barriers, TMEM slot, ones tile*/ + kBiasBytes + kStageBytes;
 };
 static_assert(DaCfg<true>::kSmemBytes <= 232448, "dattn_tc_kernel: shared memory over the sm_100 limit");
 
@@ -94,11 +98,12 @@ template <bool kFuseOut>
 __global__ void __launch_bounds__(kDaThreads, 1)
 dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_img, const uint8_t* __restrict__ wo_img,
                 const float* __restrict__ bqkv, const float* __restrict__ bo, __nv_bfloat16* __restrict__ out, int S, int T,
-                int* __restrict__ guard) {
+                int* __restrict__ guard, const __grid_constant__ CUtensorMap tm_delta, const __grid_constant__ DaBias cb) {
   using Cfg = DaCfg<kFuseOut>;
   constexpr int NS = Cfg::kWStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0u) __trap();  // the swizzled operand images need 1024-byte alignment
   uint8_t* sX = smem;                               // [2][32 KB]
   uint8_t* sW = sX + 2 * kDaXBytes;                 // [NS][12 KB]
   uint8_t* sWo = sW + NS * kDaWkbBytes;             // [8][8 KB] (kFuseOut)
@@ -135,7 +140,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
   const int U = nseq * kDaHeads;
   const int kc = (T + 15) & ~15;  // key columns the MMAs touch
   // trace builds (-DAVB_TRACE_ENABLE, scripts/trace_dattn.py): CTA 0 stamps clock64() per role and unit
-  long long* trace = (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 3 || warp == 4 || warp == 8 || warp == 12)) ? g_attn_trace : nullptr;
+  long long* trace = (blockIdx.x == 0 && lane == 0 && (warp <= 4 || warp == 8 || warp == 12)) ? g_attn_trace : nullptr;
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -159,8 +164,8 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     ptx::tmem_relinquish();
   }
   if (threadIdx.x >= 128 && threadIdx.x < 256) s_ones[threadIdx.x - 128] = 0x3F803F80u;
-  for (int i = threadIdx.x; i < kDaHeads * 32 + (kFuseOut ? 128 : 256); i += kDaThreads)
-    s_bias[i] = i < kDaHeads * 32 ? bqkv[i] : (kFuseOut ? bo[i - kDaHeads * 32] : bqkv[i + kDaHeads * 32]);  // bv = bqkv + 512
+  for (int i = threadIdx.x; i < kDaHeads * 32 + (kFuseOut ? 0 : 256); i += kDaThreads)
+    s_bias[i] = i < kDaHeads * 32 ? bqkv[i] : bqkv[i + kDaHeads * 32];  // bv = bqkv + 512
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();
@@ -225,10 +230,16 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint64_t dv = dV0 + (uint64_t)((u % kDaVBufs) * (kDaTileBytes >> 4));
-#pragma unroll 1  // compact code: the kernel's five roles share the instruction caches
-          for (int k = 0; k < ksteps; ++k) {
-            ptx::umma_bf16_ts(tO, tP + k * 8, dv + (uint64_t)(k * 64), idesc_pv, k != 0);
-            ptx::umma_bf16_ts(tL, tP + k * 8, d_ones, idesc_l, k != 0);
+          // Straight-line issue: as a rolled loop this was ~20 uniform-datapath instructions per pair of MMAs, ~1000
+          // clocks per unit for the issuing thread - long enough for G of three units ahead (ready ~400 clocks after P)
+          // to get into the in-order tensor pipe between the PV MMAs, 89 clocks each (r2g trace: p_full -> pv_done 1450
+          // clocks, the softmax warps of the next unit waiting ~500 of them to store their P tile).
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (k < ksteps) {
+              ptx::umma_bf16_ts(tO, tP + k * 8, dv + (uint64_t)(k * 64), idesc_pv, k != 0);
+              ptx::umma_bf16_ts(tL, tP + k * 8, d_ones, idesc_l, k != 0);
+            }
           }
           ptx::umma_commit(pv_done);
           ptx::umma_commit(&v_free[u % kDaVBufs]);
@@ -307,6 +318,8 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         }
         __syncwarp();
       };
+      // (Tried, r2g: OP on its own issuing warp, so that its wait for the previous sequence's Depi (d_free) does not hold
+      //  back G three units ahead - 3.70 vs 3.57 ms: the extra polling warp costs more than the decoupling gains.)
       if (kFuseOut) ptx::mbar_wait(wo_full, 0, 89, 40u);
       issue_G(0);
       if (U > 1) issue_G(1);
@@ -372,7 +385,10 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         }
       }
     };
-    auto oepi = [&](int u) {  // O / L -> bf16 -> A tile of the out-projection (or the attention output in HBM)
+    // Oepi in two parts, so that the accumulator hand-back (part A) never waits behind the Depi of the previous sequence:
+    //   A: O, L -> registers, o_free (PV of the next unit may start), O / L -> packed bf16
+    //   B: the bf16 tile -> TMEM as the A operand of OP (or the attention output in HBM), o_ready
+    auto oepi_a = [&](int u, uint4 (&pk)[4]) {
       const int h = u & 7;
       ptx::mbar_wait(pv_done, (uint32_t)(u & 1), 92, AVB_DATTN_WAIT_NS);
       AVB_TRACE(4, u, 3);
@@ -390,31 +406,18 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       if (r < T && !(lsum < 1.2676506e30f && lsum > 7.8886091e-31f)) *guard = 1;  // outside (2^-100, 2^100), inf or NaN
       float inv;
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(lsum));  // 1 ulp: far below the bf16 rounding of O
-      uint4 pk[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        pk[e].x = ptx::pack_bf16(__uint_as_float(o[e * 8 + 0]) * inv, __uint_as_float(o[e * 8 + 1]) * inv);
-        pk[e].y = ptx::pack_bf16(__uint_as_float(o[e * 8 + 2]) * inv, __uint_as_float(o[e * 8 + 3]) * inv);
-        pk[e].z = ptx::pack_bf16(__uint_as_float(o[e * 8 + 4]) * inv, __uint_as_float(o[e * 8 + 5]) * inv);
-        pk[e].w = ptx::pack_bf16(__uint_as_float(o[e * 8 + 6]) * inv, __uint_as_float(o[e * 8 + 7]) * inv);
-      }
 #ifdef AVB_DATTN_DEBUG
       if (g_dattn_dbg && blockIdx.x == 0 && u < 8)
         for (int t = 0; t < 32; ++t) g_dattn_dbg[(size_t)8 * 128 * 96 + 8 * 128 * 128 + ((size_t)u * 128 + r) * 32 + t] = __uint_as_float(o[t]) * inv;
 #endif
       if constexpr (kFuseOut) {
-        // straight back into TMEM as the A operand of OP: no shared-memory round trip, and no async-proxy fence
-        // (MEMBAR.ALL.CTA: it would drain this thread's LayerNorm loads in flight)
-        AVB_TRACE(7, u, 2);
-        if (u >= 1) ptx::mbar_wait(op_done, (uint32_t)((u - 1) & 1), 97);  // OP of unit u-1 has read the tile
-        AVB_TRACE(7, u, 3);
-        ptx::tc_fence_after();
-        uint32_t ob[16];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { ob[e * 4 + 0] = pk[e].x; ob[e * 4 + 1] = pk[e].y; ob[e * 4 + 2] = pk[e].z; ob[e * 4 + 3] = pk[e].w; }
-        ptx::tmem_st16(tOb + lane_off, ob);
-        ptx::tmem_wait_st();
-        AVB_TRACE(7, u, 4);
+        for (int e = 0; e < 4; ++e) {
+          pk[e].x = ptx::pack_bf16(__uint_as_float(o[e * 8 + 0]) * inv, __uint_as_float(o[e * 8 + 1]) * inv);
+          pk[e].y = ptx::pack_bf16(__uint_as_float(o[e * 8 + 2]) * inv, __uint_as_float(o[e * 8 + 3]) * inv);
+          pk[e].z = ptx::pack_bf16(__uint_as_float(o[e * 8 + 4]) * inv, __uint_as_float(o[e * 8 + 5]) * inv);
+          pk[e].w = ptx::pack_bf16(__uint_as_float(o[e * 8 + 6]) * inv, __uint_as_float(o[e * 8 + 7]) * inv);
+        }
       } else {
         // (the separate out-projection launch uses the plain bo, so the value bias is added here)
 #pragma unroll
@@ -426,7 +429,25 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
           pk[e].z = ptx::pack_bf16(__uint_as_float(o[e * 8 + 4]) * inv + b1.x, __uint_as_float(o[e * 8 + 5]) * inv + b1.y);
           pk[e].w = ptx::pack_bf16(__uint_as_float(o[e * 8 + 6]) * inv + b1.z, __uint_as_float(o[e * 8 + 7]) * inv + b1.w);
         }
+      }
+      AVB_TRACE(7, u, 2);
+    };
+    auto oepi_b = [&](int u, const uint4 (&pk)[4]) {
+      if constexpr (kFuseOut) {
+        // straight back into TMEM as the A operand of OP: no shared-memory round trip, and no async-proxy fence
+        // (MEMBAR.ALL.CTA: it would drain this thread's LayerNorm loads in flight)
+        if (u >= 1) ptx::mbar_wait(op_done, (uint32_t)((u - 1) & 1), 97);  // OP of unit u-1 has read the tile
+        AVB_TRACE(7, u, 3);
+        ptx::tc_fence_after();
+        uint32_t ob[16];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { ob[e * 4 + 0] = pk[e].x; ob[e * 4 + 1] = pk[e].y; ob[e * 4 + 2] = pk[e].z; ob[e * 4 + 3] = pk[e].w; }
+        ptx::tmem_st16(tOb + lane_off, ob);
+        ptx::tmem_wait_st();
+        AVB_TRACE(7, u, 4);
+      } else {
         if (r < T) {  // outproj_tc_kernel's A-operand layout: [m >> 7][head][m & 127][32 ch], chunks at c ^ ((m >> 1) & 3)
+          const int h = u & 7;
           const int s = (int)blockIdx.x + (u >> 3) * (int)gridDim.x;
           const unsigned m = (unsigned)s * (unsigned)T + (unsigned)r;
           __nv_bfloat16* orow = out + (((size_t)(m >> 7) * kDaHeads + h) * 128 + (m & 127)) * 32;
@@ -439,45 +460,61 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       ptx::mbar_arrive(&o_ready[u & 1]);
     };
     auto depi = [&](int si) {  // DELTA + bo' -> bf16 -> the sequence's 256-byte delta rows (token order)
-      // One row per thread, 64 contiguous bytes per chunk, straight from registers.  (Transposing through a shared-
-      // memory stage for 128-byte store segments measured the same ~4K clocks per sequence - the warp is latency-
-      // bound, not store-bound - and there is no shared memory left for a stage that the LayerNorm warps do not also
-      // write.)  A compact loop: this code runs once per sequence and is cold in the instruction caches.
+      // Row-per-thread 16-byte global stores cost ~1800 LSU data wavefronts per sequence and the next chunk's TMEM load
+      // waited for the stores to release their source registers (ncu r2g: 3100 clocks per sequence, with the whole unit
+      // pipeline stalled behind it once per sequence).  Each warp now stages [32 rows x 32 channels] boxes in the 64B-
+      // swizzle image (conflict-free 16-byte shared stores) and one lane hands them to the TMA: a 3-D tensor map
+      // {channel, row, sequence} clips the rows past the end of the sequence.  The stage is the warp's own 8 KB of this
+      // sequence's xhat tile: G of the last head has read it (d_full is causally behind g_full of that unit), and the
+      // next writer is this same warp's LayerNorm slice two sequences on, behind the wait_group.read in the unit loop.
+      // The bias comes from the constant bank (kernel parameter): no shared-memory loads in front of the adds.
       AVB_TRACE(6, si, 0);
       ptx::mbar_wait(d_full, (uint32_t)(si & 1), 93);
       AVB_TRACE(6, si, 1);
       ptx::tc_fence_after();
       const int s = (int)blockIdx.x + si * (int)gridDim.x;
-      __nv_bfloat16* drow = out + ((size_t)s * T + r) * 128;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tD + cc * 32 + lane_off, v);
-        float4 bb[8];
+      const uint32_t stage = ptx::smem_u32(sX + (si & 1) * kDaXBytes) + (uint32_t)(w * 4096);  // + 16 KB for chunks 2, 3
+      const uint32_t swz = (uint32_t)((lane >> 1) & 3);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) bb[e] = ptx::ld_shared_v4f(ptx::smem_u32(s_bias) + (uint32_t)((kDaHeads * 32 + cc * 32 + e * 4) * 4));
+      for (int cp = 0; cp < 4; cp += 2) {
+        uint32_t v[2][32];
+        ptx::tmem_ld32(tD + cp * 32 + lane_off, v[0]);
+        ptx::tmem_ld32(tD + cp * 32 + 32 + lane_off, v[1]);
         ptx::tmem_wait_ld();
-        if (cc == 3) {
+        if (cp == 2) {
           ptx::tc_fence_before();
           ptx::mbar_arrive(d_free);  // accumulator read: the next sequence's first OP may overwrite it
         }
+        if (cp == 0) AVB_TRACE(6, si, 2);
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int cc = cp + c2;
+          const uint32_t my = stage + (uint32_t)((cc >> 1) * 16384 + (cc & 1) * 2048 + lane * 64);
 #ifdef AVB_DATTN_DEBUG
-        if (g_dattn_dbg && blockIdx.x == 0 && si == 0)
-          for (int t = 0; t < 32; ++t)
-            g_dattn_dbg[(size_t)8 * 128 * 96 + 8 * 128 * 128 + 8 * 128 * 32 + (size_t)r * 128 + cc * 32 + t] =
-                __uint_as_float(v[t]) + reinterpret_cast<const float*>(bb)[t];
+          if (g_dattn_dbg && blockIdx.x == 0 && si == 0)
+            for (int t = 0; t < 32; ++t)
+              g_dattn_dbg[(size_t)8 * 128 * 96 + 8 * 128 * 128 + 8 * 128 * 32 + (size_t)r * 128 + cc * 32 + t] =
+                  __uint_as_float(v[c2][t]) + cb.bo[cc * 32 + t];
 #endif
-        if (r < T) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            uint4 pk;
-            pk.x = ptx::pack_bf16(__uint_as_float(v[e * 8 + 0]) + bb[e * 2].x, __uint_as_float(v[e * 8 + 1]) + bb[e * 2].y);
-            pk.y = ptx::pack_bf16(__uint_as_float(v[e * 8 + 2]) + bb[e * 2].z, __uint_as_float(v[e * 8 + 3]) + bb[e * 2].w);
-            pk.z = ptx::pack_bf16(__uint_as_float(v[e * 8 + 4]) + bb[e * 2 + 1].x, __uint_as_float(v[e * 8 + 5]) + bb[e * 2 + 1].y);
-            pk.w = ptx::pack_bf16(__uint_as_float(v[e * 8 + 6]) + bb[e * 2 + 1].z, __uint_as_float(v[e * 8 + 7]) + bb[e * 2 + 1].w);
-            *reinterpret_cast<uint4*>(drow + cc * 32 + e * 8) = pk;
+            const float* b = cb.bo + cc * 32 + e * 8;
+            const uint32_t p0 = ptx::pack_bf16(__uint_as_float(v[c2][e * 8 + 0]) + b[0], __uint_as_float(v[c2][e * 8 + 1]) + b[1]);
+            const uint32_t p1 = ptx::pack_bf16(__uint_as_float(v[c2][e * 8 + 2]) + b[2], __uint_as_float(v[c2][e * 8 + 3]) + b[3]);
+            const uint32_t p2 = ptx::pack_bf16(__uint_as_float(v[c2][e * 8 + 4]) + b[4], __uint_as_float(v[c2][e * 8 + 5]) + b[5]);
+            const uint32_t p3 = ptx::pack_bf16(__uint_as_float(v[c2][e * 8 + 6]) + b[6], __uint_as_float(v[c2][e * 8 + 7]) + b[7]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my + (((uint32_t)e ^ swz) << 4)), "r"(p0), "r"(p1), "r"(p2), "r"(p3)
+                         : "memory");
           }
         }
+        if (cp == 0) AVB_TRACE(6, si, 3);
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      AVB_TRACE(6, si, 4);
+      if (lane < 4 && w * 32 < T) {  // one box per lane: a single issue slot instead of four dependent ones
+        ptx::tma_store_3d(&tm_delta, stage + (uint32_t)((lane >> 1) * 16384 + (lane & 1) * 2048), lane * 32, w * 32, s);
+        ptx::bulk_commit();
       }
       AVB_TRACE(6, si, 5);
     };
@@ -501,13 +538,21 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         const int u = si * kDaHeads + h;
         const bool slice = has_next && h < 4;
         AVB_TRACE(4, u, 0);
+        uint4 pk[4];
         if (slice) {
           if (h == 0) ptx::mbar_wait(&x_empty[nbuf], (uint32_t)(((si + 1) >> 1) & 1) ^ 1, 90);
           ln8_load(z + (size_t)s_next * T * 128, h * 8);
         }
-        oepi(u);
+        // (Tried, r2g: the second half of the previous sequence's Depi behind this unit's accumulator hand-back, 3.72 vs
+        //  3.57 ms - the hand-back of the unit after that waits instead.)
+        oepi_a(u, pk);
+        oepi_b(u, pk);
         AVB_TRACE(4, u, 2);
         if (slice) {
+          if (kFuseOut && h == 0 && si > 0) {  // Depi of the previous sequence staged its boxes in this buffer
+            if (lane < 4) ptx::bulk_wait_read<0>();
+            __syncwarp();
+          }
           ln8_finish(ptx::smem_u32(sX + nbuf * kDaXBytes), h * 8);
           if (h == 3) {
             ptx::fence_proxy_async();
@@ -518,6 +563,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         AVB_TRACE(4, u, 5);
       }
     }
+    if (kFuseOut && lane < 4) ptx::bulk_wait_all();  // the last boxes must have left shared memory before the CTA exits
   } else if (warp < 12) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     // ======================= conv warps: thread = row r of the tile = TMEM lane.  Nothing else runs here: qkv_ready ->

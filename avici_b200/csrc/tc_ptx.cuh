@@ -197,6 +197,12 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+// 3-D variant (dattn_tc_kernel's delta rows: {channel, row of the sequence, sequence})
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int KEEP>
 __device__ __forceinline__ void bulk_wait_read() {

@@ -74,13 +74,16 @@ print(f"oepi detail: tmem ld {(oe[ok, 1] - oe[ok, 0]).mean():.0f}, math {(oe[ok,
 de = t[6, 2:48].astype(np.int64)
 ok = (de[:, 0] > 0) & (de[:, 5] > 0)
 print(f"depi detail: wait d_full {(de[ok, 1] - de[ok, 0]).mean():.0f}, body {(de[ok, 5] - de[ok, 1]).mean():.0f}")
+if (de[ok, 4] > 0).all():
+    print(f"depi parts: chunks 0-1 tmem ld {(de[ok, 2] - de[ok, 1]).mean():.0f}, math + st.shared {(de[ok, 3] - de[ok, 2]).mean():.0f}, "
+          f"chunks 2-3 + fence {(de[ok, 4] - de[ok, 3]).mean():.0f}, TMA issue {(de[ok, 5] - de[ok, 4]).mean():.0f}")
 ok = (cv[:, 2] > 0) & (cv[:, 6] > 0)
 print(f"conv detail: Q chunk {(cv[ok, 4] - cv[ok, 2]).mean():.0f}, K chunk {(cv[ok, 5] - cv[ok, 4]).mean():.0f}, V chunk {(cv[ok, 6] - cv[ok, 5]).mean():.0f}, fence+arrive {(cv[ok, 3] - cv[ok, 6]).mean():.0f}")
 if len(sys.argv) > 5:
     # merged timeline of the events that concern units u0..u0+2, in time order
     u0 = int(sys.argv[5])
     ev = []
-    for u in range(u0, u0 + 3):
+    for u in range(u0, u0 + (int(sys.argv[6]) if len(sys.argv) > 6 else 3)):
         add = lambda role, step, e, name: ev.append((int(t[role, step, e]), f"u{u} {name}")) if t[role, step, e] > 0 else None  # noqa: E731
         add(5, u - 2, 5, "G: s_free seen"); add(5, u - 2, 1, "G issued")
         add(2, u, 0, "conv top"); add(2, u, 2, "conv waits done (g_full, s_full(u-1), v_free)"); add(2, u, 3, "conv done -> qkv_ready")
@@ -92,3 +95,20 @@ if len(sys.argv) > 5:
         add(5, u + 1, 1, "proj issuer: G(u+3) issued, now OP(u)"); add(5, u + 1, 2, "OP issued")
     for tt, nm in sorted(ev):
         print(f"{tt - t0:9d}  {nm}")
+# per-head-index view: where in a sequence (h = u & 7) the unit period goes
+for role, nm in ((1, "attn issuer"), (3, "softmax"), (4, "epilogue"), (2, "conv"), (5, "proj issuer")):
+    tops = t[role, :, 0].astype(np.int64)
+    per = {h: [] for h in range(8)}
+    for u in range(16, 400):
+        if tops[u] > 0 and tops[u + 1] > 0:
+            per[u & 7].append(tops[u + 1] - tops[u])
+    print(f"{nm}: period by h:", [int(np.mean(per[h])) if per[h] else -1 for h in range(8)])
+ep, oe7 = t[4].astype(np.int64), t[7].astype(np.int64)
+for h in range(8):
+    us = [u for u in range(16, 400) if (u & 7) == h and ep[u, 0] > 0 and oe7[u, 0] > 0 and oe7[u, 4] > 0 and ep[u, 5] > 0]
+    if not us:
+        continue
+    us = np.array(us)
+    print(f"epilogue h={h}: top->pv_done seen {np.mean(oe7[us, 0] - ep[us, 0]):.0f}, ->O loaded {np.mean(oe7[us, 1] - oe7[us, 0]):.0f}, "
+          f"->math {np.mean(oe7[us, 2] - oe7[us, 1]):.0f}, ->op_done {np.mean(oe7[us, 3] - oe7[us, 2]):.0f}, ->O stored {np.mean(oe7[us, 4] - oe7[us, 3]):.0f}, "
+          f"->end of unit (ln slice / depi) {np.mean(ep[us, 5] - oe7[us, 4]):.0f}")
