@@ -79,6 +79,9 @@ static_assert(DaCfg<true>::kSmemBytes <= 232448, "dattn_tc_kernel: shared memory
 #ifndef AVB_DATTN_BOUNDED_WAITS
 #define AVB_DATTN_BOUNDED_WAITS 1
 #endif
+#ifndef AVB_DATTN_LN_H0  // first of the four units of a sequence whose epilogue carries a LayerNorm slice of the next sequence
+#define AVB_DATTN_LN_H0 1  // (r2g, ms per launch: 3.47 / 3.40 / 3.51 for 0 / 1 / 2 - the unit behind a Depi stays light)
+#endif
 #if AVB_DATTN_BOUNDED_WAITS
 #define AVB_DA_WAIT(bar_ptr, parity, tag) ptx::mbar_wait((bar_ptr), (parity), (tag))
 #else
@@ -353,34 +356,43 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         for (int k = 0; k < 4; ++k) ln[uu][k] = row < T ? __ldcg(zp + k * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto ln8_finish = [&](uint32_t a_tile, int r0) {  // same arithmetic and layout as ln_warp_rows_to_umma_tile
+    auto ln8_finish = [&](uint32_t a_tile, int r0) {  // same layout as ln_warp_rows_to_umma_tile
+      // Sum and sum of squares in one pass (as the FFN kernel's LayerNorm does), the four reductions of the slice's two
+      // row groups interleaved: three shuffle rounds on the epilogue warps' critical path instead of twelve dependent ones.
+      float sum[2], sq[2];
 #pragma unroll
       for (int uu = 0; uu < 2; ++uu) {
-        float sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) sum += (ln[uu][k].x + ln[uu][k].y) + (ln[uu][k].z + ln[uu][k].w);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-        const float mean = sum * (1.0f / 128.0f);
-        float sq = 0.f;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          ln[uu][k].x -= mean; ln[uu][k].y -= mean; ln[uu][k].z -= mean; ln[uu][k].w -= mean;
-          sq += (ln[uu][k].x * ln[uu][k].x + ln[uu][k].y * ln[uu][k].y) + (ln[uu][k].z * ln[uu][k].z + ln[uu][k].w * ln[uu][k].w);
+          s0 += ln[uu][k].x + ln[uu][k].y; s1 += ln[uu][k].z + ln[uu][k].w;
+          q0 = fmaf(ln[uu][k].x, ln[uu][k].x, q0); q1 = fmaf(ln[uu][k].y, ln[uu][k].y, q1);
+          q0 = fmaf(ln[uu][k].z, ln[uu][k].z, q0); q1 = fmaf(ln[uu][k].w, ln[uu][k].w, q1);
         }
-        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-        const float rstd = rsqrtf(sq * (1.0f / 128.0f) + kLnEps);
+        sum[uu] = s0 + s1; sq[uu] = q0 + q1;
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+        for (int uu = 0; uu < 2; ++uu) {
+          sum[uu] += __shfl_xor_sync(0xffffffffu, sum[uu], o);
+          sq[uu] += __shfl_xor_sync(0xffffffffu, sq[uu], o);
+        }
+      }
+#pragma unroll
+      for (int uu = 0; uu < 2; ++uu) {
+        const float mean = sum[uu] * (1.0f / 128.0f);
+        const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, sq[uu] * (1.0f / 128.0f)), 0.f) + kLnEps);
+        const float shift = -mean * rstd;
         const int rr = w * 32 + r0 + uu * 4 + rs;
         const uint32_t rbase = a_tile + (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128 + (j8 & 1) * 8);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int chunk = (j8 + 8 * (k & 1)) >> 1;
           const uint32_t addr = rbase + (uint32_t)((k >> 1) * (128 * 128) + ((chunk ^ (rr & 7)) << 4));
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ptx::pack_bf16(ln[uu][k].x * rstd, ln[uu][k].y * rstd)),
-                       "r"(ptx::pack_bf16(ln[uu][k].z * rstd, ln[uu][k].w * rstd))
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr),
+                       "r"(ptx::pack_bf16(fmaf(ln[uu][k].x, rstd, shift), fmaf(ln[uu][k].y, rstd, shift))),
+                       "r"(ptx::pack_bf16(fmaf(ln[uu][k].z, rstd, shift), fmaf(ln[uu][k].w, rstd, shift)))
                        : "memory");
         }
       }
@@ -536,12 +548,13 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       if (si + 2 < nseq) prefetch_rows_l2(z + (size_t)(s_next + (int)gridDim.x) * T * 128, T, w * 32, lane);
       for (int h = 0; h < kDaHeads; ++h) {
         const int u = si * kDaHeads + h;
-        const bool slice = has_next && h < 4;
+        const bool slice = has_next && h >= AVB_DATTN_LN_H0 && h < AVB_DATTN_LN_H0 + 4;
+        const int hs = h - AVB_DATTN_LN_H0;  // slice index
         AVB_TRACE(4, u, 0);
         uint4 pk[4];
         if (slice) {
-          if (h == 0) ptx::mbar_wait(&x_empty[nbuf], (uint32_t)(((si + 1) >> 1) & 1) ^ 1, 90);
-          ln8_load(z + (size_t)s_next * T * 128, h * 8);
+          if (hs == 0) ptx::mbar_wait(&x_empty[nbuf], (uint32_t)(((si + 1) >> 1) & 1) ^ 1, 90);
+          ln8_load(z + (size_t)s_next * T * 128, hs * 8);  // (issued a unit earlier, behind the previous slice: 3.50 vs 3.36 ms)
         }
         // (Tried, r2g: the second half of the previous sequence's Depi behind this unit's accumulator hand-back, 3.72 vs
         //  3.57 ms - the hand-back of the unit after that waits instead.)
@@ -549,12 +562,12 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         oepi_b(u, pk);
         AVB_TRACE(4, u, 2);
         if (slice) {
-          if (kFuseOut && h == 0 && si > 0) {  // Depi of the previous sequence staged its boxes in this buffer
+          if (kFuseOut && hs == 0 && si > 0) {  // Depi of the previous sequence staged its boxes in this buffer
             if (lane < 4) ptx::bulk_wait_read<0>();
             __syncwarp();
           }
-          ln8_finish(ptx::smem_u32(sX + nbuf * kDaXBytes), h * 8);
-          if (h == 3) {
+          ln8_finish(ptx::smem_u32(sX + nbuf * kDaXBytes), hs * 8);
+          if (hs == 3) {
             ptx::fence_proxy_async();
             ptx::mbar_arrive(&x_full[nbuf]);
           }
