@@ -51,16 +51,20 @@ constexpr int kDaWoHeadBytes = 128 * 64;    // one head's [128 rows x 32] slice 
 constexpr int kDaTileBytes = 128 * 32 * 2;  // Q / K / V / O tile
 constexpr int kDaHeads = 8;
 constexpr int kDaVBufs = 3;
+#ifndef AVB_DATTN_QKBUFS  // Q / K tile buffers: 2 = conv of the next unit does not wait for S of this one (W ring 3 stages instead of 4)
+#define AVB_DATTN_QKBUFS 1  // (r2g: 3.29-3.34 ms either way, and with OP on its own issuing warp - kept at the simpler setting)
+#endif
+constexpr int kDaQKBufs = AVB_DATTN_QKBUFS;
 
 struct DaBias { float bo[128]; };  // bo' = bo + bv Wo as a kernel parameter: Depi adds it straight from the constant bank
 
 template <bool kFuseOut>
 struct DaCfg {
-  static constexpr int kWStages = kFuseOut ? 4 : 6;
+  static constexpr int kWStages = kFuseOut ? (kDaQKBufs == 2 ? 3 : 4) : 6;
   static constexpr int kWoBytes = kFuseOut ? kDaHeads * kDaWoHeadBytes : 0;
   static constexpr int kOBufs = 0;  // the bf16 O tile of the fused out-projection lives in TMEM (A operand of OP)
   static constexpr int kDataBytes =
-      2 * kDaXBytes + kWStages * kDaWkbBytes + kWoBytes + (2 + kDaVBufs + kOBufs) * kDaTileBytes;
+      2 * kDaXBytes + kWStages * kDaWkbBytes + kWoBytes + (2 * kDaQKBufs + kDaVBufs + kOBufs) * kDaTileBytes;
   static constexpr int kBiasBytes = (kDaHeads * 32 + (kFuseOut ? 0 : 256)) * 4;  // bq (| bv when the out-projection is not fused) as fp32; bo' is a kernel parameter
   static constexpr int kStageBytes = 0;  // Depi stages its boxes in the xhat tile of the sequence it finishes
   // (no alignment slack: the dynamic shared memory window starts 1024-aligned - the kernel traps if it ever does not)
@@ -78,6 +82,9 @@ static_assert(DaCfg<true>::kSmemBytes <= 232448, "dattn_tc_kernel: shared memory
 #endif
 #ifndef AVB_DATTN_BOUNDED_WAITS
 #define AVB_DATTN_BOUNDED_WAITS 1
+#endif
+#ifndef AVB_DATTN_OP_WARP  // 1: OP has its own issuing warp (2) instead of sharing warp 3 with G
+#define AVB_DATTN_OP_WARP 0
 #endif
 #ifndef AVB_DATTN_LN_H0  // first of the four units of a sequence whose epilogue carries a LayerNorm slice of the next sequence
 #define AVB_DATTN_LN_H0 1  // (r2g, ms per launch: 3.47 / 3.40 / 3.51 for 0 / 1 / 2 - the unit behind a Depi stays light)
@@ -110,9 +117,9 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
   uint8_t* sX = smem;                               // [2][32 KB]
   uint8_t* sW = sX + 2 * kDaXBytes;                 // [NS][12 KB]
   uint8_t* sWo = sW + NS * kDaWkbBytes;             // [8][8 KB] (kFuseOut)
-  uint8_t* sQ = sWo + Cfg::kWoBytes;                // 8 KB
-  uint8_t* sK = sQ + kDaTileBytes;                  // 8 KB
-  uint8_t* sV = sK + kDaTileBytes;                  // [3][8 KB]
+  uint8_t* sQ = sWo + Cfg::kWoBytes;                // [kDaQKBufs] x { Q 8 KB | K 8 KB }
+  uint8_t* sK = sQ + kDaTileBytes;
+  uint8_t* sV = sQ + kDaQKBufs * 2 * kDaTileBytes;  // [3][8 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kDataBytes);
   uint64_t* x_full = bars;                 // [2] 128 LN threads
   uint64_t* x_empty = bars + 2;            // [2] commit
@@ -221,8 +228,9 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(u & 1) * 128u;
-          ptx::umma_bf16(d_tmem, dQ, dK, idesc_s, 0);
-          ptx::umma_bf16(d_tmem, dQ + 2, dK + 2, idesc_s, 1);
+          const uint64_t qk = (uint64_t)((u % kDaQKBufs) * ((2 * kDaTileBytes) >> 4));
+          ptx::umma_bf16(d_tmem, dQ + qk, dK + qk, idesc_s, 0);
+          ptx::umma_bf16(d_tmem, dQ + qk + 2, dK + qk + 2, idesc_s, 1);
           ptx::umma_commit(&s_full[u & 1]);
         }
         __syncwarp();
@@ -261,7 +269,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       }
       issue_PV(U - 1);
     }
-  } else if (warp == 3) {
+  } else if (warp == 3 || (AVB_DATTN_OP_WARP && warp == 2)) {
     // ======================= projection MMA issuer: G_u = xhat Wqkv_h^T two units ahead, DELTA += O_h Wo_h^T one behind
     if (U > 0) {
       constexpr uint32_t idesc_g = ptx::make_idesc_bf16(128, 96, 0, 0);
@@ -321,19 +329,24 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         }
         __syncwarp();
       };
-      // (Tried, r2g: OP on its own issuing warp, so that its wait for the previous sequence's Depi (d_free) does not hold
-      //  back G three units ahead - 3.70 vs 3.57 ms: the extra polling warp costs more than the decoupling gains.)
-      if (kFuseOut) ptx::mbar_wait(wo_full, 0, 89, 40u);
-      issue_G(0);
-      if (U > 1) issue_G(1);
-      for (int u = 0; u < U; ++u) {
-        AVB_TRACE(5, u, 0);
-        if (u + 2 < U) issue_G(u + 2);
-        AVB_TRACE(5, u, 1);
-        if (kFuseOut && u >= 1) issue_OP(u - 1);
-        AVB_TRACE(5, u, 2);
+      if (AVB_DATTN_OP_WARP && warp == 2) {
+        if (kFuseOut) {
+          ptx::mbar_wait(wo_full, 0, 89, 40u);
+          for (int u = 0; u < U; ++u) issue_OP(u);
+        }
+      } else {
+        if (kFuseOut && !AVB_DATTN_OP_WARP) ptx::mbar_wait(wo_full, 0, 89, 40u);
+        issue_G(0);
+        if (U > 1) issue_G(1);
+        for (int u = 0; u < U; ++u) {
+          AVB_TRACE(5, u, 0);
+          if (u + 2 < U) issue_G(u + 2);
+          AVB_TRACE(5, u, 1);
+          if (kFuseOut && !AVB_DATTN_OP_WARP && u >= 1) issue_OP(u - 1);
+          AVB_TRACE(5, u, 2);
+        }
+        if (kFuseOut && !AVB_DATTN_OP_WARP) issue_OP(U - 1);
       }
-      if (kFuseOut) issue_OP(U - 1);
     }
   }
   } else if (warp < 8) {
@@ -587,8 +600,9 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     const uint32_t aQ = ptx::smem_u32(sQ), aK = ptx::smem_u32(sK), aV = ptx::smem_u32(sV);
     auto conv_wait = [&](int u) {
       ptx::mbar_wait(&g_full[u & 1], (uint32_t)((u >> 1) & 1), 91, AVB_DATTN_WAIT_NS);
-      // the Q / K tiles are single-buffered: S of the previous unit (issued by another warp than G) must have read them
-      if (u >= 1) ptx::mbar_wait(&s_full[(u - 1) & 1], (uint32_t)(((u - 1) >> 1) & 1), 96);
+      // single-buffered Q / K tiles: S of the previous unit (issued by another warp than G) must have read them.  With two
+      // buffers the reader was S of unit u - 2, which the softmax had loaded before G of this unit could be issued.
+      if (kDaQKBufs == 1 && u >= 1) ptx::mbar_wait(&s_full[(u - 1) & 1], (uint32_t)(((u - 1) >> 1) & 1), 96);
       // ... and the V buffer (three of them) is last read by PV of unit u - 3
       if (u >= kDaVBufs) ptx::mbar_wait(&v_free[u % kDaVBufs], (uint32_t)((u / kDaVBufs - 1) & 1), 98);
       AVB_TRACE(2, u, 2);
@@ -615,7 +629,8 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
           for (int e = 0; e < 8; ++e) bb[e] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         ptx::tmem_wait_ld();
-        const uint32_t tile = w == 0 ? aQ : (w == 1 ? aK : aV + (uint32_t)((u % kDaVBufs) * kDaTileBytes));
+        const uint32_t qk = (uint32_t)((u % kDaQKBufs) * 2 * kDaTileBytes);
+        const uint32_t tile = w == 0 ? aQ + qk : (w == 1 ? aK + qk : aV + (uint32_t)((u % kDaVBufs) * kDaTileBytes));
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float f[8];
