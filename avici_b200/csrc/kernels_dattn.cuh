@@ -16,9 +16,9 @@
 //   S_u     : S = Q K^T                                    M=128, N=kc, K=32   -> TMEM          (kc = T rounded up to 16)
 //   softmax : P = exp2(S) without a running maximum, bf16 pairs -> TMEM (same scheme and guard as attention_tc_kernel)
 //   PV_u    : O = P V, L = P 1                             M=128, N=32|16, K=kc -> TMEM
-//   Oepi_u  : O / L -> bf16 -> shared memory A tile [128 x 32]
+//   Oepi_u  : O / L -> bf16 -> TMEM A tile [128 x 32] (tcgen05.st; shared memory / HBM when the out-projection is not fused)
 //   OP_u    : DELTA += O_h . Wo_h^T                        M=128, N=128, K=32  -> TMEM, accumulated over the 8 heads
-//   Depi    : DELTA + bo -> bf16 -> 256-byte rows of delta (token order)
+//   Depi    : DELTA + bo' -> bf16 -> 256-byte rows of delta (token order), staged in the finished xhat tile, TMA store
 // kFuseOut = false stops after Oepi and writes the attention output in outproj_tc_kernel's A-operand layout instead
 // (the out-projection then runs as its own launch); kept as the staging step of this kernel and as its A/B reference.
 //
@@ -28,17 +28,19 @@
 // copies (192 KB per sequence; the L2 -> SM path, not HBM, carries them).
 //
 // TMEM (512 columns): SBUF0 | SBUF1 (128 each: the QKV accumulator of a unit, then its S tile) | P 64 | O 32 | L 16 |
-// 16 spare | DELTA 128.  Software pipeline, while the 8 softmax warps (the MUFU-bound stage) work on unit u:
+// bf16 O tile 16 (A operand of OP) | DELTA 128.  Software pipeline, while the 8 softmax warps (the MUFU-bound stage)
+// work on unit u:
 //     attention issuer:  PV_{u-1}, S_{u+1}          projection issuer:  G_{u+2}, OP_{u-1}
 // Two issuing warps because each MMA group waits on a different producer (softmax, conv, LayerNorm + weight ring,
 // Oepi): one thread blocking on them in turn serialised everything (r2b trace: 3550 clocks per unit).  What the
 // tensor pipe's in-order execution used to guarantee between the two groups is now explicit: conv_u waits for
-// S_{u-1} before it overwrites the single-buffered Q / K tiles, Oepi_u waits for OP_{u-2} before it reuses an O tile.
+// S_{u-1} before it overwrites the single-buffered Q / K tiles, Oepi_u waits for OP_{u-1} before it rewrites the O tile.
 // Measured cost of an M = 128, K = 16 tcgen05.mma on B200 (scripts/microbench_mma.cu): ~42 + N/2 clocks with A in
-// shared memory, ~10 + N/2 with A in TMEM - per unit G 8 x 89, S 2 x 97, PV 7 x 26, L 7 x 18, OP 2 x 105 = 1420 clocks.
+// shared memory, ~10 + N/2 with A in TMEM - per unit G 8 x 89, S 2 x 97, PV 7 x 26, L 7 x 18, OP 2 x 74 = 1360 clocks.
 //   warp 0: weight producer   warp 1: attention MMA issuer   warp 2: TMEM alloc   warp 3: projection MMA issuer
-//   warps 4-7: LayerNorm      warps 8-11: conv / Oepi / Depi (TMEM lane quarter = warp & 3)
-//   warps 12-19: softmax (lane quarter x column half)
+//   warps 4-7: LayerNorm slices of the next sequence, Oepi, Depi (TMEM lane quarter = warp & 3; 120 registers)
+//   warps 8-11: conv only (88 registers)      warps 12-19: softmax (lane quarter x column half; 104 registers)
+// DESIGN.md 3.2 has the two rounds of trace / ncu findings this structure comes from (6.64 -> 3.3 ms per launch).
 #pragma once
 #include "kernels_tc.cuh"
 
