@@ -294,6 +294,17 @@ def run_ours(args):
     prof = eng.profile_read(reset=True)
     eng.profile(False)
 
+    # CUDA-graph variant of the same step: one graph launch instead of ~430 kernel launches; what it saves is
+    # the launch gaps, so at batch 64 it should equal the plain number (reported, not the headline)
+    graph_ms = None
+    try:
+        graph, _ = eng.capture(x_dev, None, standardize=_lib.AVB_STANDARDIZE_DEFAULT)
+        graph.replay()
+        graph_ms = timed(graph.replay, args.steps) / args.steps
+        del graph
+    except Exception as e:  # noqa: BLE001 - optional leg
+        graph_ms = f"{type(e).__name__}: {e}"[:200]
+
     axial = None
     if world > 1 and not args.no_axial:
         del x_dev, out  # the axial leg needs the memory of rank 0 for the single-GPU run of the same dataset
@@ -340,6 +351,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "datasets/s", "h2d_bytes_per_step": int(x_host.nbytes),
                     "d2h_bytes_per_step": int(B * N_VARS * N_VARS * 4), "steps": e2e_steps},
             "gpu_launches": launches,
+            "cuda_graph": ({"ms_per_step": graph_ms, "value": world * B / (graph_ms * 1e-3), "what": "the same step replayed as one CUDA graph"}
+                           if isinstance(graph_ms, float) else {"error": graph_ms}),
             "parity": parity,
             "clocks": clocks,
             "roofline": {"kernel": "attention_tc_kernel (attend over n)", "bound": "tensor", "achieved": achieved,
