@@ -1426,6 +1426,10 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 // |q_h|^2 and |k_h|^2 it writes: |s| <= |q||k|), so the polynomial lanes need neither the lower clamp nor the running
 // maximum - 9 instead of 12 issue slots per pair, which is what lets a larger share of the exponentials leave the MUFU.
 constexpr int kAttnFastPolyEvery = AVB_ATTN_POLY_EVERY;
+#ifndef AVB_ATTN_POLY_DEG  // degree of the exp2 polynomial of the FMA-pipe lanes (3: rel. error 7.5e-5; 2: 1.7e-3, one packed FMA less).
+#define AVB_ATTN_POLY_DEG 2  // P is rounded to bf16 right behind it (half an ulp = 2.0e-3) and the row sum L is taken over the same
+#endif                       // rounded P, so degree 2 costs nothing that the rounding does not: r2g, same box, n-axis launch 10.26 ->
+                             // 10.06 ms (8/16 share 10.08, 9/16 10.25); bench 333.8 -> 338.1 datasets/s, max|dp| 5.4e-4 -> 6.2e-4 (tol 1e-2)
 #ifndef AVB_ATTN_POLY_MASK_NC  // polynomial pairs of the unclamped variant: 7 of 16.  Measured (r2d, n-axis launch, B = 64, ms):
 #define AVB_ATTN_POLY_MASK_NC 0x52A5  // clamped 5/16 11.05 | unclamped 5/16 10.61, 6/16 10.15-10.18 (three patterns),
 #endif                                // 7/16 {0,2,5,7,9,12,14} 9.98, 7/16 {1,3,5,8,10,12,15} 10.33-10.41, 8/16 ~10.5
@@ -1435,6 +1439,9 @@ __device__ __forceinline__ void exp_chunk32(const uint32_t (&s)[32], uint32_t* p
   const uint64_t c3 = pack2(0.055171650f, 0.055171650f), c2 = pack2(0.24261113f, 0.24261113f);
   const uint64_t c1 = pack2(0.69326097f, 0.69326097f), c0 = pack2(0.99992806f, 0.99992806f);
   const uint64_t neg1 = pack2(-1.0f, -1.0f);
+#if AVB_ATTN_POLY_DEG == 2  // degree-2 minimax of 2^f on [-0.5, 0.5]: relative error 1.7e-3 (half a bf16 ulp is 2.0e-3)
+  const uint64_t q2 = pack2(0.23842894f, 0.23842894f), q1 = pack2(0.70344801f, 0.70344801f), q0 = pack2(1.00044314f, 1.00044314f);
+#endif
 #pragma unroll
   for (int e = 0; e < 16; ++e) {
     const float a = __uint_as_float(s[2 * e]), b = __uint_as_float(s[2 * e + 1]);
@@ -1444,9 +1451,14 @@ __device__ __forceinline__ void exp_chunk32(const uint32_t (&s)[32], uint32_t* p
       const uint64_t x2 = kClamp ? pack2(fmaxf(a, -126.0f), fmaxf(b, -126.0f)) : pack2(a, b);
       const uint64_t t2 = add2(x2, magic2);           // integer part lands in the low mantissa bits
       const uint64_t f2 = fma2(add2(t2, nmagic2), neg1, x2);  // f = x - round(x), in [-0.5, 0.5]
+#if AVB_ATTN_POLY_DEG == 2
+      uint64_t p2 = fma2(f2, q2, q1);
+      p2 = fma2(p2, f2, q0);
+#else
       uint64_t p2 = fma2(f2, c3, c2);
       p2 = fma2(p2, f2, c1);
       p2 = fma2(p2, f2, c0);
+#endif
       float p0, p1, t0, t1;
       unpack2(p2, p0, p1);
       unpack2(t2, t0, t1);
