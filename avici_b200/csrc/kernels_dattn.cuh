@@ -706,8 +706,18 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       }
 #endif
       uint32_t pk[32];
-      exp_chunk32(sa, pk, pmax);
-      exp_chunk32(sb, pk + 16, pmax);
+      if (nv > 0) {  // (a 32-column chunk past the end of the sequence is all zeros: no exponentials for it)
+        exp_chunk32(sa, pk, pmax);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = 0u;
+      }
+      if (nv > 32) {
+        exp_chunk32(sb, pk + 16, pmax);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[16 + e] = 0u;
+      }
       AVB_TRACE(3, u, 3);
       if (u >= 1) {  // P is free once the PV / L MMAs of the previous unit have finished
         AVB_DA_WAIT(pv_done, (uint32_t)((u - 1) & 1), 95);
