@@ -80,6 +80,7 @@ SIGNATURES = {
     "avb_test_set_dattn_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "avb_test_set_f32_tc": (C.c_int, [C.c_void_p, C.c_int32]),
     "avb_test_set_head_tc": (C.c_int, [C.c_void_p, C.c_int32]),
+    "avb_test_set_dattn_pack": (C.c_int, [C.c_void_p, C.c_int32]),
     "avb_test_dattn_bf16": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "avb_test_ffn_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

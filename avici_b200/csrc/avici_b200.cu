@@ -122,6 +122,7 @@ struct avb_model_s {
   std::mutex host_mu;
   long long launches = 0;
   int dattn_mode = 1;  // d-axis blocks with d <= 128: 1 = fully fused kernel, 2 = fused up to the attention output, 0 = unfused
+  int dattn_pack = 1;  // fused d-axis kernel: pack 128 / d sequences per tile when d <= 64 (0: one sequence per tile)
   int head_tc = 1;  // bf16 mode: edge-logit contraction of the head on the tensor cores (0: SIMT head_logits_kernel)
   int f32_tc = 1;  // fp32 mode: projections and FFN as split-precision tensor-core GEMMs (0: SIMT sgemm_kernel)
   avb_nccl_comm_t comm = nullptr;  // avb_comm_init: communicator of the axially sharded forward (one rank per handle)
@@ -399,33 +400,49 @@ int launch_dattn_tc(avb_handle h, const float* z, const Block& W, void* out, int
                     int num_sms, long long* launches, int* guard) {
   static PerDeviceOnce once;
   cudaError_t e = once.run([] {
-    cudaError_t r = cudaFuncSetAttribute(avb::dattn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t r = cudaFuncSetAttribute(avb::dattn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          avb::DaCfg<true>::kSmemBytes);
     if (r == cudaSuccess)
-      r = cudaFuncSetAttribute(avb::dattn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::DaCfg<false>::kSmemBytes);
+      r = cudaFuncSetAttribute(avb::dattn_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::DaCfg<true>::kSmemBytes);
+    if (r == cudaSuccess)
+      r = cudaFuncSetAttribute(avb::dattn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, avb::DaCfg<false>::kSmemBytes);
     return r;
   });
   if (e != cudaSuccess) return fail(h, AVB_ERR_CUDA, "cudaFuncSetAttribute(dattn_tc): %s", cudaGetErrorString(e));
   if (T < 1 || T > 128 || S < 1) return fail(h, AVB_ERR_INVALID, "dattn_tc: sequence length %d not in 1..128", T);
-  const int grid = std::min(S, num_sms);
-  CUtensorMap tm_delta;
+  // sequences of T <= 64 tokens are packed g = 128 / T to a tile (kPack): the delta rows are then {128 channels, g T rows,
+  // tiles}, and a last tile with fewer sequences gets a map of its own that clips at its own row count
+  const bool pack = fuse_out && T <= 64 && h->dattn_pack;
+  const int g = pack ? 128 / T : 1, Tt = g * T;
+  const int ntiles = (S + g - 1) / g, nfull = S / g, rem = S - nfull * g;
+  const int grid = std::min(ntiles, num_sms);
+  CUtensorMap tm_delta, tm_last;
   memset(&tm_delta, 0, sizeof tm_delta);
+  memset(&tm_last, 0, sizeof tm_last);
   if (fuse_out) {
-    // delta rows as {128 channels, T rows, S sequences} bf16, stored in [32 ch x 32 rows] boxes (64B swizzle): the row
-    // bound of the map clips what a warp's box holds past the end of its sequence
+    // delta rows as {128 channels, rows of a tile, tiles} bf16, stored in [32 ch x 32 rows] boxes (64B swizzle): the row
+    // bound of the map clips what a warp's box holds past the end of its tile
     EncodeTiledFn fn = encode_tiled_fn();
-    cuuint64_t gdim[3] = {128, (cuuint64_t)T, (cuuint64_t)S};
-    cuuint64_t gstr[2] = {256, (cuuint64_t)T * 256};
-    cuuint32_t box[3] = {32, 32, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    if (!fn || fn(&tm_delta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for the delta rows");
-    avb::dattn_tc_kernel<true><<<grid, avb::kDaThreads, avb::DaCfg<true>::kSmemBytes, st>>>(
-        z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo_d, reinterpret_cast<bf16*>(out), S, T, guard, tm_delta, W.dattn_bias);
+    auto encode = [&](CUtensorMap* tm, void* base, int rows, int tiles) {
+      cuuint64_t gdim[3] = {128, (cuuint64_t)rows, (cuuint64_t)tiles};
+      cuuint64_t gstr[2] = {256, (cuuint64_t)Tt * 256};
+      cuuint32_t box[3] = {32, 32, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      return fn && fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    bool ok = encode(&tm_delta, out, Tt, std::max(nfull, 1));
+    if (ok && rem > 0) ok = encode(&tm_last, reinterpret_cast<bf16*>(out) + (size_t)nfull * Tt * 128, rem * T, 1);
+    if (!ok) return fail(h, AVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for the delta rows");
+    if (pack)
+      avb::dattn_tc_kernel<true, true><<<grid, avb::kDaThreads, avb::DaCfg<true>::kSmemBytes, st>>>(
+          z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo_d, reinterpret_cast<bf16*>(out), S, T, guard, tm_delta, W.dattn_bias, tm_last);
+    else
+      avb::dattn_tc_kernel<true, false><<<grid, avb::kDaThreads, avb::DaCfg<true>::kSmemBytes, st>>>(
+          z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo_d, reinterpret_cast<bf16*>(out), S, T, guard, tm_delta, W.dattn_bias, tm_last);
   } else {
-    avb::dattn_tc_kernel<false><<<grid, avb::kDaThreads, avb::DaCfg<false>::kSmemBytes, st>>>(
-        z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo_d, reinterpret_cast<bf16*>(out), S, T, guard, tm_delta, W.dattn_bias);
+    avb::dattn_tc_kernel<false, false><<<grid, avb::kDaThreads, avb::DaCfg<false>::kSmemBytes, st>>>(
+        z, W.wd_qkv, W.wd_o, W.bqkv_f, W.bo_d, reinterpret_cast<bf16*>(out), S, T, guard, tm_delta, W.dattn_bias, tm_last);
   }
   if (launches) ++*launches;
   e = cudaGetLastError();
@@ -1529,6 +1546,12 @@ int avb_test_set_dattn_mode(avb_handle h, int32_t mode) {
 int avb_test_set_f32_tc(avb_handle h, int32_t on) {
   if (!h) return AVB_ERR_INVALID;
   h->f32_tc = on != 0;
+  return AVB_OK;
+}
+
+int avb_test_set_dattn_pack(avb_handle h, int32_t on) {
+  if (!h) return AVB_ERR_INVALID;
+  h->dattn_pack = on != 0;
   return AVB_OK;
 }
 

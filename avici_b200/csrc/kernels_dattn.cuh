@@ -106,11 +106,16 @@ static_assert(DaCfg<true>::kSmemBytes <= 232448, "dattn_tc_kernel: shared memory
 __device__ float* g_dattn_dbg = nullptr;
 #endif
 
-template <bool kFuseOut>
+// kPack (with kFuseOut): sequences of T <= 64 tokens are packed g = 128 / T to a tile - the tile's g T rows are g T
+// consecutive tokens, every per-row stage is unchanged, and the softmax masks the scores between different sequences
+// (block-diagonal P), so a tile costs what it always costs and a sequence 1 / g of it.  "Sequence" below then reads
+// "tile"; tm_delta_last serves a last tile that holds fewer than g sequences.
+template <bool kFuseOut, bool kPack = false>
 __global__ void __launch_bounds__(kDaThreads, 1)
 dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_img, const uint8_t* __restrict__ wo_img,
                 const float* __restrict__ bqkv, const float* __restrict__ bo, __nv_bfloat16* __restrict__ out, int S, int T,
-                int* __restrict__ guard, const __grid_constant__ CUtensorMap tm_delta, const __grid_constant__ DaBias cb) {
+                int* __restrict__ guard, const __grid_constant__ CUtensorMap tm_delta, const __grid_constant__ DaBias cb,
+                const __grid_constant__ CUtensorMap tm_delta_last) {
   using Cfg = DaCfg<kFuseOut>;
   constexpr int NS = Cfg::kWStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -148,9 +153,17 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
   float* s_bias = reinterpret_cast<float*>(smem + Cfg::kDataBytes + 1024);       // [256] bq | [128] bo' = bo + bv Wo
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int nseq = (int)blockIdx.x < S ? (S - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int g = kPack ? 128 / T : 1;       // sequences per tile
+  const int Tt = g * T;                    // rows of a full tile
+  const int ntiles = (S + g - 1) / g;
+  const int nseq = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;  // tiles of this CTA
   const int U = nseq * kDaHeads;
-  const int kc = (T + 15) & ~15;  // key columns the MMAs touch
+  const int kc = (Tt + 15) & ~15;  // key columns the MMAs touch
+  // valid rows of the CTA's tile number si (the last tile of the launch may hold fewer than g sequences)
+  auto vrows_of = [&](int si) {
+    const int tile = (int)blockIdx.x + si * (int)gridDim.x;
+    return kPack ? min(g, S - tile * g) * T : T;
+  };
   // trace builds (-DAVB_TRACE_ENABLE, scripts/trace_dattn.py): CTA 0 stamps clock64() per role and unit
   long long* trace = (blockIdx.x == 0 && lane == 0 && (warp <= 4 || warp == 8 || warp == 12)) ? g_attn_trace : nullptr;
 
@@ -362,13 +375,13 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int rs = lane >> 3, j8 = lane & 7;
     float4 ln[2][4];
-    auto ln8_load = [&](const float* zs, int r0) {  // rows 32w + r0 .. + 7 of the sequence (zeros past its end)
+    auto ln8_load = [&](const float* zs, int r0, int vr) {  // rows 32w + r0 .. + 7 of the sequence (zeros past its end)
 #pragma unroll
       for (int uu = 0; uu < 2; ++uu) {
         const int row = w * 32 + r0 + uu * 4 + rs;
         const float4* zp = reinterpret_cast<const float4*>(zs + (size_t)row * 128) + j8;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ln[uu][k] = row < T ? __ldcg(zp + k * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 4; ++k) ln[uu][k] = row < vr ? __ldcg(zp + k * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     auto ln8_finish = [&](uint32_t a_tile, int r0) {  // same layout as ln_warp_rows_to_umma_tile
@@ -430,7 +443,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       ptx::tc_fence_before();
       ptx::mbar_arrive(&o_free[u & 1]);
       AVB_TRACE(7, u, 1);
-      if (r < T && !(lsum < 1.2676506e30f && lsum > 7.8886091e-31f)) *guard = 1;  // outside (2^-100, 2^100), inf or NaN
+      if (r < vrows_of(u >> 3) && !(lsum < 1.2676506e30f && lsum > 7.8886091e-31f)) *guard = 1;  // outside (2^-100, 2^100), inf or NaN
       float inv;
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(lsum));  // 1 ulp: far below the bf16 rounding of O
 #ifdef AVB_DATTN_DEBUG
@@ -473,7 +486,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         ptx::tmem_wait_st();
         AVB_TRACE(7, u, 4);
       } else {
-        if (r < T) {  // outproj_tc_kernel's A-operand layout: [m >> 7][head][m & 127][32 ch], chunks at c ^ ((m >> 1) & 3)
+        if (r < T) {  // (never packed) outproj_tc_kernel's A-operand layout: [m >> 7][head][m & 127][32 ch], chunks at c ^ ((m >> 1) & 3)
           const int h = u & 7;
           const int s = (int)blockIdx.x + (u >> 3) * (int)gridDim.x;
           const unsigned m = (unsigned)s * (unsigned)T + (unsigned)r;
@@ -539,19 +552,23 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       ptx::fence_proxy_async();
       __syncwarp();
       AVB_TRACE(6, si, 4);
-      if (lane < 4 && w * 32 < T) {  // one box per lane: a single issue slot instead of four dependent ones
-        ptx::tma_store_3d(&tm_delta, stage + (uint32_t)((lane >> 1) * 16384 + (lane & 1) * 2048), lane * 32, w * 32, s);
+      const int vr = vrows_of(si);
+      if (lane < 4 && w * 32 < vr) {  // one box per lane: a single issue slot instead of four dependent ones
+        if (kPack && vr < Tt)         // the launch's last tile, fewer sequences: its own map clips at its own row count
+          ptx::tma_store_3d(&tm_delta_last, stage + (uint32_t)((lane >> 1) * 16384 + (lane & 1) * 2048), lane * 32, w * 32, 0);
+        else
+          ptx::tma_store_3d(&tm_delta, stage + (uint32_t)((lane >> 1) * 16384 + (lane & 1) * 2048), lane * 32, w * 32, s);
         ptx::bulk_commit();
       }
       AVB_TRACE(6, si, 5);
     };
 
     if (nseq > 0) {  // the first sequence's LayerNorm, slice by slice
-      const float* zs = z + (size_t)blockIdx.x * T * 128;
-      if (nseq > 1) prefetch_rows_l2(z + (size_t)((int)blockIdx.x + (int)gridDim.x) * T * 128, T, w * 32, lane);
+      const float* zs = z + (size_t)blockIdx.x * Tt * 128;
+      if (nseq > 1) prefetch_rows_l2(z + (size_t)((int)blockIdx.x + (int)gridDim.x) * Tt * 128, vrows_of(1), w * 32, lane);
 #pragma unroll 1
       for (int r0 = 0; r0 < 32; r0 += 8) {
-        ln8_load(zs, r0);
+        ln8_load(zs, r0, vrows_of(0));
         ln8_finish(ptx::smem_u32(sX), r0);
       }
       ptx::fence_proxy_async();
@@ -560,7 +577,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     for (int si = 0; si < nseq; ++si) {
       const int s_next = (int)blockIdx.x + (si + 1) * (int)gridDim.x, nbuf = (si + 1) & 1;
       const bool has_next = si + 1 < nseq;
-      if (si + 2 < nseq) prefetch_rows_l2(z + (size_t)(s_next + (int)gridDim.x) * T * 128, T, w * 32, lane);
+      if (si + 2 < nseq) prefetch_rows_l2(z + (size_t)(s_next + (int)gridDim.x) * Tt * 128, vrows_of(si + 2), w * 32, lane);
       for (int h = 0; h < kDaHeads; ++h) {
         const int u = si * kDaHeads + h;
         const bool slice = has_next && h >= AVB_DATTN_LN_H0 && h < AVB_DATTN_LN_H0 + 4;
@@ -569,7 +586,7 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
         uint4 pk[4];
         if (slice) {
           if (hs == 0) ptx::mbar_wait(&x_empty[nbuf], (uint32_t)(((si + 1) >> 1) & 1) ^ 1, 90);
-          ln8_load(z + (size_t)s_next * T * 128, hs * 8);  // (issued a unit earlier, behind the previous slice: 3.50 vs 3.36 ms)
+          ln8_load(z + (size_t)s_next * Tt * 128, hs * 8, vrows_of(si + 1));  // (issued a unit earlier, behind the previous slice: 3.50 vs 3.36 ms)
         }
         // (Tried, r2g: the second half of the previous sequence's Depi behind this unit's accumulator hand-back, 3.72 vs
         //  3.57 ms - the hand-back of the unit after that waits instead.)
@@ -672,6 +689,23 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
     const uint32_t a_pfull = ptx::smem_u32(p_full);
     const uint32_t tPw = tP + half * 32 + lane_off;
     const int nv = T - half * 64;  // valid key columns in this warp's half (may be <= 0)
+    // kPack: the keys of a row are those of its own sequence, columns [lo, hi) of the tile - per thread one 32-bit mask
+    // for each of its two 32-column chunks, the same for every unit (rows past the tile's sequences: empty window)
+    uint32_t m0 = 0xffffffffu, m1 = 0xffffffffu;
+    bool any0 = true, any1 = true, all0 = true, all1 = true;
+    if constexpr (kPack) {
+      const int r = q * 32 + lane, sq = r / T;
+      const int lo = sq * T, hi = sq < g ? lo + T : lo;
+      auto chunk_mask = [&](int c0) {
+        const int a = lo - c0, b = hi - c0;
+        const uint32_t mb = b >= 32 ? 0xffffffffu : (b <= 0 ? 0u : (1u << b) - 1u);
+        const uint32_t ma = a <= 0 ? 0xffffffffu : (a >= 32 ? 0u : ~((1u << a) - 1u));
+        return ma & mb;
+      };
+      m0 = chunk_mask(half * 64); m1 = chunk_mask(half * 64 + 32);
+      any0 = __any_sync(0xffffffffu, m0 != 0u); all0 = __all_sync(0xffffffffu, m0 == 0xffffffffu);
+      any1 = __any_sync(0xffffffffu, m1 != 0u); all1 = __all_sync(0xffffffffu, m1 == 0xffffffffu);
+    }
     float pmax = -INFINITY;
     for (int u = 0; u < U; ++u) {
       AVB_TRACE(3, u, 0);
@@ -686,7 +720,18 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       ptx::tc_fence_before();
       ptx::mbar_arrive_s(ptx::smem_u32(&s_free[u & 1]));  // the only read of S: the buffer may take the next-but-one unit's projection
       AVB_TRACE(3, u, 2);
-      if (nv < 64) {  // keys beyond the sequence end: score -inf, probability 0
+      if constexpr (kPack) {  // scores against other sequences' keys: -inf, probability 0
+        if (any0 && !all0) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (!((m0 >> e) & 1u)) sa[e] = 0xff800000u;
+        }
+        if (any1 && !all1) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (!((m1 >> e) & 1u)) sb[e] = 0xff800000u;
+        }
+      } else if (nv < 64) {  // keys beyond the sequence end: score -inf, probability 0
         if (nv < 32) {
 #pragma unroll
           for (int e = 0; e < 32; ++e)
@@ -706,13 +751,13 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
       }
 #endif
       uint32_t pk[32];
-      if (nv > 0) {  // (a 32-column chunk past the end of the sequence is all zeros: no exponentials for it)
+      if (kPack ? any0 : nv > 0) {  // (a 32-column chunk past the end of the sequence is all zeros: no exponentials for it)
         exp_chunk32(sa, pk, pmax);
       } else {
 #pragma unroll
         for (int e = 0; e < 16; ++e) pk[e] = 0u;
       }
-      if (nv > 32) {
+      if (kPack ? any1 : nv > 32) {
         exp_chunk32(sb, pk + 16, pmax);
       } else {
 #pragma unroll

@@ -250,6 +250,8 @@ int avb_test_dattn_bf16(avb_handle h, int32_t block_idx, const float* z_dev, int
 int avb_test_set_f32_tc(avb_handle h, int32_t on);
 /* bf16 handles: 1 (default) = the head's u . v^T contraction on the tensor cores (head_logits_tc_kernel), 0 = SIMT. */
 int avb_test_set_head_tc(avb_handle h, int32_t on);
+/* bf16 handles: 1 (default) = the fused d-axis kernel packs 128 / d sequences per 128-row tile when d <= 64, 0 = one per tile. */
+int avb_test_set_dattn_pack(avb_handle h, int32_t on);
 /* Which kernels run the attention half of a block that attends over d <= 128 (bf16 mode): 1 (default) the fully
  * fused dattn_tc_kernel, 2 the same kernel up to the attention output + the separate out-projection, 0 the unfused
  * QKV / attention / out-projection launches (what every other block uses).  A/B and test knob. */

@@ -199,6 +199,36 @@ def test_dattn_fused_sublayer_against_torch(B, n, d, fuse_out):
         assert err <= 3e-2 * max(ref.abs().max().item(), 1.0), f"dattn err {err} (scale {ref.abs().max().item()})"
 
 
+@pytest.mark.parametrize("B,n,d", [(1, 7, 50), (2, 33, 20), (1, 130, 64), (1, 5, 3), (1, 1, 1), (1, 301, 33), (3, 11, 42)])
+def test_dattn_packed_sequences_equal_one_per_tile(B, n, d):
+    """d <= 64: the fused d-axis kernel packs 128 // d sequences into one 128-row tile and masks the scores between
+    different sequences.  Against the same kernel with one sequence per tile (every stage but the softmax mask is
+    row-wise, so the two agree to the bf16 rounding of P) and against the torch reference; sequence counts that do and do
+    not fill the last tile."""
+    model = avici_b200.random_init_model(dict(layers=1), seed=5, perturb=True, compute_dtype="bf16")
+    eng = model.engine
+    lib, h = eng.lib, eng.handle
+    g = torch.Generator(device="cuda").manual_seed(B * 131 + n * 7 + d)
+    z = torch.randn(B, n, d, 128, device="cuda", generator=g) * 2 + torch.randn(B, n, d, 1, device="cuda", generator=g)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    res = {}
+    for pack in (1, 0):
+        eng._check(lib.avb_test_set_dattn_pack(h, pack))
+        delta = torch.full((B * n * d + 64, 128), float("nan"), device="cuda", dtype=torch.bfloat16)  # + 64 guard rows
+        guard = C.c_int32(-1)
+        eng._check(lib.avb_test_dattn_bf16(h, 0, z.data_ptr(), B, n, d, 1, delta.data_ptr(), C.byref(guard), st))
+        torch.cuda.synchronize()
+        assert guard.value == 0
+        assert torch.isnan(delta[B * n * d:].float()).all(), "rows written past the last sequence"
+        res[pack] = delta[:B * n * d].float()
+    eng._check(lib.avb_test_set_dattn_pack(h, 1))
+    ref = _attn_sublayer_reference(model.params, 0, z).reshape(B * n * d, 128)
+    scale = max(ref.abs().max().item(), 1.0)
+    assert torch.isfinite(res[1]).all(), "rows missing or non-finite"
+    assert (res[1] - ref).abs().max().item() <= 3e-2 * scale
+    assert (res[1] - res[0]).abs().max().item() <= 2e-2 * scale
+
+
 def test_dattn_modes_agree_and_guard_falls_back():
     """The same forward with the d-axis sub-layer fully fused (default), fused up to the attention output, and unfused:
     all within bf16 tolerance of each other; with score magnitudes far outside the fast softmax's range the fused
