@@ -85,6 +85,9 @@ static_assert(DaCfg<true>::kSmemBytes <= 232448, "dattn_tc_kernel: shared memory
 #ifndef AVB_DATTN_BOUNDED_WAITS
 #define AVB_DATTN_BOUNDED_WAITS 1
 #endif
+#ifndef AVB_DATTN_POLY_EVERY  // every n-th pair of exponentials on the FMA pipe (17 = none).  This kernel is bound by issue slots
+#define AVB_DATTN_POLY_EVERY 17  // and role latencies, not by the MUFU (XU pipe 42 %): a polynomial pair costs 11 slots, a MUFU pair 3.
+#endif                           // r2g, ms per launch: none 3.24 | 1/6 3.25 | 1/4 3.30 | 1/3 3.33 (the n-axis kernel's share) | 1/2 3.44
 #ifndef AVB_DATTN_OP_WARP  // 1: OP has its own issuing warp (2) instead of sharing warp 3 with G
 #define AVB_DATTN_OP_WARP 0
 #endif
@@ -752,13 +755,13 @@ dattn_tc_kernel(const float* __restrict__ z, const uint8_t* __restrict__ wqkv_im
 #endif
       uint32_t pk[32];
       if (kPack ? any0 : nv > 0) {  // (a 32-column chunk past the end of the sequence is all zeros: no exponentials for it)
-        exp_chunk32(sa, pk, pmax);
+        exp_chunk32<true, AVB_DATTN_POLY_EVERY>(sa, pk, pmax);
       } else {
 #pragma unroll
         for (int e = 0; e < 16; ++e) pk[e] = 0u;
       }
       if (kPack ? any1 : nv > 32) {
-        exp_chunk32(sb, pk + 16, pmax);
+        exp_chunk32<true, AVB_DATTN_POLY_EVERY>(sb, pk + 16, pmax);
       } else {
 #pragma unroll
         for (int e = 0; e < 16; ++e) pk[16 + e] = 0u;

@@ -1433,7 +1433,7 @@ constexpr int kAttnFastPolyEvery = AVB_ATTN_POLY_EVERY;
 #ifndef AVB_ATTN_POLY_MASK_NC  // polynomial pairs of the unclamped variant: 7 of 16.  Measured (r2d, n-axis launch, B = 64, ms):
 #define AVB_ATTN_POLY_MASK_NC 0x52A5  // clamped 5/16 11.05 | unclamped 5/16 10.61, 6/16 10.15-10.18 (three patterns),
 #endif                                // 7/16 {0,2,5,7,9,12,14} 9.98, 7/16 {1,3,5,8,10,12,15} 10.33-10.41, 8/16 ~10.5
-template <bool kClamp = true>
+template <bool kClamp = true, int kEvery = kAttnFastPolyEvery>
 __device__ __forceinline__ void exp_chunk32(const uint32_t (&s)[32], uint32_t* pk, float& pmax) {
   const uint64_t magic2 = pack2(12582912.0f, 12582912.0f), nmagic2 = pack2(-12582912.0f, -12582912.0f);
   const uint64_t c3 = pack2(0.055171650f, 0.055171650f), c2 = pack2(0.24261113f, 0.24261113f);
@@ -1446,7 +1446,7 @@ __device__ __forceinline__ void exp_chunk32(const uint32_t (&s)[32], uint32_t* p
   for (int e = 0; e < 16; ++e) {
     const float a = __uint_as_float(s[2 * e]), b = __uint_as_float(s[2 * e + 1]);
     constexpr unsigned kMask = kClamp ? (unsigned)(AVB_ATTN_POLY_MASK) : (unsigned)(AVB_ATTN_POLY_MASK_NC);
-    if (kMask ? ((kMask >> e) & 1) : ((e % kAttnFastPolyEvery) == kAttnFastPolyEvery - 1)) {
+    if (kMask ? ((kMask >> e) & 1) : ((e % kEvery) == kEvery - 1)) {
       if (kClamp) pmax = max3(pmax, a, b);
       const uint64_t x2 = kClamp ? pack2(fmaxf(a, -126.0f), fmaxf(b, -126.0f)) : pack2(a, b);
       const uint64_t t2 = add2(x2, magic2);           // integer part lands in the low mantissa bits
